@@ -1,0 +1,180 @@
+/*
+ * wmf_b200.h -- C ABI of libwmfb200.so: the B200 (sm_100a) implementation of WMF's
+ * raster-drainage hot path (D8 accumulation + basin delineation, SHIA cell update).
+ *
+ * This is the drop-in boundary.  The reference reaches its kernels through the
+ * namespace `cu`, the name `shia_v1` and module-level state on `cu` / `models`
+ * (wmf_heavy/wmfv2.py:36-79); each entry point below names the reference routine it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds at wmfv2.py:36-79.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *     asynchronous unless noted ("syncs") and re-entrant per stream;
+ *   - return value: 0 ok, <0 argument/semantic error (WMF_E_*), >0 a cudaError_t;
+ *     wmf_last_error() returns a thread-local message for the last failure;
+ *   - the library keeps no global mutable state (the f2py-style module state of the
+ *     reference lives in the Python shim, not here);
+ *   - workspaces are caller-owned: query the size, allocate, pass in.
+ */
+#ifndef WMF_B200_H
+#define WMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WMF_OK 0
+#define WMF_E_ARG (-1)        /* bad argument (null pointer, negative size, unknown enum) */
+#define WMF_E_WORKSPACE (-2)  /* workspace too small */
+#define WMF_E_OUTLET_RANGE (-3) /* outlet outside grid  (basics.py:225-226) */
+#define WMF_E_OUTLET_MASK (-4)  /* outlet not in mask   (basics.py:227-228) */
+#define WMF_E_CODE5 (-5)      /* keypad code 5 inside the basin (self-draining cell, f90:538) */
+#define WMF_E_CYCLE (-6)      /* drainage cycle through the outlet (Fortran BFS would not end) */
+#define WMF_E_TOO_LARGE (-7)  /* raster exceeds the index width of this entry point */
+#define WMF_E_CAPACITY (-8)   /* output capacity too small */
+
+/* DIR encodings */
+#define WMF_ENC_INTERNAL 0 /* wmf_py: 0 E,1 SE,2 S,3 SW,4 W,5 NW,6 N,7 NE (basics.py:37-46) */
+#define WMF_ENC_KEYPAD 1   /* Fortran: 7 8 9 / 4 5 6 / 1 2 3, rows downwards (cuencas_heavy.f90:1338-1362) */
+
+/* accumulation output types */
+#define WMF_ACC_I32 0
+#define WMF_ACC_I64 1
+#define WMF_ACC_F64 2 /* what wmf_py.basin_acum returns (integral values) */
+
+/* accumulation algorithms (wmf_d8_accum `algo`) */
+#define WMF_ALGO_AUTO 0
+#define WMF_ALGO_WALK 1  /* in-degree driven chain walk with L2 atomics: any input */
+#define WMF_ALGO_SWEEP 2 /* warp strip sweeps + contracted boundary forest: any input, fastest when flow is sweep-coherent */
+
+const char *wmf_last_error(void);
+int wmf_version(void);
+/* device properties the host layer needs: out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=L2 bytes */
+int wmf_device_info(int64_t *out4);
+
+/* ---------------------------------------------------------------- D1: full-raster D8 accumulation
+ * Replaces wmf_py/cu_py/basics.py:124-177 basin_acum(flowdir, mask).
+ * dir: int8 [ny][nx]; mask: uint8 [ny][nx] (nonzero = active) or NULL (= all active);
+ * acc: [ny][nx] of acc_dtype.  Cells outside the mask get 0; cells on or below a
+ * drainage cycle keep the partial sum of their finished tree inflows (reference semantics).
+ * Bit-exact for any schedule (integer adds). */
+size_t wmf_d8_accum_workspace(int64_t ny, int64_t nx, int acc_dtype, int algo);
+int wmf_d8_accum(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx,
+                 int encoding, int algo, void *workspace, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------- D2: basin mask (raster form)
+ * Replaces the traversal of wmf_py/cu_py/basics.py:206-248 basin_cut: basin_mask[c] = 1 iff c is
+ * active and its D8 path through active cells reaches (outlet_r, outlet_c).  Syncs (reads back the
+ * cell count).  Needs ny*nx < 2^31. */
+size_t wmf_basin_mask_workspace(int64_t ny, int64_t nx);
+int wmf_basin_mask(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int encoding,
+                   int64_t outlet_r, int64_t outlet_c, uint8_t *basin_mask, int64_t *ncells_host,
+                   void *workspace, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------- D3: basin structure (vector form)
+ * Replaces cu.basin_find + cu.basin_cut (wmf_heavy/cuencas_heavy.f90:507-576; call sites
+ * wmfv2.py:823-824).  dir: keypad int8 [nrows][ncols] (== Fortran DIR(col, fil)); outlet
+ * (col, fil) 1-based, from wmf_coord2fil_col_host.  Output structure int32 [3][capacity]:
+ * rows = drain id, col, fil, written with row stride `capacity`; *ncells_host = n.  Order is
+ * bit-identical to the Fortran BFS (upstream-first).  Syncs. */
+size_t wmf_basin_structure_workspace(int64_t nrows, int64_t ncols);
+int wmf_basin_structure(const int8_t *dir, int64_t nrows, int64_t ncols, int32_t col, int32_t fil,
+                        int32_t *structure, int64_t capacity, int64_t *ncells_host, void *workspace,
+                        size_t ws_bytes, void *stream);
+/* cuencas_heavy.f90:355-365 in fp32, host side; col/fil = -999 when out of range. */
+void wmf_coord2fil_col_host(float x, float y, float xll, float yll, float dx, int32_t ncols, int32_t nrows,
+                            int32_t *col, int32_t *fil);
+
+/* ---------------------------------------------------------------- D4/D6: vector-form accumulation + basics
+ * structure: int32 [3][n] with row stride `stride`.  wmf_basin_acum_vec == cu.basin_acum(structure,
+ * ncells) (wmfv2.py:1868) == the acum of basin_basics (cuencas_heavy.f90:593-606). */
+size_t wmf_basin_vec_workspace(int64_t n);
+int wmf_basin_acum_vec(const int32_t *structure, int64_t stride, int64_t n, int32_t *acum, void *workspace,
+                       size_t ws_bytes, void *stream);
+/* cuencas_heavy.f90:581-627.  geo = {dxp, xll, yll, dx, nrows(as float)}.  scalars_host[6] = area,
+ * pend_media, elevacion, centroX, centroY, 0.  Syncs. */
+int wmf_basin_basics(const int32_t *structure, int64_t stride, int64_t n, const float *dem, const int32_t *dirv,
+                     const float *geo5_host, int32_t *acum, float *long_cel, float *pend, float *elev,
+                     float *scalars_host, void *workspace, size_t ws_bytes, void *stream);
+/* cuencas_heavy.f90:639-646 */
+int wmf_basin_coordxy(const int32_t *structure, int64_t stride, int64_t n, float xll, float yll, float dx,
+                      int32_t nrows, float *X, float *Y, void *stream);
+/* cu.basin_map2basin / cu.basin_2map (wmfv2.py:1085,1167-1169): gather/scatter by (col, fil).
+ * elem_size 1, 4 or 8 bytes; raster is [nrows][ncols]. */
+int wmf_basin_map2basin(const int32_t *structure, int64_t stride, int64_t n, const void *raster, int64_t nrows,
+                        int64_t ncols, int elem_size, void *vec, void *stream);
+int wmf_basin_2map(const int32_t *structure, int64_t stride, int64_t n, const void *vec, int64_t nrows,
+                   int64_t ncols, int elem_size, void *raster /* pre-filled with nodata */, void *stream);
+
+/* ---------------------------------------------------------------- D5: stream / node marks
+ * Replaces cu.basin_stream_nod (cuencas_heavy.f90:780-809).  counts_host = {n_nodos, n_cauce}.  Syncs. */
+int wmf_stream_nod(const int32_t *structure, int64_t stride, int64_t n, const int32_t *acum, int32_t umbral,
+                   int32_t *cauce, int32_t *nodos, int32_t *trazado, int32_t *counts_host, void *stream);
+
+/* ---------------------------------------------------------------- S1/S2: SHIA 5-tank (Fortran semantics)
+ * Replaces models.shia_v1 as shipped (wmf_heavy/Modelos_heavy.f90:169-548) incl. calc_speed
+ * (:907-919): vertical cascade + lateral outflow of tanks 2..4 (discarded), fp32.
+ * P parameter sets are advanced in one launch (NSGA-II populations, wmfv2.py:2060-2106).
+ * Layouts (N cells, SoA):
+ *   cell_static float [17][N]: rows 0-3 v_coef, 4-7 h_coef, 8-11 h_exp, 12 max_capilar,
+ *                              13 max_gravita, 14 max_aquifer, 15 hill_long, 16 elem_area
+ *   rain_records int32 [n_rec][N] (record k at row k-1); pos_evento int32 [N_reg], 1-based,
+ *   1 == "no rain" (no read, Modelos:366-367); evp float [N_reg]; calib float [P][11];
+ *   sto float [P][5][N] in/out; hspeed float [P][4][N] in/out (read only if hspeed_given);
+ *   outputs: balance [P][N_reg]; mean_rain [N_reg]; acum_rain [N];
+ *   mean_storage [P][5][N_reg] / mean_speed [P][4][N_reg] nullable.
+ * Per-step diagnostics are reduced deterministically (fixed tree, fp64 partials). */
+typedef struct {
+    float dt;
+    float retorno_gr;
+    float retorno_aq;
+    int32_t calc_niter;
+    int32_t speed_type[3];
+    int32_t hspeed_given;
+} wmf_shia5_params;
+size_t wmf_shia5_workspace(int64_t N, int64_t N_reg, int32_t P);
+int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,
+                  const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento,
+                  const float *evp, const float *calib, float *sto, float *hspeed, float *balance,
+                  float *mean_rain, float *acum_rain, float *mean_storage, float *mean_speed,
+                  void *workspace, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------- S4: SHIA 3-tank (wmf_py semantics)
+ * Replaces wmf_py/models_py/core.py:64-295 shia_v1, fp64.  rain/et double [nsteps][ncell]
+ * (et nullable, already multiplied by nothing: et_scale = dt/3600 or dt/86400 is applied
+ * inside); cap/grav/aqu in/out [ncell]; q_super_last/q_base_last out [ncell];
+ * sums double [nsteps+1][6] out = per-step {q_total, storage, P, ET, q_super, q_base} sums (row 0
+ * holds the initial storage sum, row t+1 belongs to step t), from which the host layer forms q_outlet and the mass-balance diagnostics (core.py:234-256);
+ * series pointers nullable [nsteps][ncell]. */
+typedef struct {
+    double dt, max_capilar, max_gravita, max_aquifer, drena, retorno_gr;
+    double k_perc_cap_to_grav, k_perc_grav_to_aqu, k_baseflow, max_infil_mm_h;
+    double et_scale;
+    int32_t proportional;
+    int32_t pad;
+} wmf_shia3_params;
+size_t wmf_shia3_workspace(int64_t ncell, int64_t nsteps);
+int wmf_shia3_run(const wmf_shia3_params *params_host, int64_t nsteps, int64_t ncell, const double *rain,
+                  const double *et, double *cap, double *grav, double *aqu, double *q_super_last,
+                  double *q_base_last, double *sums, double *q_super_t, double *q_base_t, double *q_total_t,
+                  double *cap_t, double *grav_t, double *aqu_t, void *workspace, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------- synthetic inputs
+ * Scheidegger network: per cell a counter-based RNG keyed by (seed, linear index) draws
+ * internal code 0 (E) / 1 (SE) / 2 (S) with p = 1/4, 1/2, 1/4 (keypad: 6 / 3 / 2).
+ * (row0, col0) place the [ny][nx] window inside a raster nx_total columns wide, so stripes and
+ * oracle sub-windows of one large raster agree cell by cell. */
+int wmf_synth_scheidegger(int8_t *dir, int64_t ny, int64_t nx, int64_t row0, int64_t col0, int64_t nx_total,
+                          uint64_t seed, int encoding, void *stream);
+/* same generator on the host, for oracles and CPU baselines (host pointer). */
+void wmf_synth_scheidegger_host(int8_t *dir_host, int64_t ny, int64_t nx, int64_t row0, int64_t col0,
+                                int64_t nx_total, uint64_t seed, int encoding);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMF_B200_H */

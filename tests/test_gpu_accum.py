@@ -1,0 +1,134 @@
+"""D8 accumulation parity: CUDA path (through the C ABI) vs the CPU oracle / golden vectors, bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import oracle
+from conftest import golden_names
+from wmf_heavy_b200 import _lib, ops
+from wmf_heavy_b200.cu_py import basics
+
+pytestmark = pytest.mark.gpu
+ALGOS = [_lib.ALGO_WALK, _lib.ALGO_SWEEP]
+
+
+def run(fd, mask, algo, acc_dtype=_lib.ACC_I32, enc=_lib.ENC_INTERNAL):
+    d = torch.from_numpy(np.ascontiguousarray(fd, dtype=np.int8)).cuda()
+    m = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask, dtype=np.uint8)).cuda()
+    return ops.d8_accum(d, m, acc_dtype=acc_dtype, encoding=enc, algo=algo).cpu().numpy()
+
+
+def test_reference_fixture_7x7():              # wmf_py/tests/test_cu_basics.py:35-58 through the drop-in API
+    flowdir = np.zeros((7, 7), dtype=int)
+    flowdir[:, -1] = 2
+    flowdir[-1, -1] = -1
+    mask = np.ones_like(flowdir, dtype=bool)
+    acc = basics.basin_acum(flowdir, mask)
+    expected = np.tile(np.arange(1, 8, dtype=float), (7, 1))
+    expected[:, -1] = 7 * np.arange(1, 8)
+    assert acc.dtype == np.float64 and np.array_equal(acc, expected)
+    big = basics.basin_acum(np.zeros((200, 200), dtype=int), np.ones((200, 200), dtype=bool))
+    assert np.array_equal(big, np.tile(np.arange(1, 201, dtype=float), (200, 1)))
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_quirks(algo):                         # SURVEY 8(c) known answers measured on the reference
+    a = run(np.array([[0, 2, -1], [6, 4, 4], [0, 0, 6]]), None, algo)
+    assert np.array_equal(a, [[0, 0, 1], [0, 4, 4], [1, 2, 3]])
+    a = run(np.zeros((1, 5)), np.array([[1, 1, 0, 1, 1]]), algo)
+    assert np.array_equal(a, [[1, 2, 0, 1, 2]])
+    a = run(np.array([[0, 0, 8, 0, 0]]), None, algo)
+    assert np.array_equal(a, [[1, 2, 3, 1, 2]])
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", golden_names("acum"))
+def test_golden(golden, name, algo):
+    fd, mask = golden[f"acum/{name}/flowdir"], golden[f"acum/{name}/mask"]
+    assert np.array_equal(run(fd, mask, algo), golden[f"acum/{name}/acc"])
+    assert np.array_equal(basics.basin_acum(fd.astype(np.int64), mask), golden[f"acum/{name}/acc"].astype(float))
+
+
+CASES = {
+    "sch_1024": lambda: (ops.synth_scheidegger_host(1024, 1024, seed=5), None),
+    "sch_ragged": lambda: (ops.synth_scheidegger_host(517, 1301, seed=6), None),
+    "steep_700x513": lambda: (helpers.steepest(700, 513, 7), None),
+    "steep_mask": lambda: (helpers.steepest(389, 641, 8), np.random.default_rng(8).random((389, 641)) > 0.05),
+    "random_cycles": lambda: (helpers.random_codes(311, 277, 9), np.random.default_rng(9).random((311, 277)) > 0.1),
+    "serpentine": lambda: (helpers.serpentine(96, 131), None),
+    "all_east": lambda: (np.zeros((130, 4099), np.int8), None),
+    "all_north": lambda: (np.full((1500, 70), 6, np.int8), None),
+    "all_west_sw": lambda: (np.where(np.random.default_rng(3).random((257, 400)) < 0.5, 4, 3).astype(np.int8), None),
+    "thin_col": lambda: (helpers.steepest(3000, 1, 10), None),
+    "thin_row": lambda: (helpers.steepest(1, 3000, 11), None),
+    "one_cell": lambda: (np.array([[0]], np.int8), None),
+    "all_masked_out": lambda: (helpers.steepest(40, 50, 12), np.zeros((40, 50), bool)),
+}
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_vs_oracle(case, algo):
+    fd, mask = CASES[case]()
+    m = np.ones(fd.shape, bool) if mask is None else mask
+    exp = oracle.basin_acum(fd, m)
+    got = run(fd, mask, algo)
+    assert got.dtype == np.int32
+    assert np.array_equal(got, exp.astype(np.int32)), f"{(got != exp).sum()} cells differ"
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_dtypes_and_keypad(algo):
+    fd = helpers.steepest(300, 420, 13)
+    exp = oracle.basin_acum(fd, np.ones(fd.shape, bool))
+    g64 = run(fd, None, algo, _lib.ACC_I64)
+    assert g64.dtype == np.int64 and np.array_equal(g64, exp.astype(np.int64))
+    gf = run(fd, None, algo, _lib.ACC_F64)
+    assert gf.dtype == np.float64 and np.array_equal(gf, exp)
+    gk = run(helpers.to_keypad(fd), None, algo, _lib.ACC_I32, _lib.ENC_KEYPAD)
+    assert np.array_equal(gk, exp.astype(np.int32))
+
+
+def test_empty_and_errors():
+    assert basics.basin_acum(np.zeros((0, 5), int), np.zeros((0, 5), bool)).shape == (0, 5)
+    d = torch.zeros((4, 4), dtype=torch.int8, device="cuda")
+    with pytest.raises(_lib.WmfError):
+        ops.d8_accum(d, None, encoding=7)
+
+
+def _local_consistency(dir_t, acc):
+    """Size-independent property: acc[c] == 1 + sum of acc over the neighbours draining into c, for an
+    acyclic all-active raster; and the accumulation at the terminal cells adds up to the cell count."""
+    ny, nx = dir_t.shape
+    total = torch.ones_like(acc, dtype=torch.int64)
+    for k in range(8):
+        dr, dc = int(helpers.DR[k]), int(helpers.DC[k])
+        src = torch.where(dir_t == k, acc, torch.zeros_like(acc)).to(torch.int64)
+        # cell (r, c) with code k drains into (r+dr, c+dc): shift the source by (dr, dc), dropping wraparound
+        sh = torch.zeros_like(src)
+        r0, r1 = max(dr, 0), ny + min(dr, 0)
+        c0, c1 = max(dc, 0), nx + min(dc, 0)
+        sh[r0:r1, c0:c1] = src[r0 - dr:r1 - dr, c0 - dc:c1 - dc]
+        total += sh
+        del src, sh
+    return bool((total == acc.to(torch.int64)).all())
+
+
+@pytest.mark.parametrize("n", [4096, 16384])
+def test_full_size_properties(n):
+    """BASELINE config 2 (16384^2 Scheidegger): local consistency everywhere + mass conservation, and
+    the two algorithms agree bit for bit."""
+    d = ops.synth_scheidegger(n, n, seed=20260101)
+    acc = ops.d8_accum(d, None, algo=_lib.ALGO_SWEEP)
+    assert _local_consistency(d, acc)
+    # terminal cells: E on the last column, S on the last row, SE on either
+    term = torch.zeros_like(d, dtype=torch.bool)
+    term[:, -1] |= (d[:, -1] == 0) | (d[:, -1] == 1)
+    term[-1, :] |= (d[-1, :] == 2) | (d[-1, :] == 1)
+    assert int(acc[term].to(torch.int64).sum()) == n * n
+    if n <= 4096:
+        acc2 = ops.d8_accum(d, None, algo=_lib.ALGO_WALK)
+        assert torch.equal(acc, acc2)
+        sub = ops.synth_scheidegger_host(n, n, seed=20260101)
+        assert np.array_equal(sub, d.cpu().numpy())

@@ -1,0 +1,193 @@
+"""SHIA parity.  fp64 3-tank (wmf_py semantics): storages 1e-12 relative, q_outlet 1e-10 relative.
+fp32 5-tank (Fortran semantics): storages 1e-5 relative (north_star tolerance); `balance` is a
+catastrophic-cancellation quantity and is compared with an absolute tolerance scaled by sum(StoOut)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import oracle
+from conftest import golden_names
+from test_oracle import _forc
+from wmf_heavy_b200 import models, ops, wmfv2
+from wmf_heavy_b200.models_py.core import ModelParams, ModelState, shia_v1
+
+pytestmark = pytest.mark.gpu
+
+
+def _mp(p, **kw):
+    return ModelParams(dt=p.dt, h_coef=1, h_exp=1, v_coef=1, v_exp=1, max_capilar=p.max_capilar,
+                       max_gravita=p.max_gravita, max_aquifer=p.max_aquifer, drena=p.drena, retorno_gr=p.retorno_gr,
+                       storage_constant=0.0, k_perc_cap_to_grav=p.k_perc_cap_to_grav,
+                       k_perc_grav_to_aqu=p.k_perc_grav_to_aqu, k_baseflow=p.k_baseflow,
+                       max_infil_mm_h=p.max_infil_mm_h, eta_priority=p.eta_priority, **kw)
+
+
+@pytest.mark.parametrize("name", golden_names("shia3"))
+def test_shia3_golden(golden, name):
+    f, grid, p = _forc(golden, name)
+    s0 = golden[f"shia3/{name}/state0"]
+    nt = f["rain_mm_h"].shape[0]
+    st = ModelState(s0[0].copy(), s0[1].copy(), s0[2].copy())
+    if int(golden[f"shia3/{name}/raises"]):
+        with pytest.raises(RuntimeError, match="cumulative mass balance error >1%"):
+            shia_v1(f, grid, _mp(p), st, nt)
+        return
+    st2, d = shia_v1(f, grid, _mp(p), st, nt)
+    assert np.array_equal(st.storage_capilar, s0[0])                       # inputs are not mutated
+    s1 = golden[f"shia3/{name}/state1"]
+    for got, exp in zip((st2.storage_capilar, st2.storage_gravita, st2.storage_aquifer), s1):
+        np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(st2.q_super_last, golden[f"shia3/{name}/q_last"][0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(st2.q_base_last, golden[f"shia3/{name}/q_last"][1], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(d["q_outlet"], golden[f"shia3/{name}/q_outlet"], rtol=1e-10)
+    np.testing.assert_allclose(d["diag"]["mass_error_cum"], golden[f"shia3/{name}/mass_error_cum"], atol=1e-11)
+
+
+def test_shia3_reference_tests():              # wmf_py/tests/test_models_core.py:57-192 through the drop-in API
+    base = dict(dt=3600.0, h_coef=1, h_exp=1, v_coef=1, v_exp=1, drena=0.0, retorno_gr=0.0, storage_constant=0.0)
+    z = lambda: ModelState(np.zeros((1, 1)), np.zeros((1, 1)), np.zeros((1, 1)))
+    p = ModelParams(**base, max_capilar=100, max_gravita=100, max_aquifer=500, k_perc_cap_to_grav=1.0,
+                    k_perc_grav_to_aqu=1.0, k_baseflow=0.2, max_infil_mm_h=100.0, separate_fluxes=True)
+    _, out = shia_v1({"rain_mm_h": np.array([[[10.0]], [[0.0]]])}, {}, p, z(), nsteps=2)
+    assert np.isclose(out["q_base_t"][0, 0, 0], 2.0) and np.isclose(out["q_base_t"][1, 0, 0], 1.6)
+    p = ModelParams(**base, max_capilar=200, max_gravita=200, max_aquifer=200, max_infil_mm_h=100.0)
+    s2, _ = shia_v1({"rain_mm_h": np.zeros((1, 1, 1)), "et_mm_h": np.array([[[60.0]]])}, {}, p,
+                    ModelState(np.array([[50.0]]), np.array([[20.0]]), np.array([[10.0]])), nsteps=1)
+    assert np.isclose(s2.storage_capilar[0, 0], 0.0) and np.isclose(s2.storage_gravita[0, 0], 10.0)
+    assert np.isclose(s2.storage_aquifer[0, 0], 10.0)
+    p = ModelParams(**base, max_capilar=100, max_gravita=100, max_aquifer=100, max_infil_mm_h=10.0,
+                    separate_fluxes=True, save_storage=True)
+    _, out = shia_v1({"rain_mm_h": np.array([[[50.0]]])}, {}, p, z(), nsteps=1)
+    assert out["q_super_t"].shape == (1, 1, 1) and out["storage_aquifer_t"].shape == (1, 1, 1)
+    assert np.isclose(out["q_super_t"][0, 0, 0], 40.0) and np.isclose(out["q_outlet"][0], 40.0)
+    p2 = ModelParams(**base, max_capilar=100, max_gravita=100, max_aquifer=100, max_infil_mm_h=10.0)
+    _, out2 = shia_v1({"rain_mm_h": np.array([[[50.0]]])}, {}, p2, z(), nsteps=1)
+    assert "q_super_t" not in out2 and "storage_capilar_t" not in out2
+    with pytest.raises(KeyError):
+        shia_v1({}, {}, p2, z(), nsteps=1)
+    # test_mass_balance_24_steps
+    rain = np.full((24, 5, 5), 10.0)
+    p = ModelParams(**base, max_capilar=100, max_gravita=200, max_aquifer=400, max_infil_mm_h=1e6)
+    st = ModelState(np.zeros((5, 5)), np.zeros((5, 5)), np.zeros((5, 5)))
+    st2, out = shia_v1({"rain_mm_h": rain}, {"dx": 30.0, "dy": 30.0}, p, st, nsteps=24)
+    dS = st2.storage_capilar.sum() + st2.storage_gravita.sum() + st2.storage_aquifer.sum()
+    q_mm = out["q_outlet"] * 3600.0 / (900.0 * 1e-3)
+    assert abs(rain.sum() - dS - q_mm.sum()) / rain.sum() <= 0.005
+    assert np.all(out["diag"]["mass_error_cum"] <= 0.005)
+
+
+def test_shia3_vs_oracle_larger():
+    rng = np.random.default_rng(50)
+    ny, nx, nt = 70, 93, 60
+    rain = np.where(rng.random((nt, ny, nx)) < 0.3, rng.gamma(2.0, 5.0, (nt, ny, nx)), 0.0)
+    et = rng.random((nt, ny, nx)) * 0.4
+    p = ModelParams(dt=600.0, h_coef=1, h_exp=1, v_coef=1, v_exp=1, max_capilar=80.0, max_gravita=60.0,
+                    max_aquifer=400.0, drena=0.0, retorno_gr=0.02, storage_constant=0.0, k_perc_cap_to_grav=0.05,
+                    k_perc_grav_to_aqu=0.04, k_baseflow=0.02, max_infil_mm_h=15.0, separate_fluxes=True, save_storage=True)
+    s0 = [rng.random((ny, nx)) * m for m in (40, 30, 200)]
+    for prio in ("capilar_first", "proportional"):
+        p.eta_priority = prio
+        f = {"rain_mm_h": rain, "et_mm_h": et}
+        o = oracle.shia3(f, {"dx": 30.0, "dy": 30.0}, p, *s0, nt, separate_fluxes=True, save_storage=True)
+        st2, d = shia_v1(f, {"dx": 30.0, "dy": 30.0}, p, ModelState(*[s.copy() for s in s0]), nt)
+        for k, got in (("storage_capilar", st2.storage_capilar), ("storage_gravita", st2.storage_gravita),
+                       ("storage_aquifer", st2.storage_aquifer)):
+            np.testing.assert_allclose(got, o[k], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(d["q_outlet"], o["q_outlet"], rtol=1e-10)
+        for k in ("q_super_t", "q_base_t", "q_total_t", "storage_capilar_t", "storage_gravita_t", "storage_aquifer_t"):
+            np.testing.assert_allclose(d[k], o[k], rtol=1e-12, atol=1e-12)
+
+
+def _run5(inp, calibs, sto0, show=True):
+    cs = torch.from_numpy(helpers.cell_static(inp)).cuda()
+    P = calibs.shape[0]
+    N = sto0.shape[-1]
+    sto = torch.from_numpy(np.broadcast_to(sto0, (P, 5, N)).copy()).cuda()
+    return ops.shia5_run(cs, torch.from_numpy(inp.rain_records).cuda(), torch.from_numpy(inp.pos_evento).cuda(),
+                         torch.from_numpy(inp.evp).cuda(), torch.from_numpy(calibs).cuda(), sto, None, dt=inp.dt,
+                         retorno_gr=inp.retorno_gr, retorno_aq=inp.retorno_aq, calc_niter=inp.calc_niter,
+                         speed_type=inp.speed_type, show_storage=show, show_mean_speed=show)
+
+
+@pytest.mark.parametrize("speed_type", [(1, 1, 1), (2, 2, 2), (1, 2, 1)])
+@pytest.mark.parametrize("ret", [(0.0, 0.0), (1.0, 1.0)])
+def test_shia5_vs_oracle(speed_type, ret):
+    N, T = 3001, 120
+    inp = helpers.shia5_inputs(oracle, N, T, 60, speed_type=speed_type)
+    inp.retorno_gr, inp.retorno_aq = ret
+    rng = np.random.default_rng(61)
+    calibs = np.vstack([np.ones(11), rng.uniform(0.5, 2.0, (2, 11))]).astype(np.float32)
+    sto0 = (rng.random((5, N)) * np.array([[40], [10], [5], [100], [1]])).astype(np.float32) + 0.001
+    out = _run5(inp, calibs, sto0)
+    for p in range(calibs.shape[0]):
+        o = oracle.f_shia_v1(inp, calibs[p], sto0)
+        got = out["StoOut"][p].cpu().numpy()
+        np.testing.assert_allclose(got, o["StoOut"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out["hspeed"][p].cpu().numpy(), o["hspeed"], rtol=1e-5, atol=1e-9)
+        scale = float(o["StoOut"].sum())
+        np.testing.assert_allclose(out["balance"][p].cpu().numpy(), o["balance"], atol=2e-6 * scale)
+        np.testing.assert_allclose(out["mean_storage"][p].cpu().numpy(), o["mean_storage"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(out["mean_speed"][p].cpu().numpy(), o["mean_speed"], rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(out["mean_rain"].cpu().numpy(), o["mean_rain"], rtol=2e-5, atol=1e-7)
+    assert np.array_equal(out["acum_rain"].cpu().numpy(), o["acum_rain"])   # same fp32 additions in the same order
+
+
+def test_shia5_no_diag_and_resume():
+    """Checkpoint/resume: running T steps == running T/2, feeding StoOut/hspeed back (StoIn/HspeedIn), T/2 more."""
+    N, T = 1000, 64
+    inp = helpers.shia5_inputs(oracle, N, T, 70, speed_type=(2, 2, 2))
+    cal = np.ones((1, 11), np.float32)
+    sto0 = np.full((5, N), 0.001, np.float32)
+    full = _run5(inp, cal, sto0, show=False)
+    assert full["mean_storage"] is None
+    o = oracle.f_shia_v1(inp, cal[0], sto0)
+    np.testing.assert_allclose(full["StoOut"][0].cpu().numpy(), o["StoOut"], rtol=1e-5, atol=1e-6)
+    cs = torch.from_numpy(helpers.cell_static(inp)).cuda()
+    rr, ev = torch.from_numpy(inp.rain_records).cuda(), torch.from_numpy(inp.evp).cuda()
+    pe = torch.from_numpy(inp.pos_evento).cuda()
+    kw = dict(dt=inp.dt, calc_niter=inp.calc_niter, speed_type=inp.speed_type)
+    sto = torch.from_numpy(sto0[None].copy()).cuda()
+    a = ops.shia5_run(cs, rr, pe[: T // 2].contiguous(), ev[: T // 2].contiguous(), torch.from_numpy(cal).cuda(), sto, None, **kw)
+    b = ops.shia5_run(cs, rr, pe[T // 2:].contiguous(), ev[T // 2:].contiguous(), torch.from_numpy(cal).cuda(), a["StoOut"],
+                      a["hspeed"], **kw)
+    assert torch.equal(b["StoOut"], full["StoOut"]) and torch.equal(b["hspeed"], full["hspeed"])
+
+
+def test_run_shia_object_api(tmp_path):
+    """SimuBasin(...).run_shia(Calibracion, rain_path, N_intervals) with the reference's signature and
+    returned dict keys (wmfv2.py:1924-2040), checked against the oracle run on the same files."""
+    ny, nx = 120, 150
+    fd = helpers.steepest(ny, nx, 80)
+    acc = oracle.basin_acum(fd, np.ones(fd.shape, bool))
+    r0, c0 = np.unravel_index(np.argmax(acc), acc.shape)
+    key = helpers.to_keypad(fd)
+    wmfv2.set_map_properties(ncols=nx, nrows=ny, xll=0.0, yll=0.0, dx=30.0, dxp=30.0)
+    x, y = 30.0 * (c0 + 0.5), 30.0 * ((ny - (r0 + 1)) + 0.5)
+    DIR = np.asfortranarray(key.T.astype(np.int32))
+    DEM = np.asfortranarray((1000 - 0.3 * np.add.outer(np.arange(nx), np.arange(ny))).astype(np.float32))
+    sb = wmfv2.SimuBasin(x, y, DEM, DIR, dt=300, threshold=30)
+    N, T = sb.ncells, 48
+    assert N == int(acc[r0, c0])
+    inp = helpers.shia5_inputs(oracle, N, T, 81)
+    inp.hill_long = models.hill_long[0].copy()
+    inp.elem_area = models.elem_area[0].copy()
+    models.v_coef, models.h_coef, models.h_exp = inp.v_coef, inp.h_coef, inp.h_exp
+    models.max_capilar, models.max_gravita, models.max_aquifer = (a[None] for a in (inp.max_capilar, inp.max_gravita, inp.max_aquifer))
+    models.speed_type = np.array([1, 1, 1])
+    models.show_storage = 1
+    path = str(tmp_path / "lluvia")
+    models.write_rain(path + ".bin", path + ".hdr", inp.rain_records, inp.pos_evento)
+    cal = np.ones(11, np.float32)
+    ret, qdf = sb.run_shia(cal, path, T, EvpSerie=inp.evp)
+    assert set(ret) >= {"Qsim", "Balance", "Storage", "Rain_Acum", "Rain_hietogram"}
+    o = oracle.f_shia_v1(inp, cal, np.full((5, N), 0.001, np.float32))
+    np.testing.assert_allclose(ret["Storage"], o["StoOut"], rtol=1e-5, atol=1e-6)
+    assert ret["Storage"].shape == (5, N) and ret["Qsim"].shape[1] == T and not ret["Qsim"].any()
+    np.testing.assert_allclose(ret["Rain_hietogram"][0], o["mean_rain"], rtol=2e-5, atol=1e-7)
+    assert np.array_equal(ret["Rain_Acum"][0], o["acum_rain"])
+    assert len(qdf) == T
+    pop = sb.run_shia_population([cal, cal * 1.5], path, T, EvpSerie=inp.evp)
+    np.testing.assert_allclose(pop["StoOut"][0], o["StoOut"], rtol=1e-5, atol=1e-6)
+    o2 = oracle.f_shia_v1(inp, cal * 1.5, np.full((5, N), 0.001, np.float32))
+    np.testing.assert_allclose(pop["StoOut"][1], o2["StoOut"], rtol=1e-5, atol=1e-6)

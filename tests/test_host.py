@@ -1,0 +1,109 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares,
+host-only entry points agree with the oracle, and the host logic of the shims behaves like the
+reference (error messages, formats)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT
+from wmf_heavy_b200 import _lib, models, ops
+from wmf_heavy_b200.cu_py import basics
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "wmf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(wmf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/wmf_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.wmf_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        basics.basin_acum(np.zeros((3, 3), int), np.ones((3, 3), bool))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "wmf_heavy_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "wmforacle" not in src and "orc_" not in src, f
+
+
+def test_coord2fil_col_matches_oracle():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        x, y = rng.uniform(-50, 400, 2)
+        args = (x, y, 3.25, -7.5, 30.0, 11, 9)
+        assert ops.coord2fil_col(*args) == oracle.f_coord2fil_col(*args)
+    assert ops.coord2fil_col(75.0, 15.0, 0, 0, 30.0, 3, 3) == (3, 3)
+
+
+def test_basin_find_py():                      # wmf_py/tests/test_cu_basics.py:14-16 + golden
+    assert basics.basin_find(x=60, y=60, xll=0, yll=0, dx=30, dy=30, ncols=3, nrows=3) == (2, 2)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "wmf_py_golden.npz"))
+    for a, rc in zip(g["find/args"], g["find/rc"]):
+        assert basics.basin_find(*a[:6], int(a[6]), int(a[7])) == tuple(rc)
+    with pytest.raises(ValueError, match="point outside raster bounds"):
+        basics.basin_find(1e9, 0, 0, 0, 30, 30, 3, 3)
+
+
+def test_reclass_like_reference():             # wmf_py/tests/test_cu_basics.py:19-32
+    src = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 1]])
+    res = basics.dir_reclass_opentopo(src)
+    assert set(np.unique(res)) <= set(range(8))
+    assert np.array_equal(res, basics.dir_reclass_opentopo(res))
+    with pytest.raises(ValueError):
+        basics.dir_reclass_opentopo(np.array([[9]]))
+    res = basics.dir_reclass_rwatershed(np.arange(1, 9).reshape(2, 4))
+    assert np.array_equal(res, np.array([0, 7, 6, 5, 4, 3, 2, 1]).reshape(2, 4))
+
+
+def test_transform_like_reference():           # wmf_py/tests/test_transform.py:15-37
+    idx = np.array([0, 10, 101, 555, 999, 1234, 2345, 3456, 4321, 4999])
+    values = np.arange(idx.size)
+    raster = basics.basin_2map(values, idx, (50, 50), -1.0)
+    assert np.all(raster.ravel()[idx] == values) and (raster != -1.0).sum() == values.size
+    assert np.array_equal(basics.basin_map2basin(raster, idx, (idx.size,)), values)
+    with pytest.raises(ValueError):
+        basics.basin_2map(np.array([1, 2, 3]), np.array([0, 1]), (2, 2), 0.0)
+
+
+def test_scheidegger_host_is_deterministic_and_windowed():
+    a = ops.synth_scheidegger_host(64, 96, seed=7)
+    assert set(np.unique(a)) <= {0, 1, 2}
+    frac = [(a == k).mean() for k in range(3)]
+    assert abs(frac[1] - 0.5) < 0.05 and abs(frac[0] - 0.25) < 0.05
+    w = ops.synth_scheidegger_host(10, 20, seed=7, row0=5, col0=30, nx_total=96)
+    assert np.array_equal(w, a[5:15, 30:50])
+    k = ops.synth_scheidegger_host(64, 96, seed=7, encoding=_lib.ENC_KEYPAD)
+    assert np.array_equal(k, np.array([6, 3, 2], dtype=np.int8)[a])
+
+
+def test_rain_file_roundtrip(tmp_path):        # Modelos_heavy.f90:580-590, 631-663
+    N, T = 37, 12
+    rng = np.random.default_rng(1)
+    rec = np.vstack([np.zeros((1, N), np.int32), rng.integers(0, 5000, (4, N)).astype(np.int32)])
+    pos = rng.integers(1, 6, T).astype(np.int32)
+    b, h = str(tmp_path / "rain.bin"), str(tmp_path / "rain.hdr")
+    models.write_rain(b, h, rec, pos)
+    models.rain_first_point = 1
+    ids, p2 = models.rain_read_ascii_table(h, T)
+    assert np.array_equal(p2, pos) and np.array_equal(ids, np.arange(1, T + 1))
+    assert np.array_equal(models.read_int_basin(b, 3, N), rec[2])
+    assert np.array_equal(models.read_rain_records(b, N), rec)
+    with pytest.raises(ValueError):
+        models.rain_read_ascii_table(h, T + 5)

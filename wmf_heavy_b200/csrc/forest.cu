@@ -1,0 +1,91 @@
+// forest.cu -- accumulation over an explicit forest (parent pointers) with an in-degree driven
+// chain walk: every leaf starts a walker that pushes its finished sum into its parent with an L2
+// atomic and carries on downstream only if it was the parent's last unfinished child.  Work is
+// O(n), there is no level barrier, and integer adds make any schedule bit-exact.
+// Used for: the vector-form accumulation of cu.basin_basics / cu.basin_acum
+// (cuencas_heavy.f90:593-606), subtree sizes for the BFS ordering of cu.basin_find, and the
+// contracted boundary forest of the sweep accumulation.
+#include "common.cuh"
+
+namespace {
+
+__global__ void k_forest_count(const int32_t *__restrict__ parent, int32_t *__restrict__ cnt, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t p = parent[i];
+    if (p >= 0) atomicAdd(&cnt[p], 1);
+}
+
+template <typename T>
+struct AtomT;
+template <>
+struct AtomT<int32_t> {
+    static __device__ __forceinline__ int32_t add(int32_t *p, int32_t v) { return atomicAdd(p, v); }
+};
+template <>
+struct AtomT<int64_t> {
+    static __device__ __forceinline__ int64_t add(int64_t *p, int64_t v)
+    {
+        return (int64_t)atomicAdd((unsigned long long *)p, (unsigned long long)v);
+    }
+};
+
+// cnt holds the number of children after k_forest_count; a node with cnt == 0 is a leaf and is
+// never decremented by anybody, so reading cnt[i] == 0 here cannot race with a walker -- but a
+// non-leaf can *reach* 0.  Leaves are therefore told apart by a second array-free trick: the
+// walk kernel is launched after a marking pass that rewrites leaf counters to -1.
+__global__ void k_forest_mark(int32_t *__restrict__ cnt, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && cnt[i] == 0) cnt[i] = -1;
+}
+
+template <typename T>
+__global__ void k_forest_walk(const int32_t *__restrict__ parent, const T *__restrict__ w, T *acc,
+                              int32_t *cnt, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (cnt[i] != -1) return;               // only leaves start walkers
+    T v = w ? w[i] : (T)1;
+    acc[i] = v;                             // nobody else writes a leaf
+    int64_t cur = i;
+    while (true) {
+        int32_t p = parent[cur];
+        if (p < 0) break;
+        AtomT<T>::add(&acc[p], v);
+        __threadfence();
+        int32_t old = atomicSub(&cnt[p], 1);
+        if (old != 1) break;                // other children still running: they will finish p
+        __threadfence();
+        T own = w ? w[p] : (T)1;
+        v = AtomT<T>::add(&acc[p], own) + own;
+        cur = p;
+    }
+}
+
+template <typename T>
+int forest_accum_t(const int32_t *parent, const T *w, T *acc, int32_t *cnt, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    WMF_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(T) * n, st));
+    const int th = 256;
+    k_forest_count<<<blocks_for(n, th), th, 0, st>>>(parent, cnt, n);
+    k_forest_mark<<<blocks_for(n, th), th, 0, st>>>(cnt, n);
+    k_forest_walk<T><<<blocks_for(n, th), th, 0, st>>>(parent, w, acc, cnt, n);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int forest_accum_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int32_t *cnt, int64_t n, cudaStream_t st)
+{
+    return forest_accum_t<int32_t>(parent, w, acc, cnt, n, st);
+}
+int forest_accum_i64(const int32_t *parent, const int64_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st)
+{
+    return forest_accum_t<int64_t>(parent, w, acc, cnt, n, st);
+}

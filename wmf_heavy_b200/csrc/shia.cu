@@ -1,0 +1,390 @@
+// shia.cu -- SHIA per-cell tank update, time loop fused in the kernel.
+//
+//   k_shia5  replaces models.shia_v1 as shipped (wmf_heavy/Modelos_heavy.f90:169-548) with
+//            calc_speed (:907-919): fp32, Fortran evaluation order.  This translation unit is
+//            compiled with -fmad=false so a*b+c rounds twice like the un-contracted Fortran.
+//   k_shia3  replaces wmf_py/models_py/core.py:64-295: fp64, numpy evaluation order.
+//
+// As shipped, cells do not interact inside shia_v1 (the lateral outflow is computed, subtracted
+// and dropped), so one thread owns one cell for all N_reg steps: state stays in
+// registers and the only per-step HBM traffic is the 4-byte rain word (8 bytes for fp64).
+// The per-step whole-basin sums the reference forms (balance, Mean_Rain, mean_storage,
+// mean_speed; q_outlet and the mass-balance terms) are reduced deterministically:
+// warp shuffle -> per-block partial every TB steps (fixed order, fp64) -> one pass over blocks.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TH = 256;        // threads per block
+constexpr int WARPS = TH / 32;
+constexpr int TB = 16;         // time steps batched between block-level reductions
+
+template <typename V>
+__device__ __forceinline__ V warp_sum(V v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Stages per-warp sums for TB steps in shared memory, then folds warps in fixed order and
+// writes part[blk][t][k] (fp64).  Every thread of the block must call add()/flush() uniformly.
+template <int K, typename V>
+struct StepReducer {
+    double (*stage)[TB][K];     // [WARPS][TB][K] in shared memory
+    double *part;               // this block's [T1][K] slice in global memory
+    int slot;
+    int64_t t0;
+    __device__ StepReducer(double (*s)[TB][K], double *p) : stage(s), part(p), slot(0), t0(0) {}
+    __device__ __forceinline__ void add(const V (&v)[K])
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            V s = warp_sum<V>(v[k]);
+            if (lane == 0) stage[warp][slot][k] = (double)s;
+        }
+        if (++slot == TB) flush();
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (slot == 0) return;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < slot * K; idx += TH) {
+            int s = idx / K, k = idx - s * K;
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) a += stage[w][s][k];
+            part[(t0 + s) * K + k] = a;
+        }
+        __syncthreads();
+        t0 += slot;
+        slot = 0;
+    }
+};
+
+// totals[g][t][k] = sum over blocks of part[g][blk][t][k]   (g = parameter set)
+__global__ void k_fold_blocks(const double *__restrict__ part, int nblk, int64_t TK, double *__restrict__ totals)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TK) return;
+    const double *p = part + (int64_t)blockIdx.y * nblk * TK;
+    double a = 0.0;
+    for (int b = 0; b < nblk; b++) a += p[(int64_t)b * TK + i];
+    totals[(int64_t)blockIdx.y * TK + i] = a;
+}
+
+// ------------------------------------------------------------------------------------ SHIA 5-tank
+// Modelos_heavy.f90:907-919
+__device__ __forceinline__ void calc_speed(float sm, float coef, float expo, float L, float dt, int niter, float &sp,
+                                           float &area)
+{
+    for (int i = 0; i < niter; i++) {
+        area = sm / (L + sp * dt);
+        float nw = coef * powf(area, expo);
+        sp = (2.0f * nw + sp) / 3.0f;
+    }
+}
+
+struct Shia5Args {
+    wmf_shia5_params p;
+    int64_t N, N_reg;
+    const float *cs;            // [17][N]
+    const int32_t *rain;        // [n_rec][N]
+    const int32_t *pos;         // [N_reg]
+    const float *evp;           // [N_reg]
+    const float *calib;         // [P][11]
+    float *sto;                 // [P][5][N]
+    float *hspeed;              // [P][4][N]
+    float *acum_rain;           // [N]
+    double *part;               // [P][nblk][N_reg+1][K]
+    int nblk;
+};
+
+// K = 3: {entradas, salidas, S1+..+S4};  DIAG adds {S1,S2,S3,S4,h1,h2,h3} -> K = 10
+template <bool DIAG>
+__global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
+{
+    constexpr int K = DIAG ? 10 : 3;
+    __shared__ double stage[WARPS][TB][K];
+    const int64_t N = a.N, T = a.N_reg;
+    const int pset = blockIdx.y;
+    const int64_t c = (int64_t)blockIdx.x * TH + threadIdx.x;
+    const bool live = c < N;
+    const int64_t cc = live ? c : 0;
+    const float *cal = a.calib + (int64_t)pset * 11;
+    const float dt = a.p.dt;
+    StepReducer<K, float> red(stage, a.part + ((int64_t)pset * a.nblk + blockIdx.x) * (T + 1) * K);
+
+    // ---- setup (Modelos:229-254)
+    float vs[4], hs[4], coef[3], expo[3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) vs[i] = a.cs[(0 + i) * N + cc] * cal[i] * dt;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (a.p.hspeed_given) hs[i] = a.hspeed[((int64_t)pset * 4 + i) * N + cc];
+        else {
+            int st = i < 3 ? a.p.speed_type[i] : 1;
+            hs[i] = st == 1 ? a.cs[(4 + i) * N + cc] * cal[4 + i] : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        coef[i] = a.cs[(4 + i) * N + cc] * cal[4 + i];
+        expo[i] = a.cs[(8 + i) * N + cc];
+    }
+    const float H1 = a.cs[12 * N + cc] * cal[8], H2 = a.cs[13 * N + cc] * cal[9], H3 = a.cs[14 * N + cc] * cal[10];
+    const float L = a.cs[15 * N + cc], m3mm = a.cs[16 * N + cc] / 1000.0f;
+    float *sto = a.sto + (int64_t)pset * 5 * N;
+    float S1 = sto[0 * N + cc], S2 = sto[1 * N + cc], S3 = sto[2 * N + cc], S4 = sto[3 * N + cc];
+    const float S5 = sto[4 * N + cc];
+    float fl[3];                              // type-1 outflow fraction, constant in time (Modelos:462)
+#pragma unroll
+    for (int i = 0; i < 3; i++) fl[i] = 1.0f - L / (hs[i] * dt + L);
+    const bool t2_0 = a.p.speed_type[0] != 1, t2_1 = a.p.speed_type[1] != 1, t2_2 = a.p.speed_type[2] != 1;
+    const bool raq = a.p.retorno_aq > 0.0f, rgr = a.p.retorno_gr > 0.0f;
+    const int niter = a.p.calc_niter;
+    float acum = 0.0f;
+
+    {   // slot 0: initial sums.  {S5 sum, h4 sum, S1+..+S4, S1..S4, h1..h3}
+        float v[K];
+        v[0] = live ? S5 : 0.0f;
+        v[1] = live ? hs[3] : 0.0f;
+        v[2] = live ? ((S1 + S2) + (S3 + S4)) : 0.0f;
+        if (DIAG) {
+            v[3] = live ? S1 : 0.0f; v[4] = live ? S2 : 0.0f; v[5] = live ? S3 : 0.0f; v[6] = live ? S4 : 0.0f;
+            v[7] = live ? hs[0] : 0.0f; v[8] = live ? hs[1] : 0.0f; v[9] = live ? hs[2] : 0.0f;
+        }
+        red.add(v);
+    }
+
+    for (int64_t t = 0; t < T; t++) {
+        const int pos = a.pos[t];
+        float R = 0.0f;
+        if (pos != 1) R = (float)a.rain[(int64_t)(pos - 1) * N + cc] / 1000.0f;          // :370
+        acum = acum + R;                                                                   // :380
+        float v1 = fmaxf(0.0f, (R - H1) + S1);                                             // :393
+        S1 = (S1 + R) - v1;                                                                // :394
+        float evl = fminf((a.evp[t] * vs[0]) * powf(S1 / H1, 0.6f), S1);                   // :396-398
+        S1 = S1 - evl;                                                                     // :407
+        float v2 = fminf(v1, vs[1]); S2 = (S2 + v1) - v2;                                  // :409-412
+        float v3 = fminf(v2, vs[2]); S3 = (S3 + v2) - v3;
+        float v4 = fminf(v3, vs[3]); S4 = (S4 + v3) - v4;
+        if (raq) { float ra = fmaxf(0.0f, S4 - H3); S3 = S3 + ra; S4 = S4 - ra; }          // :414-418
+        if (rgr) { float rg = fmaxf(0.0f, S3 - H2); S2 = S2 + rg; S3 = S3 - rg; }          // :420-427
+        float hf, ar;
+        if (!t2_0) hf = fl[0] * S2;                                                        // :461-491
+        else { ar = 0.0f; calc_speed(S2 * m3mm, coef[0], expo[0], L, dt, niter, hs[0], ar); hf = fminf(((ar * hs[0]) * dt) / m3mm, S2); }
+        S2 = S2 - hf;
+        if (!t2_1) hf = fl[1] * S3;
+        else { ar = 0.0f; calc_speed(S3 * m3mm, coef[1], expo[1], L, dt, niter, hs[1], ar); hf = fminf(((ar * hs[1]) * dt) / m3mm, S3); }
+        S3 = S3 - hf;
+        if (!t2_2) hf = fl[2] * S4;
+        else { ar = 0.0f; calc_speed(S4 * m3mm, coef[2], expo[2], L, dt, niter, hs[2], ar); hf = fminf(((ar * hs[2]) * dt) / m3mm, S4); }
+        S4 = S4 - hf;
+
+        float v[K];
+        v[0] = live ? R : 0.0f;
+        v[1] = live ? (v4 + evl) : 0.0f;                                                   // :459
+        v[2] = live ? ((S1 + S2) + (S3 + S4)) : 0.0f;
+        if (DIAG) {
+            v[3] = live ? S1 : 0.0f; v[4] = live ? S2 : 0.0f; v[5] = live ? S3 : 0.0f; v[6] = live ? S4 : 0.0f;
+            v[7] = live ? hs[0] : 0.0f; v[8] = live ? hs[1] : 0.0f; v[9] = live ? hs[2] : 0.0f;
+        }
+        red.add(v);
+    }
+    red.flush();
+    if (live) {
+        sto[0 * N + c] = S1; sto[1 * N + c] = S2; sto[2 * N + c] = S3; sto[3 * N + c] = S4;
+        float *hso = a.hspeed + (int64_t)pset * 4 * N;
+#pragma unroll
+        for (int i = 0; i < 4; i++) hso[i * N + c] = hs[i];
+        if (pset == 0 && a.acum_rain) a.acum_rain[c] = acum;
+    }
+}
+
+// totals [P][T+1][K] -> reference outputs.  balance(t) = sum(StoOut) - StoAtras - entradas + salidas
+// (Modelos:533); Mean_Rain(t) = rain_sum / N (:494); mean_storage (:518); mean_speed (:522).
+__global__ void k_shia5_outputs(const double *__restrict__ totals, int K, int64_t T, int64_t N, int P,
+                                float *__restrict__ balance, float *__restrict__ mean_rain,
+                                float *__restrict__ mean_storage, float *__restrict__ mean_speed)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)P * T) return;
+    int p = (int)(i / T);
+    int64_t t = i - (int64_t)p * T;
+    const double *tot = totals + (int64_t)p * (T + 1) * K;
+    const double *now = tot + (t + 1) * K, *prev = tot + t * K;
+    balance[i] = (float)(((now[2] - prev[2]) - now[0]) + now[1]);
+    if (p == 0 && mean_rain) mean_rain[t] = (float)(now[0] / (double)N);
+    if (K == 10) {
+        if (mean_storage) {
+            float *ms = mean_storage + (int64_t)p * 5 * T;
+            for (int k = 0; k < 4; k++) ms[k * T + t] = (float)(now[3 + k] / (double)N);
+            ms[4 * T + t] = (float)(tot[0] / (double)N);       // tank 5 is never touched
+        }
+        if (mean_speed) {
+            float *mv = mean_speed + (int64_t)p * 4 * T;
+            for (int k = 0; k < 3; k++) mv[k * T + t] = (float)(now[7 + k] / (double)N);
+            mv[3 * T + t] = (float)(tot[1] / (double)N);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ SHIA 3-tank
+struct Shia3Args {
+    wmf_shia3_params p;
+    int64_t nsteps, ncell;
+    const double *rain, *et;
+    double *cap, *grav, *aqu, *qsl, *qbl;
+    double *qs_t, *qb_t, *qt_t, *cap_t, *grav_t, *aqu_t;
+    double *part;               // [nblk][nsteps+1][6]
+};
+
+__global__ void __launch_bounds__(TH) k_shia3(const Shia3Args a)
+{
+    constexpr int K = 6;        // {q_total, storage, P, ET, q_super, q_base}
+    __shared__ double stage[WARPS][TB][K];
+    const int64_t n = a.ncell, T = a.nsteps;
+    const int64_t i = (int64_t)blockIdx.x * TH + threadIdx.x;
+    const bool live = i < n;
+    const int64_t ii = live ? i : 0;
+    StepReducer<K, double> red(stage, a.part + (int64_t)blockIdx.x * (T + 1) * K);
+    const wmf_shia3_params &p = a.p;
+    const double dt_h = p.dt / 3600.0;
+    const double infil_cap = p.max_infil_mm_h * dt_h;
+    double c = a.cap[ii], g = a.grav[ii], q = a.aqu[ii];
+    double q_super = 0.0, q_base = 0.0;
+    {
+        double v[K] = {0.0, live ? (c + g) + q : 0.0, 0.0, 0.0, 0.0, 0.0};       // core.py:147
+        red.add(v);
+    }
+    for (int64_t t = 0; t < T; t++) {
+        double rain_step = fmax(a.rain[t * n + ii], 0.0) * dt_h;                  // :152
+        double et_step = a.et ? fmax(a.et[t * n + ii], 0.0) * p.et_scale : 0.0;   // :154-158
+        double infil = fmin(rain_step, infil_cap);                                // :160
+        double exceso = rain_step - infil;
+        c += infil;
+        double et_c, et_g, et_a;
+        if (p.proportional) {                                                     // :165-176
+            double w = (c + g) + q, fc = 0.0, fg = 0.0, fa = 0.0;
+            if (w > 0) { fc = c / w; fg = g / w; fa = q / w; }
+            et_c = fmin(et_step * fc, c); et_g = fmin(et_step * fg, g); et_a = fmin(et_step * fa, q);
+        } else {                                                                  // :177-182
+            et_c = fmin(et_step, c);
+            double rem = et_step - et_c;
+            et_g = fmin(rem, g);
+            double rem2 = rem - et_g;
+            et_a = fmin(rem2, q);
+        }
+        c -= et_c; g -= et_g; q -= et_a;
+        double et_total = (et_c + et_g) + et_a;                                   // :187
+        double perc_cg = fmin(p.k_perc_cap_to_grav * c, c);                       // :189-193
+        c -= perc_cg; g += perc_cg;
+        double perc_ga = fmin(p.k_perc_grav_to_aqu * g, g);                       // :195-200
+        double retorno = p.retorno_gr * g;
+        g = (g - perc_ga) - retorno;
+        q += perc_ga;
+        q_base = fmin(p.k_baseflow * q, q);                                       // :202-204
+        double drena = p.drena * q;
+        q = (q - q_base) + drena;
+        double overflow = fmax(c - p.max_capilar, 0.0);                           // :206-208
+        c -= overflow; exceso += overflow;
+        c = fmin(fmax(c, 0.0), p.max_capilar);                                    // :210-212
+        g = fmin(fmax(g, 0.0), p.max_gravita);
+        q = fmin(fmax(q, 0.0), p.max_aquifer);
+        q_super = exceso + retorno;                                               // :214-215
+        double q_total = q_super + q_base;
+        if (live) {
+            if (a.qs_t) { a.qs_t[t * n + i] = q_super; a.qb_t[t * n + i] = q_base; a.qt_t[t * n + i] = q_total; }
+            if (a.cap_t) { a.cap_t[t * n + i] = c; a.grav_t[t * n + i] = g; a.aqu_t[t * n + i] = q; }
+        }
+        double v[K];
+        v[0] = live ? q_total : 0.0; v[1] = live ? (c + g) + q : 0.0; v[2] = live ? rain_step : 0.0;
+        v[3] = live ? et_total : 0.0; v[4] = live ? q_super : 0.0; v[5] = live ? q_base : 0.0;
+        red.add(v);
+    }
+    red.flush();
+    if (live) {
+        a.cap[i] = c; a.grav[i] = g; a.aqu[i] = q;
+        if (a.qsl) a.qsl[i] = q_super;
+        if (a.qbl) a.qbl[i] = q_base;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t wmf_shia5_workspace(int64_t N, int64_t N_reg, int32_t P)
+{
+    int64_t nblk = (N + TH - 1) / TH;
+    size_t part = (size_t)P * nblk * (N_reg + 1) * 10 * sizeof(double);
+    size_t tot = (size_t)P * (N_reg + 1) * 10 * sizeof(double);
+    return wmf_align(part) + wmf_align(tot) + 1024;
+}
+
+int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,
+                  const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento, const float *evp,
+                  const float *calib, float *sto, float *hspeed, float *balance, float *mean_rain, float *acum_rain,
+                  float *mean_storage, float *mean_speed, void *workspace, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = as_stream(stream);
+    WMF_REQUIRE(params_host && cell_static && rain_records && pos_evento && evp && calib && sto && hspeed && balance,
+                WMF_E_ARG, "null pointer");
+    WMF_REQUIRE(N > 0 && N_reg > 0 && n_rec > 0 && P > 0 && P <= 65535, WMF_E_ARG, "bad size");
+    const bool diag = mean_storage || mean_speed;
+    const int K = diag ? 10 : 3;
+    const int nblk = (int)((N + TH - 1) / TH);
+    WsCursor cur(workspace, ws_bytes);
+    double *part = cur.take<double>((size_t)P * nblk * (N_reg + 1) * K);
+    double *totals = cur.take<double>((size_t)P * (N_reg + 1) * K);
+    WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
+    Shia5Args a;
+    a.p = *params_host; a.N = N; a.N_reg = N_reg; a.cs = cell_static; a.rain = rain_records; a.pos = pos_evento;
+    a.evp = evp; a.calib = calib; a.sto = sto; a.hspeed = hspeed; a.acum_rain = acum_rain; a.part = part; a.nblk = nblk;
+    dim3 grid(nblk, P);
+    if (diag) k_shia5<true><<<grid, TH, 0, st>>>(a);
+    else k_shia5<false><<<grid, TH, 0, st>>>(a);
+    const int64_t TK = (N_reg + 1) * K;
+    k_fold_blocks<<<dim3(blocks_for(TK, 256), P), 256, 0, st>>>(part, nblk, TK, totals);
+    k_shia5_outputs<<<blocks_for((int64_t)P * N_reg, 256), 256, 0, st>>>(totals, K, N_reg, N, P, balance, mean_rain,
+                                                                         mean_storage, mean_speed);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t wmf_shia3_workspace(int64_t ncell, int64_t nsteps)
+{
+    int64_t nblk = (ncell + TH - 1) / TH;
+    return wmf_align((size_t)nblk * (nsteps + 1) * 6 * sizeof(double)) + 1024;
+}
+
+int wmf_shia3_run(const wmf_shia3_params *params_host, int64_t nsteps, int64_t ncell, const double *rain,
+                  const double *et, double *cap, double *grav, double *aqu, double *q_super_last, double *q_base_last,
+                  double *sums, double *q_super_t, double *q_base_t, double *q_total_t, double *cap_t, double *grav_t,
+                  double *aqu_t, void *workspace, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = as_stream(stream);
+    WMF_REQUIRE(params_host && rain && cap && grav && aqu && sums, WMF_E_ARG, "null pointer");
+    WMF_REQUIRE(nsteps > 0 && ncell > 0, WMF_E_ARG, "bad size");
+    WMF_REQUIRE((q_super_t == nullptr) == (q_base_t == nullptr) && (q_super_t == nullptr) == (q_total_t == nullptr),
+                WMF_E_ARG, "flux series must be all set or all null");
+    WMF_REQUIRE((cap_t == nullptr) == (grav_t == nullptr) && (cap_t == nullptr) == (aqu_t == nullptr), WMF_E_ARG,
+                "storage series must be all set or all null");
+    const int nblk = (int)((ncell + TH - 1) / TH);
+    WsCursor cur(workspace, ws_bytes);
+    double *part = cur.take<double>((size_t)nblk * (nsteps + 1) * 6);
+    WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
+    Shia3Args a;
+    a.p = *params_host; a.nsteps = nsteps; a.ncell = ncell; a.rain = rain; a.et = et; a.cap = cap; a.grav = grav;
+    a.aqu = aqu; a.qsl = q_super_last; a.qbl = q_base_last; a.qs_t = q_super_t; a.qb_t = q_base_t; a.qt_t = q_total_t;
+    a.cap_t = cap_t; a.grav_t = grav_t; a.aqu_t = aqu_t; a.part = part;
+    k_shia3<<<nblk, TH, 0, st>>>(a);
+    const int64_t TK = (nsteps + 1) * 6;
+    k_fold_blocks<<<dim3(blocks_for(TK, 256), 1), 256, 0, st>>>(part, nblk, TK, sums);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""f2py-style namespace ``models``: module-level state + ``shia_v1`` with the call shape
+``wmf_heavy/wmfv2.py:2000-2020`` uses against the Fortran module ``models`` (Modelos_heavy.f90).
+
+State attributes are the lower-cased Fortran module variables (Modelos_heavy.f90:20-120) that
+``SimuBasin.__init__`` / ``run_shia`` assign (wmfv2.py:1872-1916, 1967-1995) and read back
+(``models.acum_rain``, ``models.mean_rain`` :2024; ``models.control`` :2036).  Per-cell tables have
+the Fortran shapes ``(k, N)``.
+
+In scope: the shipped 5-tank update (S1/S2) with its diagnostics, and the rain record formats (S5).
+Out of scope, rejected loudly: sediments, slides, floods, separate_rain.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._dev import require_cuda, to_dev
+
+# ---- module state -----------------------------------------------------------------------------
+drena = None
+v_coef = h_coef = v_exp = h_exp = None
+max_capilar = max_gravita = max_aquifer = None
+hill_long = hill_slope = elem_area = None
+storage = None
+storage_constant = 0.001
+evpserie = None
+dt = 300.0
+dxp = 30.0
+calc_niter = 5
+retorno_gr = 0
+retorno_aq = 0
+verbose = 0
+rain_first_point = 1
+speed_type = np.ones(3, dtype=np.int32)
+control = None
+control_h = None
+sim_sediments = sim_slides = sim_floods = 0
+save_storage = save_speed = save_retorno = save_vfluxes = save_rc = 0
+show_storage = show_speed = show_mean_speed = show_mean_retorno = show_area = 0
+separate_fluxes = separate_rain = 0
+guarda_cond = None
+# outputs
+mean_rain = None
+acum_rain = None
+mean_storage = None
+mean_speed = None
+idevento = None
+posevento = None
+
+_dev_cache = {}
+
+
+# ---- rain record formats (Modelos_heavy.f90:580-590, 631-663) -----------------------------------
+def rain_read_ascii_table(ruta_hdr: str, n_intervals: int):
+    """Header table -> (idEvento, posEvento).  3 lines whose 4th token is an integer (the last one is
+    Ntotal), 3 skipped lines, ``rain_first_point`` skipped lines if > 1, then ``idEvento, posEvento, text``."""
+    global idevento, posevento
+    with open(ruta_hdr, "r") as fh:
+        lines = fh.read().splitlines()
+    ntotal = 0
+    for i in range(3):
+        toks = lines[i].replace(",", " ").split()
+        ntotal = int(float(toks[3]))
+    body = lines[6:]
+    if not (n_intervals + rain_first_point <= ntotal + 1):
+        raise ValueError("rain header: N_intervals + rain_first_point exceeds the number of records")
+    if rain_first_point > 1:
+        body = body[rain_first_point:]
+    ids = np.zeros(n_intervals, dtype=np.int32)
+    pos = np.zeros(n_intervals, dtype=np.int32)
+    for i in range(n_intervals):
+        toks = body[i].replace(",", " ").split()
+        ids[i], pos[i] = int(toks[0]), int(toks[1])
+    idevento, posevento = ids, pos
+    return ids, pos
+
+
+def read_int_basin(ruta_bin: str, record: int, n_cel: int) -> np.ndarray:
+    """Record ``record`` (1-based) of a direct-access int32 file with RECL = 4*N_cel bytes."""
+    with open(ruta_bin, "rb") as fh:
+        fh.seek((record - 1) * 4 * n_cel)
+        v = np.fromfile(fh, dtype="<i4", count=n_cel)
+    if v.size != n_cel:
+        print("Error: Se ha tratado de leer un valor fuera del rango")
+        v = np.zeros(n_cel, dtype=np.int32)
+    return v
+
+
+def read_rain_records(ruta_bin: str, n_cel: int) -> np.ndarray:
+    """All records of the rain file as int32 [n_rec, N_cel]."""
+    size = os.path.getsize(ruta_bin)
+    n_rec = size // (4 * n_cel)
+    return np.fromfile(ruta_bin, dtype="<i4", count=n_rec * n_cel).reshape(n_rec, n_cel)
+
+
+def write_rain(ruta_bin: str, ruta_hdr: str, records: np.ndarray, pos_evento: np.ndarray, n_hills: int = 0) -> None:
+    """Write a rain binary + header in the format the readers above (and the Fortran) expect."""
+    rec = np.ascontiguousarray(records, dtype="<i4")
+    rec.tofile(ruta_bin)
+    n_cel = rec.shape[1]
+    with open(ruta_hdr, "w") as fh:
+        fh.write(f"Numero de celdas: {n_cel}\n")
+        fh.write(f"Numero de laderas: {n_hills}\n")
+        fh.write(f"Numero de registros: {len(pos_evento)}\n")
+        fh.write(f"Numero de campos no cero: {rec.shape[0] - 1}\n")
+        fh.write("Tipo de interpolacion: synthetic\n")
+        fh.write("IDfecha, Record, Lluvia, Fecha\n")
+        for i, p in enumerate(pos_evento):
+            mean = 0.0 if p == 1 else float(rec[p - 1].mean()) / 1000.0
+            fh.write(f"{i + 1}, {int(p)}, {mean:.2f}, step{i + 1}\n")
+
+
+# ---- the model ------------------------------------------------------------------------------------
+def _table(a, k: int, n: int, name: str) -> np.ndarray:
+    if a is None:
+        raise ValueError(f"models.{name} is not set")
+    a = np.asarray(a, dtype=np.float32)
+    if a.shape != (k, n):
+        raise ValueError(f"models.{name} must have shape ({k}, {n}), got {a.shape}")
+    return a
+
+
+def cell_static_table(n: int) -> np.ndarray:
+    """Pack the per-cell module tables into the [17][N] SoA block of the C ABI."""
+    cs = np.empty((17, n), dtype=np.float32)
+    cs[0:4] = _table(v_coef, 4, n, "v_coef")
+    cs[4:8] = _table(h_coef, 4, n, "h_coef")
+    cs[8:12] = _table(h_exp, 4, n, "h_exp")
+    cs[12] = _table(max_capilar, 1, n, "max_capilar")[0]
+    cs[13] = _table(max_gravita, 1, n, "max_gravita")[0]
+    cs[14] = _table(max_aquifer, 1, n, "max_aquifer")[0]
+    cs[15] = _table(hill_long, 1, n, "hill_long")[0]
+    cs[16] = _table(elem_area, 1, n, "elem_area")[0]
+    return cs
+
+
+def _reject_out_of_scope():
+    for nm in ("sim_sediments", "sim_slides", "sim_floods", "separate_rain", "save_storage", "save_speed",
+               "save_retorno", "save_vfluxes", "save_rc"):
+        if int(globals()[nm]) == 1:
+            raise NotImplementedError(f"models.{nm} = 1 is outside the B200 hot path (see DESIGN.md, out of scope)")
+
+
+def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int, sto_in=None, hspeed_in=None,
+                       device_out: bool = False):
+    """P parameter sets x one basin in one launch.  ``calibs`` (P, 11); ``sto_in`` (5, N) or (P, 5, N)."""
+    global mean_rain, acum_rain, mean_storage, mean_speed
+    _reject_out_of_scope()
+    dev = require_cuda()
+    cal = np.atleast_2d(np.asarray(calibs, dtype=np.float32))
+    if cal.shape[1] != 11:
+        raise ValueError("calib must have 11 entries (Modelos_heavy.f90:177)")
+    P = cal.shape[0]
+    key = (id(v_coef), id(h_coef), id(max_capilar), id(elem_area), n_cel)
+    cs = _dev_cache.get("cs")
+    if cs is None or cs[0] != key:
+        cs = (key, to_dev(cell_static_table(n_cel)))
+        _dev_cache["cs"] = cs
+    rr = rain_records if isinstance(rain_records, torch.Tensor) else to_dev(np.ascontiguousarray(rain_records, dtype=np.int32))
+    pe = pos_evento if isinstance(pos_evento, torch.Tensor) else to_dev(np.asarray(pos_evento, dtype=np.int32)[:n_reg])
+    if evpserie is None:
+        raise ValueError("models.evpserie must be set (the Fortran dereferences EvpSerie(t), Modelos:396)")
+    ev = to_dev(np.asarray(evpserie, dtype=np.float32)[:n_reg])
+    if ev.shape[0] < n_reg:
+        raise ValueError("models.evpserie is shorter than N_reg")
+    # StoOut = StoIn if StoIn(1,1) > 0 else Storage + storage_constant (Modelos:229-233)
+    if sto_in is not None and float(np.asarray(sto_in).reshape(-1)[0]) > 0:
+        s0 = np.asarray(sto_in, dtype=np.float32)
+    else:
+        base = np.zeros((5, n_cel), np.float32) if storage is None else np.asarray(storage, dtype=np.float32)
+        s0 = base + np.float32(storage_constant)
+    s0 = s0.reshape((-1, 5, n_cel))
+    if s0.shape[0] != P:
+        if s0.shape[0] != 1:
+            raise ValueError('StoIn must be (5, N) or (P, 5, N)')
+        s0 = np.broadcast_to(s0, (P, 5, n_cel))
+    sto = to_dev(np.ascontiguousarray(s0))
+    hs = None
+    if hspeed_in is not None and float(np.asarray(hspeed_in).reshape(-1)[0]) > 0:
+        h0 = np.asarray(hspeed_in, dtype=np.float32)
+        h0 = np.broadcast_to(h0.reshape((-1, 4, n_cel)), (P, 4, n_cel))
+        hs = to_dev(np.ascontiguousarray(h0))
+    st = np.asarray(speed_type).astype(int).reshape(-1)[:3]
+    out = ops.shia5_run(cs[1], rr, pe, ev, to_dev(cal), sto, hs, dt=float(dt), retorno_gr=float(retorno_gr),
+                        retorno_aq=float(retorno_aq), calc_niter=int(calc_niter), speed_type=tuple(st),
+                        show_storage=bool(show_storage), show_mean_speed=bool(show_mean_speed))
+    mean_rain = out["mean_rain"].cpu().numpy().reshape(1, n_reg)
+    acum_rain = out["acum_rain"].cpu().numpy().reshape(1, n_cel)
+    if out["mean_storage"] is not None:
+        mean_storage = out["mean_storage"][0].cpu().numpy()
+    if out["mean_speed"] is not None:
+        mean_speed = out["mean_speed"][0].cpu().numpy()
+    return out if device_out else {k: (None if v is None else v.cpu().numpy()) for k, v in out.items()}
+
+
+def shia_v1(ruta_bin, ruta_hdr, calib, n_cel, n_cont, n_conth, n_reg, stoin=None, hspeedin=None, ruta_storage=None,
+            ruta_speed=None, ruta_vfluxes=None, ruta_binconv=None, ruta_binstra=None, ruta_hdrconv=None,
+            ruta_hdrstra=None, ruta_retorno=None, ruta_rc=None):
+    """models.shia_v1(...) with the positional order of wmfv2.py:2000-2020 and the 11 outputs of
+    Modelos_heavy.f90:169-174: Q, Qsed, Qseparated, Hum, St1, St3, balance, speed, AreaControl, StoOut,
+    Qsep_byrain.  As shipped, Q == 0 and the control/humidity series are never written."""
+    n_cel, n_cont, n_conth, n_reg = int(n_cel), int(n_cont), int(n_conth), int(n_reg)
+    _, pos = rain_read_ascii_table(ruta_hdr, n_reg)
+    records = read_rain_records(ruta_bin, n_cel)
+    cal = np.asarray(calib, dtype=np.float32).reshape(-1)
+    out = shia_v1_population(cal[None, :], records, pos, n_cel, n_reg, stoin, hspeedin)
+    f32 = np.float32
+    Q = np.zeros((n_cont, n_reg), f32, order="F")
+    Qsed = np.zeros((n_cont, 3, n_reg), f32, order="F")
+    Qsep = np.zeros((n_cont, 3, n_reg), f32, order="F")
+    Hum = np.zeros((n_conth, n_reg), f32, order="F")
+    St1 = np.zeros((n_conth, n_reg), f32, order="F")
+    St3 = np.zeros((n_conth, n_reg), f32, order="F")
+    speed = np.zeros((n_cont, n_reg), f32, order="F")
+    area_c = np.zeros((n_cont, n_reg), f32, order="F")
+    Qsep_rain = np.zeros((n_cont, 2, n_reg), f32, order="F")
+    return (Q, Qsed, Qsep, Hum, St1, St3, out["balance"][0], speed, area_c, np.asfortranarray(out["StoOut"][0]),
+            Qsep_rain)

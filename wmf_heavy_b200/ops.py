@@ -1,0 +1,268 @@
+"""Device-level operators: CUDA tensors in, CUDA tensors out, every one a thin call into the
+C ABI of ``libwmfb200.so``.  The two reference-facing shims (``cu_py``/``models_py`` with the
+wmf_py signatures, ``cu``/``models`` with the f2py signatures) are built on these; no numerics
+happen in Python."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._dev import ptr, require_cuda, stream_ptr, workspace
+from ._lib import (ACC_F64, ACC_I32, ACC_I64, ALGO_AUTO, ALGO_SWEEP, ALGO_WALK, ENC_INTERNAL, ENC_KEYPAD, check)
+
+_ACC_TORCH = {ACC_I32: torch.int32, ACC_I64: torch.int64, ACC_F64: torch.float64}
+
+
+def _chk_dev(t: torch.Tensor, dtype, name: str):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous CUDA tensor of dtype {dtype}")
+
+
+# --------------------------------------------------------------------------------------- D1
+def d8_accum(dir_t: torch.Tensor, mask_t: Optional[torch.Tensor] = None, acc_dtype: int = ACC_I32,
+             encoding: int = ENC_INTERNAL, algo: int = ALGO_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Full-raster D8 accumulation (replaces wmf_py/cu_py/basics.py:124-177)."""
+    require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    ny, nx = dir_t.shape
+    if mask_t is not None:
+        _chk_dev(mask_t, torch.uint8, "mask")
+    if out is None:
+        out = torch.empty((ny, nx), dtype=_ACC_TORCH[acc_dtype], device=dir_t.device)
+    else:
+        _chk_dev(out, _ACC_TORCH[acc_dtype], "out")
+    lib = _lib.load()
+    nb = lib.wmf_d8_accum_workspace(ny, nx, acc_dtype, algo)
+    ws = workspace(nb)
+    check(lib.wmf_d8_accum(ptr(dir_t), ptr(mask_t), ptr(out), acc_dtype, ny, nx, encoding, algo, ptr(ws), ws.numel(),
+                           stream_ptr()))
+    return out
+
+
+# --------------------------------------------------------------------------------------- D2
+def basin_mask(dir_t: torch.Tensor, mask_t: Optional[torch.Tensor], outlet_rc: Tuple[int, int],
+               encoding: int = ENC_INTERNAL) -> Tuple[torch.Tensor, int]:
+    """Mask of the cells whose D8 path reaches the outlet (traversal of basics.py:206-248)."""
+    require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    ny, nx = dir_t.shape
+    if mask_t is not None:
+        _chk_dev(mask_t, torch.uint8, "mask")
+    out = torch.empty((ny, nx), dtype=torch.uint8, device=dir_t.device)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_basin_mask_workspace(ny, nx))
+    n = C.c_int64(0)
+    check(lib.wmf_basin_mask(ptr(dir_t), ptr(mask_t), ny, nx, encoding, int(outlet_rc[0]), int(outlet_rc[1]), ptr(out),
+                             C.addressof(n), ptr(ws), ws.numel(), stream_ptr()))
+    return out, int(n.value)
+
+
+# --------------------------------------------------------------------------------------- D3
+def coord2fil_col(x, y, xll, yll, dx, ncols, nrows) -> Tuple[int, int]:
+    """cuencas_heavy.f90:355-365 in fp32 (host)."""
+    col, fil = C.c_int32(0), C.c_int32(0)
+    _lib.load().wmf_coord2fil_col_host(float(x), float(y), float(xll), float(yll), float(dx), int(ncols), int(nrows),
+                                       C.addressof(col), C.addressof(fil))
+    return col.value, fil.value
+
+
+def basin_structure(dir_keypad_t: torch.Tensor, col: int, fil: int) -> torch.Tensor:
+    """BFS-ordered basin vector (cu.basin_find + cu.basin_cut, cuencas_heavy.f90:507-576).
+    ``dir_keypad_t`` is the GIS-oriented raster int8 [nrows][ncols].  Returns int32 [3][n]."""
+    require_cuda()
+    _chk_dev(dir_keypad_t, torch.int8, "dir")
+    nrows, ncols = dir_keypad_t.shape
+    lib = _lib.load()
+    ws = workspace(lib.wmf_basin_structure_workspace(nrows, ncols))
+    cap = nrows * ncols
+    st = torch.empty((3, cap), dtype=torch.int32, device=dir_keypad_t.device)
+    n = C.c_int64(0)
+    check(lib.wmf_basin_structure(ptr(dir_keypad_t), nrows, ncols, int(col), int(fil), ptr(st), cap, C.addressof(n),
+                                  ptr(ws), ws.numel(), stream_ptr()))
+    return st[:, : n.value].contiguous()
+
+
+# --------------------------------------------------------------------------------------- D4-D6
+def _st_args(st: torch.Tensor):
+    _chk_dev(st, torch.int32, "structure")
+    if st.dim() != 2 or st.shape[0] != 3:
+        raise ValueError("structure must have shape (3, n)")
+    return st.shape[1], st.shape[1]
+
+
+def basin_acum_vec(st: torch.Tensor) -> torch.Tensor:
+    require_cuda()
+    n, stride = _st_args(st)
+    out = torch.empty(n, dtype=torch.int32, device=st.device)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_basin_vec_workspace(n))
+    check(lib.wmf_basin_acum_vec(ptr(st), stride, n, ptr(out), ptr(ws), ws.numel(), stream_ptr()))
+    return out
+
+
+def basin_basics(st: torch.Tensor, dem_t: torch.Tensor, dirv_t: torch.Tensor, dxp: float, xll: float, yll: float,
+                 dx: float, nrows: int):
+    """cu.basin_basics (cuencas_heavy.f90:581-627) -> acum, long_cel, pend, elev, scalars[6]."""
+    require_cuda()
+    n, stride = _st_args(st)
+    _chk_dev(dem_t, torch.float32, "DEM")
+    _chk_dev(dirv_t, torch.int32, "DIR")
+    dev = st.device
+    acum = torch.empty(n, dtype=torch.int32, device=dev)
+    lon, pend, elev = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+    geo = (C.c_float * 5)(dxp, xll, yll, dx, float(nrows))
+    sc = (C.c_float * 6)()
+    lib = _lib.load()
+    ws = workspace(lib.wmf_basin_vec_workspace(n))
+    check(lib.wmf_basin_basics(ptr(st), stride, n, ptr(dem_t), ptr(dirv_t), C.addressof(geo), ptr(acum), ptr(lon),
+                               ptr(pend), ptr(elev), C.addressof(sc), ptr(ws), ws.numel(), stream_ptr()))
+    return acum, lon, pend, elev, np.array(list(sc), dtype=np.float32)
+
+
+def basin_coordxy(st: torch.Tensor, xll: float, yll: float, dx: float, nrows: int):
+    require_cuda()
+    n, stride = _st_args(st)
+    X = torch.empty(n, dtype=torch.float32, device=st.device)
+    Y = torch.empty(n, dtype=torch.float32, device=st.device)
+    check(_lib.load().wmf_basin_coordxy(ptr(st), stride, n, xll, yll, dx, int(nrows), ptr(X), ptr(Y), stream_ptr()))
+    return X, Y
+
+
+def basin_map2basin(st: torch.Tensor, raster_t: torch.Tensor) -> torch.Tensor:
+    """Gather a GIS-oriented raster [nrows][ncols] into the basin vector by (col, fil)."""
+    require_cuda()
+    n, stride = _st_args(st)
+    if not (raster_t.is_cuda and raster_t.is_contiguous() and raster_t.element_size() in (1, 4, 8)):
+        raise TypeError("raster must be a contiguous CUDA tensor with 1, 4 or 8-byte elements")
+    nrows, ncols = raster_t.shape
+    out = torch.zeros(n, dtype=raster_t.dtype, device=st.device)
+    check(_lib.load().wmf_basin_map2basin(ptr(st), stride, n, ptr(raster_t), nrows, ncols, raster_t.element_size(),
+                                          ptr(out), stream_ptr()))
+    return out
+
+
+def basin_2map(st: torch.Tensor, vec_t: torch.Tensor, nrows: int, ncols: int, nodata) -> torch.Tensor:
+    require_cuda()
+    n, stride = _st_args(st)
+    if not (vec_t.is_cuda and vec_t.is_contiguous() and vec_t.element_size() in (1, 4, 8) and vec_t.numel() == n):
+        raise TypeError("vec must be a contiguous CUDA tensor of n elements of 1, 4 or 8 bytes")
+    out = torch.full((nrows, ncols), nodata, dtype=vec_t.dtype, device=st.device)
+    check(_lib.load().wmf_basin_2map(ptr(st), stride, n, ptr(vec_t), nrows, ncols, vec_t.element_size(), ptr(out),
+                                     stream_ptr()))
+    return out
+
+
+def stream_nod(st: torch.Tensor, acum_t: torch.Tensor, umbral: int):
+    """cu.basin_stream_nod (cuencas_heavy.f90:780-809) -> cauce, nodos, trazado, n_nodos, n_cauce."""
+    require_cuda()
+    n, stride = _st_args(st)
+    _chk_dev(acum_t, torch.int32, "acum")
+    cauce, nodos, traz = (torch.empty(n, dtype=torch.int32, device=st.device) for _ in range(3))
+    cnt = (C.c_int32 * 2)()
+    check(_lib.load().wmf_stream_nod(ptr(st), stride, n, ptr(acum_t), int(umbral), ptr(cauce), ptr(nodos), ptr(traz),
+                                     C.addressof(cnt), stream_ptr()))
+    return cauce, nodos, traz, int(cnt[0]), int(cnt[1])
+
+
+# --------------------------------------------------------------------------------------- S1/S2
+def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento: torch.Tensor, evp: torch.Tensor,
+              calib: torch.Tensor, sto: torch.Tensor, hspeed: Optional[torch.Tensor] = None, *, dt: float,
+              retorno_gr: float = 0.0, retorno_aq: float = 0.0, calc_niter: int = 5, speed_type=(1, 1, 1),
+              show_storage: bool = False, show_mean_speed: bool = False):
+    """SHIA 5-tank update as shipped (Modelos_heavy.f90:169-548) for P parameter sets at once.
+    ``sto`` [P,5,N] and ``hspeed`` [P,4,N] are advanced IN PLACE.  Returns a dict of device tensors."""
+    require_cuda()
+    _chk_dev(cell_static, torch.float32, "cell_static")
+    _chk_dev(rain_records, torch.int32, "rain_records")
+    _chk_dev(pos_evento, torch.int32, "pos_evento")
+    _chk_dev(evp, torch.float32, "evp")
+    _chk_dev(calib, torch.float32, "calib")
+    _chk_dev(sto, torch.float32, "sto")
+    P = calib.shape[0]
+    N = cell_static.shape[1]
+    n_reg = pos_evento.shape[0]
+    n_rec = rain_records.shape[0]
+    if cell_static.shape != (17, N) or calib.shape != (P, 11) or sto.shape != (P, 5, N) or rain_records.shape != (n_rec, N):
+        raise ValueError("shape mismatch: cell_static (17,N), calib (P,11), sto (P,5,N), rain_records (n_rec,N)")
+    if evp.shape[0] < n_reg:
+        raise ValueError("evp must have at least N_reg entries")
+    dev = sto.device
+    given = hspeed is not None
+    if given:
+        _chk_dev(hspeed, torch.float32, "hspeed")
+        if hspeed.shape != (P, 4, N):
+            raise ValueError("hspeed must be (P,4,N)")
+    else:
+        hspeed = torch.empty((P, 4, N), dtype=torch.float32, device=dev)
+    balance = torch.empty((P, n_reg), dtype=torch.float32, device=dev)
+    mean_rain = torch.empty(n_reg, dtype=torch.float32, device=dev)
+    acum_rain = torch.empty(N, dtype=torch.float32, device=dev)
+    ms = torch.empty((P, 5, n_reg), dtype=torch.float32, device=dev) if show_storage else None
+    mv = torch.empty((P, 4, n_reg), dtype=torch.float32, device=dev) if show_mean_speed else None
+    prm = _lib.Shia5Params(dt, retorno_gr, retorno_aq, int(calc_niter), (C.c_int32 * 3)(*[int(s) for s in speed_type]),
+                           int(given))
+    lib = _lib.load()
+    ws = workspace(lib.wmf_shia5_workspace(N, n_reg, P))
+    check(lib.wmf_shia5_run(C.addressof(prm), N, n_reg, n_rec, P, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
+                            ptr(evp), ptr(calib), ptr(sto), ptr(hspeed), ptr(balance), ptr(mean_rain), ptr(acum_rain),
+                            ptr(ms), ptr(mv), ptr(ws), ws.numel(), stream_ptr()))
+    return {"StoOut": sto, "hspeed": hspeed, "balance": balance, "mean_rain": mean_rain, "acum_rain": acum_rain,
+            "mean_storage": ms, "mean_speed": mv}
+
+
+# --------------------------------------------------------------------------------------- S4
+def shia3_run(rain: torch.Tensor, et: Optional[torch.Tensor], cap: torch.Tensor, grav: torch.Tensor,
+              aqu: torch.Tensor, prm: "_lib.Shia3Params", nsteps: int, separate_fluxes: bool = False,
+              save_storage: bool = False):
+    """SHIA 3-tank balance (wmf_py/models_py/core.py:64-295); cap/grav/aqu advanced IN PLACE.
+    Returns dict with per-step sums [nsteps+1, 6] and optional series."""
+    require_cuda()
+    for t, nm in ((rain, "rain"), (cap, "cap"), (grav, "grav"), (aqu, "aqu")):
+        _chk_dev(t, torch.float64, nm)
+    if et is not None:
+        _chk_dev(et, torch.float64, "et")
+    ncell = cap.numel()
+    dev = cap.device
+    qsl = torch.empty(ncell, dtype=torch.float64, device=dev)
+    qbl = torch.empty(ncell, dtype=torch.float64, device=dev)
+    sums = torch.empty((nsteps + 1, 6), dtype=torch.float64, device=dev)
+    ser = {}
+    if separate_fluxes:
+        for k in ("q_super_t", "q_base_t", "q_total_t"):
+            ser[k] = torch.empty((nsteps, ncell), dtype=torch.float64, device=dev)
+    if save_storage:
+        for k in ("storage_capilar_t", "storage_gravita_t", "storage_aquifer_t"):
+            ser[k] = torch.empty((nsteps, ncell), dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_shia3_workspace(ncell, nsteps))
+    check(lib.wmf_shia3_run(C.addressof(prm), nsteps, ncell, ptr(rain), ptr(et), ptr(cap), ptr(grav), ptr(aqu),
+                            ptr(qsl), ptr(qbl), ptr(sums), ptr(ser.get("q_super_t")), ptr(ser.get("q_base_t")),
+                            ptr(ser.get("q_total_t")), ptr(ser.get("storage_capilar_t")),
+                            ptr(ser.get("storage_gravita_t")), ptr(ser.get("storage_aquifer_t")), ptr(ws), ws.numel(),
+                            stream_ptr()))
+    out = {"q_super_last": qsl, "q_base_last": qbl, "sums": sums}
+    out.update(ser)
+    return out
+
+
+# --------------------------------------------------------------------------------------- synthetic inputs
+def synth_scheidegger(ny: int, nx: int, seed: int = 20260101, encoding: int = ENC_INTERNAL, row0: int = 0,
+                      col0: int = 0, nx_total: Optional[int] = None) -> torch.Tensor:
+    dev = require_cuda()
+    out = torch.empty((ny, nx), dtype=torch.int8, device=dev)
+    check(_lib.load().wmf_synth_scheidegger(ptr(out), ny, nx, row0, col0, nx if nx_total is None else nx_total,
+                                            seed, encoding, stream_ptr()))
+    return out
+
+
+def synth_scheidegger_host(ny: int, nx: int, seed: int = 20260101, encoding: int = ENC_INTERNAL, row0: int = 0,
+                           col0: int = 0, nx_total: Optional[int] = None) -> np.ndarray:
+    """Same generator on the host (no GPU needed): used by oracles and CPU baselines."""
+    out = np.empty((ny, nx), dtype=np.int8)
+    _lib.load().wmf_synth_scheidegger_host(out.ctypes.data, ny, nx, row0, col0, nx if nx_total is None else nx_total,
+                                           seed, encoding)
+    return out

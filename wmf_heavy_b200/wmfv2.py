@@ -1,0 +1,199 @@
+"""Object API of the hot path: ``Basin``, ``SimuBasin`` (+ ``run_shia``) and the population
+evaluation behind ``Calib_NSGAII`` with the signatures of ``wmf_heavy/wmfv2.py`` (:758-877,
+:1792-2106), calling the f2py-style shims ``cu`` / ``models`` with the very call expressions the
+reference uses.  The reference's own classes cannot execute as shipped (methods dedented
+to module level, undefined helpers, mismatched signatures); this module carries the same
+signatures so the path is callable.  GIS I/O, plotting, polygons, NetCDF persistence and the DEAP
+bookkeeping are out of scope."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import cu, models
+
+Global_EPSG = 4326
+
+
+def set_map_properties(ncols: int, nrows: int, xll: float, yll: float, dx: float, dy: Optional[float] = None,
+                       dxp: Optional[float] = None, nodata: float = -9999.0) -> None:
+    """What read_map_raster(isDEMorDIR=True) does to the module state (wmfv2.py:227-241), without GDAL."""
+    cu.ncols, cu.nrows, cu.xll, cu.yll = int(ncols), int(nrows), float(xll), float(yll)
+    cu.dx = float(dx)
+    cu.dy = float(dx if dy is None else dy)
+    cu.dxp = float(dxp if dxp is not None else 30.0)
+    cu.nodata = nodata
+    models.dxp = cu.dxp
+
+
+def __Add_hdr_bin_2route__(path: str, storage: bool = False):
+    """'<base>[.bin|.hdr]' -> ('<base>.bin', '<base>.hdr') (undefined helper of wmfv2.py:1962)."""
+    base = path
+    for ext in (".bin", ".hdr", ".StObin", ".StOhdr"):
+        if base.endswith(ext):
+            base = base[: -len(ext)]
+    return (base + ".StObin", base + ".StOhdr") if storage else (base + ".bin", base + ".hdr")
+
+
+class Basin:
+    """wmfv2.py:758-877.  DEM and DIR are (ncols, nrows) arrays as read_map_raster returns them
+    (``Mapa.T``), DIR in keypad codes; (lat, lon) are the outlet's x, y map coordinates."""
+
+    def __init__(self, lat=0, lon=0, DEM=None, DIR=None, name='NaN', stream=None, threshold=1000, path=None,
+                 useCauceMap=None):
+        self.DEM = DEM
+        self.DIR = DIR
+        self.name = name
+        self.threshold = threshold
+        if path is not None:
+            raise NotImplementedError("NetCDF basins (Basin(path=...)) are outside the hot path")
+        if stream is not None and useCauceMap is None:           # wmfv2.py:805-811
+            err = [np.sqrt((lat - i[0]) ** 2 + (lon - i[1]) ** 2) for i in stream.structure.T]
+            loc = int(np.argmin(err))
+            lat, lon = stream.structure[0, loc], stream.structure[1, loc]
+        # === TRAZAR LA CUENCA ===  (wmfv2.py:823-828)
+        self.ncells = cu.basin_find(lat, lon, DIR, cu.ncols, cu.nrows)
+        self.structure = cu.basin_cut(self.ncells)
+        self.DEMvec = self.Transform_Map2Basin(DEM, [cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy])
+        self.DIRvec = self.Transform_Map2Basin(DIR, [cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy])
+
+    # wmfv2.py:1151-1170
+    def Transform_Map2Basin(self, Map, MapProp):
+        return cu.basin_map2basin(self.structure, Map, MapProp[2], MapProp, MapProp, MapProp, cu.nodata,
+                                  self.ncells, MapProp, MapProp[1])
+
+    # wmfv2.py:1172-1199 (raster writing omitted)
+    def Transform_Basin2Map(self, BasinVar, path=None, DriverFormat='GTiff', EPSG=4326):
+        map_ncols, map_nrows = cu.basin_2map_find(self.structure, self.ncells)
+        M, mxll, myll = cu.basin_2map(self.structure, BasinVar, map_ncols, map_nrows, self.ncells)
+        return M, [map_ncols, map_nrows, mxll, myll, cu.dx, cu.dy, cu.nodata]
+
+    # wmfv2.py:974-982
+    def GetGeo_Cell_Basics(self):
+        acum, longCeld, S0, Elev = cu.basin_basics(self.structure, self.DEMvec, self.DIRvec, self.ncells)
+        self.CellAcum = acum
+        self.CellLong = longCeld
+        self.CellSlope = S0
+        self.CellHeight = Elev
+        self.CellCauce = np.where(self.CellAcum > self.threshold, 1, 0)
+
+    # wmfv2.py:1076-1089
+    def GetGeo_IT(self):
+        acum = cu.basin_acum(self.structure, self.ncells)
+        _, _, slope, _ = cu.basin_basics(self.structure, self.DEMvec, self.DIRvec, self.ncells)
+        slope = np.arctan(slope)
+        slope[slope == 0] = 0.0001
+        return np.log((acum * cu.dxp) / np.tan(slope))
+
+
+class SimuBasin(Basin):
+    """wmfv2.py:1792-1922 (modelType='cells').  Sets up the ``models`` module state for shia_v1."""
+
+    def __init__(self, lat=None, lon=None, DEM=None, DIR=None, path=None, name='NaN', stream=None, threshold=500,
+                 useCauceMap=None, noData=-999, modelType='cells', SimSed=False, SimSlides=False, dt=60,
+                 SaveStorage='no', SaveSpeed='no', retorno=0, SeparateFluxes='no', SeparateRain='no',
+                 ShowStorage='no', SimFloods='no', controlNodos=True, storageConstant=0.001):
+        if path is not None:
+            raise NotImplementedError("SimuBasin(path=...) (NetCDF) is outside the hot path")
+        if modelType[0] != 'c':
+            raise NotImplementedError("modelType='hills' is outside the hot path (SURVEY 8(a) S1)")
+        self.segunda_cuenca = False
+        self.name, self.DEM, self.DIR = name, DEM, DIR
+        self.modelType, self.nodata, self.threshold, self.epsg = modelType, noData, threshold, Global_EPSG
+        # TRAZAR la cuenca (wmfv2.py:1862-1866)
+        self.ncells = cu.basin_find(lat, lon, DIR, cu.ncols, cu.nrows)
+        self.structure = cu.basin_cut(self.ncells)
+        self.DEMvec = self.Transform_Map2Basin(DEM, [cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy])
+        self.DIRvec = self.Transform_Map2Basin(DIR, [cu.ncols, cu.nrows, cu.xll, cu.yll, cu.dx, cu.dy])
+        acum = cu.basin_acum(self.structure, self.ncells)                     # :1868
+        models.drena = self.structure                                          # :1872
+        N = self.ncells
+        # Variables físicas (:1881-1893)
+        models.v_coef = np.ones((4, N), np.float32)
+        models.h_coef = np.ones((4, N), np.float32)
+        models.v_exp = np.ones((4, N), np.float32)
+        models.h_exp = np.ones((4, N), np.float32)
+        models.max_capilar = np.ones((1, N), np.float32)
+        models.max_gravita = np.ones((1, N), np.float32)
+        models.max_aquifer = np.ones((1, N), np.float32)
+        models.storage = np.zeros((5, N), np.float32)
+        models.dt = dt
+        models.calc_niter = 5
+        models.retorno_gr = retorno
+        models.verbose = 0
+        models.control = np.zeros((1, N))
+        self.GetGeo_Cell_Basics()                                              # :1898
+        models.hill_long = self.CellLong.reshape(1, N).astype(np.float32)
+        models.elem_area = np.full((1, N), cu.dxp ** 2, np.float32)
+        if controlNodos:                                                       # :1899-1903
+            cauce, nodos, trazado, n_nodos, n_cauce = cu.basin_stream_nod(self.structure, self.CellAcum, threshold,
+                                                                           self.ncells)
+            pos = np.where(nodos != 0)[0]
+            models.control[0, pos] = np.arange(1, pos.size + 1)
+            self.CellNodos = nodos
+        self.CellAcumVec = acum
+        models.control_h = np.zeros((1, N))                                    # :1906-1916
+        models.sim_sediments = int(SimSed == 'si')
+        models.sim_slides = int(bool(SimSlides))
+        models.save_storage = int(SaveStorage == 'si')
+        models.save_speed = int(SaveSpeed == 'si')
+        models.separate_fluxes = int(SeparateFluxes == 'si')
+        models.separate_rain = int(SeparateRain == 'si')
+        models.show_storage = int(ShowStorage == 'si')
+        models.sim_floods = int(SimFloods == 'si')
+        models.storage_constant = storageConstant
+        self.isSetGeo = False
+
+    # wmfv2.py:1924-2040
+    def run_shia(self, Calibracion, rain_path, N_intervals, start_point=1, StorageLoc=None, HspeedLoc=None,
+                 path_storage=None, path_speed=None, path_conv=None, path_stra=None, path_retorno=None, kinematicN=5,
+                 QsimDataFrame=True, EvpVariable='sun', EvpSerie=None, WheretoStore=None, path_vfluxes=None,
+                 Dates2Save=None, FluxesDates2Save=None, path_rc=None):
+        rain_pathBin, rain_pathHdr = __Add_hdr_bin_2route__(rain_path)
+        N = self.ncells
+        models.rain_first_point = start_point
+        models.calc_niter = kinematicN
+        if path_storage is not None or path_vfluxes is not None or path_speed is not None:
+            raise NotImplementedError("per-step storage/speed/vfluxes files are outside the hot path")
+        models.save_storage = 0
+        models.save_vfluxes = 0
+        if EvpSerie is not None:
+            models.evpserie = np.asarray(EvpSerie, dtype=np.float32)
+        elif models.evpserie is None or len(models.evpserie) < N_intervals:
+            models.evpserie = np.ones(N_intervals, dtype=np.float32)
+        calib = np.asarray(Calibracion, dtype=np.float32).reshape(-1)
+        if calib.size == 10:                      # NSGA genes carry 10 entries (wmfv2.py:2171-2182); Fortran wants 11
+            calib = np.append(calib, np.float32(1.0))
+        Qsim, Qsed, Qsep, Humedad, St1, St3, Balance, Speed, Area, Alm, Qsep_byrain = models.shia_v1(
+            rain_pathBin, rain_pathHdr, calib, N, np.count_nonzero(models.control) + 1,
+            np.count_nonzero(models.control_h), N_intervals, StorageLoc, HspeedLoc, 'no_save.StObin', path_speed,
+            'no_save.bin', path_conv, path_stra, "", "", path_retorno, path_rc)
+        Retornos = {'Qsim': Qsim, 'Balance': Balance, 'Storage': Alm, 'Rain_Acum': models.acum_rain,
+                    'Rain_hietogram': models.mean_rain}
+        if np.count_nonzero(models.control_h) > 0:
+            Retornos.update({'Humedad': Humedad, 'Humedad_t1': St1, 'Humedad_t2': St3})
+        if QsimDataFrame:
+            import pandas as pd
+            ids = models.control[models.control != 0]
+            Qdict = {str(int(j)): i for i, j in zip(Retornos['Qsim'][1:], ids)}
+            return Retornos, pd.DataFrame(Qdict, index=np.arange(N_intervals))
+        return Retornos
+
+    def run_shia_population(self, Calibraciones: Sequence, rain_path, N_intervals, start_point=1, StorageLoc=None,
+                            HspeedLoc=None, kinematicN=5, EvpSerie=None):
+        """The hot part of Calib_NSGAII (wmfv2.py:2060-2106): one launch advances every parameter set of
+        a population over the same basin and rain (what ``__ejec_parallel__`` + ``Pool`` were meant to do)."""
+        rain_pathBin, rain_pathHdr = __Add_hdr_bin_2route__(rain_path)
+        models.rain_first_point = start_point
+        models.calc_niter = kinematicN
+        if EvpSerie is not None:
+            models.evpserie = np.asarray(EvpSerie, dtype=np.float32)
+        elif models.evpserie is None or len(models.evpserie) < N_intervals:
+            models.evpserie = np.ones(N_intervals, dtype=np.float32)
+        cal = np.asarray([np.asarray(c, dtype=np.float32).reshape(-1) for c in Calibraciones], dtype=np.float32)
+        if cal.shape[1] == 10:
+            cal = np.concatenate([cal, np.ones((cal.shape[0], 1), np.float32)], axis=1)
+        _, pos = models.rain_read_ascii_table(rain_pathHdr, N_intervals)
+        records = models.read_rain_records(rain_pathBin, self.ncells)
+        return models.shia_v1_population(cal, records, pos, self.ncells, N_intervals, StorageLoc, HspeedLoc)
