@@ -235,6 +235,7 @@ def f_shia_v1(inp: Shia5Inputs, calib, sto_in, hspeed_in=None, show_storage=True
     ms = np.zeros((5, n_reg), np.float32) if show_storage else None
     msp = np.zeros((4, n_reg), np.float32) if show_mean_speed else None
     mr = np.zeros(n_reg, np.float32) if show_mean_retorno else None
+    b64 = np.zeros(n_reg, np.float64)
     f32 = np.float32
     rc = lib().orc_f_shia_v1(C.byref(p), C.c_int64(N), C.c_int64(n_reg), _p(cal),
                              _p(_c(inp.v_coef, f32)), _p(_c(inp.h_coef, f32)), _p(_c(inp.h_exp, f32)),
@@ -242,7 +243,7 @@ def f_shia_v1(inp: Shia5Inputs, calib, sto_in, hspeed_in=None, show_storage=True
                              _p(_c(inp.max_aquifer, f32)), _p(_c(inp.hill_long, f32)), _p(_c(inp.elem_area, f32)),
                              _p(_c(inp.rain_records, np.int32)), _p(_c(inp.pos_evento, np.int32)),
                              _p(_c(inp.evp, f32)), _p(sto), _p(hs), _p(balance), _p(mean_rain), _p(acum_rain),
-                             _p(ms), _p(msp), _p(mr))
+                             _p(ms), _p(msp), _p(mr), _p(b64))
     assert rc == 0
-    return {"StoOut": sto, "hspeed": hs, "balance": balance, "mean_rain": mean_rain, "acum_rain": acum_rain,
+    return {"StoOut": sto, "hspeed": hs, "balance": balance, "balance64": b64, "mean_rain": mean_rain, "acum_rain": acum_rain,
             "mean_storage": ms, "mean_speed": msp, "mean_retorno": mr}

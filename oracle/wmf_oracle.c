@@ -410,7 +410,11 @@ void orc_f_calc_speed(float sm, float coef, float expo, float elem_long, float d
  * 1-based, ==1 meaning "no rain" without reading (:366-367).
  * Outputs: balance [N_reg], mean_rain [N_reg], acum_rain [N],
  * mean_storage [5][N_reg] (nullable == show_storage off),
- * mean_speed [4][N_reg] (nullable), retorned_mean [N_reg] (nullable). */
+ * mean_speed [4][N_reg] (nullable), retorned_mean [N_reg] (nullable).
+ * balance64 [N_reg] (nullable) is NOT a reference output: the same balance terms (the very fp32
+ * per-cell values) summed in fp64, i.e. the quantity the Fortran's fp32 running sums approximate.
+ * `balance` is a difference of two ~N*5-term fp32 sums (catastrophic cancellation), so tests pin the
+ * CUDA path against balance64 tightly and against `balance` only within that fp32 summation noise. */
 typedef struct {
     float dt, retorno_gr, retorno_aq;
     int32_t calc_niter;
@@ -424,7 +428,7 @@ int orc_f_shia_v1(const orc_shia5_params *p, int64_t N, int64_t N_reg, const flo
                   const float *hill_long, const float *elem_area,
                   const int32_t *rain_records, const int32_t *pos_evento, const float *evp,
                   float *sto, float *hspeed, float *balance, float *mean_rain, float *acum_rain,
-                  float *mean_storage, float *mean_speed, float *mean_retorno)
+                  float *mean_storage, float *mean_speed, float *mean_retorno, double *balance64)
 {
     float dt = p->dt;
     float *vspeed = (float *)malloc(sizeof(float) * 4 * N);
@@ -449,7 +453,8 @@ int orc_f_shia_v1(const orc_shia5_params *p, int64_t N, int64_t N_reg, const flo
     float entradas = 0.0f, salidas = 0.0f;
     for (int64_t t = 0; t < N_reg; t++) {
         float sto_atras = 0.0f;                                          /* :364, Fortran memory order */
-        for (int64_t c = 0; c < N; c++) for (int k = 0; k < 5; k++) sto_atras += sto[k * N + c];
+        double d_atras = 0.0, d_ent = 0.0, d_sal = 0.0, d_now = 0.0;
+        for (int64_t c = 0; c < N; c++) for (int k = 0; k < 5; k++) { sto_atras += sto[k * N + c]; d_atras += sto[k * N + c]; }
         if (pos_evento[t] == 1) for (int64_t c = 0; c < N; c++) rain[c] = 0.0f;
         else {
             const int32_t *rec = rain_records + (int64_t)(pos_evento[t] - 1) * N;
@@ -462,7 +467,7 @@ int orc_f_shia_v1(const orc_shia5_params *p, int64_t N, int64_t N_reg, const flo
             float S1 = sto[0 * N + c], S2 = sto[1 * N + c], S3 = sto[2 * N + c], S4 = sto[3 * N + c];
             float H1 = H[0 * N + c];
             float vflux[4], S[5];
-            entradas = entradas + R; rain_sum = rain_sum + R;
+            entradas = entradas + R; rain_sum = rain_sum + R; d_ent += R;
             vflux[0] = fmaxf(0.0f, (R - H1) + S1);                       /* :393 */
             S1 = (S1 + R) - vflux[0];                                    /* :394 */
             float evp_loss = fminf((evp[t] * vspeed[0 * N + c]) * powf(S1 / H1, 0.6f), S1); /* :396-398 */
@@ -483,6 +488,7 @@ int orc_f_shia_v1(const orc_shia5_params *p, int64_t N, int64_t N_reg, const flo
                 vflux[1] = vflux[1] + rg; vflux[2] = vflux[2] - rg;
             }
             salidas = (salidas + vflux[3]) + evp_loss;                   /* :459 */
+            d_sal += (double)(vflux[3] + evp_loss);
             float L = hill_long[c], m3mm = elem_area[c] / 1000.0f;       /* :224 */
             for (int i = 0; i < 3; i++) {                                /* :461-491 */
                 float hf;
@@ -516,8 +522,9 @@ int orc_f_shia_v1(const orc_shia5_params *p, int64_t N, int64_t N_reg, const flo
             for (int64_t c = 0; c < N; c++) retorned[c] = 0.0f;
         }
         float sto_now = 0.0f;                                            /* :533 */
-        for (int64_t c = 0; c < N; c++) for (int k = 0; k < 5; k++) sto_now += sto[k * N + c];
+        for (int64_t c = 0; c < N; c++) for (int k = 0; k < 5; k++) { sto_now += sto[k * N + c]; d_now += sto[k * N + c]; }
         balance[t] = ((sto_now - sto_atras) - entradas) + salidas;
+        if (balance64) balance64[t] = ((d_now - d_atras) - d_ent) + d_sal;
         entradas = 0.0f; salidas = 0.0f;
     }
     free(vspeed); free(H); free(rain); free(retorned);

@@ -126,7 +126,10 @@ def test_shia5_vs_oracle(speed_type, ret):
         np.testing.assert_allclose(got, o["StoOut"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(out["hspeed"][p].cpu().numpy(), o["hspeed"], rtol=1e-5, atol=1e-9)
         scale = float(o["StoOut"].sum())
-        np.testing.assert_allclose(out["balance"][p].cpu().numpy(), o["balance"], atol=2e-6 * scale)
+        # tight against the fp64 sum of the same fp32 terms; loose (fp32 running-sum noise of the Fortran
+        # formula itself, ~eps32 * sum(StoOut) * sqrt(5N)) against the reference-order fp32 balance
+        np.testing.assert_allclose(out["balance"][p].cpu().numpy(), o["balance64"], rtol=1e-4, atol=1e-6 * scale)
+        np.testing.assert_allclose(out["balance"][p].cpu().numpy(), o["balance"], atol=3e-5 * scale)
         np.testing.assert_allclose(out["mean_storage"][p].cpu().numpy(), o["mean_storage"], rtol=2e-5, atol=1e-6)
         np.testing.assert_allclose(out["mean_speed"][p].cpu().numpy(), o["mean_speed"], rtol=2e-5, atol=1e-9)
     np.testing.assert_allclose(out["mean_rain"].cpu().numpy(), o["mean_rain"], rtol=2e-5, atol=1e-7)
