@@ -107,5 +107,9 @@ static inline unsigned int blocks_for(int64_t n, int threads) { return (unsigned
 // weight (the reference's cycle semantics, basics.py:166-175).
 //   parent: int32 [n], -1 = none.  w: weights (nullptr = 1).  acc: out.  cnt: int32 [n] scratch.
 // ---------------------------------------------------------------------------------------------
-int forest_accum_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int32_t *cnt, int64_t n, cudaStream_t st);
-int forest_accum_i64(const int32_t *parent, const int64_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st);
+// blocked (nullable): nodes that must never finalise (their own value is itself unresolved).
+// After the call cnt[i] is -1 (leaf) or 0 for finalised nodes and > 0 for unresolved ones.
+int forest_accum_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int32_t *cnt, int64_t n, cudaStream_t st,
+                     const uint8_t *blocked = nullptr);
+int forest_accum_i64(const int32_t *parent, const int32_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st,
+                     const uint8_t *blocked = nullptr);

@@ -1,11 +1,731 @@
-// d8_sweep.cu -- placeholder, replaced below
+// d8_sweep.cu -- full-raster D8 accumulation, tiled algorithm (WMF_ALGO_SWEEP).
+// Replaces wmf_py/cu_py/basics.py:124-177 for ANY input, bit-exact, in three device phases:
+//
+//   A  per tile (TW x TH cells), in isolation: the accumulation every boundary cell would have if
+//      nothing entered the tile (exit_acc), and for every boundary cell the boundary cell where flow
+//      entering there leaves the tile again (link).
+//   G  the tiles' exit cells form a contracted forest (parent(x) = link(receiver(x)), weight =
+//      exit_acc(x)); it is accumulated with the in-degree chain walk of forest.cu, and every exit
+//      pushes its total into the entry cell it drains to (inflow).
+//   C  per tile again, now with the external inflow injected at its boundary cells -> final ACC.
+//
+// Per-tile solvers.  FAST: one warp owns a tile and streams its rows top to bottom with the
+// running row held in registers -- contributions from the row above are lane-local or one shuffle
+// away, and East / West chains inside a row are segmented warp scans (shuffle); the reverse sweep
+// for `link` is the same machinery bottom to top.  No shared-memory atomics, no barriers.  It is
+// exact for tiles whose in-tile flow never points upwards and has no E<->W two-cycles ("simple"
+// tiles; a Scheidegger network is all simple).  GENERAL: every other tile (and every tile that
+// receives flow from an unresolved, i.e. cyclic, upstream) is solved by one thread block with the
+// in-degree chain walk in shared memory.  Both produce the same outputs, so the result does not
+// depend on which solver ran: integer adds, any schedule is bit-exact.
+//
+// Cycle semantics (basics.py:166-175): a cell is finalised only when all its donors are; others
+// keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
+// contracted forest carries this through `blocked` nodes and the `ext_unres` entry flags.
 #include "common.cuh"
-size_t d8_walk_workspace(int64_t ny, int64_t nx);
-int d8_walk(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx, int encoding,
-            void *ws, size_t ws_bytes, cudaStream_t st);
-size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype) { return d8_walk_workspace(ny, nx); }
+
+namespace {
+
+constexpr int TW = 128;                 // tile width  (one warp, 4 cells per lane)
+constexpr int TH = 64;                  // tile height
+constexpr int NSLOT = 2 * TW + 2 * TH;  // boundary slots: top row, bottom row, left col, right col
+constexpr int WPB = 4;                  // warps (= tiles) per block in the fast kernels
+constexpr uint32_t LNONE = 0xFFFFu;
+constexpr uint32_t FULL = 0xffffffffu;
+
+// meta word of a boundary slot: [15:0] link, [19:16] k, [20] locally unresolved, [21] active
+__host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t link, int k, bool unres, bool active)
+{
+    return (link & 0xFFFFu) | ((uint32_t)k << 16) | ((uint32_t)unres << 20) | ((uint32_t)active << 21);
+}
+
+struct Geo {
+    int64_t ny, nx;
+    int tiles_x, tiles_y;
+};
+
+// canonical boundary slot of local cell (lr, lc) in a tile of th x tw cells, or -1
+__host__ __device__ __forceinline__ int slot_of(int lr, int lc, int th, int tw)
+{
+    if (lr == 0) return lc;
+    if (lr == th - 1) return TW + lc;
+    if (lc == 0) return 2 * TW + lr;
+    if (lc == tw - 1) return 2 * TW + TH + lr;
+    return -1;
+}
+// inverse: local cell of a slot, false when the slot is unused / non-canonical for this tile
+__host__ __device__ __forceinline__ bool cell_of(int s, int th, int tw, int &lr, int &lc)
+{
+    if (s < TW) { lr = 0; lc = s; return lc < tw; }
+    if (s < 2 * TW) { lr = th - 1; lc = s - TW; return th > 1 && lc < tw; }
+    if (s < 2 * TW + TH) { lr = s - 2 * TW; lc = 0; return lr > 0 && lr < th - 1; }
+    lr = s - 2 * TW - TH; lc = tw - 1;
+    return tw > 1 && lr > 0 && lr < th - 1;
+}
+
+__device__ __forceinline__ void tile_dims(const Geo &g, int tile, int &ty, int &tx, int &th, int &tw)
+{
+    ty = tile / g.tiles_x;
+    tx = tile - ty * g.tiles_x;
+    int64_t rem_r = g.ny - (int64_t)ty * TH, rem_c = g.nx - (int64_t)tx * TW;
+    th = rem_r < TH ? (int)rem_r : TH;
+    tw = rem_c < TW ? (int)rem_c : TW;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row loader for the fast kernels: 4 cells per lane -> k[4] (0..7, 8 = none) and an active nibble.
+// A valid code whose receiver lies outside the raster is turned into "none" here, so every k < 8
+// downstream has an in-raster receiver.
+// ---------------------------------------------------------------------------------------------
+template <int ENC, bool AL>
+__device__ __forceinline__ void load_row(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+                                         const Geo &g, int64_t gr, int64_t gc0, int (&k)[4], int &am)
+{
+    uint32_t w = 0, mw = 0x01010101u;
+    if (AL) {
+        if (gc0 < g.nx) {
+            w = *reinterpret_cast<const uint32_t *>(dir + gr * g.nx + gc0);
+            if (mask) mw = *reinterpret_cast<const uint32_t *>(mask + gr * g.nx + gc0);
+        } else mw = 0;
+    } else {
+        mw = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (gc0 + j < g.nx) {
+                w |= (uint32_t)(uint8_t)dir[gr * g.nx + gc0 + j] << (8 * j);
+                mw |= (uint32_t)(mask ? (mask[gr * g.nx + gc0 + j] != 0) : 1) << (8 * j);
+            }
+    }
+    am = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int code = (int)(int8_t)(w >> (8 * j));
+        bool a = ((mw >> (8 * j)) & 0xFFu) != 0;
+        int kk = a ? d8_norm<ENC>(code) : 8;
+        if (kk != 8) {
+            int64_t rr = gr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
+            if (rr < 0 || rr >= g.ny || cc < 0 || cc >= g.nx) kk = 8;
+        }
+        k[j] = kk;
+        am |= (int)a << j;
+    }
+}
+
+// segmented warp scan of an East chain: returns the inflow arriving at this lane's cell 0 from the
+// lane on its left.  (A, P) = value leaving the lane to the right with zero carry-in, and whether
+// the lane is all-pass.
+template <typename T>
+__device__ __forceinline__ T chain_carry_from_left(T A, bool P, int lane)
+{
+    if (__ballot_sync(FULL, P) == 0) {              // no lane passes a carry through: one hop is exact
+        T c = __shfl_up_sync(FULL, A, 1);
+        return lane == 0 ? (T)0 : c;
+    }
+    int p = P;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        T a2 = __shfl_up_sync(FULL, A, off);
+        int p2 = __shfl_up_sync(FULL, p, off);
+        if (lane >= off) { if (p) A += a2; p &= p2; }
+    }
+    T c = __shfl_up_sync(FULL, A, 1);
+    return lane == 0 ? (T)0 : c;
+}
+template <typename T>
+__device__ __forceinline__ T chain_carry_from_right(T A, bool P, int lane)
+{
+    if (__ballot_sync(FULL, P) == 0) {
+        T c = __shfl_down_sync(FULL, A, 1);
+        return lane == 31 ? (T)0 : c;
+    }
+    int p = P;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        T a2 = __shfl_down_sync(FULL, A, off);
+        int p2 = __shfl_down_sync(FULL, p, off);
+        if (lane + off < 32) { if (p) A += a2; p &= p2; }
+    }
+    T c = __shfl_down_sync(FULL, A, 1);
+    return lane == 31 ? (T)0 : c;
+}
+// copy-scans for labels: value of the chain end is copied back along the chain
+__device__ __forceinline__ uint32_t label_carry_from_right(uint32_t V, bool P, int lane)
+{
+    if (__ballot_sync(FULL, P) != 0) {
+        int p = P;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t v2 = __shfl_down_sync(FULL, V, off);
+            int p2 = __shfl_down_sync(FULL, p, off);
+            if (lane + off < 32) { if (p) V = v2; p &= p2; }
+            else if (p) { V = LNONE; }
+        }
+    }
+    uint32_t c = __shfl_down_sync(FULL, V, 1);
+    return lane == 31 ? LNONE : c;
+}
+__device__ __forceinline__ uint32_t label_carry_from_left(uint32_t V, bool P, int lane)
+{
+    if (__ballot_sync(FULL, P) != 0) {
+        int p = P;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t v2 = __shfl_up_sync(FULL, V, off);
+            int p2 = __shfl_up_sync(FULL, p, off);
+            if (lane >= off) { if (p) V = v2; p &= p2; }
+            else if (p) { V = LNONE; }
+        }
+    }
+    uint32_t c = __shfl_up_sync(FULL, V, 1);
+    return lane == 0 ? LNONE : c;
+}
+
+// One row of the downward sweep.  b[] = base (own cell + inflow from above + external inflow) for
+// active cells; returns tot[] (final for this sweep) and updates d[] = contributions to the row below.
+// Sets `complex_row` when the row breaks the "simple tile" conditions.
+template <typename T>
+__device__ __forceinline__ void sweep_row_down(const int (&k)[4], int am, const T (&b)[4], T (&tot)[4], T (&d)[4],
+                                               int lane, bool &twocycle)
+{
+    // East chains: e_in[j] = inflow from the west neighbour
+    T e_in[4], w_in[4];
+    {
+        T S = 0;
+        bool P = true;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { bool ps = k[j] == 0; S = ps ? b[j] + S : (T)0; P = P && ps; }
+        T carry = chain_carry_from_left<T>(S, P, lane);
+        e_in[0] = carry;
+#pragma unroll
+        for (int j = 1; j < 4; j++) e_in[j] = (k[j - 1] == 0) ? b[j - 1] + e_in[j - 1] : (T)0;
+    }
+    const bool anyW = __any_sync(FULL, k[0] == 4 || k[1] == 4 || k[2] == 4 || k[3] == 4);
+    if (anyW) {
+        T S = 0;
+        bool P = true;
+#pragma unroll
+        for (int j = 3; j >= 0; j--) { bool ps = k[j] == 4; S = ps ? b[j] + S : (T)0; P = P && ps; }
+        T carry = chain_carry_from_right<T>(S, P, lane);
+        w_in[3] = carry;
+#pragma unroll
+        for (int j = 2; j >= 0; j--) w_in[j] = (k[j + 1] == 4) ? b[j + 1] + w_in[j + 1] : (T)0;
+        // E -> W adjacent pairs are two-cycles: not handled by the scans
+        int k0_right = __shfl_down_sync(FULL, k[0], 1);
+        bool tc = (k[0] == 0 && k[1] == 4) || (k[1] == 0 && k[2] == 4) || (k[2] == 0 && k[3] == 4) ||
+                  (lane < 31 && k[3] == 0 && k0_right == 4);
+        twocycle = twocycle || __any_sync(FULL, tc);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) w_in[j] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) tot[j] = ((am >> j) & 1) ? b[j] + e_in[j] + w_in[j] : (T)0;
+    // contributions to the row below: S from the same column, SE from the left neighbour, SW from the right one
+    T se_out = (k[3] == 1) ? tot[3] : (T)0, sw_out = (k[0] == 3) ? tot[0] : (T)0;
+    T from_left = __shfl_up_sync(FULL, se_out, 1), from_right = __shfl_down_sync(FULL, sw_out, 1);
+    if (lane == 0) from_left = 0;
+    if (lane == 31) from_right = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        T v = (k[j] == 2) ? tot[j] : (T)0;
+        v += (j > 0) ? ((k[j > 0 ? j - 1 : 0] == 1) ? tot[j > 0 ? j - 1 : 0] : (T)0) : from_left;
+        v += (j < 3) ? ((k[j < 3 ? j + 1 : 3] == 3) ? tot[j < 3 ? j + 1 : 3] : (T)0) : from_right;
+        d[j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase A, fast solver
+// ---------------------------------------------------------------------------------------------
+template <int ENC, bool AL>
+__global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+                                                     Geo g, int ntiles, uint32_t *__restrict__ meta,
+                                                     int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class)
+{
+    __shared__ uint32_t rows[WPB][TH][32];          // per row: k nibbles [15:0], active nibble [19:16]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * WPB + warp;
+    if (tile >= ntiles) return;
+    int ty, tx, th, tw;
+    tile_dims(g, tile, ty, tx, th, tw);
+    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + 4 * lane;
+    uint32_t *m_t = meta + (int64_t)tile * NSLOT;
+    int32_t *x_t = exit_acc + (int64_t)tile * NSLOT;
+    const int rlane = (tw - 1) >> 2, rj = (tw - 1) & 3;       // lane / sub-cell holding the right column
+
+    // ---- downward sweep: local accumulation
+    int32_t d[4] = {0, 0, 0, 0};
+    bool complex_tile = false;
+    for (int lr = 0; lr < th; lr++) {
+        int k[4], am;
+        load_row<ENC, AL>(dir, mask, g, gr0 + lr, gc0, k, am);
+        if (lr > 0) {
+            bool up = (k[0] >= 5 && k[0] <= 7) || (k[1] >= 5 && k[1] <= 7) || (k[2] >= 5 && k[2] <= 7) || (k[3] >= 5 && k[3] <= 7);
+            complex_tile = complex_tile || __any_sync(FULL, up);
+        }
+        rows[warp][lr][lane] = (uint32_t)(k[0] | (k[1] << 4) | (k[2] << 8) | (k[3] << 12) | (am << 16));
+        int32_t b[4], tot[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? 1 + d[j] : 0;
+        sweep_row_down<int32_t>(k, am, b, tot, d, lane, complex_tile);
+        if (complex_tile) break;
+        if (lr == 0) *reinterpret_cast<int4 *>(x_t + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
+        else if (lr == th - 1) *reinterpret_cast<int4 *>(x_t + TW + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
+        else {
+            if (lane == 0) x_t[2 * TW + lr] = tot[0];
+            if (lane == rlane && tw > 1) x_t[2 * TW + TH + lr] = tot[rj];
+        }
+    }
+    if (complex_tile) {                              // the general solver redoes this tile
+        if (lane == 0) tile_class[tile] = 1;
+        return;
+    }
+    if (lane == 0) tile_class[tile] = 0;
+    __syncwarp();
+
+    // ---- upward sweep: exit labels
+    uint32_t lb[4] = {LNONE, LNONE, LNONE, LNONE};   // labels of the row below
+    for (int lr = th - 1; lr >= 0; lr--) {
+        uint32_t pk = rows[warp][lr][lane];
+        int k[4], am = (pk >> 16) & 0xF;
+#pragma unroll
+        for (int j = 0; j < 4; j++) k[j] = (pk >> (4 * j)) & 0xF;
+        uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left3 = __shfl_up_sync(FULL, lb[3], 1);
+        uint32_t own[4];
+        bool pe[4], pw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int lc = 4 * lane + j, kk = k[j];
+            const bool top = lr == 0, bot = lr == th - 1, lft = lc == 0, rgt = lc == tw - 1;
+            bool exits = (bot && kk >= 1 && kk <= 3) || (top && kk >= 5 && kk <= 7) ||
+                         (rgt && (kk == 0 || kk == 1 || kk == 7)) || (lft && kk >= 3 && kk <= 5);
+            uint32_t v = LNONE;
+            pe[j] = pw[j] = false;
+            if (kk != 8) {
+                if (exits) v = (uint32_t)slot_of(lr, lc, th, tw);
+                else if (kk == 2) v = lb[j];
+                else if (kk == 1) v = (j < 3) ? lb[j < 3 ? j + 1 : 3] : lb_right0;
+                else if (kk == 3) v = (j > 0) ? lb[j > 0 ? j - 1 : 0] : lb_left3;
+                else if (kk == 0) pe[j] = true;
+                else if (kk == 4) pw[j] = true;
+            }
+            own[j] = v;
+        }
+        uint32_t lab[4];
+        {   // East cells copy the label of the chain end on their right
+            uint32_t V = LNONE;
+            bool P = true;
+#pragma unroll
+            for (int j = 3; j >= 0; j--) { V = pe[j] ? V : own[j]; P = P && pe[j]; }
+            // V = label at cell 0 with carry NONE; recompute with the real carry
+            uint32_t carry = label_carry_from_right(V, P, lane);
+            uint32_t cur = carry;
+#pragma unroll
+            for (int j = 3; j >= 0; j--) { cur = pe[j] ? cur : own[j]; lab[j] = cur; }
+        }
+        if (__any_sync(FULL, pw[0] || pw[1] || pw[2] || pw[3])) {
+            uint32_t V = LNONE;
+            bool P = true;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { V = pw[j] ? V : lab[j]; P = P && pw[j]; }
+            uint32_t carry = label_carry_from_left(V, P, lane);
+            uint32_t cur = carry;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { cur = pw[j] ? cur : lab[j]; lab[j] = cur; }
+        }
+        uint32_t mw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            lb[j] = lab[j];
+            mw[j] = meta_pack(lab[j], k[j], false, (am >> j) & 1);
+        }
+        if (lr == 0) *reinterpret_cast<uint4 *>(m_t + 4 * lane) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        else if (lr == th - 1) *reinterpret_cast<uint4 *>(m_t + TW + 4 * lane) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        else {
+            if (lane == 0) m_t[2 * TW + lr] = mw[0];
+            if (lane == rlane && tw > 1) m_t[2 * TW + TH + lr] = mw[rj];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase C, fast solver
+// ---------------------------------------------------------------------------------------------
+template <int ENC, bool AL, typename T>
+__global__ void __launch_bounds__(WPB * 32) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+                                                     Geo g, int ntiles, const T *__restrict__ inflow,
+                                                     const uint8_t *__restrict__ tile_class, T *__restrict__ acc)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * WPB + warp;
+    if (tile >= ntiles) return;
+    if (tile_class[tile] != 0) return;              // general solver
+    int ty, tx, th, tw;
+    tile_dims(g, tile, ty, tx, th, tw);
+    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + 4 * lane;
+    const T *in_t = inflow + (int64_t)tile * NSLOT;
+    const int rlane = (tw - 1) >> 2, rj = (tw - 1) & 3;
+    // left / right column inflows of all rows, two rows per lane
+    T inL0 = in_t[2 * TW + lane], inL1 = in_t[2 * TW + 32 + lane];
+    T inR0 = in_t[2 * TW + TH + lane], inR1 = in_t[2 * TW + TH + 32 + lane];
+    T d[4] = {0, 0, 0, 0};
+    bool dummy = false;
+    for (int lr = 0; lr < th; lr++) {
+        int k[4], am;
+        load_row<ENC, AL>(dir, mask, g, gr0 + lr, gc0, k, am);
+        T ext[4] = {0, 0, 0, 0};
+        if (lr == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ext[j] = in_t[4 * lane + j];
+        } else if (lr == th - 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ext[j] = in_t[TW + 4 * lane + j];
+        } else {
+            T l = __shfl_sync(FULL, lr < 32 ? inL0 : inL1, lr & 31);
+            T r = __shfl_sync(FULL, lr < 32 ? inR0 : inR1, lr & 31);
+            if (lane == 0) ext[0] = l;
+            if (lane == rlane && tw > 1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (j == rj) ext[j] += r;
+            }
+        }
+        T b[4], tot[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? (T)1 + d[j] + ext[j] : (T)0;
+        sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
+        const int64_t off = (gr0 + lr) * g.nx + gc0;
+        if (AL) {
+            if (gc0 < g.nx) {
+                if (sizeof(T) == 4) *reinterpret_cast<int4 *>(acc + off) = make_int4((int)tot[0], (int)tot[1], (int)tot[2], (int)tot[3]);
+                else {
+                    *reinterpret_cast<longlong2 *>(acc + off) = make_longlong2((long long)tot[0], (long long)tot[1]);
+                    *reinterpret_cast<longlong2 *>(acc + off + 2) = make_longlong2((long long)tot[2], (long long)tot[3]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (gc0 + j < g.nx) acc[off + j] = tot[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// general tile solver (one block per tile, chain walk in shared memory), phases A and C
+// ---------------------------------------------------------------------------------------------
+constexpr int GTH = 256;   // threads per block
+constexpr int TCELLS = TW * TH;
+
+template <int ENC>
+__device__ __forceinline__ void general_load(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, const Geo &g,
+                                             int ty, int tx, int th, int tw, uint8_t *kk)
+{
+    for (int idx = threadIdx.x; idx < TCELLS; idx += GTH) {
+        int lr = idx / TW, lc = idx - lr * TW;
+        uint8_t v = 8;
+        if (lr < th && lc < tw) {
+            int64_t gr = (int64_t)ty * TH + lr, gc = (int64_t)tx * TW + lc, gi = gr * g.nx + gc;
+            if (cell_active(mask, gi)) {
+                int k = d8_norm<ENC>(dir[gi]);
+                if (k != 8) {
+                    int64_t rr = gr + d8_dr(k), cc = gc + d8_dc(k);
+                    if (rr < 0 || rr >= g.ny || cc < 0 || cc >= g.nx) k = 8;
+                }
+                v = (uint8_t)(k | 16);
+            }
+        }
+        kk[idx] = v;
+    }
+}
+
+// in-tile receiver of cell idx: >= 0 index, -1 none / inactive receiver, -2 leaves the tile
+__device__ __forceinline__ int local_recv(const uint8_t *kk, int idx, int th, int tw)
+{
+    int k = kk[idx] & 15;
+    if (k == 8) return -1;
+    int lr = idx / TW, lc = idx - lr * TW;
+    int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
+    if (rr < 0 || rr >= th || cc < 0 || cc >= tw) return -2;
+    int j = rr * TW + cc;
+    return (kk[j] & 16) ? j : -1;
+}
+
+__device__ __forceinline__ void general_indegree(const uint8_t *kk, uint8_t *cnt, int th, int tw)
+{
+    for (int idx = threadIdx.x; idx < TCELLS; idx += GTH) {
+        uint8_t c = 0;
+        if (kk[idx] & 16) {
+            int lr = idx / TW, lc = idx - lr * TW, n = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int rr = lr - d8_dr(k), cc = lc - d8_dc(k);
+                if (rr < 0 || rr >= th || cc < 0 || cc >= tw) continue;
+                uint8_t v = kk[rr * TW + cc];
+                if ((v & 16) && (v & 15) == k) n++;
+            }
+            c = n == 0 ? 0xFF : (uint8_t)n;
+        }
+        cnt[idx] = c;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T smem_add(T *p, T v);
+template <>
+__device__ __forceinline__ int32_t smem_add<int32_t>(int32_t *p, int32_t v) { return atomicAdd(p, v); }
+template <>
+__device__ __forceinline__ int64_t smem_add<int64_t>(int64_t *p, int64_t v)
+{
+    return (int64_t)atomicAdd((unsigned long long *)p, (unsigned long long)v);
+}
+
+template <typename T>
+__device__ __forceinline__ void general_walk(const uint8_t *kk, uint8_t *cnt, T *acc, int th, int tw)
+{
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(cnt);
+    for (int idx = threadIdx.x; idx < TCELLS; idx += GTH) {
+        if (cnt[idx] != 0xFF) continue;                  // leaves only; 0xFF is never produced by a decrement
+        T v = acc[idx] + 1;                              // acc holds the external inflow (0 in phase A)
+        acc[idx] = v;
+        int cur = idx;
+        while (true) {
+            int j = local_recv(kk, cur, th, tw);
+            if (j < 0) break;
+            smem_add<T>(&acc[j], v);
+            __threadfence_block();
+            unsigned sh = 8u * (unsigned)(j & 3);
+            uint32_t old = atomicSub(&cnt32[j >> 2], 1u << sh);
+            if (((old >> sh) & 0xFFu) != 1u) break;
+            __threadfence_block();
+            v = smem_add<T>(&acc[j], (T)1) + 1;
+            cur = j;
+        }
+    }
+}
+
+template <int ENC>
+__global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g,
+                                                  const uint8_t *__restrict__ tile_class, uint32_t *__restrict__ meta,
+                                                  int32_t *__restrict__ exit_acc)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tile = blockIdx.x;
+    if (!(tile_class[tile] & 1)) return;
+    int32_t *acc = reinterpret_cast<int32_t *>(smem);
+    uint8_t *kk = smem + sizeof(int32_t) * TCELLS;
+    uint8_t *cnt = kk + TCELLS;
+    int ty, tx, th, tw;
+    tile_dims(g, tile, ty, tx, th, tw);
+    general_load<ENC>(dir, mask, g, ty, tx, th, tw, kk);
+    for (int idx = threadIdx.x; idx < TCELLS; idx += GTH) acc[idx] = 0;
+    __syncthreads();
+    general_indegree(kk, cnt, th, tw);
+    __syncthreads();
+    general_walk<int32_t>(kk, cnt, acc, th, tw);
+    __syncthreads();
+    for (int s = threadIdx.x; s < NSLOT; s += GTH) {
+        int lr, lc;
+        uint32_t m = 0;
+        int32_t xa = 0;
+        if (cell_of(s, th, tw, lr, lc)) {
+            int idx = lr * TW + lc;
+            uint8_t v = kk[idx];
+            if (v & 16) {
+                bool unres = cnt[idx] != 0xFF && cnt[idx] != 0;
+                uint32_t link = LNONE;
+                int cur = idx;
+                for (int steps = 0; steps <= th * tw; steps++) {
+                    int j = local_recv(kk, cur, th, tw);
+                    if (j == -2) { link = (uint32_t)slot_of(cur / TW, cur % TW, th, tw); break; }
+                    if (j < 0) break;
+                    cur = j;
+                }
+                m = meta_pack(link, v & 15, unres, true);
+                xa = acc[idx];
+            }
+        }
+        meta[(int64_t)tile * NSLOT + s] = m;
+        exit_acc[(int64_t)tile * NSLOT + s] = xa;
+    }
+}
+
+template <int ENC, typename T>
+__global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g,
+                                                  const uint8_t *__restrict__ tile_class, const T *__restrict__ inflow,
+                                                  const uint8_t *__restrict__ ext_unres, T *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tile = blockIdx.x;
+    if (tile_class[tile] == 0) return;
+    T *acc = reinterpret_cast<T *>(smem);
+    uint8_t *kk = smem + sizeof(T) * TCELLS;
+    uint8_t *cnt = kk + TCELLS;
+    int ty, tx, th, tw;
+    tile_dims(g, tile, ty, tx, th, tw);
+    general_load<ENC>(dir, mask, g, ty, tx, th, tw, kk);
+    for (int idx = threadIdx.x; idx < TCELLS; idx += GTH) acc[idx] = 0;
+    __syncthreads();
+    general_indegree(kk, cnt, th, tw);
+    __syncthreads();
+    for (int s = threadIdx.x; s < NSLOT; s += GTH) {
+        int lr, lc;
+        if (!cell_of(s, th, tw, lr, lc)) continue;
+        int idx = lr * TW + lc;
+        if (!(kk[idx] & 16)) continue;
+        acc[idx] = inflow[(int64_t)tile * NSLOT + s];
+        if (ext_unres[(int64_t)tile * NSLOT + s]) cnt[idx] = cnt[idx] == 0xFF ? 1 : cnt[idx] + 1;   // phantom donor
+    }
+    __syncthreads();
+    general_walk<T>(kk, cnt, acc, th, tw);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TCELLS; idx += GTH) {
+        int lr = idx / TW, lc = idx - lr * TW;
+        if (lr < th && lc < tw) out[((int64_t)ty * TH + lr) * g.nx + (int64_t)tx * TW + lc] = acc[idx];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase G: contracted forest over boundary slots
+// ---------------------------------------------------------------------------------------------
+// entry slot (global node id) that exit slot (tile, s) drains to, or -1 when s is not an exit
+__device__ __forceinline__ int64_t entry_of(const Geo &g, const uint32_t *__restrict__ meta, int tile, int s,
+                                            uint32_t &m_entry)
+{
+    int ty, tx, th, tw, lr, lc;
+    tile_dims(g, tile, ty, tx, th, tw);
+    if (!cell_of(s, th, tw, lr, lc)) return -1;
+    uint32_t m = meta[(int64_t)tile * NSLOT + s];
+    if (!((m >> 21) & 1)) return -1;
+    int k = (m >> 16) & 0xF;
+    if (k == 8) return -1;
+    int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
+    if (rr >= 0 && rr < th && cc >= 0 && cc < tw) return -1;            // stays in the tile: not an exit
+    int64_t gr = (int64_t)ty * TH + rr, gc = (int64_t)tx * TW + cc;     // in raster by construction
+    int ty2 = (int)(gr / TH), tx2 = (int)(gc / TW);
+    int tile2 = ty2 * g.tiles_x + tx2, ty3, tx3, th2, tw2;
+    tile_dims(g, tile2, ty3, tx3, th2, tw2);
+    int s2 = slot_of((int)(gr - (int64_t)ty2 * TH), (int)(gc - (int64_t)tx2 * TW), th2, tw2);
+    int64_t node = (int64_t)tile2 * NSLOT + s2;
+    m_entry = meta[node];
+    return node;
+}
+
+__global__ void k_build_forest(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, int32_t *__restrict__ parent,
+                               uint8_t *__restrict__ blocked)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    int tile = (int)(i / NSLOT), s = (int)(i - (int64_t)tile * NSLOT);
+    uint32_t me = 0;
+    int64_t e = entry_of(g, meta, tile, s, me);
+    int32_t p = -1;
+    if (e >= 0 && ((me >> 21) & 1)) {
+        uint32_t link = me & 0xFFFFu;
+        if (link != LNONE) p = (int32_t)((e / NSLOT) * NSLOT + link);
+    }
+    parent[i] = p;
+    blocked[i] = (uint8_t)((meta[i] >> 20) & 1);
+}
+
+template <typename T>
+__device__ __forceinline__ void inflow_add(T *p, T v);
+template <>
+__device__ __forceinline__ void inflow_add<int32_t>(int32_t *p, int32_t v) { atomicAdd(p, v); }
+template <>
+__device__ __forceinline__ void inflow_add<int64_t>(int64_t *p, int64_t v)
+{
+    atomicAdd((unsigned long long *)p, (unsigned long long)v);
+}
+
+template <typename T>
+__global__ void k_push_inflow(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const T *__restrict__ A,
+                              const int32_t *__restrict__ cnt, T *__restrict__ inflow, uint8_t *__restrict__ ext_unres,
+                              uint8_t *__restrict__ tile_class)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    int tile = (int)(i / NSLOT), s = (int)(i - (int64_t)tile * NSLOT);
+    uint32_t me = 0;
+    int64_t e = entry_of(g, meta, tile, s, me);
+    if (e < 0 || !((me >> 21) & 1)) return;                           // not an exit, or the receiver is inactive
+    if (cnt[i] <= 0) inflow_add<T>(&inflow[e], A[i]);                 // finalised exit: push its total
+    else {                                                            // unresolved upstream: the entry never finalises
+        ext_unres[e] = 1;
+        tile_class[e / NSLOT] = 2;                                    // (racing writers all store non-zero)
+    }
+}
+
+template <int ENC, typename T>
+int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                cudaStream_t st)
+{
+    Geo g;
+    g.ny = ny; g.nx = nx;
+    g.tiles_x = (int)((nx + TW - 1) / TW);
+    g.tiles_y = (int)((ny + TH - 1) / TH);
+    const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
+    WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "raster too large for the tiled accumulation");
+    const int ntiles = (int)ntiles64;
+    const int64_t nnodes = ntiles64 * NSLOT;
+    WsCursor cur(ws, ws_bytes);
+    uint32_t *meta = cur.take<uint32_t>((size_t)nnodes);
+    int32_t *exit_acc = cur.take<int32_t>((size_t)nnodes);
+    int32_t *parent = cur.take<int32_t>((size_t)nnodes);
+    int32_t *cnt = cur.take<int32_t>((size_t)nnodes);
+    T *A = cur.take<T>((size_t)nnodes);
+    T *inflow = cur.take<T>((size_t)nnodes);
+    uint8_t *blocked = cur.take<uint8_t>((size_t)nnodes);
+    uint8_t *ext_unres = cur.take<uint8_t>((size_t)nnodes);
+    uint8_t *tile_class = cur.take<uint8_t>((size_t)ntiles);
+    WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
+    const bool al = (nx % 4 == 0) && (((uintptr_t)dir & 3) == 0) && (mask == nullptr || ((uintptr_t)mask & 3) == 0) &&
+                    (((uintptr_t)acc & 15) == 0);
+    const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
+    const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS, smemC = sizeof(T) * TCELLS + 2 * TCELLS;
+    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    WMF_CUDA_CHECK(cudaMemsetAsync(inflow, 0, sizeof(T) * nnodes, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(ext_unres, 0, (size_t)nnodes, st));
+    // phase A
+    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class);
+    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class);
+    k_generalA<ENC><<<ntiles, GTH, smemA, st>>>(dir, mask, g, tile_class, meta, exit_acc);
+    // phase G
+    k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, parent, blocked);
+    WMF_LAUNCH_CHECK();
+    int rc = sizeof(T) == 4 ? forest_accum_i32(parent, exit_acc, (int32_t *)A, cnt, nnodes, st, blocked)
+                            : forest_accum_i64(parent, exit_acc, (int64_t *)A, cnt, nnodes, st, blocked);
+    if (rc) return rc;
+    k_push_inflow<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, A, cnt, inflow, ext_unres, tile_class);
+    // phase C
+    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, acc);
+    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, acc);
+    k_generalC<ENC, T><<<ntiles, GTH, smemC, st>>>(dir, mask, g, tile_class, inflow, ext_unres, acc);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int d8_convert_i64_to_f64(void *buf, int64_t n, cudaStream_t st);
+
+size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
+{
+    int64_t ntiles = ((nx + TW - 1) / TW) * ((ny + TH - 1) / TH);
+    size_t nn = (size_t)ntiles * NSLOT, tsz = acc_dtype == WMF_ACC_I32 ? 4 : 8;
+    return 4 * wmf_align(nn * 4) + 2 * wmf_align(nn * tsz) + 2 * wmf_align(nn) + wmf_align((size_t)ntiles) + 4096;
+}
+
 int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx, int encoding,
              void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    return d8_walk(dir, mask, acc, acc_dtype, ny, nx, encoding, ws, ws_bytes, st);
+    int rc;
+    if (acc_dtype == WMF_ACC_I32)
+        rc = encoding == WMF_ENC_INTERNAL ? run_sweep_t<WMF_ENC_INTERNAL, int32_t>(dir, mask, (int32_t *)acc, ny, nx, ws, ws_bytes, st)
+                                          : run_sweep_t<WMF_ENC_KEYPAD, int32_t>(dir, mask, (int32_t *)acc, ny, nx, ws, ws_bytes, st);
+    else
+        rc = encoding == WMF_ENC_INTERNAL ? run_sweep_t<WMF_ENC_INTERNAL, int64_t>(dir, mask, (int64_t *)acc, ny, nx, ws, ws_bytes, st)
+                                          : run_sweep_t<WMF_ENC_KEYPAD, int64_t>(dir, mask, (int64_t *)acc, ny, nx, ws, ws_bytes, st);
+    if (rc) return rc;
+    if (acc_dtype == WMF_ACC_F64) return d8_convert_i64_to_f64(acc, ny * nx, st);
+    return 0;
 }

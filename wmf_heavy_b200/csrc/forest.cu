@@ -35,20 +35,23 @@ struct AtomT<int64_t> {
 // never decremented by anybody, so reading cnt[i] == 0 here cannot race with a walker -- but a
 // non-leaf can *reach* 0.  Leaves are therefore told apart by a second array-free trick: the
 // walk kernel is launched after a marking pass that rewrites leaf counters to -1.
-__global__ void k_forest_mark(int32_t *__restrict__ cnt, int64_t n)
+__global__ void k_forest_mark(int32_t *__restrict__ cnt, const uint8_t *__restrict__ blocked, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && cnt[i] == 0) cnt[i] = -1;
+    if (i >= n) return;
+    int32_t c = cnt[i];
+    if (blocked && blocked[i]) cnt[i] = c + 1;        // a phantom child that never finishes
+    else if (c == 0) cnt[i] = -1;
 }
 
-template <typename T>
-__global__ void k_forest_walk(const int32_t *__restrict__ parent, const T *__restrict__ w, T *acc,
+template <typename T, typename W>
+__global__ void k_forest_walk(const int32_t *__restrict__ parent, const W *__restrict__ w, T *acc,
                               int32_t *cnt, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (cnt[i] != -1) return;               // only leaves start walkers
-    T v = w ? w[i] : (T)1;
+    T v = w ? (T)w[i] : (T)1;
     acc[i] = v;                             // nobody else writes a leaf
     int64_t cur = i;
     while (true) {
@@ -59,33 +62,36 @@ __global__ void k_forest_walk(const int32_t *__restrict__ parent, const T *__res
         int32_t old = atomicSub(&cnt[p], 1);
         if (old != 1) break;                // other children still running: they will finish p
         __threadfence();
-        T own = w ? w[p] : (T)1;
+        T own = w ? (T)w[p] : (T)1;
         v = AtomT<T>::add(&acc[p], own) + own;
         cur = p;
     }
 }
 
-template <typename T>
-int forest_accum_t(const int32_t *parent, const T *w, T *acc, int32_t *cnt, int64_t n, cudaStream_t st)
+template <typename T, typename W>
+int forest_accum_t(const int32_t *parent, const W *w, T *acc, int32_t *cnt, const uint8_t *blocked, int64_t n,
+                   cudaStream_t st)
 {
     if (n <= 0) return 0;
     WMF_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n, st));
     WMF_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(T) * n, st));
     const int th = 256;
     k_forest_count<<<blocks_for(n, th), th, 0, st>>>(parent, cnt, n);
-    k_forest_mark<<<blocks_for(n, th), th, 0, st>>>(cnt, n);
-    k_forest_walk<T><<<blocks_for(n, th), th, 0, st>>>(parent, w, acc, cnt, n);
+    k_forest_mark<<<blocks_for(n, th), th, 0, st>>>(cnt, blocked, n);
+    k_forest_walk<T, W><<<blocks_for(n, th), th, 0, st>>>(parent, w, acc, cnt, n);
     WMF_LAUNCH_CHECK();
     return 0;
 }
 
 }  // namespace
 
-int forest_accum_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int32_t *cnt, int64_t n, cudaStream_t st)
+int forest_accum_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int32_t *cnt, int64_t n, cudaStream_t st,
+                     const uint8_t *blocked)
 {
-    return forest_accum_t<int32_t>(parent, w, acc, cnt, n, st);
+    return forest_accum_t<int32_t, int32_t>(parent, w, acc, cnt, blocked, n, st);
 }
-int forest_accum_i64(const int32_t *parent, const int64_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st)
+int forest_accum_i64(const int32_t *parent, const int32_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st,
+                     const uint8_t *blocked)
 {
-    return forest_accum_t<int64_t>(parent, w, acc, cnt, n, st);
+    return forest_accum_t<int64_t, int32_t>(parent, w, acc, cnt, blocked, n, st);
 }
