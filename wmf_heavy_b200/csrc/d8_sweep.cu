@@ -22,6 +22,8 @@
 // Cycle semantics (basics.py:166-175): a cell is finalised only when all its donors are; others
 // keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
 // contracted forest carries this through `blocked` nodes and the `ext_unres` entry flags.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace {
@@ -235,14 +237,188 @@ __device__ __forceinline__ void sweep_row_down(const int (&k)[4], int am, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// fast solver: staging, row classification and the lean "plain row" step
+// ---------------------------------------------------------------------------------------------
+// Stage the tile's raw DIR words (4 codes per lane per row) -- and the active nibbles when the
+// tile has a mask or is ragged -- into shared memory with asynchronous copies, so the sweeps never
+// wait on HBM row by row.
+template <bool AL>
+__device__ __forceinline__ void stage_tile(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, const Geo &g,
+                                           int64_t gr0, int64_t gc0, int th, bool need_active,
+                                           uint32_t (*wrow)[32], uint8_t (*arow)[32], int lane)
+{
+    if (AL && gc0 + 3 < g.nx) {
+        const int8_t *src = dir + gr0 * g.nx + gc0;
+        for (int lr = 0; lr < th; lr++) {
+            __pipeline_memcpy_async(&wrow[lr][lane], src, 4);
+            src += g.nx;
+        }
+        __pipeline_commit();
+        if (need_active) {
+            for (int lr = 0; lr < th; lr++) {
+                uint32_t mw = 0x01010101u;
+                if (mask) mw = *reinterpret_cast<const uint32_t *>(mask + (gr0 + lr) * g.nx + gc0);
+                int am = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) am |= (int)(((mw >> (8 * j)) & 0xFFu) != 0) << j;
+                arow[lr][lane] = (uint8_t)am;
+            }
+        }
+        __pipeline_wait_prior(0);
+    } else {
+        for (int lr = 0; lr < th; lr++) {
+            uint32_t w = 0;
+            int am = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (gc0 + j < g.nx) {
+                    int64_t gi = (gr0 + lr) * g.nx + gc0 + j;
+                    w |= (uint32_t)(uint8_t)dir[gi] << (8 * j);
+                    am |= (int)(mask ? (mask[gi] != 0) : 1) << j;
+                }
+            wrow[lr][lane] = w;
+            arow[lr][lane] = (uint8_t)am;
+        }
+    }
+    __syncwarp();
+}
+
+// decode a staged word: k[4] (8 = none; inactive cells are none) ; on border tiles a code whose
+// receiver lies outside the raster becomes none.
+template <int ENC>
+__device__ __forceinline__ void decode_row(uint32_t w, int am, const Geo &g, int64_t gr, int64_t gc0, bool border,
+                                           int (&k)[4])
+{
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int kk = ((am >> j) & 1) ? d8_norm<ENC>((int)(int8_t)(w >> (8 * j))) : 8;
+        if (border && kk != 8) {
+            int64_t rr = gr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
+            if (rr < 0 || rr >= g.ny || cc < 0 || cc >= g.nx) kk = 8;
+        }
+        k[j] = kk;
+    }
+}
+
+// ---- lean "plain row" machinery ---------------------------------------------------------------
+// A plain row holds only E / SE / S / SW codes (every cell active, tile interior).  Its four codes
+// per lane are turned into byte masks with two multiplies and four LOP3s, and every (cell, dir)
+// select is one PRMT (sign-replicate) + one LOP3 -- no predicates, so nothing spills to P2R.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// all-ones / all-zeros from the top bit of byte j of m
+template <int J>
+__device__ __forceinline__ int32_t bmask(uint32_t m) { return (int32_t)prmt(m, 0u, 0x8888u + 0x1111u * J); }
+
+// internal-coded word of a row (E 0, SE 1, S 2, SW 3), or "needs the generic row" when any byte is
+// something else.  Keypad words are translated with a PRMT table lookup.
+template <int ENC>
+__device__ __forceinline__ uint32_t plain_word(uint32_t w, bool &generic)
+{
+    if (ENC == WMF_ENC_INTERNAL) {
+        generic = (w & 0xFCFCFCFCu) != 0;
+        return w;
+    }
+    // keypad 1 SW, 2 S, 3 SE, 6 E -> 3, 2, 1, 0 ; anything else -> 4 (generic)
+    bool junk = (w & 0xF8F8F8F8u) != 0;                       // codes >= 8 (N, NE) and negatives
+    uint32_t t = (w & 0x00070007u) | ((w & 0x07000700u) >> 4); // two nibbles per half word
+    uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);        // selector nibbles = the four codes (0..7)
+    uint32_t k = prmt(0x01020304u, 0x04000404u, sel);         // table[code]: 0:4 1:3 2:2 3:1 | 4:4 5:4 6:0 7:4
+    generic = junk || (k & 0x04040404u) != 0;
+    return k;
+}
+
+// Direction tests of the four cells as packed 0/1 bytes.  Every select below is a multiply by 0/1
+// fused into an IMAD, which runs on the FMA pipe: the kernel is ALU-pipe bound (LOP3 / PRMT / SEL),
+// so moving the selects off that pipe matters more than the instruction count.
+struct RowBits { uint32_t e, se, s, sw; };
+__device__ __forceinline__ RowBits row_bits(uint32_t k)
+{
+    const uint32_t x0 = k & 0x01010101u, x1 = (k >> 1) & 0x01010101u;
+    RowBits m;
+    m.sw = x0 & x1; m.se = x0 ^ m.sw; m.s = x1 ^ m.sw; m.e = (x0 | x1) ^ 0x01010101u;
+    return m;
+}
+// byte J of m as a 0/1 integer
+template <int J>
+__device__ __forceinline__ uint32_t bit01(uint32_t m) { return prmt(m, 0u, 0x4440u + J); }
+
+// Downward step of a plain row.  d[] holds, for each cell, 1 + the inflow from the row above (the
+// cell's own +1 is folded into the accumulate chain of the row above); tot[] out; d[] out for the
+// row below.  extL / extR: external inflow of the left- / right-column cell (phase C), else zero.
+template <typename T>
+__device__ __forceinline__ void plain_row_down(uint32_t k, T (&d)[4], T (&tot)[4], int lane, T extL, T extR)
+{
+    const RowBits m = row_bits(k);
+    const T E0 = bit01<0>(m.e), E1 = bit01<1>(m.e), E2 = bit01<2>(m.e), E3 = bit01<3>(m.e);
+    T t0 = d[0] + extL;
+    T t1 = t0 * E0 + d[1];
+    T t2 = t1 * E1 + d[2];
+    T t3 = t2 * E2 + d[3] + extR;
+    T carry = chain_carry_from_left<T>(t3 * E3, m.e == 0x01010101u, lane);
+    tot[0] = t0 + carry; carry *= E0;
+    tot[1] = t1 + carry; carry *= E1;
+    tot[2] = t2 + carry; carry *= E2;
+    tot[3] = t3 + carry;
+    T from_left = __shfl_up_sync(FULL, tot[3] * (T)bit01<3>(m.se), 1);
+    T from_right = __shfl_down_sync(FULL, tot[0] * (T)bit01<0>(m.sw), 1);
+    from_left = lane == 0 ? (T)1 : from_left + 1;            // the "+1" of the cell below rides along
+    if (lane == 31) from_right = 0;
+    d[0] = tot[0] * (T)bit01<0>(m.s) + from_left;
+    d[0] = tot[1] * (T)bit01<1>(m.sw) + d[0];
+    d[1] = tot[1] * (T)bit01<1>(m.s) + 1;
+    d[1] = tot[0] * (T)bit01<0>(m.se) + d[1];
+    d[1] = tot[2] * (T)bit01<2>(m.sw) + d[1];
+    d[2] = tot[2] * (T)bit01<2>(m.s) + 1;
+    d[2] = tot[1] * (T)bit01<1>(m.se) + d[2];
+    d[2] = tot[3] * (T)bit01<3>(m.sw) + d[2];
+    d[3] = tot[3] * (T)bit01<3>(m.s) + from_right;
+    d[3] = tot[2] * (T)bit01<2>(m.se) + d[3] + 1;
+}
+
+// Upward (label) step of a plain row, middle rows of a full interior tile.  A plain row has no pits,
+// so an East cell's own term is 0 and "copy the chain end" is own + next * E.
+__device__ __forceinline__ void plain_row_up(uint32_t k, uint32_t (&lb)[4], int lr, int lane, uint32_t &metaL, uint32_t &metaR)
+{
+    const RowBits m = row_bits(k);
+    const uint32_t lbR0 = __shfl_down_sync(FULL, lb[0], 1), lbL3 = __shfl_up_sync(FULL, lb[3], 1);
+    uint32_t own[4];
+    own[0] = lb[0] * bit01<0>(m.s) + lb[1] * bit01<0>(m.se) + lbL3 * bit01<0>(m.sw);
+    own[1] = lb[1] * bit01<1>(m.s) + lb[2] * bit01<1>(m.se) + lb[0] * bit01<1>(m.sw);
+    own[2] = lb[2] * bit01<2>(m.s) + lb[3] * bit01<2>(m.se) + lb[1] * bit01<2>(m.sw);
+    own[3] = lb[3] * bit01<3>(m.s) + lbR0 * bit01<3>(m.se) + lb[2] * bit01<3>(m.sw);
+    uint32_t E0 = bit01<0>(m.e), E1 = bit01<1>(m.e), E2 = bit01<2>(m.e), E3 = bit01<3>(m.e);
+    if (lane == 31 && ((k >> 24) & 0xFFu) <= 1u) { own[3] = (uint32_t)(2 * TW + TH + lr); E3 = 0; }   // E / SE leave through the right column
+    if (lane == 0 && (k & 0xFFu) == 3u) own[0] = (uint32_t)(2 * TW + lr);                               // SW leaves through the left column
+    uint32_t V = own[3] + LNONE * E3;                        // label at cell 0 if nothing comes from the right
+    V = V * E2 + own[2];
+    V = V * E1 + own[1];
+    V = V * E0 + own[0];
+    uint32_t cur = label_carry_from_right(V, (E0 & E1 & E2 & E3) != 0, lane);
+    cur = cur * E3 + own[3]; lb[3] = cur;
+    cur = cur * E2 + own[2]; lb[2] = cur;
+    cur = cur * E1 + own[1]; lb[1] = cur;
+    cur = cur * E0 + own[0]; lb[0] = cur;
+    metaL = meta_pack(lb[0], (int)(k & 0xFFu), false, true);
+    metaR = meta_pack(lb[3], (int)((k >> 24) & 0xFFu), false, true);
+}
+
+// ---------------------------------------------------------------------------------------------
 // phase A, fast solver
 // ---------------------------------------------------------------------------------------------
 template <int ENC, bool AL>
 __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
                                                      Geo g, int ntiles, uint32_t *__restrict__ meta,
-                                                     int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class)
+                                                     int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
+                                                     unsigned long long *__restrict__ row_plain,
+                                                     unsigned long long *__restrict__ wq)
 {
-    __shared__ uint32_t rows[WPB][TH][32];          // per row: k nibbles [15:0], active nibble [19:16]
+    __shared__ uint32_t s_w[WPB][TH][32];            // staged DIR words
+    __shared__ uint8_t s_a[WPB][TH][32];             // active nibbles (masked / ragged tiles only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
@@ -251,24 +427,47 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ 
     const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + 4 * lane;
     uint32_t *m_t = meta + (int64_t)tile * NSLOT;
     int32_t *x_t = exit_acc + (int64_t)tile * NSLOT;
+    unsigned long long *w_t = wq + (int64_t)tile * NSLOT;     // packed forest words: pending << 32 | sum
+    constexpr unsigned long long BIAS = 1ull << 32;           // every node waits for its own walker
     const int rlane = (tw - 1) >> 2, rj = (tw - 1) & 3;       // lane / sub-cell holding the right column
+    const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
+    const bool full = th == TH && tw == TW;
+    const bool plain_tile = mask == nullptr && full && !border;
+    uint32_t (*wrow)[32] = s_w[warp];
+    uint8_t (*arow)[32] = s_a[warp];
+    stage_tile<AL>(dir, mask, g, gr0, gc0, th, !(mask == nullptr && full), wrow, arow, lane);
 
     // ---- downward sweep: local accumulation
-    int32_t d[4] = {0, 0, 0, 0};
+    int32_t d[4] = {1, 1, 1, 1};                     // 1 + inflow from the row above
     bool complex_tile = false;
+    unsigned long long plain_rows = 0;               // bit lr set: row lr takes the lean path (both sweeps, phase C too)
     for (int lr = 0; lr < th; lr++) {
-        int k[4], am;
-        load_row<ENC, AL>(dir, mask, g, gr0 + lr, gc0, k, am);
-        if (lr > 0) {
-            bool up = (k[0] >= 5 && k[0] <= 7) || (k[1] >= 5 && k[1] <= 7) || (k[2] >= 5 && k[2] <= 7) || (k[3] >= 5 && k[3] <= 7);
-            complex_tile = complex_tile || __any_sync(FULL, up);
-        }
-        rows[warp][lr][lane] = (uint32_t)(k[0] | (k[1] << 4) | (k[2] << 8) | (k[3] << 12) | (am << 16));
-        int32_t b[4], tot[4];
+        const uint32_t w = wrow[lr][lane];
+        int32_t tot[4];
+        const bool edge_row = lr == 0 || lr == th - 1;
+        bool gen = true;
+        uint32_t kw = 0;
+        if (plain_tile && !edge_row) { kw = plain_word<ENC>(w, gen); gen = __any_sync(FULL, gen); }
+        if (!gen) {
+            plain_rows |= 1ull << lr;
+            if (ENC != WMF_ENC_INTERNAL) wrow[lr][lane] = kw;     // keep the translated word for the upward sweep
+            plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
+        } else {
+            int k[4];
+            const int am = (mask == nullptr && full) ? 0xF : arow[lr][lane];
+            decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
+            if (lr > 0) {
+                bool up = (k[0] >= 5 && k[0] <= 7) || (k[1] >= 5 && k[1] <= 7) || (k[2] >= 5 && k[2] <= 7) || (k[3] >= 5 && k[3] <= 7);
+                complex_tile = complex_tile || __any_sync(FULL, up);
+            }
+            int32_t b[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? 1 + d[j] : 0;
-        sweep_row_down<int32_t>(k, am, b, tot, d, lane, complex_tile);
-        if (complex_tile) break;
+            for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] : 0;
+            sweep_row_down<int32_t>(k, am, b, tot, d, lane, complex_tile);
+            if (complex_tile) break;
+#pragma unroll
+            for (int j = 0; j < 4; j++) d[j] += 1;
+        }
         if (lr == 0) *reinterpret_cast<int4 *>(x_t + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
         else if (lr == th - 1) *reinterpret_cast<int4 *>(x_t + TW + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
         else {
@@ -280,16 +479,26 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ 
         if (lane == 0) tile_class[tile] = 1;
         return;
     }
-    if (lane == 0) tile_class[tile] = 0;
-    __syncwarp();
+    if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
 
     // ---- upward sweep: exit labels
     uint32_t lb[4] = {LNONE, LNONE, LNONE, LNONE};   // labels of the row below
     for (int lr = th - 1; lr >= 0; lr--) {
-        uint32_t pk = rows[warp][lr][lane];
-        int k[4], am = (pk >> 16) & 0xF;
-#pragma unroll
-        for (int j = 0; j < 4; j++) k[j] = (pk >> (4 * j)) & 0xF;
+        {   // a run of lean rows going up
+            unsigned long long rest = ~(plain_rows << (63 - lr));
+            const int run = rest ? __clzll((long long)rest) : lr + 1;
+            for (const int end = lr - run; lr > end; lr--) {
+                uint32_t mL, mR;
+                plain_row_up(wrow[lr][lane], lb, lr, lane, mL, mR);
+                if (lane == 0) { m_t[2 * TW + lr] = mL; w_t[2 * TW + lr] = BIAS; }
+                if (lane == 31) { m_t[2 * TW + TH + lr] = mR; w_t[2 * TW + TH + lr] = BIAS; }
+            }
+            if (lr < 0) break;
+        }
+        const uint32_t w = wrow[lr][lane];
+        int k[4];
+        const int am = (mask == nullptr && full) ? 0xF : arow[lr][lane];
+        decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
         uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left3 = __shfl_up_sync(FULL, lb[3], 1);
         uint32_t own[4];
         bool pe[4], pw[4];
@@ -317,9 +526,7 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ 
             bool P = true;
 #pragma unroll
             for (int j = 3; j >= 0; j--) { V = pe[j] ? V : own[j]; P = P && pe[j]; }
-            // V = label at cell 0 with carry NONE; recompute with the real carry
-            uint32_t carry = label_carry_from_right(V, P, lane);
-            uint32_t cur = carry;
+            uint32_t cur = label_carry_from_right(V, P, lane);
 #pragma unroll
             for (int j = 3; j >= 0; j--) { cur = pe[j] ? cur : own[j]; lab[j] = cur; }
         }
@@ -328,8 +535,7 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ 
             bool P = true;
 #pragma unroll
             for (int j = 0; j < 4; j++) { V = pw[j] ? V : lab[j]; P = P && pw[j]; }
-            uint32_t carry = label_carry_from_left(V, P, lane);
-            uint32_t cur = carry;
+            uint32_t cur = label_carry_from_left(V, P, lane);
 #pragma unroll
             for (int j = 0; j < 4; j++) { cur = pw[j] ? cur : lab[j]; lab[j] = cur; }
         }
@@ -339,11 +545,14 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ 
             lb[j] = lab[j];
             mw[j] = meta_pack(lab[j], k[j], false, (am >> j) & 1);
         }
-        if (lr == 0) *reinterpret_cast<uint4 *>(m_t + 4 * lane) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-        else if (lr == th - 1) *reinterpret_cast<uint4 *>(m_t + TW + 4 * lane) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-        else {
-            if (lane == 0) m_t[2 * TW + lr] = mw[0];
-            if (lane == rlane && tw > 1) m_t[2 * TW + TH + lr] = mw[rj];
+        if (lr == 0 || lr == th - 1) {
+            const int base = (lr == 0 ? 0 : TW) + 4 * lane;
+            *reinterpret_cast<uint4 *>(m_t + base) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            *reinterpret_cast<ulonglong2 *>(w_t + base) = make_ulonglong2(BIAS, BIAS);
+            *reinterpret_cast<ulonglong2 *>(w_t + base + 2) = make_ulonglong2(BIAS, BIAS);
+        } else {
+            if (lane == 0) { m_t[2 * TW + lr] = mw[0]; w_t[2 * TW + lr] = BIAS; }
+            if (lane == rlane && tw > 1) { m_t[2 * TW + TH + lr] = mw[rj]; w_t[2 * TW + TH + lr] = BIAS; }
         }
     }
 }
@@ -351,11 +560,39 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // phase C, fast solver
 // ---------------------------------------------------------------------------------------------
+template <bool AL, typename T>
+__device__ __forceinline__ void store_row(T *out, const T (&tot)[4], int64_t gc0, int64_t nx)
+{
+    if (AL) {
+        if (gc0 < nx) {
+            if (sizeof(T) == 4) *reinterpret_cast<int4 *>(out) = make_int4((int)tot[0], (int)tot[1], (int)tot[2], (int)tot[3]);
+            else {
+                *reinterpret_cast<longlong2 *>(out) = make_longlong2((long long)tot[0], (long long)tot[1]);
+                *reinterpret_cast<longlong2 *>(out + 2) = make_longlong2((long long)tot[2], (long long)tot[3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (gc0 + j < nx) out[j] = tot[j];
+    }
+}
+
+// number of consecutive set bits of `rows` starting at bit lr
+__device__ __forceinline__ int plain_run(unsigned long long rows, int lr)
+{
+    unsigned long long rest = ~(rows >> lr);            // first zero bit = first generic row
+    return rest ? __ffsll((long long)rest) - 1 : 64 - lr;
+}
+
 template <int ENC, bool AL, typename T>
 __global__ void __launch_bounds__(WPB * 32) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
                                                      Geo g, int ntiles, const T *__restrict__ inflow,
-                                                     const uint8_t *__restrict__ tile_class, T *__restrict__ acc)
+                                                     const uint8_t *__restrict__ tile_class,
+                                                     const unsigned long long *__restrict__ row_plain, T *__restrict__ acc)
 {
+    __shared__ uint32_t s_w[WPB][TH][32];
+    __shared__ uint8_t s_a[WPB][TH][32];
+    __shared__ T s_ext[WPB][2][TH];                  // external inflow of the left / right column cells
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
@@ -365,46 +602,57 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepC(const int8_t *__restrict__ 
     const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + 4 * lane;
     const T *in_t = inflow + (int64_t)tile * NSLOT;
     const int rlane = (tw - 1) >> 2, rj = (tw - 1) & 3;
-    // left / right column inflows of all rows, two rows per lane
-    T inL0 = in_t[2 * TW + lane], inL1 = in_t[2 * TW + 32 + lane];
-    T inR0 = in_t[2 * TW + TH + lane], inR1 = in_t[2 * TW + TH + 32 + lane];
-    T d[4] = {0, 0, 0, 0};
+    const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
+    const bool full = th == TH && tw == TW;
+    uint32_t (*wrow)[32] = s_w[warp];
+    uint8_t (*arow)[32] = s_a[warp];
+    T *extL = s_ext[warp][0], *extR = s_ext[warp][1];
+    extL[lane] = in_t[2 * TW + lane]; extL[lane + 32] = in_t[2 * TW + 32 + lane];
+    extR[lane] = in_t[2 * TW + TH + lane]; extR[lane + 32] = in_t[2 * TW + TH + 32 + lane];
+    stage_tile<AL>(dir, mask, g, gr0, gc0, th, !(mask == nullptr && full), wrow, arow, lane);
+    T d[4] = {1, 1, 1, 1};                           // 1 + inflow from the row above
     bool dummy = false;
-    for (int lr = 0; lr < th; lr++) {
-        int k[4], am;
-        load_row<ENC, AL>(dir, mask, g, gr0 + lr, gc0, k, am);
-        T ext[4] = {0, 0, 0, 0};
-        if (lr == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) ext[j] = in_t[4 * lane + j];
-        } else if (lr == th - 1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) ext[j] = in_t[TW + 4 * lane + j];
-        } else {
-            T l = __shfl_sync(FULL, lr < 32 ? inL0 : inL1, lr & 31);
-            T r = __shfl_sync(FULL, lr < 32 ? inR0 : inR1, lr & 31);
-            if (lane == 0) ext[0] = l;
-            if (lane == rlane && tw > 1) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) if (j == rj) ext[j] += r;
-            }
+    T *out = acc + gr0 * g.nx + gc0;
+    const unsigned long long plain_rows = row_plain[tile];
+    const bool is_l = lane == 0, is_r = lane == 31;
+    int lr = 0;
+    while (lr < th) {
+        // a run of lean rows: no per-row classification, no divergent control flow
+        for (int end = lr + plain_run(plain_rows, lr); lr < end; lr++, out += g.nx) {
+            T tot[4];
+            bool gen;
+            const T l = extL[lr], r = extR[lr];
+            plain_row_down<T>(plain_word<ENC>(wrow[lr][lane], gen), d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
+            store_row<AL, T>(out, tot, gc0, g.nx);
         }
-        T b[4], tot[4];
+        if (lr >= th) break;
+        {   // one generic row
+            T tot[4];
+            int k[4];
+            const int am = (mask == nullptr && full) ? 0xF : arow[lr][lane];
+            decode_row<ENC>(wrow[lr][lane], am, g, gr0 + lr, gc0, border, k);
+            T ext[4] = {0, 0, 0, 0};
+            if (lr == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? (T)1 + d[j] + ext[j] : (T)0;
-        sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
-        const int64_t off = (gr0 + lr) * g.nx + gc0;
-        if (AL) {
-            if (gc0 < g.nx) {
-                if (sizeof(T) == 4) *reinterpret_cast<int4 *>(acc + off) = make_int4((int)tot[0], (int)tot[1], (int)tot[2], (int)tot[3]);
-                else {
-                    *reinterpret_cast<longlong2 *>(acc + off) = make_longlong2((long long)tot[0], (long long)tot[1]);
-                    *reinterpret_cast<longlong2 *>(acc + off + 2) = make_longlong2((long long)tot[2], (long long)tot[3]);
+                for (int j = 0; j < 4; j++) ext[j] = in_t[4 * lane + j];
+            } else if (lr == th - 1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) ext[j] = in_t[TW + 4 * lane + j];
+            } else {
+                if (lane == 0) ext[0] = extL[lr];
+                if (lane == rlane && tw > 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (j == rj) ext[j] += extR[lr];
                 }
             }
-        } else {
+            T b[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) if (gc0 + j < g.nx) acc[off + j] = tot[j];
+            for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] + ext[j] : (T)0;
+            sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
+#pragma unroll
+            for (int j = 0; j < 4; j++) d[j] += 1;
+            store_row<AL, T>(out, tot, gc0, g.nx);
+            lr++; out += g.nx;
         }
     }
 }
@@ -503,13 +751,14 @@ __device__ __forceinline__ void general_walk(const uint8_t *kk, uint8_t *cnt, T 
 }
 
 template <int ENC>
-__global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g,
+__global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
                                                   const uint8_t *__restrict__ tile_class, uint32_t *__restrict__ meta,
-                                                  int32_t *__restrict__ exit_acc)
+                                                  int32_t *__restrict__ exit_acc, unsigned long long *__restrict__ wq)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tile = blockIdx.x;
-    if (!(tile_class[tile] & 1)) return;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (!(tile_class[tile] & 1)) continue;
+    __syncthreads();                                   // previous tile of this block is done with smem
     int32_t *acc = reinterpret_cast<int32_t *>(smem);
     uint8_t *kk = smem + sizeof(int32_t) * TCELLS;
     uint8_t *cnt = kk + TCELLS;
@@ -545,17 +794,20 @@ __global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir
         }
         meta[(int64_t)tile * NSLOT + s] = m;
         exit_acc[(int64_t)tile * NSLOT + s] = xa;
+        wq[(int64_t)tile * NSLOT + s] = (1ull + ((m >> 20) & 1u)) << 32;      // a locally unresolved exit never finalises
     }
+  }
 }
 
 template <int ENC, typename T>
-__global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g,
+__global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
                                                   const uint8_t *__restrict__ tile_class, const T *__restrict__ inflow,
                                                   const uint8_t *__restrict__ ext_unres, T *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tile = blockIdx.x;
-    if (tile_class[tile] == 0) return;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile_class[tile] == 0) continue;
+    __syncthreads();
     T *acc = reinterpret_cast<T *>(smem);
     uint8_t *kk = smem + sizeof(T) * TCELLS;
     uint8_t *cnt = kk + TCELLS;
@@ -581,6 +833,7 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
         int lr = idx / TW, lc = idx - lr * TW;
         if (lr < th && lc < tw) out[((int64_t)ty * TH + lr) * g.nx + (int64_t)tx * TW + lc] = acc[idx];
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -624,6 +877,68 @@ __global__ void k_build_forest(Geo g, int64_t nnodes, const uint32_t *__restrict
     }
     parent[i] = p;
     blocked[i] = (uint8_t)((meta[i] >> 20) & 1);
+}
+
+// ---- packed variant for int32 accumulations -----------------------------------------------------
+// One 64-bit word per node: pending children (+1 for the node's own walker, +1 more when the node is
+// blocked) in the high half, the sum of finished children in the low half.  A walker brings its
+// total and its "-1 pending" in ONE atomic; whoever takes pending to zero finalises the node, pushes
+// the total into the entry cell it drains to, and carries on downstream.  No fences, no leaf pass.
+constexpr unsigned long long PEND1 = 1ull << 32;
+
+__global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__restrict__ meta, int32_t *__restrict__ parent,
+                                                   int32_t *__restrict__ entry, unsigned long long *wq)
+{
+    const int tile = blockIdx.x, s = threadIdx.x;
+    const int64_t i = (int64_t)tile * NSLOT + s;
+    uint32_t me = 0;
+    int64_t e = entry_of(g, meta, tile, s, me);
+    int32_t p = -1, en = -1;
+    if (e >= 0 && ((me >> 21) & 1)) {                       // an exit whose receiver is active
+        en = (int32_t)e;
+        uint32_t link = me & 0xFFFFu;
+        if (link != LNONE) {
+            p = (int32_t)((e / NSLOT) * NSLOT + link);
+            atomicAdd(&wq[p], PEND1);
+        }
+    }
+    parent[i] = p;
+    entry[i] = en;
+}
+
+__global__ void k_g_walk(int64_t nnodes, const int32_t *__restrict__ parent, const int32_t *__restrict__ entry,
+                         const int32_t *__restrict__ w, unsigned long long *wq, int32_t *__restrict__ inflow)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    int32_t en = entry[i];
+    if (en < 0) return;                                     // not an exit: nothing to carry
+    int64_t cur = i;
+    unsigned long long old = atomicAdd(&wq[cur], (unsigned long long)(-(long long)PEND1));   // own arrival
+    uint32_t add = 0;
+    while ((uint32_t)(old >> 32) == 1u) {                   // we took pending to zero: cur is final
+        uint32_t total = (uint32_t)old + add + (uint32_t)w[cur];
+        if (en >= 0) atomicAdd(&inflow[en], (int32_t)total);
+        int32_t p = parent[cur];
+        if (p < 0) break;
+        en = entry[p];
+        old = atomicAdd(&wq[p], (unsigned long long)total - PEND1);
+        add = total;
+        cur = p;
+    }
+}
+
+__global__ void k_g_unres(int64_t nnodes, const int32_t *__restrict__ entry, const unsigned long long *__restrict__ wq,
+                          uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    int32_t en = entry[i];
+    if (en < 0) return;
+    if ((uint32_t)(wq[i] >> 32) != 0u) {                    // never finalised: the entry it feeds never finalises
+        ext_unres[en] = 1;
+        tile_class[en / NSLOT] = 2;                         // (racing writers all store non-zero)
+    }
 }
 
 template <typename T>
@@ -676,30 +991,40 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
     uint8_t *blocked = cur.take<uint8_t>((size_t)nnodes);
     uint8_t *ext_unres = cur.take<uint8_t>((size_t)nnodes);
     uint8_t *tile_class = cur.take<uint8_t>((size_t)ntiles);
+    unsigned long long *row_plain = cur.take<unsigned long long>((size_t)ntiles);
+    unsigned long long *wq = cur.take<unsigned long long>((size_t)nnodes);
     WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = (nx % 4 == 0) && (((uintptr_t)dir & 3) == 0) && (mask == nullptr || ((uintptr_t)mask & 3) == 0) &&
                     (((uintptr_t)acc & 15) == 0);
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
+    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS, smemC = sizeof(T) * TCELLS + 2 * TCELLS;
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     WMF_CUDA_CHECK(cudaMemsetAsync(inflow, 0, sizeof(T) * nnodes, st));
     WMF_CUDA_CHECK(cudaMemsetAsync(ext_unres, 0, (size_t)nnodes, st));
     // phase A
-    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class);
-    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class);
-    k_generalA<ENC><<<ntiles, GTH, smemA, st>>>(dir, mask, g, tile_class, meta, exit_acc);
+    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class, row_plain, wq);
+    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class, row_plain, wq);
+    k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, tile_class, meta, exit_acc, wq);
     // phase G
-    k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, parent, blocked);
-    WMF_LAUNCH_CHECK();
-    int rc = sizeof(T) == 4 ? forest_accum_i32(parent, exit_acc, (int32_t *)A, cnt, nnodes, st, blocked)
-                            : forest_accum_i64(parent, exit_acc, (int64_t *)A, cnt, nnodes, st, blocked);
-    if (rc) return rc;
-    k_push_inflow<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, A, cnt, inflow, ext_unres, tile_class);
+    if (sizeof(T) == 4) {
+        int32_t *entry = cnt;                                // reuse: the packed walk needs no counters
+        k_g_build<<<ntiles, NSLOT, 0, st>>>(g, meta, parent, entry, wq);
+        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, parent, entry, exit_acc, wq, (int32_t *)inflow);
+        k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, wq, ext_unres, tile_class);
+        WMF_LAUNCH_CHECK();
+    } else {
+        k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, parent, blocked);
+        WMF_LAUNCH_CHECK();
+        int rc = forest_accum_i64(parent, exit_acc, (int64_t *)A, cnt, nnodes, st, blocked);
+        if (rc) return rc;
+        k_push_inflow<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, A, cnt, inflow, ext_unres, tile_class);
+    }
     // phase C
-    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, acc);
-    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, acc);
-    k_generalC<ENC, T><<<ntiles, GTH, smemC, st>>>(dir, mask, g, tile_class, inflow, ext_unres, acc);
+    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, row_plain, acc);
+    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, row_plain, acc);
+    k_generalC<ENC, T><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, tile_class, inflow, ext_unres, acc);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -712,7 +1037,7 @@ size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
 {
     int64_t ntiles = ((nx + TW - 1) / TW) * ((ny + TH - 1) / TH);
     size_t nn = (size_t)ntiles * NSLOT, tsz = acc_dtype == WMF_ACC_I32 ? 4 : 8;
-    return 4 * wmf_align(nn * 4) + 2 * wmf_align(nn * tsz) + 2 * wmf_align(nn) + wmf_align((size_t)ntiles) + 4096;
+    return 4 * wmf_align(nn * 4) + wmf_align(nn * 8) + 2 * wmf_align(nn * tsz) + 2 * wmf_align(nn) + wmf_align((size_t)ntiles) + wmf_align((size_t)ntiles * 8) + 4096;
 }
 
 int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx, int encoding,
