@@ -186,10 +186,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- workload: this rank's stripe of the (world*n) x n Scheidegger raster, generated on the device
     d = ops.synth_scheidegger(n, n, seed=SEED, row0=rank * n, nx_total=n)
-    acc = torch.empty((n, n), dtype=torch.int32, device=dev)
+    if world == 1:
+        acc = torch.empty((n, n), dtype=torch.int32, device=dev)
 
-    def step():
-        ops.d8_accum(d, None, algo=algo, out=acc)
+        def step():
+            ops.d8_accum(d, None, algo=algo, out=acc)
+    else:
+        # row stripes with one boundary exchange (all-gather over NCCL); int64 ACC: the whole raster can
+        # exceed 2^31 cells
+        from wmf_heavy_b200 import stripes
+        acc = torch.empty((n, n), dtype=torch.int64, device=dev)
+
+        def step():
+            stripes.accumulate_striped(d, rank * n, world * n, out=acc)
 
     def barrier():
         if world > 1:
@@ -217,11 +226,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     cells_total = float(n) * n * world
     value = cells_total / (ms_per_step * 1e-3) / 1e6
     op_ms = statistics.mean(per)
-    achieved = ALGO_BYTES_PER_CELL * n * n / (op_ms * 1e-3) / 1e9
+    bytes_per_cell = ALGO_BYTES_PER_CELL if world == 1 else 9.0      # int64 ACC on stripes: 1 + 8 B/cell
+    achieved = bytes_per_cell * n * n / (op_ms * 1e-3) / 1e9
 
     # ---- e2e through the reference-facing API: host flowdir + mask in (pinned), float64 raster out
     e2e = None
-    if args.e2e_steps > 0:
+    if args.e2e_steps > 0 and world == 1:
         h_dir = torch.empty((n, n), dtype=torch.int8).pin_memory()
         h_dir.copy_(d)
         h_mask = torch.ones((n, n), dtype=torch.bool).pin_memory()
@@ -243,6 +253,32 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                "d2h_bytes_per_step": 8 * n * n, "ms_per_step": 1e3 * e2e_s,
                "api": "wmf_heavy_b200.cu_py.basics.basin_acum(flowdir int8, mask bool) -> float64"}
         del h_dir, h_mask, h_out
+
+    if args.e2e_steps > 0 and world > 1:
+        from wmf_heavy_b200 import stripes
+        h_dir = torch.empty((n, n), dtype=torch.int8).pin_memory()
+        h_dir.copy_(d)
+        h_out = torch.empty((n, n), dtype=torch.int64).pin_memory()
+
+        def e2e_step():
+            dd = h_dir.to(dev, non_blocking=True)
+            a = stripes.accumulate_striped(dd, rank * n, world * n)
+            h_out.copy_(a)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e = {"value": cells_total / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": n * n,
+               "d2h_bytes_per_step": 8 * n * n, "ms_per_step": 1e3 * e2e_s,
+               "api": "wmf_heavy_b200.stripes.accumulate_striped(host int8 stripe) -> host int64 stripe, per rank"}
+        del h_dir, h_out
 
     shia = None
     if not args.no_shia:
@@ -269,14 +305,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "int32" if world == 1 else "int64", "data": "synthetic",
             "config": {"workload": f"D8 flow accumulation, synthetic Scheidegger DIR {n}x{n} per GPU (seed {SEED}), "
-                                   "int8 DIR -> int32 ACC, mask = all valid", "algo": args.algo,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent row stripes of {n} rows",
+                                   f"int8 DIR -> {'int32' if world == 1 else 'int64'} ACC, mask = all valid", "algo": args.algo,
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"{world} row stripes of {n} rows of one {world * n}x{n} raster, one NCCL all-gather of the "
+                       "boundary records per accumulation",
                        "l2": "inputs (DIR 0.27 GB + ACC 1.07 GB) exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "wmf_d8_accum, all passes of one accumulation (5 B/cell algorithmic)"},
+                         "kernel": "wmf_d8_accum, all passes of one accumulation "
+                                   f"({bytes_per_cell:.0f} B/cell algorithmic)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(), "shia": shia,
         }

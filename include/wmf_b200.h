@@ -66,6 +66,41 @@ size_t wmf_d8_accum_workspace(int64_t ny, int64_t nx, int acc_dtype, int algo);
 int wmf_d8_accum(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx,
                  int encoding, int algo, void *workspace, size_t ws_bytes, void *stream);
 
+/* ---------------------------------------------------------------- D1 on row stripes
+ * A raster of ny_total rows is cut into row stripes, one per GPU; this stripe holds rows
+ * [row0, row0 + ny), ny >= 2, and accumulates in int64.  Two device phases around ONE exchange:
+ *   wmf_d8_stripe_local  solves the stripe in isolation and condenses it to 2*nx boundary records
+ *                        (index side*nx + col; side 0 = first row, side 1 = last row):
+ *                          s_k        int8   normalised D8 code of the cell (0..7 clockwise from E,
+ *                                            8 none, 9 inactive)
+ *                          s_exit_acc int64  stripe-local accumulation of a cell draining across the
+ *                                            stripe edge (0 elsewhere)
+ *                          s_unres    uint8  that accumulation is unresolved (cycle upstream)
+ *                          s_link     int32  boundary index where flow ENTERING at this cell leaves the
+ *                                            stripe again, -1 if it ends inside
+ *   (exchange: all-gather of the records; every rank solves the 2*G*nx-node boundary forest with
+ *    wmf_forest_accum and sums, for each of its boundary cells, what arrives from the neighbours --
+ *    wmf_heavy_b200/stripes.py)
+ *   wmf_d8_stripe_finish injects that inflow (ext_inflow int64 [2][nx], ext_unres uint8 [2][nx]
+ *                        nullable) and writes the final acc [ny][nx] (WMF_ACC_I64 or WMF_ACC_F64).
+ * The SAME workspace must be passed to both calls (phase-A state lives in it). */
+size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx);
+int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
+                        int encoding, int8_t *s_k, int64_t *s_exit_acc, int32_t *s_link, uint8_t *s_unres,
+                        void *workspace, size_t ws_bytes, void *stream);
+int wmf_d8_stripe_finish(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx,
+                         int64_t row0, int64_t ny_total, int encoding, const int64_t *ext_inflow,
+                         const uint8_t *ext_unres, void *workspace, size_t ws_bytes, void *stream);
+
+/* Accumulation over an explicit forest: acc[i] = weight[i] + sum over children acc[child] (parent int32,
+ * -1 = root; weight nullable = 1; blocked nullable: nodes that never finalise).  Nodes with an
+ * unfinished (cyclic or blocked) upstream keep the partial sum of finished children without their own
+ * weight and get resolved[i] = 0 (resolved nullable).  The vector-form accumulation of cu.basin_basics
+ * (cuencas_heavy.f90:593-606) and the stripe boundary forest are instances. */
+size_t wmf_forest_accum_workspace(int64_t n);
+int wmf_forest_accum(const int32_t *parent, const int64_t *weight, const uint8_t *blocked, int64_t n, int64_t *acc,
+                     uint8_t *resolved, void *workspace, size_t ws_bytes, void *stream);
+
 /* ---------------------------------------------------------------- D2: basin mask (raster form)
  * Replaces the traversal of wmf_py/cu_py/basics.py:206-248 basin_cut: basin_mask[c] = 1 iff c is
  * active and its D8 path through active cells reaches (outlet_r, outlet_c).  Syncs (reads back the

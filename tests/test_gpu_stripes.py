@@ -1,0 +1,70 @@
+"""Row-striped accumulation on ONE device (stripes processed one after the other through the same two
+CUDA phases + boundary forest the multi-GPU path uses): bit-identical to the unstriped accumulation."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import oracle
+from wmf_heavy_b200 import _lib, ops, stripes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case,G", [("sch", 2), ("sch", 5), ("steep", 3), ("random", 4), ("mask", 3), ("keypad", 2)])
+def test_striped_equals_oracle(case, G):
+    mask = None
+    enc = _lib.ENC_INTERNAL
+    if case == "sch":
+        fd = ops.synth_scheidegger_host(700, 515, seed=4)
+    elif case == "steep":
+        fd = helpers.steepest(533, 390, 5)
+    elif case == "random":
+        fd = helpers.random_codes(300, 260, 6)
+    elif case == "mask":
+        fd, mask = helpers.steepest(420, 333, 7), np.random.default_rng(7).random((420, 333)) > 0.06
+    else:
+        fd = helpers.steepest(400, 300, 8)
+    exp = oracle.basin_acum(fd, np.ones(fd.shape, bool) if mask is None else mask).astype(np.int64)
+    src = helpers.to_keypad(fd) if case == "keypad" else fd
+    if case == "keypad":
+        enc = _lib.ENC_KEYPAD
+    d = torch.from_numpy(np.ascontiguousarray(src, dtype=np.int8)).cuda()
+    m = None if mask is None else torch.from_numpy(mask.astype(np.uint8)).cuda()
+    got = stripes.accumulate_striped_single_device(d, G, encoding=enc, mask_t=m)
+    assert got.dtype == torch.int64
+    assert np.array_equal(got.cpu().numpy(), exp), f"{(got.cpu().numpy() != exp).sum()} cells differ"
+
+
+def test_striped_records_match_numpy_restatement():
+    fd = ops.synth_scheidegger_host(130, 200, seed=11)
+    rows = stripes.stripe_rows(130, 2)
+    for r0, n in rows:
+        rec, _ = ops.d8_stripe_local(torch.from_numpy(fd[r0:r0 + n].copy()).cuda(), r0, 130)
+        acc_local = oracle.basin_acum(fd[r0:r0 + n], np.ones((n, 200), bool))
+        exp = helpers.stripe_records_numpy(fd, r0, n, acc_local)
+        for key in ("k", "exit_acc", "link", "unres"):
+            assert np.array_equal(rec[key].cpu().numpy(), exp[key]), key
+
+
+def test_striped_full_size_int64_and_f64():
+    n = 4096
+    d = ops.synth_scheidegger(n, n, seed=20260101)
+    ref = ops.d8_accum(d, None, acc_dtype=_lib.ACC_I64)
+    got = stripes.accumulate_striped_single_device(d, 4)
+    assert torch.equal(got, ref)
+    gf = stripes.accumulate_striped_single_device(d, 8, acc_dtype=_lib.ACC_F64)
+    assert gf.dtype == torch.float64 and torch.equal(gf.to(torch.int64), ref)
+
+
+def test_forest_accum_matches_numpy():
+    rng = np.random.default_rng(1)
+    n = 5000
+    parent = np.array([rng.integers(i + 1, n) if (i < n - 1 and rng.random() < 0.9) else -1 for i in range(n)], np.int32)
+    parent[10], parent[20] = 20, 10                       # a two-cycle: both (and their downstream) stay unresolved
+    w = rng.integers(0, 100, n).astype(np.int64)
+    blocked = (rng.random(n) < 0.01).astype(np.uint8)
+    acc, res = ops.forest_accum(torch.from_numpy(parent).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(blocked).cuda())
+    e_acc, e_res = helpers.forest_numpy(parent, w, blocked)
+    assert np.array_equal(res.cpu().numpy(), e_res)
+    assert np.array_equal(acc.cpu().numpy(), e_acc)

@@ -48,6 +48,11 @@ SIGNATURES = {
     "wmf_device_info": (_int, [_vp]),
     "wmf_d8_accum_workspace": (_sz, [_i64, _i64, _int, _int]),
     "wmf_d8_accum": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _int, _int, _vp, _sz, _vp]),
+    "wmf_d8_stripe_workspace": (_sz, [_i64, _i64]),
+    "wmf_d8_stripe_local": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "wmf_d8_stripe_finish": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    "wmf_forest_accum_workspace": (_sz, [_i64]),
+    "wmf_forest_accum": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "wmf_basin_mask_workspace": (_sz, [_i64, _i64]),
     "wmf_basin_mask": (_int, [_vp, _vp, _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "wmf_basin_structure_workspace": (_sz, [_i64, _i64]),

@@ -42,8 +42,9 @@ __host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t link, int k, boo
 }
 
 struct Geo {
-    int64_t ny, nx;
+    int64_t ny, nx;          // this raster (or row stripe)
     int tiles_x, tiles_y;
+    int64_t gy0, gny;        // the stripe holds rows [gy0, gy0 + ny) of a raster of gny rows (gy0 = 0, gny = ny when whole)
 };
 
 // canonical boundary slot of local cell (lr, lc) in a tile of th x tw cells, or -1
@@ -72,45 +73,6 @@ __device__ __forceinline__ void tile_dims(const Geo &g, int tile, int &ty, int &
     int64_t rem_r = g.ny - (int64_t)ty * TH, rem_c = g.nx - (int64_t)tx * TW;
     th = rem_r < TH ? (int)rem_r : TH;
     tw = rem_c < TW ? (int)rem_c : TW;
-}
-
-// ---------------------------------------------------------------------------------------------
-// row loader for the fast kernels: 4 cells per lane -> k[4] (0..7, 8 = none) and an active nibble.
-// A valid code whose receiver lies outside the raster is turned into "none" here, so every k < 8
-// downstream has an in-raster receiver.
-// ---------------------------------------------------------------------------------------------
-template <int ENC, bool AL>
-__device__ __forceinline__ void load_row(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
-                                         const Geo &g, int64_t gr, int64_t gc0, int (&k)[4], int &am)
-{
-    uint32_t w = 0, mw = 0x01010101u;
-    if (AL) {
-        if (gc0 < g.nx) {
-            w = *reinterpret_cast<const uint32_t *>(dir + gr * g.nx + gc0);
-            if (mask) mw = *reinterpret_cast<const uint32_t *>(mask + gr * g.nx + gc0);
-        } else mw = 0;
-    } else {
-        mw = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (gc0 + j < g.nx) {
-                w |= (uint32_t)(uint8_t)dir[gr * g.nx + gc0 + j] << (8 * j);
-                mw |= (uint32_t)(mask ? (mask[gr * g.nx + gc0 + j] != 0) : 1) << (8 * j);
-            }
-    }
-    am = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int code = (int)(int8_t)(w >> (8 * j));
-        bool a = ((mw >> (8 * j)) & 0xFFu) != 0;
-        int kk = a ? d8_norm<ENC>(code) : 8;
-        if (kk != 8) {
-            int64_t rr = gr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
-            if (rr < 0 || rr >= g.ny || cc < 0 || cc >= g.nx) kk = 8;
-        }
-        k[j] = kk;
-        am |= (int)a << j;
-    }
 }
 
 // segmented warp scan of an East chain: returns the inflow arriving at this lane's cell 0 from the
@@ -293,8 +255,8 @@ __device__ __forceinline__ void decode_row(uint32_t w, int am, const Geo &g, int
     for (int j = 0; j < 4; j++) {
         int kk = ((am >> j) & 1) ? d8_norm<ENC>((int)(int8_t)(w >> (8 * j))) : 8;
         if (border && kk != 8) {
-            int64_t rr = gr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
-            if (rr < 0 || rr >= g.ny || cc < 0 || cc >= g.nx) kk = 8;
+            int64_t rr = g.gy0 + gr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
+            if (rr < 0 || rr >= g.gny || cc < 0 || cc >= g.nx) kk = 8;
         }
         k[j] = kk;
     }
@@ -675,8 +637,8 @@ __device__ __forceinline__ void general_load(const int8_t *__restrict__ dir, con
             if (cell_active(mask, gi)) {
                 int k = d8_norm<ENC>(dir[gi]);
                 if (k != 8) {
-                    int64_t rr = gr + d8_dr(k), cc = gc + d8_dc(k);
-                    if (rr < 0 || rr >= g.ny || cc < 0 || cc >= g.nx) k = 8;
+                    int64_t rr = g.gy0 + gr + d8_dr(k), cc = gc + d8_dc(k);
+                    if (rr < 0 || rr >= g.gny || cc < 0 || cc >= g.nx) k = 8;
                 }
                 v = (uint8_t)(k | 16);
             }
@@ -839,7 +801,8 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
 // ---------------------------------------------------------------------------------------------
 // phase G: contracted forest over boundary slots
 // ---------------------------------------------------------------------------------------------
-// entry slot (global node id) that exit slot (tile, s) drains to, or -1 when s is not an exit
+// entry slot (node id) that exit slot (tile, s) drains to; -1 when s is not an exit; -2 when the
+// receiver lies in a neighbouring row stripe (a stripe exit: it has no parent in this stripe)
 __device__ __forceinline__ int64_t entry_of(const Geo &g, const uint32_t *__restrict__ meta, int tile, int s,
                                             uint32_t &m_entry)
 {
@@ -853,6 +816,7 @@ __device__ __forceinline__ int64_t entry_of(const Geo &g, const uint32_t *__rest
     int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
     if (rr >= 0 && rr < th && cc >= 0 && cc < tw) return -1;            // stays in the tile: not an exit
     int64_t gr = (int64_t)ty * TH + rr, gc = (int64_t)tx * TW + cc;     // in raster by construction
+    if (gr < 0 || gr >= g.ny) return -2;
     int ty2 = (int)(gr / TH), tx2 = (int)(gc / TW);
     int tile2 = ty2 * g.tiles_x + tx2, ty3, tx3, th2, tw2;
     tile_dims(g, tile2, ty3, tx3, th2, tw2);
@@ -969,64 +933,266 @@ __global__ void k_push_inflow(Geo g, int64_t nnodes, const uint32_t *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// row stripes: the stripe is solved like a raster whose top / bottom
+// neighbours exist but are elsewhere.  Cells of its first / last row that drain across are "stripe
+// exits"; k_stripe_summary condenses the stripe to 2*nx boundary records, k_stripe_inject feeds the
+// inflow arriving from the other stripes back in before the second forest walk.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t boundary_node(const Geo &g, int side, int64_t col, int &tile)
+{
+    const int64_t row = side == 0 ? 0 : g.ny - 1;
+    const int ty = (int)(row / TH), tx = (int)(col / TW);
+    tile = ty * g.tiles_x + tx;
+    int ty2, tx2, th, tw;
+    tile_dims(g, tile, ty2, tx2, th, tw);
+    return (int64_t)tile * NSLOT + slot_of((int)(row - (int64_t)ty * TH), (int)(col - (int64_t)tx * TW), th, tw);
+}
+
+// s_k: normalised code of the boundary cell (8 none, 9 inactive); s_exit_acc: stripe-local total of a
+// stripe exit; s_unres: the exit is locally unresolved; s_link: boundary index (side*nx + col) of the
+// stripe exit that flow entering at this cell reaches, -1 if it ends inside the stripe.
+__global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int64_t *__restrict__ A,
+                                 const int32_t *__restrict__ cnt, int8_t *__restrict__ s_k,
+                                 int64_t *__restrict__ s_exit_acc, int32_t *__restrict__ s_link,
+                                 uint8_t *__restrict__ s_unres)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * g.nx) return;
+    const int side = (int)(i / g.nx);
+    const int64_t col = i - (int64_t)side * g.nx;
+    int tile;
+    const int64_t node = boundary_node(g, side, col, tile);
+    const uint32_t m = meta[node];
+    const bool active = (m >> 21) & 1;
+    const int k = (m >> 16) & 0xF;
+    const bool is_exit = active && ((side == 0 && k >= 5 && k <= 7) || (side == 1 && k >= 1 && k <= 3));
+    const bool resolved = cnt[node] <= 0;
+    s_k[i] = (int8_t)(active ? k : 9);
+    s_exit_acc[i] = (is_exit && resolved) ? A[node] : 0;
+    s_unres[i] = (is_exit && !resolved) ? 1 : 0;
+    int32_t link = -1;
+    if (active) {
+        int64_t e = node;
+        for (int64_t hops = 0; hops <= nnodes; hops++) {
+            const uint32_t l = meta[e] & 0xFFFFu;
+            if (l == LNONE) break;
+            const int xt = (int)(e / NSLOT);
+            uint32_t me = 0;
+            const int64_t ent = entry_of(g, meta, xt, (int)l, me);
+            if (ent == -2) {                          // leaves the stripe here
+                int ty, tx, th, tw, lr, lc;
+                tile_dims(g, xt, ty, tx, th, tw);
+                cell_of((int)l, th, tw, lr, lc);
+                const int64_t row = (int64_t)ty * TH + lr, c2 = (int64_t)tx * TW + lc;
+                link = (int32_t)((row == 0 ? 0 : 1) * g.nx + c2);
+                break;
+            }
+            if (ent < 0 || !((me >> 21) & 1)) break;  // ends at an inactive receiver
+            e = ent;
+        }
+    }
+    s_link[i] = link;
+}
+
+__global__ void k_w64_init(const int32_t *__restrict__ exit_acc, int64_t *__restrict__ w64, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w64[i] = exit_acc[i];
+}
+
+__global__ void k_stripe_inject(Geo g, const uint32_t *__restrict__ meta, const int64_t *__restrict__ ext_inflow,
+                                const uint8_t *__restrict__ ext_un, int64_t *__restrict__ inflow,
+                                uint8_t *__restrict__ ext_unres, int64_t *__restrict__ w64, uint8_t *__restrict__ blocked,
+                                uint8_t *__restrict__ tile_class)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * g.nx) return;
+    const int side = (int)(i / g.nx);
+    const int64_t col = i - (int64_t)side * g.nx;
+    int64_t v = ext_inflow[i];
+    uint8_t u = ext_un ? ext_un[i] : 0;
+    if (v == 0 && !u) return;
+    int tile;
+    const int64_t node = boundary_node(g, side, col, tile);
+    const uint32_t m = meta[node];
+    if (!((m >> 21) & 1)) return;                     // inactive cells take nothing
+    inflow[node] = v;
+    if (u) { ext_unres[node] = 1; tile_class[tile] = 2; }
+    const uint32_t l = m & 0xFFFFu;
+    if (l != LNONE) {                                 // the exit this entry feeds carries the inflow on
+        const int64_t x = (int64_t)tile * NSLOT + l;
+        atomicAdd((unsigned long long *)&w64[x], (unsigned long long)v);
+        if (u) blocked[x] = 1;
+    }
+}
+
+template <typename T>
+struct SweepWs {
+    uint32_t *meta; int32_t *exit_acc, *parent, *cnt; T *A, *inflow; uint8_t *blocked, *ext_unres, *tile_class;
+    unsigned long long *row_plain, *wq; int64_t *w64;
+    bool ok;
+};
+template <typename T>
+SweepWs<T> carve_ws(void *ws, size_t ws_bytes, int64_t nnodes, int ntiles, bool stripe)
+{
+    WsCursor cur(ws, ws_bytes);
+    SweepWs<T> w;
+    w.meta = cur.take<uint32_t>((size_t)nnodes);
+    w.exit_acc = cur.take<int32_t>((size_t)nnodes);
+    w.parent = cur.take<int32_t>((size_t)nnodes);
+    w.cnt = cur.take<int32_t>((size_t)nnodes);
+    w.A = cur.take<T>((size_t)nnodes);
+    w.inflow = cur.take<T>((size_t)nnodes);
+    w.blocked = cur.take<uint8_t>((size_t)nnodes);
+    w.ext_unres = cur.take<uint8_t>((size_t)nnodes);
+    w.tile_class = cur.take<uint8_t>((size_t)ntiles);
+    w.row_plain = cur.take<unsigned long long>((size_t)ntiles);
+    w.wq = cur.take<unsigned long long>((size_t)nnodes);
+    w.w64 = stripe ? cur.take<int64_t>((size_t)nnodes) : nullptr;
+    w.ok = cur.ok;
+    return w;
+}
+
+static Geo make_geo(int64_t ny, int64_t nx, int64_t gy0, int64_t gny)
+{
+    Geo g;
+    g.ny = ny; g.nx = nx; g.gy0 = gy0; g.gny = gny;
+    g.tiles_x = (int)((nx + TW - 1) / TW);
+    g.tiles_y = (int)((ny + TH - 1) / TH);
+    return g;
+}
+
+template <int ENC, typename T>
+int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, cudaStream_t st)
+{
+    const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
+    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);   // persistent: most tiles are skipped
+    const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
+    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
+    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
+    k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int ENC, typename T>
+int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, T *acc,
+                 cudaStream_t st)
+{
+    const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
+    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+    const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
+    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
+    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
+    k_generalC<ENC, T><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, w.inflow, w.ext_unres, acc);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+// forest walk of the int64 path: weights int32 (first pass) or the int64 copy with stripe inflow added
+template <typename T>
+int sweep_phaseG_i64(const Geo &g, int64_t nnodes, const SweepWs<T> &w, bool use_w64, cudaStream_t st)
+{
+    int rc = use_w64 ? forest_accum_i64w(w.parent, w.w64, (int64_t *)w.A, w.cnt, nnodes, st, w.blocked)
+                     : forest_accum_i64(w.parent, w.exit_acc, (int64_t *)w.A, w.cnt, nnodes, st, w.blocked);
+    if (rc) return rc;
+    k_push_inflow<int64_t><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, (int64_t *)w.A, w.cnt, (int64_t *)w.inflow,
+                                                                    w.ext_unres, w.tile_class);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+static bool aligned4(const void *dir, const void *mask, const void *acc, int64_t nx)
+{
+    return (nx % 4 == 0) && (((uintptr_t)dir & 3) == 0) && (mask == nullptr || ((uintptr_t)mask & 3) == 0) &&
+           (((uintptr_t)acc & 15) == 0);
+}
+
 template <int ENC, typename T>
 int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
                 cudaStream_t st)
 {
-    Geo g;
-    g.ny = ny; g.nx = nx;
-    g.tiles_x = (int)((nx + TW - 1) / TW);
-    g.tiles_y = (int)((ny + TH - 1) / TH);
+    const Geo g = make_geo(ny, nx, 0, ny);
     const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
     WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "raster too large for the tiled accumulation");
     const int ntiles = (int)ntiles64;
     const int64_t nnodes = ntiles64 * NSLOT;
-    WsCursor cur(ws, ws_bytes);
-    uint32_t *meta = cur.take<uint32_t>((size_t)nnodes);
-    int32_t *exit_acc = cur.take<int32_t>((size_t)nnodes);
-    int32_t *parent = cur.take<int32_t>((size_t)nnodes);
-    int32_t *cnt = cur.take<int32_t>((size_t)nnodes);
-    T *A = cur.take<T>((size_t)nnodes);
-    T *inflow = cur.take<T>((size_t)nnodes);
-    uint8_t *blocked = cur.take<uint8_t>((size_t)nnodes);
-    uint8_t *ext_unres = cur.take<uint8_t>((size_t)nnodes);
-    uint8_t *tile_class = cur.take<uint8_t>((size_t)ntiles);
-    unsigned long long *row_plain = cur.take<unsigned long long>((size_t)ntiles);
-    unsigned long long *wq = cur.take<unsigned long long>((size_t)nnodes);
-    WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
-    const bool al = (nx % 4 == 0) && (((uintptr_t)dir & 3) == 0) && (mask == nullptr || ((uintptr_t)mask & 3) == 0) &&
-                    (((uintptr_t)acc & 15) == 0);
-    const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
-    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);   // persistent: most tiles are skipped
-    const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS, smemC = sizeof(T) * TCELLS + 2 * TCELLS;
-    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-    WMF_CUDA_CHECK(cudaMemsetAsync(inflow, 0, sizeof(T) * nnodes, st));
-    WMF_CUDA_CHECK(cudaMemsetAsync(ext_unres, 0, (size_t)nnodes, st));
-    // phase A
-    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class, row_plain, wq);
-    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, meta, exit_acc, tile_class, row_plain, wq);
-    k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, tile_class, meta, exit_acc, wq);
-    // phase G
+    const SweepWs<T> w = carve_ws<T>(ws, ws_bytes, nnodes, ntiles, false);
+    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
+    const bool al = aligned4(dir, mask, acc, nx);
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(T) * nnodes, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
+    int rc = sweep_phaseA<ENC, T>(dir, mask, g, ntiles, w, al, st);
+    if (rc) return rc;
     if (sizeof(T) == 4) {
-        int32_t *entry = cnt;                                // reuse: the packed walk needs no counters
-        k_g_build<<<ntiles, NSLOT, 0, st>>>(g, meta, parent, entry, wq);
-        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, parent, entry, exit_acc, wq, (int32_t *)inflow);
-        k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, wq, ext_unres, tile_class);
+        int32_t *entry = w.cnt;                              // reuse: the packed walk needs no counters
+        k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
+        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, (int32_t *)w.inflow);
+        k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class);
         WMF_LAUNCH_CHECK();
     } else {
-        k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, parent, blocked);
+        k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
         WMF_LAUNCH_CHECK();
-        int rc = forest_accum_i64(parent, exit_acc, (int64_t *)A, cnt, nnodes, st, blocked);
+        rc = sweep_phaseG_i64<T>(g, nnodes, w, false, st);
         if (rc) return rc;
-        k_push_inflow<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, A, cnt, inflow, ext_unres, tile_class);
     }
-    // phase C
-    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, row_plain, acc);
-    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, inflow, tile_class, row_plain, acc);
-    k_generalC<ENC, T><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, tile_class, inflow, ext_unres, acc);
+    return sweep_phaseC<ENC, T>(dir, mask, g, ntiles, w, al, acc, st);
+}
+
+// ---- stripe entry points (int64 accumulation) ---------------------------------------------------
+template <int ENC>
+int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
+                   int8_t *s_k, int64_t *s_exit_acc, int32_t *s_link, uint8_t *s_unres, void *ws, size_t ws_bytes,
+                   cudaStream_t st)
+{
+    const Geo g = make_geo(ny, nx, row0, ny_total);
+    const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
+    WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "stripe too large for the tiled accumulation");
+    const int ntiles = (int)ntiles64;
+    const int64_t nnodes = ntiles64 * NSLOT;
+    const SweepWs<int64_t> w = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true);
+    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
+    const bool al = aligned4(dir, mask, nullptr, nx);
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(int64_t) * nnodes, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
+    int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st);
+    if (rc) return rc;
+    k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
+    WMF_LAUNCH_CHECK();
+    rc = sweep_phaseG_i64<int64_t>(g, nnodes, w, false, st);
+    if (rc) return rc;
+    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.A, w.cnt, s_k, s_exit_acc, s_link, s_unres);
     WMF_LAUNCH_CHECK();
     return 0;
+}
+
+template <int ENC>
+int stripe_finish_t(const int8_t *dir, const uint8_t *mask, int64_t *acc, int64_t ny, int64_t nx, int64_t row0,
+                    int64_t ny_total, const int64_t *ext_inflow, const uint8_t *ext_un, void *ws, size_t ws_bytes,
+                    cudaStream_t st)
+{
+    const Geo g = make_geo(ny, nx, row0, ny_total);
+    const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
+    const int ntiles = (int)ntiles64;
+    const int64_t nnodes = ntiles64 * NSLOT;
+    const SweepWs<int64_t> w = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true);
+    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
+    const bool al = aligned4(dir, mask, acc, nx);
+    // second forest walk: same forest (meta / exit_acc / tile classes of phase A are still in the workspace),
+    // weights + the inflow that arrives from the other stripes
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(int64_t) * nnodes, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
+    k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
+    k_w64_init<<<blocks_for(nnodes, 256), 256, 0, st>>>(w.exit_acc, w.w64, nnodes);
+    k_stripe_inject<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, ext_inflow, ext_un, w.inflow, w.ext_unres, w.w64,
+                                                           w.blocked, w.tile_class);
+    WMF_LAUNCH_CHECK();
+    int rc = sweep_phaseG_i64<int64_t>(g, nnodes, w, true, st);
+    if (rc) return rc;
+    return sweep_phaseC<ENC, int64_t>(dir, mask, g, ntiles, w, al, acc, st);
 }
 
 }  // namespace
@@ -1037,7 +1203,8 @@ size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
 {
     int64_t ntiles = ((nx + TW - 1) / TW) * ((ny + TH - 1) / TH);
     size_t nn = (size_t)ntiles * NSLOT, tsz = acc_dtype == WMF_ACC_I32 ? 4 : 8;
-    return 4 * wmf_align(nn * 4) + wmf_align(nn * 8) + 2 * wmf_align(nn * tsz) + 2 * wmf_align(nn) + wmf_align((size_t)ntiles) + wmf_align((size_t)ntiles * 8) + 4096;
+    return 4 * wmf_align(nn * 4) + 2 * wmf_align(nn * 8) + 2 * wmf_align(nn * tsz) + 2 * wmf_align(nn) +
+           wmf_align((size_t)ntiles) + wmf_align((size_t)ntiles * 8) + 4096;
 }
 
 int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx, int encoding,
@@ -1054,3 +1221,40 @@ int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, i
     if (acc_dtype == WMF_ACC_F64) return d8_convert_i64_to_f64(acc, ny * nx, st);
     return 0;
 }
+
+extern "C" {
+
+size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx) { return d8_sweep_workspace(ny, nx, WMF_ACC_I64); }
+
+int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
+                        int encoding, int8_t *s_k, int64_t *s_exit_acc, int32_t *s_link, uint8_t *s_unres,
+                        void *workspace, size_t ws_bytes, void *stream)
+{
+    WMF_REQUIRE(dir && s_k && s_exit_acc && s_link && s_unres && workspace, WMF_E_ARG, "null pointer");
+    WMF_REQUIRE(ny >= 2 && nx > 0 && row0 >= 0 && row0 + ny <= ny_total, WMF_E_ARG, "bad stripe geometry (ny >= 2)");
+    WMF_REQUIRE(2 * nx < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "nx too large");
+    WMF_REQUIRE(encoding == WMF_ENC_INTERNAL || encoding == WMF_ENC_KEYPAD, WMF_E_ARG, "unknown encoding");
+    cudaStream_t st = (cudaStream_t)stream;
+    return encoding == WMF_ENC_INTERNAL
+               ? stripe_local_t<WMF_ENC_INTERNAL>(dir, mask, ny, nx, row0, ny_total, s_k, s_exit_acc, s_link, s_unres, workspace, ws_bytes, st)
+               : stripe_local_t<WMF_ENC_KEYPAD>(dir, mask, ny, nx, row0, ny_total, s_k, s_exit_acc, s_link, s_unres, workspace, ws_bytes, st);
+}
+
+int wmf_d8_stripe_finish(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx,
+                         int64_t row0, int64_t ny_total, int encoding, const int64_t *ext_inflow,
+                         const uint8_t *ext_unres, void *workspace, size_t ws_bytes, void *stream)
+{
+    WMF_REQUIRE(dir && acc && ext_inflow && workspace, WMF_E_ARG, "null pointer");
+    WMF_REQUIRE(acc_dtype == WMF_ACC_I64 || acc_dtype == WMF_ACC_F64, WMF_E_ARG, "stripes accumulate in int64 (or float64)");
+    WMF_REQUIRE(ny >= 2 && nx > 0 && row0 >= 0 && row0 + ny <= ny_total, WMF_E_ARG, "bad stripe geometry (ny >= 2)");
+    WMF_REQUIRE(encoding == WMF_ENC_INTERNAL || encoding == WMF_ENC_KEYPAD, WMF_E_ARG, "unknown encoding");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = encoding == WMF_ENC_INTERNAL
+                 ? stripe_finish_t<WMF_ENC_INTERNAL>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st)
+                 : stripe_finish_t<WMF_ENC_KEYPAD>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st);
+    if (rc) return rc;
+    if (acc_dtype == WMF_ACC_F64) return d8_convert_i64_to_f64(acc, ny * nx, st);
+    return 0;
+}
+
+}  // extern "C"

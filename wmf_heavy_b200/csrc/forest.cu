@@ -95,3 +95,41 @@ int forest_accum_i64(const int32_t *parent, const int32_t *w, int64_t *acc, int3
 {
     return forest_accum_t<int64_t, int32_t>(parent, w, acc, cnt, blocked, n, st);
 }
+int forest_accum_i64w(const int32_t *parent, const int64_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st,
+                      const uint8_t *blocked)
+{
+    return forest_accum_t<int64_t, int64_t>(parent, w, acc, cnt, blocked, n, st);
+}
+
+namespace {
+__global__ void k_resolved(const int32_t *__restrict__ cnt, uint8_t *__restrict__ resolved, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) resolved[i] = cnt[i] <= 0 ? 1 : 0;
+}
+}  // namespace
+
+extern "C" {
+
+size_t wmf_forest_accum_workspace(int64_t n) { return wmf_align((size_t)n * 4) + 256; }
+
+int wmf_forest_accum(const int32_t *parent, const int64_t *weight, const uint8_t *blocked, int64_t n, int64_t *acc,
+                     uint8_t *resolved, void *workspace, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = as_stream(stream);
+    WMF_REQUIRE(parent && acc && n >= 0, WMF_E_ARG, "bad argument");
+    WMF_REQUIRE(n < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "n must be < 2^31");
+    if (n == 0) return 0;
+    WsCursor cur(workspace, ws_bytes);
+    int32_t *cnt = cur.take<int32_t>((size_t)n);
+    WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
+    int rc = forest_accum_t<int64_t, int64_t>(parent, weight, acc, cnt, blocked, n, st);
+    if (rc) return rc;
+    if (resolved) {
+        k_resolved<<<blocks_for(n, 256), 256, 0, st>>>(cnt, resolved, n);
+        WMF_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // extern "C"

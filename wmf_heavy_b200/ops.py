@@ -266,3 +266,57 @@ def synth_scheidegger_host(ny: int, nx: int, seed: int = 20260101, encoding: int
     _lib.load().wmf_synth_scheidegger_host(out.ctypes.data, ny, nx, row0, col0, nx if nx_total is None else nx_total,
                                            seed, encoding)
     return out
+
+
+# --------------------------------------------------------------------------------------- forest / stripes
+def forest_accum(parent: torch.Tensor, weight: Optional[torch.Tensor] = None, blocked: Optional[torch.Tensor] = None):
+    """acc[i] = weight[i] + sum of acc over children (parent int32, -1 root) -> (acc int64, resolved uint8)."""
+    require_cuda()
+    _chk_dev(parent, torch.int32, "parent")
+    n = parent.numel()
+    if weight is not None:
+        _chk_dev(weight, torch.int64, "weight")
+    if blocked is not None:
+        _chk_dev(blocked, torch.uint8, "blocked")
+    acc = torch.empty(n, dtype=torch.int64, device=parent.device)
+    res = torch.empty(n, dtype=torch.uint8, device=parent.device)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_forest_accum_workspace(n))
+    check(lib.wmf_forest_accum(ptr(parent), ptr(weight), ptr(blocked), n, ptr(acc), ptr(res), ptr(ws), ws.numel(),
+                               stream_ptr()))
+    return acc, res
+
+
+def d8_stripe_local(dir_t: torch.Tensor, row0: int, ny_total: int, mask_t: Optional[torch.Tensor] = None,
+                    encoding: int = ENC_INTERNAL):
+    """Phase 1 of the striped accumulation -> (records dict of [2, nx] tensors, private workspace tensor)."""
+    dev = require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    ny, nx = dir_t.shape
+    if mask_t is not None:
+        _chk_dev(mask_t, torch.uint8, "mask")
+    lib = _lib.load()
+    ws = torch.empty(lib.wmf_d8_stripe_workspace(ny, nx), dtype=torch.uint8, device=dev)   # lives until finish
+    rec = {"k": torch.empty((2, nx), dtype=torch.int8, device=dev),
+           "exit_acc": torch.empty((2, nx), dtype=torch.int64, device=dev),
+           "link": torch.empty((2, nx), dtype=torch.int32, device=dev),
+           "unres": torch.empty((2, nx), dtype=torch.uint8, device=dev)}
+    check(lib.wmf_d8_stripe_local(ptr(dir_t), ptr(mask_t), ny, nx, int(row0), int(ny_total), encoding, ptr(rec["k"]),
+                                  ptr(rec["exit_acc"]), ptr(rec["link"]), ptr(rec["unres"]), ptr(ws), ws.numel(),
+                                  stream_ptr()))
+    return rec, ws
+
+
+def d8_stripe_finish(dir_t: torch.Tensor, ws: torch.Tensor, row0: int, ny_total: int, ext_inflow: torch.Tensor,
+                     ext_unres: Optional[torch.Tensor] = None, mask_t: Optional[torch.Tensor] = None,
+                     encoding: int = ENC_INTERNAL, acc_dtype: int = ACC_I64, out: Optional[torch.Tensor] = None):
+    """Phase 2 of the striped accumulation: inject the inflow from the other stripes, write the final ACC."""
+    require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    _chk_dev(ext_inflow, torch.int64, "ext_inflow")
+    ny, nx = dir_t.shape
+    if out is None:
+        out = torch.empty((ny, nx), dtype=_ACC_TORCH[acc_dtype], device=dir_t.device)
+    check(_lib.load().wmf_d8_stripe_finish(ptr(dir_t), ptr(mask_t), ptr(out), acc_dtype, ny, nx, int(row0), int(ny_total),
+                                           encoding, ptr(ext_inflow), ptr(ext_unres), ptr(ws), ws.numel(), stream_ptr()))
+    return out
