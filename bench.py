@@ -49,50 +49,66 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML polled from a thread every ~2 ms;
+    `nvidia-smi -lms` cannot deliver a sample inside a 30 ms region)."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop, self.t, self.h = index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    @staticmethod
+    def _physical_index(i: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, why))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.t is not None:
+            self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for nm, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({nm for _, why in self.rows for nm, b in bits.items() if why & b})
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.rows)}
 
 
 def cpu_oracle_accum(sample: int, steps: int = 1):
@@ -178,7 +194,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL may print its version banner on stdout; the driver wants ONE JSON line there
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     n = args.size
     peak, peak_src = measured_peaks()
@@ -195,21 +216,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # row stripes with one boundary exchange (all-gather over NCCL); int64 ACC: the whole raster can
         # exceed 2^31 cells
         from wmf_heavy_b200 import stripes
-        acc = torch.empty((n, n), dtype=torch.int64, device=dev)
+        wide = world * n * n > 2**31 - 1
+        acc = torch.empty((n, n), dtype=torch.int64 if wide else torch.int32, device=dev)
+        stripe_dtype = _lib.ACC_I64 if wide else _lib.ACC_I32
 
         def step():
-            stripes.accumulate_striped(d, rank * n, world * n, out=acc)
+            stripes.accumulate_striped(d, rank * n, world * n, acc_dtype=stripe_dtype, out=acc)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:            # sampled over warm-up + timed region (the same load)
+        for _ in range(max(args.warmup, 3)):
+            step()
         barrier()
         ev[0].record()
         for i in range(args.steps):
@@ -226,7 +248,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     cells_total = float(n) * n * world
     value = cells_total / (ms_per_step * 1e-3) / 1e6
     op_ms = statistics.mean(per)
-    bytes_per_cell = ALGO_BYTES_PER_CELL if world == 1 else 9.0      # int64 ACC on stripes: 1 + 8 B/cell
+    bytes_per_cell = 1.0 + acc.element_size()                       # int8 DIR read + ACC write
     achieved = bytes_per_cell * n * n / (op_ms * 1e-3) / 1e9
 
     # ---- e2e through the reference-facing API: host flowdir + mask in (pinned), float64 raster out
@@ -258,11 +280,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         from wmf_heavy_b200 import stripes
         h_dir = torch.empty((n, n), dtype=torch.int8).pin_memory()
         h_dir.copy_(d)
-        h_out = torch.empty((n, n), dtype=torch.int64).pin_memory()
+        h_out = torch.empty((n, n), dtype=acc.dtype).pin_memory()
 
         def e2e_step():
             dd = h_dir.to(dev, non_blocking=True)
-            a = stripes.accumulate_striped(dd, rank * n, world * n)
+            a = stripes.accumulate_striped(dd, rank * n, world * n, acc_dtype=stripe_dtype)
             h_out.copy_(a)
 
         e2e_step()
@@ -276,7 +298,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
         e2e = {"value": cells_total / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": n * n,
-               "d2h_bytes_per_step": 8 * n * n, "ms_per_step": 1e3 * e2e_s,
+               "d2h_bytes_per_step": acc.element_size() * n * n, "ms_per_step": 1e3 * e2e_s,
                "api": "wmf_heavy_b200.stripes.accumulate_striped(host int8 stripe) -> host int64 stripe, per rank"}
         del h_dir, h_out
 
@@ -301,13 +323,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                    "sample": f"{args.ref_sample}x{args.ref_sample} top-left window of the same raster, C restatement "
                              "of wmf_py basin_acum (oracle/wmf_oracle.c, gcc -O2, 1 thread); "
                              f"{times[0]:.2f} s"}
-        launches_per_step = {"walk": 2, "sweep": 2, "auto": 2}[args.algo]
+        # kernels of libwmfb200.so per accumulation (profiles/*launches*.csv): walk = indegree + walk; sweep = sweepA,
+        # generalA, g_build, g_walk, g_unres, sweepC, generalC; stripes = 8 (local) + 4 (boundary forest) + 9 (finish)
+        launches_per_step = {"walk": 2, "sweep": 7, "auto": 7}[args.algo] if world == 1 else 21
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32" if world == 1 else "int64", "data": "synthetic",
+            "vs_baseline": None, "dtype": str(acc.dtype).replace("torch.", ""), "data": "synthetic",
             "config": {"workload": f"D8 flow accumulation, synthetic Scheidegger DIR {n}x{n} per GPU (seed {SEED}), "
-                                   f"int8 DIR -> {'int32' if world == 1 else 'int64'} ACC, mask = all valid", "algo": args.algo,
+                                   f"int8 DIR -> {str(acc.dtype).replace('torch.', '')} ACC, mask = all valid", "algo": args.algo,
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} row stripes of {n} rows of one {world * n}x{n} raster, one NCCL all-gather of the "
                        "boundary records per accumulation",
@@ -319,6 +343,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(), "shia": shia,
         }
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -55,6 +55,8 @@ def test_striped_full_size_int64_and_f64():
     assert torch.equal(got, ref)
     gf = stripes.accumulate_striped_single_device(d, 8, acc_dtype=_lib.ACC_F64)
     assert gf.dtype == torch.float64 and torch.equal(gf.to(torch.int64), ref)
+    g32 = stripes.accumulate_striped_single_device(d, 3, acc_dtype=_lib.ACC_I32)
+    assert g32.dtype == torch.int32 and torch.equal(g32.to(torch.int64), ref)
 
 
 def test_forest_accum_matches_numpy():

@@ -857,7 +857,7 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__rest
     const int64_t i = (int64_t)tile * NSLOT + s;
     uint32_t me = 0;
     int64_t e = entry_of(g, meta, tile, s, me);
-    int32_t p = -1, en = -1;
+    int32_t p = -1, en = e == -2 ? -2 : -1;                 // -2: drains into a neighbouring row stripe
     if (e >= 0 && ((me >> 21) & 1)) {                       // an exit whose receiver is active
         en = (int32_t)e;
         uint32_t link = me & 0xFFFFu;
@@ -871,18 +871,20 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__rest
 }
 
 __global__ void k_g_walk(int64_t nnodes, const int32_t *__restrict__ parent, const int32_t *__restrict__ entry,
-                         const int32_t *__restrict__ w, unsigned long long *wq, int32_t *__restrict__ inflow)
+                         const int32_t *__restrict__ w, unsigned long long *wq, int32_t *__restrict__ inflow,
+                         int32_t *__restrict__ stripe_total)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnodes) return;
     int32_t en = entry[i];
-    if (en < 0) return;                                     // not an exit: nothing to carry
+    if (en == -1) return;                                   // not an exit: nothing to carry
     int64_t cur = i;
     unsigned long long old = atomicAdd(&wq[cur], (unsigned long long)(-(long long)PEND1));   // own arrival
     uint32_t add = 0;
     while ((uint32_t)(old >> 32) == 1u) {                   // we took pending to zero: cur is final
         uint32_t total = (uint32_t)old + add + (uint32_t)w[cur];
         if (en >= 0) atomicAdd(&inflow[en], (int32_t)total);
+        else if (en == -2) stripe_total[cur] = (int32_t)total;     // a stripe exit keeps its stripe-local total
         int32_t p = parent[cur];
         if (p < 0) break;
         en = entry[p];
@@ -949,11 +951,20 @@ __device__ __forceinline__ int64_t boundary_node(const Geo &g, int side, int64_t
     return (int64_t)tile * NSLOT + slot_of((int)(row - (int64_t)ty * TH), (int)(col - (int64_t)tx * TW), th, tw);
 }
 
+// Follow the contracted path of flow that enters at boundary-slot node e0: exit x1 = link(e0), then
+// x_{i+1} = parent[x_i].  Returns the last exit of the path (or -1 when link(e0) is none).
+__device__ __forceinline__ int64_t first_exit(const uint32_t *__restrict__ meta, int64_t e0)
+{
+    const uint32_t l = meta[e0] & 0xFFFFu;
+    return l == LNONE ? -1 : (e0 / NSLOT) * NSLOT + l;
+}
+
 // s_k: normalised code of the boundary cell (8 none, 9 inactive); s_exit_acc: stripe-local total of a
 // stripe exit; s_unres: the exit is locally unresolved; s_link: boundary index (side*nx + col) of the
 // stripe exit that flow entering at this cell reaches, -1 if it ends inside the stripe.
-__global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int64_t *__restrict__ A,
-                                 const int32_t *__restrict__ cnt, int8_t *__restrict__ s_k,
+__global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
+                                 const int32_t *__restrict__ entry, const int32_t *__restrict__ stripe_total,
+                                 const unsigned long long *__restrict__ wq, int8_t *__restrict__ s_k,
                                  int64_t *__restrict__ s_exit_acc, int32_t *__restrict__ s_link,
                                  uint8_t *__restrict__ s_unres)
 {
@@ -966,64 +977,67 @@ __global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restri
     const uint32_t m = meta[node];
     const bool active = (m >> 21) & 1;
     const int k = (m >> 16) & 0xF;
-    const bool is_exit = active && ((side == 0 && k >= 5 && k <= 7) || (side == 1 && k >= 1 && k <= 3));
-    const bool resolved = cnt[node] <= 0;
+    const bool is_exit = active && entry[node] == -2 &&
+                         ((side == 0 && k >= 5 && k <= 7) || (side == 1 && k >= 1 && k <= 3));
+    const bool resolved = (uint32_t)(wq[node] >> 32) == 0u;
     s_k[i] = (int8_t)(active ? k : 9);
-    s_exit_acc[i] = (is_exit && resolved) ? A[node] : 0;
+    s_exit_acc[i] = (is_exit && resolved) ? (int64_t)stripe_total[node] : 0;
     s_unres[i] = (is_exit && !resolved) ? 1 : 0;
     int32_t link = -1;
     if (active) {
-        int64_t e = node;
-        for (int64_t hops = 0; hops <= nnodes; hops++) {
-            const uint32_t l = meta[e] & 0xFFFFu;
-            if (l == LNONE) break;
-            const int xt = (int)(e / NSLOT);
-            uint32_t me = 0;
-            const int64_t ent = entry_of(g, meta, xt, (int)l, me);
-            if (ent == -2) {                          // leaves the stripe here
-                int ty, tx, th, tw, lr, lc;
-                tile_dims(g, xt, ty, tx, th, tw);
-                cell_of((int)l, th, tw, lr, lc);
-                const int64_t row = (int64_t)ty * TH + lr, c2 = (int64_t)tx * TW + lc;
-                link = (int32_t)((row == 0 ? 0 : 1) * g.nx + c2);
-                break;
-            }
-            if (ent < 0 || !((me >> 21) & 1)) break;  // ends at an inactive receiver
-            e = ent;
+        int64_t x = first_exit(meta, node);
+        for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
+            const int32_t p = parent[x];
+            if (p < 0) break;
+            x = p;
+        }
+        if (x >= 0 && entry[x] == -2) {               // the path leaves the stripe at exit x
+            const int xt = (int)(x / NSLOT);
+            int ty, tx, th, tw, lr, lc;
+            tile_dims(g, xt, ty, tx, th, tw);
+            cell_of((int)(x - (int64_t)xt * NSLOT), th, tw, lr, lc);
+            const int64_t row = (int64_t)ty * TH + lr, c2 = (int64_t)tx * TW + lc;
+            link = (int32_t)((row == 0 ? 0 : 1) * g.nx + c2);
         }
     }
     s_link[i] = link;
 }
 
-__global__ void k_w64_init(const int32_t *__restrict__ exit_acc, int64_t *__restrict__ w64, int64_t n)
+template <typename T>
+__global__ void k_widen(const int32_t *__restrict__ a, T *__restrict__ b, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) w64[i] = exit_acc[i];
+    if (i < n) b[i] = (T)a[i];
 }
 
-__global__ void k_stripe_inject(Geo g, const uint32_t *__restrict__ meta, const int64_t *__restrict__ ext_inflow,
-                                const uint8_t *__restrict__ ext_un, int64_t *__restrict__ inflow,
-                                uint8_t *__restrict__ ext_unres, int64_t *__restrict__ w64, uint8_t *__restrict__ blocked,
-                                uint8_t *__restrict__ tile_class)
+// Route what arrives from the other stripes along the contracted paths: every entry on the path of a
+// boundary cell gets the cell's external inflow added (linearity of the accumulation).
+template <typename T>
+__global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
+                               const int32_t *__restrict__ entry, const int64_t *__restrict__ ext_inflow,
+                               const uint8_t *__restrict__ ext_un, T *__restrict__ inflow, uint8_t *__restrict__ ext_unres,
+                               uint8_t *__restrict__ tile_class)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * g.nx) return;
     const int side = (int)(i / g.nx);
     const int64_t col = i - (int64_t)side * g.nx;
-    int64_t v = ext_inflow[i];
-    uint8_t u = ext_un ? ext_un[i] : 0;
+    const int64_t v = ext_inflow[i];
+    const bool u = ext_un && ext_un[i];
     if (v == 0 && !u) return;
     int tile;
     const int64_t node = boundary_node(g, side, col, tile);
-    const uint32_t m = meta[node];
-    if (!((m >> 21) & 1)) return;                     // inactive cells take nothing
-    inflow[node] = v;
-    if (u) { ext_unres[node] = 1; tile_class[tile] = 2; }
-    const uint32_t l = m & 0xFFFFu;
-    if (l != LNONE) {                                 // the exit this entry feeds carries the inflow on
-        const int64_t x = (int64_t)tile * NSLOT + l;
-        atomicAdd((unsigned long long *)&w64[x], (unsigned long long)v);
-        if (u) blocked[x] = 1;
+    if (!((meta[node] >> 21) & 1)) return;            // inactive cells take nothing
+    int64_t e = node;
+    int64_t x = first_exit(meta, node);
+    for (int64_t hops = 0; hops <= nnodes; hops++) {
+        inflow_add<T>(&inflow[e], (T)v);
+        if (u) { ext_unres[e] = 1; tile_class[e / NSLOT] = 2; }
+        if (x < 0) break;
+        const int32_t en = entry[x];
+        if (en < 0) break;                            // leaves the stripe (or ends at an inactive receiver)
+        e = en;
+        x = parent[x];                                // = first_exit(meta, en)
     }
 }
 
@@ -1130,7 +1144,7 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
     if (sizeof(T) == 4) {
         int32_t *entry = w.cnt;                              // reuse: the packed walk needs no counters
         k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
-        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, (int32_t *)w.inflow);
+        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, (int32_t *)w.inflow, nullptr);
         k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class);
         WMF_LAUNCH_CHECK();
     } else {
@@ -1142,7 +1156,9 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
     return sweep_phaseC<ENC, T>(dir, mask, g, ntiles, w, al, acc, st);
 }
 
-// ---- stripe entry points (int64 accumulation) ---------------------------------------------------
+// ---- stripe entry points --------------------------------------------------------------------------
+// The stripe-local pass always runs the packed int32 forest walk (a stripe holds < 2^31 cells); only
+// the finish pass is typed by the output accumulation.
 template <int ENC>
 int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
                    int8_t *s_k, int64_t *s_exit_acc, int32_t *s_link, uint8_t *s_unres, void *ws, size_t ws_bytes,
@@ -1156,21 +1172,22 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     const SweepWs<int64_t> w = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, nullptr, nx);
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(int64_t) * nnodes, st));
+    int32_t *inflow32 = (int32_t *)w.w64, *entry = w.cnt, *stripe_total = (int32_t *)w.A;
+    WMF_CUDA_CHECK(cudaMemsetAsync(inflow32, 0, sizeof(int32_t) * nnodes, st));
     WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
     int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st);
     if (rc) return rc;
-    k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
-    WMF_LAUNCH_CHECK();
-    rc = sweep_phaseG_i64<int64_t>(g, nnodes, w, false, st);
-    if (rc) return rc;
-    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.A, w.cnt, s_k, s_exit_acc, s_link, s_unres);
+    k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
+    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, inflow32, stripe_total);
+    k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class);
+    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, stripe_total, w.wq, s_k,
+                                                            s_exit_acc, s_link, s_unres);
     WMF_LAUNCH_CHECK();
     return 0;
 }
 
-template <int ENC>
-int stripe_finish_t(const int8_t *dir, const uint8_t *mask, int64_t *acc, int64_t ny, int64_t nx, int64_t row0,
+template <int ENC, typename T>
+int stripe_finish_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int64_t nx, int64_t row0,
                     int64_t ny_total, const int64_t *ext_inflow, const uint8_t *ext_un, void *ws, size_t ws_bytes,
                     cudaStream_t st)
 {
@@ -1178,21 +1195,21 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, int64_t *acc, int64_
     const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
     const int ntiles = (int)ntiles64;
     const int64_t nnodes = ntiles64 * NSLOT;
-    const SweepWs<int64_t> w = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true);
-    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
+    const SweepWs<int64_t> w0 = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true);
+    WMF_REQUIRE(w0.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, acc, nx);
-    // second forest walk: same forest (meta / exit_acc / tile classes of phase A are still in the workspace),
-    // weights + the inflow that arrives from the other stripes
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(int64_t) * nnodes, st));
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
-    k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
-    k_w64_init<<<blocks_for(nnodes, 256), 256, 0, st>>>(w.exit_acc, w.w64, nnodes);
-    k_stripe_inject<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, ext_inflow, ext_un, w.inflow, w.ext_unres, w.w64,
-                                                           w.blocked, w.tile_class);
+    int32_t *inflow32 = (int32_t *)w0.w64, *entry = w0.cnt;
+    // phase-A state, the forest (parent / entry) and the stripe-local inflows are still in the workspace:
+    // widen the inflows to the output type, add what the other stripes send, run phase C.
+    SweepWs<T> w;
+    w.meta = w0.meta; w.exit_acc = w0.exit_acc; w.parent = w0.parent; w.cnt = w0.cnt; w.A = (T *)w0.A;
+    w.inflow = (T *)w0.inflow; w.blocked = w0.blocked; w.ext_unres = w0.ext_unres; w.tile_class = w0.tile_class;
+    w.row_plain = w0.row_plain; w.wq = w0.wq; w.w64 = w0.w64; w.ok = true;
+    k_widen<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(inflow32, w.inflow, nnodes);
+    k_stripe_route<T><<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, ext_inflow, ext_un, w.inflow,
+                                                             w.ext_unres, w.tile_class);
     WMF_LAUNCH_CHECK();
-    int rc = sweep_phaseG_i64<int64_t>(g, nnodes, w, true, st);
-    if (rc) return rc;
-    return sweep_phaseC<ENC, int64_t>(dir, mask, g, ntiles, w, al, acc, st);
+    return sweep_phaseC<ENC, T>(dir, mask, g, ntiles, w, al, acc, st);
 }
 
 }  // namespace
@@ -1232,7 +1249,7 @@ int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int6
 {
     WMF_REQUIRE(dir && s_k && s_exit_acc && s_link && s_unres && workspace, WMF_E_ARG, "null pointer");
     WMF_REQUIRE(ny >= 2 && nx > 0 && row0 >= 0 && row0 + ny <= ny_total, WMF_E_ARG, "bad stripe geometry (ny >= 2)");
-    WMF_REQUIRE(2 * nx < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "nx too large");
+    WMF_REQUIRE(2 * nx < ((int64_t)1 << 31) && ny * nx < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "a stripe must hold fewer than 2^31 cells");
     WMF_REQUIRE(encoding == WMF_ENC_INTERNAL || encoding == WMF_ENC_KEYPAD, WMF_E_ARG, "unknown encoding");
     cudaStream_t st = (cudaStream_t)stream;
     return encoding == WMF_ENC_INTERNAL
@@ -1245,13 +1262,21 @@ int wmf_d8_stripe_finish(const int8_t *dir, const uint8_t *mask, void *acc, int 
                          const uint8_t *ext_unres, void *workspace, size_t ws_bytes, void *stream)
 {
     WMF_REQUIRE(dir && acc && ext_inflow && workspace, WMF_E_ARG, "null pointer");
-    WMF_REQUIRE(acc_dtype == WMF_ACC_I64 || acc_dtype == WMF_ACC_F64, WMF_E_ARG, "stripes accumulate in int64 (or float64)");
+    WMF_REQUIRE(acc_dtype == WMF_ACC_I32 || acc_dtype == WMF_ACC_I64 || acc_dtype == WMF_ACC_F64, WMF_E_ARG, "unknown acc_dtype");
+    WMF_REQUIRE(!(acc_dtype == WMF_ACC_I32 && ny_total * nx > 0x7fffffffLL), WMF_E_TOO_LARGE,
+                "int32 accumulation can overflow beyond 2^31-1 cells: use WMF_ACC_I64");
     WMF_REQUIRE(ny >= 2 && nx > 0 && row0 >= 0 && row0 + ny <= ny_total, WMF_E_ARG, "bad stripe geometry (ny >= 2)");
     WMF_REQUIRE(encoding == WMF_ENC_INTERNAL || encoding == WMF_ENC_KEYPAD, WMF_E_ARG, "unknown encoding");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = encoding == WMF_ENC_INTERNAL
-                 ? stripe_finish_t<WMF_ENC_INTERNAL>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st)
-                 : stripe_finish_t<WMF_ENC_KEYPAD>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st);
+    int rc;
+    if (acc_dtype == WMF_ACC_I32)
+        rc = encoding == WMF_ENC_INTERNAL
+                 ? stripe_finish_t<WMF_ENC_INTERNAL, int32_t>(dir, mask, (int32_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st)
+                 : stripe_finish_t<WMF_ENC_KEYPAD, int32_t>(dir, mask, (int32_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st);
+    else
+        rc = encoding == WMF_ENC_INTERNAL
+                 ? stripe_finish_t<WMF_ENC_INTERNAL, int64_t>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st)
+                 : stripe_finish_t<WMF_ENC_KEYPAD, int64_t>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st);
     if (rc) return rc;
     if (acc_dtype == WMF_ACC_F64) return d8_convert_i64_to_f64(acc, ny * nx, st);
     return 0;

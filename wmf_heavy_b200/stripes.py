@@ -66,26 +66,34 @@ def boundary_inflow(records: Sequence[Records], forest_fn: Optional[Callable] = 
     parent = torch.where(feeds & (recv_link >= 0), g2 * 2 * nx + recv_link, torch.full_like(recv_link, -1))
     acc, resolved = forest_fn(parent.reshape(-1).to(torch.int32).contiguous(), w.contiguous(), blocked.contiguous())
     feeds_f, recv_f, ok = feeds.reshape(-1), recv.reshape(-1), resolved.reshape(-1) != 0
+    # scatter-adds with zero contributions instead of boolean-mask indexing: no host synchronisation
     inflow = torch.zeros(G * 2 * nx, dtype=torch.int64, device=dev)
-    sel = feeds_f & ok
-    inflow.index_add_(0, recv_f[sel], acc[sel])
-    unres = torch.zeros(G * 2 * nx, dtype=torch.uint8, device=dev)
-    bad = feeds_f & ~ok
-    unres[recv_f[bad]] = 1
-    return inflow.view(G, 2, nx), unres.view(G, 2, nx)
+    inflow.index_add_(0, recv_f, torch.where(feeds_f & ok, acc, torch.zeros_like(acc)))
+    bad = torch.zeros(G * 2 * nx, dtype=torch.int32, device=dev)
+    bad.index_add_(0, recv_f, (feeds_f & ~ok).to(torch.int32))
+    return inflow.view(G, 2, nx), (bad > 0).to(torch.uint8).view(G, 2, nx)
+
+
+def pack_records(rec: Records) -> torch.Tensor:
+    """[2, 2, nx] int64: plane 0 = exit_acc, plane 1 = link (low 32 bits) | k << 32 | unres << 40."""
+    meta = (rec["link"].to(torch.int64) & 0xFFFFFFFF) | (rec["k"].to(torch.int64) << 32) | (rec["unres"].to(torch.int64) << 40)
+    return torch.stack([rec["exit_acc"], meta])
+
+
+def unpack_records(t: torch.Tensor) -> Records:
+    meta = t[1]
+    return {"exit_acc": t[0], "link": (meta & 0xFFFFFFFF).to(torch.int32), "k": ((meta >> 32) & 0xFF).to(torch.int8),
+            "unres": ((meta >> 40) & 1).to(torch.uint8)}
 
 
 def gather_records(rec: Records, group=None) -> List[Records]:
-    """The one exchange step: all-gather every rank's boundary records."""
+    """The one exchange step: a single all-gather of every rank's packed boundary records."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out: List[Records] = [dict() for _ in range(world)]
-    for key, t in rec.items():
-        bufs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(bufs, t.contiguous(), group=group)
-        for g in range(world):
-            out[g][key] = bufs[g]
-    return out
+    mine = pack_records(rec).contiguous()
+    buf = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(buf, mine, group=group)
+    return [unpack_records(buf[g]) for g in range(world)]
 
 
 def accumulate_striped(dir_stripe: torch.Tensor, row0: int, ny_total: int, group=None, encoding: int = ENC_INTERNAL,
@@ -115,7 +123,7 @@ def accumulate_striped_single_device(dir_t: torch.Tensor, n_stripes: int, encodi
         recs.append(rec)
         wss.append(ws)
     inflow, unres = boundary_inflow(recs)
-    out = torch.empty((ny, nx), dtype=torch.int64 if acc_dtype == ACC_I64 else torch.float64, device=dir_t.device)
+    out = torch.empty((ny, nx), dtype=ops._ACC_TORCH[acc_dtype], device=dir_t.device)
     for g, (r0, n) in enumerate(rows):
         m = None if mask_t is None else mask_t[r0:r0 + n].contiguous()
         ops.d8_stripe_finish(dir_t[r0:r0 + n].contiguous(), wss[g], r0, ny, inflow[g].contiguous(), unres[g].contiguous(),
