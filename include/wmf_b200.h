@@ -68,26 +68,28 @@ int wmf_d8_accum(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtyp
 
 /* ---------------------------------------------------------------- D1 on row stripes
  * A raster of ny_total rows is cut into row stripes, one per GPU; this stripe holds rows
- * [row0, row0 + ny), ny >= 2, and accumulates in int64.  Two device phases around ONE exchange:
- *   wmf_d8_stripe_local  solves the stripe in isolation and condenses it to 2*nx boundary records
- *                        (index side*nx + col; side 0 = first row, side 1 = last row):
- *                          s_k        int8   normalised D8 code of the cell (0..7 clockwise from E,
- *                                            8 none, 9 inactive)
- *                          s_exit_acc int64  stripe-local accumulation of a cell draining across the
- *                                            stripe edge (0 elsewhere)
- *                          s_unres    uint8  that accumulation is unresolved (cycle upstream)
- *                          s_link     int32  boundary index where flow ENTERING at this cell leaves the
- *                                            stripe again, -1 if it ends inside
- *   (exchange: all-gather of the records; every rank solves the 2*G*nx-node boundary forest with
- *    wmf_forest_accum and sums, for each of its boundary cells, what arrives from the neighbours --
- *    wmf_heavy_b200/stripes.py)
- *   wmf_d8_stripe_finish injects that inflow (ext_inflow int64 [2][nx], ext_unres uint8 [2][nx]
- *                        nullable) and writes the final acc [ny][nx] (WMF_ACC_I64 or WMF_ACC_F64).
- * The SAME workspace must be passed to both calls (phase-A state lives in it). */
+ * [row0, row0 + ny), ny >= 2 and fewer than 2^31 cells.  Device phases around ONE exchange:
+ *   wmf_d8_stripe_local  solves the stripe in isolation and condenses it to packed boundary records,
+ *                        int64 [2][2][nx] (index side*nx + col in a plane; side 0 = first row, 1 = last row):
+ *                          plane 0  exit_acc: stripe-local accumulation of a cell draining across the
+ *                                   stripe edge (0 elsewhere)
+ *                          plane 1  link (low 32 bits: boundary index where flow ENTERING at this cell
+ *                                   leaves the stripe again, -1 if it ends inside) | k << 32 (normalised D8
+ *                                   code 0..7 clockwise from E, 8 none, 9 inactive) | unres << 40 (that
+ *                                   accumulation is unresolved: cycle upstream)
+ *   (exchange: ONE all-gather of the records -> recs_all int64 [G][2][2][nx])
+ *   wmf_stripe_boundary_inflow  every rank solves the 2*G*nx-node boundary forest and sums, for each
+ *                        boundary cell of stripe `me`, what arrives from the neighbouring stripes:
+ *                        ext_inflow int64 [2][nx], ext_unres uint8 [2][nx]
+ *   wmf_d8_stripe_finish injects that inflow and writes the final acc [ny][nx] (WMF_ACC_I32 only when
+ *                        ny_total*nx < 2^31, WMF_ACC_I64, WMF_ACC_F64).
+ * The SAME workspace must be passed to stripe_local and stripe_finish (phase-A state lives in it). */
 size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx);
 int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
-                        int encoding, int8_t *s_k, int64_t *s_exit_acc, int32_t *s_link, uint8_t *s_unres,
-                        void *workspace, size_t ws_bytes, void *stream);
+                        int encoding, int64_t *records, void *workspace, size_t ws_bytes, void *stream);
+size_t wmf_stripe_boundary_workspace(int G, int64_t nx);
+int wmf_stripe_boundary_inflow(const int64_t *recs_all, int G, int64_t nx, int me, int64_t *ext_inflow,
+                               uint8_t *ext_unres, void *workspace, size_t ws_bytes, void *stream);
 int wmf_d8_stripe_finish(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx,
                          int64_t row0, int64_t ny_total, int encoding, const int64_t *ext_inflow,
                          const uint8_t *ext_unres, void *workspace, size_t ws_bytes, void *stream);

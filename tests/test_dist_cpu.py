@@ -29,8 +29,8 @@ def _worker(rank, world, port, fd, q):
         r0, n = rows[rank]
         acc_local = oracle.basin_acum(fd[r0:r0 + n], np.ones((n, fd.shape[1]), bool))
         rec = {k: torch.from_numpy(v) for k, v in helpers.stripe_records_numpy(fd, r0, n, acc_local).items()}
-        allrec = stripes.gather_records(rec)
-        inflow, unres = stripes.boundary_inflow(allrec, forest_fn=_forest_cpu)
+        recs_all = stripes.gather_records(stripes.pack_records(rec))
+        inflow, unres = stripes.stripe_inflow(recs_all, rank, forest_fn=_forest_cpu)
         # SHIA shard bookkeeping: per-shard diagnostics recombine to the whole-basin ones
         N, T = 101, 7
         rng = np.random.default_rng(5)
@@ -69,7 +69,7 @@ def test_stripe_exchange_gloo_world2(kind):
     acc_full = oracle.basin_acum(fd, np.ones(fd.shape, bool))
     exp = helpers.expected_stripe_inflow(fd, acc_full, stripes.stripe_rows(fd.shape[0], world))
     for rank, inflow, unres, bal, mr, bal_exp, mr_exp in res:
-        assert np.array_equal(inflow, exp), f"rank {rank}"
+        assert np.array_equal(inflow, exp[rank]), f"rank {rank}"
         assert not unres.any()
         np.testing.assert_allclose(bal, bal_exp, rtol=1e-6)
         np.testing.assert_allclose(mr, mr_exp, rtol=1e-6)

@@ -40,11 +40,25 @@ def test_striped_records_match_numpy_restatement():
     fd = ops.synth_scheidegger_host(130, 200, seed=11)
     rows = stripes.stripe_rows(130, 2)
     for r0, n in rows:
-        rec, _ = ops.d8_stripe_local(torch.from_numpy(fd[r0:r0 + n].copy()).cuda(), r0, 130)
+        packed, _ = ops.d8_stripe_local(torch.from_numpy(fd[r0:r0 + n].copy()).cuda(), r0, 130)
+        rec = stripes.unpack_records(packed)
         acc_local = oracle.basin_acum(fd[r0:r0 + n], np.ones((n, 200), bool))
         exp = helpers.stripe_records_numpy(fd, r0, n, acc_local)
         for key in ("k", "exit_acc", "link", "unres"):
             assert np.array_equal(rec[key].cpu().numpy(), exp[key]), key
+        assert torch.equal(stripes.pack_records(rec), packed)
+
+
+def test_boundary_kernels_match_tensor_restatement():
+    """The library's boundary forest kernels == the tensor-indexing restatement the CPU/gloo tests cover."""
+    fd = helpers.random_codes(211, 157, 12, lo=0, hi=8)           # includes cycles across stripes
+    d = torch.from_numpy(fd).cuda()
+    rows = stripes.stripe_rows(211, 4)
+    recs = torch.stack([ops.d8_stripe_local(d[r0:r0 + n].contiguous(), r0, 211)[0] for r0, n in rows])
+    ref_in, ref_un = stripes.boundary_inflow([stripes.unpack_records(recs[g]) for g in range(4)])
+    for g in range(4):
+        inflow, unres = ops.stripe_boundary_inflow(recs, g)
+        assert torch.equal(inflow, ref_in[g]) and torch.equal(unres, ref_un[g])
 
 
 def test_striped_full_size_int64_and_f64():

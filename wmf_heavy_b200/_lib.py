@@ -49,7 +49,9 @@ SIGNATURES = {
     "wmf_d8_accum_workspace": (_sz, [_i64, _i64, _int, _int]),
     "wmf_d8_accum": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _int, _int, _vp, _sz, _vp]),
     "wmf_d8_stripe_workspace": (_sz, [_i64, _i64]),
-    "wmf_d8_stripe_local": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "wmf_d8_stripe_local": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _sz, _vp]),
+    "wmf_stripe_boundary_workspace": (_sz, [_int, _i64]),
+    "wmf_stripe_boundary_inflow": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     "wmf_d8_stripe_finish": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     "wmf_forest_accum_workspace": (_sz, [_i64]),
     "wmf_forest_accum": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),

@@ -959,14 +959,13 @@ __device__ __forceinline__ int64_t first_exit(const uint32_t *__restrict__ meta,
     return l == LNONE ? -1 : (e0 / NSLOT) * NSLOT + l;
 }
 
-// s_k: normalised code of the boundary cell (8 none, 9 inactive); s_exit_acc: stripe-local total of a
-// stripe exit; s_unres: the exit is locally unresolved; s_link: boundary index (side*nx + col) of the
-// stripe exit that flow entering at this cell reaches, -1 if it ends inside the stripe.
+// Packed boundary records, int64 [2][2][nx] (index side*nx + col inside a plane):
+//   plane 0  exit_acc: stripe-local total of a cell draining across the stripe edge (0 elsewhere)
+//   plane 1  link (low 32 bits: boundary index where flow ENTERING here leaves the stripe, -1 = ends inside)
+//            | k << 32 (normalised code, 8 none, 9 inactive) | unres << 40 (the exit is locally unresolved)
 __global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
                                  const int32_t *__restrict__ entry, const int32_t *__restrict__ stripe_total,
-                                 const unsigned long long *__restrict__ wq, int8_t *__restrict__ s_k,
-                                 int64_t *__restrict__ s_exit_acc, int32_t *__restrict__ s_link,
-                                 uint8_t *__restrict__ s_unres)
+                                 const unsigned long long *__restrict__ wq, int64_t *__restrict__ recs)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * g.nx) return;
@@ -980,9 +979,9 @@ __global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restri
     const bool is_exit = active && entry[node] == -2 &&
                          ((side == 0 && k >= 5 && k <= 7) || (side == 1 && k >= 1 && k <= 3));
     const bool resolved = (uint32_t)(wq[node] >> 32) == 0u;
-    s_k[i] = (int8_t)(active ? k : 9);
-    s_exit_acc[i] = (is_exit && resolved) ? (int64_t)stripe_total[node] : 0;
-    s_unres[i] = (is_exit && !resolved) ? 1 : 0;
+    const int64_t rec_k = active ? k : 9;
+    const int64_t rec_unres = (is_exit && !resolved) ? 1 : 0;
+    recs[i] = (is_exit && resolved) ? (int64_t)stripe_total[node] : 0;       // plane 0: exit_acc
     int32_t link = -1;
     if (active) {
         int64_t x = first_exit(meta, node);
@@ -1000,7 +999,7 @@ __global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restri
             link = (int32_t)((row == 0 ? 0 : 1) * g.nx + c2);
         }
     }
-    s_link[i] = link;
+    recs[2 * g.nx + i] = (int64_t)(uint32_t)link | (rec_k << 32) | (rec_unres << 40);   // plane 1: link | k | unres
 }
 
 template <typename T>
@@ -1161,8 +1160,7 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
 // the finish pass is typed by the output accumulation.
 template <int ENC>
 int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
-                   int8_t *s_k, int64_t *s_exit_acc, int32_t *s_link, uint8_t *s_unres, void *ws, size_t ws_bytes,
-                   cudaStream_t st)
+                   int64_t *recs, void *ws, size_t ws_bytes, cudaStream_t st)
 {
     const Geo g = make_geo(ny, nx, row0, ny_total);
     const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
@@ -1180,8 +1178,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
     k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, inflow32, stripe_total);
     k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class);
-    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, stripe_total, w.wq, s_k,
-                                                            s_exit_acc, s_link, s_unres);
+    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, stripe_total, w.wq, recs);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1244,17 +1241,16 @@ extern "C" {
 size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx) { return d8_sweep_workspace(ny, nx, WMF_ACC_I64); }
 
 int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
-                        int encoding, int8_t *s_k, int64_t *s_exit_acc, int32_t *s_link, uint8_t *s_unres,
-                        void *workspace, size_t ws_bytes, void *stream)
+                        int encoding, int64_t *records, void *workspace, size_t ws_bytes, void *stream)
 {
-    WMF_REQUIRE(dir && s_k && s_exit_acc && s_link && s_unres && workspace, WMF_E_ARG, "null pointer");
+    WMF_REQUIRE(dir && records && workspace, WMF_E_ARG, "null pointer");
     WMF_REQUIRE(ny >= 2 && nx > 0 && row0 >= 0 && row0 + ny <= ny_total, WMF_E_ARG, "bad stripe geometry (ny >= 2)");
     WMF_REQUIRE(2 * nx < ((int64_t)1 << 31) && ny * nx < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "a stripe must hold fewer than 2^31 cells");
     WMF_REQUIRE(encoding == WMF_ENC_INTERNAL || encoding == WMF_ENC_KEYPAD, WMF_E_ARG, "unknown encoding");
     cudaStream_t st = (cudaStream_t)stream;
     return encoding == WMF_ENC_INTERNAL
-               ? stripe_local_t<WMF_ENC_INTERNAL>(dir, mask, ny, nx, row0, ny_total, s_k, s_exit_acc, s_link, s_unres, workspace, ws_bytes, st)
-               : stripe_local_t<WMF_ENC_KEYPAD>(dir, mask, ny, nx, row0, ny_total, s_k, s_exit_acc, s_link, s_unres, workspace, ws_bytes, st);
+               ? stripe_local_t<WMF_ENC_INTERNAL>(dir, mask, ny, nx, row0, ny_total, records, workspace, ws_bytes, st)
+               : stripe_local_t<WMF_ENC_KEYPAD>(dir, mask, ny, nx, row0, ny_total, records, workspace, ws_bytes, st);
 }
 
 int wmf_d8_stripe_finish(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx,

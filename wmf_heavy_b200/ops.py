@@ -289,7 +289,7 @@ def forest_accum(parent: torch.Tensor, weight: Optional[torch.Tensor] = None, bl
 
 def d8_stripe_local(dir_t: torch.Tensor, row0: int, ny_total: int, mask_t: Optional[torch.Tensor] = None,
                     encoding: int = ENC_INTERNAL):
-    """Phase 1 of the striped accumulation -> (records dict of [2, nx] tensors, private workspace tensor)."""
+    """Phase 1 of the striped accumulation -> (packed boundary records int64 [2, 2, nx], private workspace)."""
     dev = require_cuda()
     _chk_dev(dir_t, torch.int8, "dir")
     ny, nx = dir_t.shape
@@ -297,14 +297,25 @@ def d8_stripe_local(dir_t: torch.Tensor, row0: int, ny_total: int, mask_t: Optio
         _chk_dev(mask_t, torch.uint8, "mask")
     lib = _lib.load()
     ws = torch.empty(lib.wmf_d8_stripe_workspace(ny, nx), dtype=torch.uint8, device=dev)   # lives until finish
-    rec = {"k": torch.empty((2, nx), dtype=torch.int8, device=dev),
-           "exit_acc": torch.empty((2, nx), dtype=torch.int64, device=dev),
-           "link": torch.empty((2, nx), dtype=torch.int32, device=dev),
-           "unres": torch.empty((2, nx), dtype=torch.uint8, device=dev)}
-    check(lib.wmf_d8_stripe_local(ptr(dir_t), ptr(mask_t), ny, nx, int(row0), int(ny_total), encoding, ptr(rec["k"]),
-                                  ptr(rec["exit_acc"]), ptr(rec["link"]), ptr(rec["unres"]), ptr(ws), ws.numel(),
-                                  stream_ptr()))
+    rec = torch.empty((2, 2, nx), dtype=torch.int64, device=dev)
+    check(lib.wmf_d8_stripe_local(ptr(dir_t), ptr(mask_t), ny, nx, int(row0), int(ny_total), encoding, ptr(rec),
+                                  ptr(ws), ws.numel(), stream_ptr()))
     return rec, ws
+
+
+def stripe_boundary_inflow(recs_all: torch.Tensor, me: int):
+    """Boundary forest of all stripes (recs_all int64 [G, 2, 2, nx]) -> (ext_inflow int64 [2, nx],
+    ext_unres uint8 [2, nx]) of stripe `me`."""
+    require_cuda()
+    _chk_dev(recs_all, torch.int64, "recs_all")
+    G, _, _, nx = recs_all.shape
+    inflow = torch.empty((2, nx), dtype=torch.int64, device=recs_all.device)
+    unres = torch.empty((2, nx), dtype=torch.uint8, device=recs_all.device)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_stripe_boundary_workspace(G, nx))
+    check(lib.wmf_stripe_boundary_inflow(ptr(recs_all), G, nx, int(me), ptr(inflow), ptr(unres), ptr(ws), ws.numel(),
+                                         stream_ptr()))
+    return inflow, unres
 
 
 def d8_stripe_finish(dir_t: torch.Tensor, ws: torch.Tensor, row0: int, ny_total: int, ext_inflow: torch.Tensor,

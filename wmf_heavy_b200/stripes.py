@@ -4,8 +4,8 @@ GPU g owns rows [row0_g, row0_g + ny_g) of a raster too large (or too slow) for 
     1. local   every rank solves its stripe in isolation and condenses it to 2*nx boundary records
                (ops.d8_stripe_local);
     2. exchange ONE all-gather of the records (NCCL over NVLink; ~15 bytes per boundary cell);
-    3. boundary every rank redundantly solves the 2*G*nx-node boundary forest (ops.forest_accum) and
-               sums, for each of its own boundary cells, what the neighbouring stripes send in;
+    3. boundary every rank redundantly solves the 2*G*nx-node boundary forest and sums, for each of its own
+               boundary cells, what the neighbouring stripes send in (ops.stripe_boundary_inflow);
     4. finish  every rank injects that inflow and writes its final ACC rows (ops.d8_stripe_finish).
 Integer adds make the result bit-identical to the single-device accumulation.  The boundary logic
 (`boundary_inflow`) is plain tensor indexing and runs on any device, so it is covered on CPU with
@@ -75,9 +75,10 @@ def boundary_inflow(records: Sequence[Records], forest_fn: Optional[Callable] = 
 
 
 def pack_records(rec: Records) -> torch.Tensor:
-    """[2, 2, nx] int64: plane 0 = exit_acc, plane 1 = link (low 32 bits) | k << 32 | unres << 40."""
+    """[2, 2, nx] int64: plane 0 = exit_acc, plane 1 = link (low 32 bits) | k << 32 | unres << 40
+    (the layout wmf_d8_stripe_local writes, include/wmf_b200.h)."""
     meta = (rec["link"].to(torch.int64) & 0xFFFFFFFF) | (rec["k"].to(torch.int64) << 32) | (rec["unres"].to(torch.int64) << 40)
-    return torch.stack([rec["exit_acc"], meta])
+    return torch.stack([rec["exit_acc"].to(torch.int64), meta])
 
 
 def unpack_records(t: torch.Tensor) -> Records:
@@ -86,14 +87,23 @@ def unpack_records(t: torch.Tensor) -> Records:
             "unres": ((meta >> 40) & 1).to(torch.uint8)}
 
 
-def gather_records(rec: Records, group=None) -> List[Records]:
-    """The one exchange step: a single all-gather of every rank's packed boundary records."""
+def gather_records(rec_packed: torch.Tensor, group=None) -> torch.Tensor:
+    """The one exchange step: a single all-gather of the packed boundary records -> [G, 2, 2, nx]."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    mine = pack_records(rec).contiguous()
-    buf = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-    dist.all_gather_into_tensor(buf, mine, group=group)
-    return [unpack_records(buf[g]) for g in range(world)]
+    bufs = [torch.empty_like(rec_packed) for _ in range(world)]
+    dist.all_gather(bufs, rec_packed.contiguous(), group=group)
+    return torch.stack(bufs)
+
+
+def stripe_inflow(recs_all: torch.Tensor, me: int, forest_fn: Optional[Callable] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(ext_inflow [2, nx], ext_unres [2, nx]) of stripe `me`.  CUDA tensors go through the library's boundary
+    kernels; CPU tensors (tests, gloo) through the tensor-indexing restatement above."""
+    if recs_all.is_cuda and forest_fn is None:
+        return ops.stripe_boundary_inflow(recs_all.contiguous(), me)
+    inflow, unres = boundary_inflow([unpack_records(recs_all[g]) for g in range(recs_all.shape[0])], forest_fn)
+    return inflow[me].contiguous(), unres[me].contiguous()
 
 
 def accumulate_striped(dir_stripe: torch.Tensor, row0: int, ny_total: int, group=None, encoding: int = ENC_INTERNAL,
@@ -103,11 +113,9 @@ def accumulate_striped(dir_stripe: torch.Tensor, row0: int, ny_total: int, group
     Ranks must own the stripes in rank order."""
     import torch.distributed as dist
     rec, ws = ops.d8_stripe_local(dir_stripe, row0, ny_total, mask_stripe, encoding)
-    allrec = gather_records(rec, group)
-    inflow, unres = boundary_inflow(allrec)
-    me = dist.get_rank(group)
-    return ops.d8_stripe_finish(dir_stripe, ws, row0, ny_total, inflow[me].contiguous(), unres[me].contiguous(),
-                                mask_stripe, encoding, acc_dtype, out)
+    recs_all = gather_records(rec, group)
+    inflow, unres = stripe_inflow(recs_all, dist.get_rank(group))
+    return ops.d8_stripe_finish(dir_stripe, ws, row0, ny_total, inflow, unres, mask_stripe, encoding, acc_dtype, out)
 
 
 def accumulate_striped_single_device(dir_t: torch.Tensor, n_stripes: int, encoding: int = ENC_INTERNAL,
@@ -122,10 +130,11 @@ def accumulate_striped_single_device(dir_t: torch.Tensor, n_stripes: int, encodi
         rec, ws = ops.d8_stripe_local(dir_t[r0:r0 + n].contiguous(), r0, ny, m, encoding)
         recs.append(rec)
         wss.append(ws)
-    inflow, unres = boundary_inflow(recs)
+    recs_all = torch.stack(recs)
     out = torch.empty((ny, nx), dtype=ops._ACC_TORCH[acc_dtype], device=dir_t.device)
     for g, (r0, n) in enumerate(rows):
         m = None if mask_t is None else mask_t[r0:r0 + n].contiguous()
-        ops.d8_stripe_finish(dir_t[r0:r0 + n].contiguous(), wss[g], r0, ny, inflow[g].contiguous(), unres[g].contiguous(),
-                             m, encoding, acc_dtype, out[r0:r0 + n])
+        inflow, unres = stripe_inflow(recs_all, g)
+        ops.d8_stripe_finish(dir_t[r0:r0 + n].contiguous(), wss[g], r0, ny, inflow, unres, m, encoding, acc_dtype,
+                             out[r0:r0 + n])
     return out
