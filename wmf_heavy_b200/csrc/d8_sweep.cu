@@ -201,49 +201,94 @@ __device__ __forceinline__ void sweep_row_down(const int (&k)[4], int am, const 
 // ---------------------------------------------------------------------------------------------
 // fast solver: staging, row classification and the lean "plain row" step
 // ---------------------------------------------------------------------------------------------
-// Stage the tile's raw DIR words (4 codes per lane per row) -- and the active nibbles when the
-// tile has a mask or is ragged -- into shared memory with asynchronous copies, so the sweeps never
-// wait on HBM row by row.
+// The tile's raw DIR words (4 codes per lane per row) -- and the mask words when there is a mask --
+// stream through shared memory in chunks of CH rows, double buffered with cp.async (LDGSTS): while a
+// chunk is swept the next one is in flight, so the sweeps never wait on HBM row by row and a warp
+// holds only 2 * CH rows (2 KB) of shared memory, which keeps occupancy register-bound.
+constexpr int CH = 8;
 template <bool AL>
-__device__ __forceinline__ void stage_tile(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, const Geo &g,
-                                           int64_t gr0, int64_t gc0, int th, bool need_active,
-                                           uint32_t (*wrow)[32], uint8_t (*arow)[32], int lane)
-{
-    if (AL && gc0 + 3 < g.nx) {
-        const int8_t *src = dir + gr0 * g.nx + gc0;
-        for (int lr = 0; lr < th; lr++) {
-            __pipeline_memcpy_async(&wrow[lr][lane], src, 4);
-            src += g.nx;
-        }
-        __pipeline_commit();
-        if (need_active) {
-            for (int lr = 0; lr < th; lr++) {
-                uint32_t mw = 0x01010101u;
-                if (mask) mw = *reinterpret_cast<const uint32_t *>(mask + (gr0 + lr) * g.nx + gc0);
-                int am = 0;
+struct TileRows {
+    uint32_t *wbase, *mbase;    // this lane's column of the two DIR / mask chunk buffers (stride 32 per row, CH*32 per buffer)
+    const int8_t *dir0;         // &dir[gr0][gc0]
+    const uint8_t *mask0;       // &mask[gr0][gc0] or nullptr
+    int64_t nx, gc0;
+    int th;
+
+    __device__ __forceinline__ void init(uint32_t *smem_words, int warp, int lane, const int8_t *dir, const uint8_t *mask,
+                                         int64_t nx_, int64_t gr0, int64_t gc0_, int th_)
+    {
+        wbase = smem_words + (size_t)warp * 2 * CH * 32 + lane;
+        mbase = smem_words + (size_t)(WPB + warp) * 2 * CH * 32 + lane;
+        dir0 = dir + gr0 * nx_ + gc0_;
+        mask0 = mask ? mask + gr0 * nx_ + gc0_ : nullptr;
+        nx = nx_; gc0 = gc0_; th = th_;
+    }
+    __device__ __forceinline__ void prefetch(int c) const      // chunk c -> buffer c & 1
+    {
+        uint32_t *dw = wbase + (c & 1) * CH * 32, *dm = mbase + (c & 1) * CH * 32;
+        const int r0 = c * CH;
+        if (AL) {
+            if (gc0 < nx) {
+                const int8_t *sd = dir0 + (int64_t)r0 * nx;
+                const uint8_t *sm = mask0 ? mask0 + (int64_t)r0 * nx : nullptr;
+                if (r0 + CH <= th) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) am |= (int)(((mw >> (8 * j)) & 0xFFu) != 0) << j;
-                arow[lr][lane] = (uint8_t)am;
+                    for (int r = 0; r < CH; r++, sd += nx) __pipeline_memcpy_async(dw + r * 32, sd, 4);
+                    if (sm) {
+#pragma unroll
+                        for (int r = 0; r < CH; r++, sm += nx) __pipeline_memcpy_async(dm + r * 32, sm, 4);
+                    }
+                } else {
+                    for (int r = 0; r0 + r < th; r++, sd += nx) {
+                        __pipeline_memcpy_async(dw + r * 32, sd, 4);
+                        if (sm) { __pipeline_memcpy_async(dm + r * 32, sm, 4); sm += nx; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < CH; r++) { dw[r * 32] = 0; if (mask0) dm[r * 32] = 0; }
+            }
+        } else {
+            for (int r = 0; r < CH && r0 + r < th; r++) {
+                uint32_t ww = 0, mm = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (gc0 + j < nx) {
+                        const int64_t o = (int64_t)(r0 + r) * nx + j;
+                        ww |= (uint32_t)(uint8_t)dir0[o] << (8 * j);
+                        if (mask0) mm |= (uint32_t)(mask0[o] != 0) << (8 * j);
+                    }
+                dw[r * 32] = ww;
+                if (mask0) dm[r * 32] = mm;
             }
         }
-        __pipeline_wait_prior(0);
-    } else {
-        for (int lr = 0; lr < th; lr++) {
-            uint32_t w = 0;
-            int am = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (gc0 + j < g.nx) {
-                    int64_t gi = (gr0 + lr) * g.nx + gc0 + j;
-                    w |= (uint32_t)(uint8_t)dir[gi] << (8 * j);
-                    am |= (int)(mask ? (mask[gi] != 0) : 1) << j;
-                }
-            wrow[lr][lane] = w;
-            arow[lr][lane] = (uint8_t)am;
-        }
+        __pipeline_commit();
     }
-    __syncwarp();
-}
+    // chunk c has arrived; start fetching chunk `next` (or nothing when out of range) into the other buffer
+    __device__ __forceinline__ void arrive(int next, int nchunks) const
+    {
+        __pipeline_wait_prior(0);
+        __syncwarp();
+        if (next >= 0 && next < nchunks) prefetch(next);
+    }
+    // this lane's words of chunk c: row r of the chunk at [r * 32]
+    __device__ __forceinline__ const uint32_t *chunk(int c) const { return wbase + (c & 1) * CH * 32; }
+    __device__ __forceinline__ uint32_t word(int lr) const { return wbase[((lr / CH) & 1) * CH * 32 + (lr % CH) * 32]; }
+    // active nibble of the lane's 4 cells in row lr
+    __device__ __forceinline__ int active(int lr) const
+    {
+        int am = 0;
+        if (mask0) {
+            const uint32_t mw = mbase[((lr / CH) & 1) * CH * 32 + (lr % CH) * 32];
+#pragma unroll
+            for (int j = 0; j < 4; j++) am |= (int)(((mw >> (8 * j)) & 0xFFu) != 0 && gc0 + j < nx) << j;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) am |= (int)(gc0 + j < nx) << j;
+        }
+        return am;
+    }
+};
 
 // decode a staged word: k[4] (8 = none; inactive cells are none) ; on border tiles a code whose
 // receiver lies outside the raster becomes none.
@@ -373,14 +418,13 @@ __device__ __forceinline__ void plain_row_up(uint32_t k, uint32_t (&lb)[4], int 
 // phase A, fast solver
 // ---------------------------------------------------------------------------------------------
 template <int ENC, bool AL>
-__global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
-                                                     Geo g, int ntiles, uint32_t *__restrict__ meta,
-                                                     int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
-                                                     unsigned long long *__restrict__ row_plain,
-                                                     unsigned long long *__restrict__ wq)
+__global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+                                                        Geo g, int ntiles, uint32_t *__restrict__ meta,
+                                                        int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
+                                                        unsigned long long *__restrict__ row_plain,
+                                                        unsigned long long *__restrict__ wq)
 {
-    __shared__ uint32_t s_w[WPB][TH][32];            // staged DIR words
-    __shared__ uint8_t s_a[WPB][TH][32];             // active nibbles (masked / ragged tiles only)
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][32] DIR words (+ the same again for mask words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
@@ -395,126 +439,143 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepA(const int8_t *__restrict__ 
     const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
     const bool full = th == TH && tw == TW;
     const bool plain_tile = mask == nullptr && full && !border;
-    uint32_t (*wrow)[32] = s_w[warp];
-    uint8_t (*arow)[32] = s_a[warp];
-    stage_tile<AL>(dir, mask, g, gr0, gc0, th, !(mask == nullptr && full), wrow, arow, lane);
+    TileRows<AL> rows;
+    rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
+    const int nch = (th + CH - 1) / CH;
 
     // ---- downward sweep: local accumulation
     int32_t d[4] = {1, 1, 1, 1};                     // 1 + inflow from the row above
     bool complex_tile = false;
     unsigned long long plain_rows = 0;               // bit lr set: row lr takes the lean path (both sweeps, phase C too)
-    for (int lr = 0; lr < th; lr++) {
-        const uint32_t w = wrow[lr][lane];
-        int32_t tot[4];
-        const bool edge_row = lr == 0 || lr == th - 1;
-        bool gen = true;
-        uint32_t kw = 0;
-        if (plain_tile && !edge_row) { kw = plain_word<ENC>(w, gen); gen = __any_sync(FULL, gen); }
-        if (!gen) {
-            plain_rows |= 1ull << lr;
-            if (ENC != WMF_ENC_INTERNAL) wrow[lr][lane] = kw;     // keep the translated word for the upward sweep
-            plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
-        } else {
-            int k[4];
-            const int am = (mask == nullptr && full) ? 0xF : arow[lr][lane];
-            decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
-            if (lr > 0) {
-                bool up = (k[0] >= 5 && k[0] <= 7) || (k[1] >= 5 && k[1] <= 7) || (k[2] >= 5 && k[2] <= 7) || (k[3] >= 5 && k[3] <= 7);
-                complex_tile = complex_tile || __any_sync(FULL, up);
+    rows.prefetch(0);
+    for (int c = 0; c < nch && !complex_tile; c++) {
+        rows.arrive(c + 1, nch);
+        const int cend = th < (c + 1) * CH ? th : (c + 1) * CH;
+        const uint32_t *wp = rows.chunk(c);
+        for (int lr = c * CH; lr < cend; lr++) {
+            const uint32_t w = wp[(lr - c * CH) * 32];
+            int32_t tot[4];
+            const bool edge_row = lr == 0 || lr == th - 1;
+            bool gen = true;
+            uint32_t kw = 0;
+            if (plain_tile && !edge_row) { kw = plain_word<ENC>(w, gen); gen = __any_sync(FULL, gen); }
+            if (!gen) {
+                plain_rows |= 1ull << lr;
+                plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
+            } else {
+                int k[4];
+                const int am = rows.active(lr);
+                decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
+                if (lr > 0) {
+                    bool up = (k[0] >= 5 && k[0] <= 7) || (k[1] >= 5 && k[1] <= 7) || (k[2] >= 5 && k[2] <= 7) || (k[3] >= 5 && k[3] <= 7);
+                    complex_tile = complex_tile || __any_sync(FULL, up);
+                }
+                int32_t b[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] : 0;
+                sweep_row_down<int32_t>(k, am, b, tot, d, lane, complex_tile);
+                if (complex_tile) break;
+#pragma unroll
+                for (int j = 0; j < 4; j++) d[j] += 1;
             }
-            int32_t b[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] : 0;
-            sweep_row_down<int32_t>(k, am, b, tot, d, lane, complex_tile);
-            if (complex_tile) break;
-#pragma unroll
-            for (int j = 0; j < 4; j++) d[j] += 1;
-        }
-        if (lr == 0) *reinterpret_cast<int4 *>(x_t + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
-        else if (lr == th - 1) *reinterpret_cast<int4 *>(x_t + TW + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
-        else {
-            if (lane == 0) x_t[2 * TW + lr] = tot[0];
-            if (lane == rlane && tw > 1) x_t[2 * TW + TH + lr] = tot[rj];
+            if (lr == 0) *reinterpret_cast<int4 *>(x_t + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
+            else if (lr == th - 1) *reinterpret_cast<int4 *>(x_t + TW + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
+            else {
+                if (lane == 0) x_t[2 * TW + lr] = tot[0];
+                if (lane == rlane && tw > 1) x_t[2 * TW + TH + lr] = tot[rj];
+            }
         }
     }
+    __pipeline_wait_prior(0);
+    __syncwarp();
     if (complex_tile) {                              // the general solver redoes this tile
         if (lane == 0) tile_class[tile] = 1;
         return;
     }
     if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
 
-    // ---- upward sweep: exit labels
+    // ---- upward sweep: exit labels (the chunks come back from L2 in reverse order)
     uint32_t lb[4] = {LNONE, LNONE, LNONE, LNONE};   // labels of the row below
-    for (int lr = th - 1; lr >= 0; lr--) {
-        {   // a run of lean rows going up
-            unsigned long long rest = ~(plain_rows << (63 - lr));
-            const int run = rest ? __clzll((long long)rest) : lr + 1;
-            for (const int end = lr - run; lr > end; lr--) {
-                uint32_t mL, mR;
-                plain_row_up(wrow[lr][lane], lb, lr, lane, mL, mR);
-                if (lane == 0) { m_t[2 * TW + lr] = mL; w_t[2 * TW + lr] = BIAS; }
-                if (lane == 31) { m_t[2 * TW + TH + lr] = mR; w_t[2 * TW + TH + lr] = BIAS; }
+    rows.prefetch(nch - 1);
+    for (int c = nch - 1; c >= 0; c--) {
+        rows.arrive(c - 1, nch);
+        const int cbeg = c * CH;
+        const uint32_t *wp = rows.chunk(c);
+        int lr = (th < (c + 1) * CH ? th : (c + 1) * CH) - 1;
+        while (lr >= cbeg) {
+            {   // a run of lean rows going up (bounded by the chunk)
+                unsigned long long rest = ~(plain_rows << (63 - lr));
+                int run = rest ? __clzll((long long)rest) : lr + 1;
+                run = run < lr - cbeg + 1 ? run : lr - cbeg + 1;
+                for (const int end = lr - run; lr > end; lr--) {
+                    uint32_t mL, mR;
+                    bool gen;
+                    plain_row_up(plain_word<ENC>(wp[(lr - cbeg) * 32], gen), lb, lr, lane, mL, mR);
+                    if (lane == 0) { m_t[2 * TW + lr] = mL; w_t[2 * TW + lr] = BIAS; }
+                    if (lane == 31) { m_t[2 * TW + TH + lr] = mR; w_t[2 * TW + TH + lr] = BIAS; }
+                }
+                if (lr < cbeg) break;
             }
-            if (lr < 0) break;
-        }
-        const uint32_t w = wrow[lr][lane];
-        int k[4];
-        const int am = (mask == nullptr && full) ? 0xF : arow[lr][lane];
-        decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
-        uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left3 = __shfl_up_sync(FULL, lb[3], 1);
-        uint32_t own[4];
-        bool pe[4], pw[4];
+            const uint32_t w = wp[(lr - cbeg) * 32];
+            int k[4];
+            const int am = rows.active(lr);
+            decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
+            uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left3 = __shfl_up_sync(FULL, lb[3], 1);
+            uint32_t own[4];
+            bool pe[4], pw[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int lc = 4 * lane + j, kk = k[j];
-            const bool top = lr == 0, bot = lr == th - 1, lft = lc == 0, rgt = lc == tw - 1;
-            bool exits = (bot && kk >= 1 && kk <= 3) || (top && kk >= 5 && kk <= 7) ||
-                         (rgt && (kk == 0 || kk == 1 || kk == 7)) || (lft && kk >= 3 && kk <= 5);
-            uint32_t v = LNONE;
-            pe[j] = pw[j] = false;
-            if (kk != 8) {
-                if (exits) v = (uint32_t)slot_of(lr, lc, th, tw);
-                else if (kk == 2) v = lb[j];
-                else if (kk == 1) v = (j < 3) ? lb[j < 3 ? j + 1 : 3] : lb_right0;
-                else if (kk == 3) v = (j > 0) ? lb[j > 0 ? j - 1 : 0] : lb_left3;
-                else if (kk == 0) pe[j] = true;
-                else if (kk == 4) pw[j] = true;
+            for (int j = 0; j < 4; j++) {
+                const int lc = 4 * lane + j, kk = k[j];
+                const bool top = lr == 0, bot = lr == th - 1, lft = lc == 0, rgt = lc == tw - 1;
+                bool exits = (bot && kk >= 1 && kk <= 3) || (top && kk >= 5 && kk <= 7) ||
+                             (rgt && (kk == 0 || kk == 1 || kk == 7)) || (lft && kk >= 3 && kk <= 5);
+                uint32_t v = LNONE;
+                pe[j] = pw[j] = false;
+                if (kk != 8) {
+                    if (exits) v = (uint32_t)slot_of(lr, lc, th, tw);
+                    else if (kk == 2) v = lb[j];
+                    else if (kk == 1) v = (j < 3) ? lb[j < 3 ? j + 1 : 3] : lb_right0;
+                    else if (kk == 3) v = (j > 0) ? lb[j > 0 ? j - 1 : 0] : lb_left3;
+                    else if (kk == 0) pe[j] = true;
+                    else if (kk == 4) pw[j] = true;
+                }
+                own[j] = v;
             }
-            own[j] = v;
-        }
-        uint32_t lab[4];
-        {   // East cells copy the label of the chain end on their right
-            uint32_t V = LNONE;
-            bool P = true;
+            uint32_t lab[4];
+            {   // East cells copy the label of the chain end on their right
+                uint32_t V = LNONE;
+                bool P = true;
 #pragma unroll
-            for (int j = 3; j >= 0; j--) { V = pe[j] ? V : own[j]; P = P && pe[j]; }
-            uint32_t cur = label_carry_from_right(V, P, lane);
+                for (int j = 3; j >= 0; j--) { V = pe[j] ? V : own[j]; P = P && pe[j]; }
+                uint32_t cur = label_carry_from_right(V, P, lane);
 #pragma unroll
-            for (int j = 3; j >= 0; j--) { cur = pe[j] ? cur : own[j]; lab[j] = cur; }
-        }
-        if (__any_sync(FULL, pw[0] || pw[1] || pw[2] || pw[3])) {
-            uint32_t V = LNONE;
-            bool P = true;
+                for (int j = 3; j >= 0; j--) { cur = pe[j] ? cur : own[j]; lab[j] = cur; }
+            }
+            if (__any_sync(FULL, pw[0] || pw[1] || pw[2] || pw[3])) {
+                uint32_t V = LNONE;
+                bool P = true;
 #pragma unroll
-            for (int j = 0; j < 4; j++) { V = pw[j] ? V : lab[j]; P = P && pw[j]; }
-            uint32_t cur = label_carry_from_left(V, P, lane);
+                for (int j = 0; j < 4; j++) { V = pw[j] ? V : lab[j]; P = P && pw[j]; }
+                uint32_t cur = label_carry_from_left(V, P, lane);
 #pragma unroll
-            for (int j = 0; j < 4; j++) { cur = pw[j] ? cur : lab[j]; lab[j] = cur; }
-        }
-        uint32_t mw[4];
+                for (int j = 0; j < 4; j++) { cur = pw[j] ? cur : lab[j]; lab[j] = cur; }
+            }
+            uint32_t mw[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            lb[j] = lab[j];
-            mw[j] = meta_pack(lab[j], k[j], false, (am >> j) & 1);
-        }
-        if (lr == 0 || lr == th - 1) {
-            const int base = (lr == 0 ? 0 : TW) + 4 * lane;
-            *reinterpret_cast<uint4 *>(m_t + base) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-            *reinterpret_cast<ulonglong2 *>(w_t + base) = make_ulonglong2(BIAS, BIAS);
-            *reinterpret_cast<ulonglong2 *>(w_t + base + 2) = make_ulonglong2(BIAS, BIAS);
-        } else {
-            if (lane == 0) { m_t[2 * TW + lr] = mw[0]; w_t[2 * TW + lr] = BIAS; }
-            if (lane == rlane && tw > 1) { m_t[2 * TW + TH + lr] = mw[rj]; w_t[2 * TW + TH + lr] = BIAS; }
+            for (int j = 0; j < 4; j++) {
+                lb[j] = lab[j];
+                mw[j] = meta_pack(lab[j], k[j], false, (am >> j) & 1);
+            }
+            if (lr == 0 || lr == th - 1) {
+                const int base = (lr == 0 ? 0 : TW) + 4 * lane;
+                *reinterpret_cast<uint4 *>(m_t + base) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+                *reinterpret_cast<ulonglong2 *>(w_t + base) = make_ulonglong2(BIAS, BIAS);
+                *reinterpret_cast<ulonglong2 *>(w_t + base + 2) = make_ulonglong2(BIAS, BIAS);
+            } else {
+                if (lane == 0) { m_t[2 * TW + lr] = mw[0]; w_t[2 * TW + lr] = BIAS; }
+                if (lane == rlane && tw > 1) { m_t[2 * TW + TH + lr] = mw[rj]; w_t[2 * TW + TH + lr] = BIAS; }
+            }
+            lr--;
         }
     }
 }
@@ -547,14 +608,12 @@ __device__ __forceinline__ int plain_run(unsigned long long rows, int lr)
 }
 
 template <int ENC, bool AL, typename T>
-__global__ void __launch_bounds__(WPB * 32) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
-                                                     Geo g, int ntiles, const T *__restrict__ inflow,
-                                                     const uint8_t *__restrict__ tile_class,
-                                                     const unsigned long long *__restrict__ row_plain, T *__restrict__ acc)
+__global__ void __launch_bounds__(WPB * 32, 8) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+                                                        Geo g, int ntiles, const T *__restrict__ inflow,
+                                                        const uint8_t *__restrict__ tile_class,
+                                                        const unsigned long long *__restrict__ row_plain, T *__restrict__ acc)
 {
-    __shared__ uint32_t s_w[WPB][TH][32];
-    __shared__ uint8_t s_a[WPB][TH][32];
-    __shared__ T s_ext[WPB][2][TH];                  // external inflow of the left / right column cells
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][32] DIR words (+ mask words) + the side inflows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
@@ -565,56 +624,67 @@ __global__ void __launch_bounds__(WPB * 32) k_sweepC(const int8_t *__restrict__ 
     const T *in_t = inflow + (int64_t)tile * NSLOT;
     const int rlane = (tw - 1) >> 2, rj = (tw - 1) & 3;
     const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
-    const bool full = th == TH && tw == TW;
-    uint32_t (*wrow)[32] = s_w[warp];
-    uint8_t (*arow)[32] = s_a[warp];
-    T *extL = s_ext[warp][0], *extR = s_ext[warp][1];
+    TileRows<AL> rows;
+    rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
+    const int nch = (th + CH - 1) / CH;
+    rows.prefetch(0);
+    // external inflow of the left / right column cells
+    T *extL = reinterpret_cast<T *>(s_dyn + (mask ? 4 : 2) * WPB * CH * 32) + 2 * TH * warp, *extR = extL + TH;
     extL[lane] = in_t[2 * TW + lane]; extL[lane + 32] = in_t[2 * TW + 32 + lane];
     extR[lane] = in_t[2 * TW + TH + lane]; extR[lane + 32] = in_t[2 * TW + TH + 32 + lane];
-    stage_tile<AL>(dir, mask, g, gr0, gc0, th, !(mask == nullptr && full), wrow, arow, lane);
     T d[4] = {1, 1, 1, 1};                           // 1 + inflow from the row above
     bool dummy = false;
     T *out = acc + gr0 * g.nx + gc0;
     const unsigned long long plain_rows = row_plain[tile];
     const bool is_l = lane == 0, is_r = lane == 31;
-    int lr = 0;
-    while (lr < th) {
-        // a run of lean rows: no per-row classification, no divergent control flow
-        for (int end = lr + plain_run(plain_rows, lr); lr < end; lr++, out += g.nx) {
-            T tot[4];
-            bool gen;
-            const T l = extL[lr], r = extR[lr];
-            plain_row_down<T>(plain_word<ENC>(wrow[lr][lane], gen), d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
-            store_row<AL, T>(out, tot, gc0, g.nx);
-        }
-        if (lr >= th) break;
-        {   // one generic row
-            T tot[4];
-            int k[4];
-            const int am = (mask == nullptr && full) ? 0xF : arow[lr][lane];
-            decode_row<ENC>(wrow[lr][lane], am, g, gr0 + lr, gc0, border, k);
-            T ext[4] = {0, 0, 0, 0};
-            if (lr == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) ext[j] = in_t[4 * lane + j];
-            } else if (lr == th - 1) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) ext[j] = in_t[TW + 4 * lane + j];
-            } else {
-                if (lane == 0) ext[0] = extL[lr];
-                if (lane == rlane && tw > 1) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) if (j == rj) ext[j] += extR[lr];
-                }
+    for (int c = 0; c < nch; c++) {
+        rows.arrive(c + 1, nch);
+        const int cend = th < (c + 1) * CH ? th : (c + 1) * CH;
+        int lr = c * CH;
+        const uint32_t *wp = rows.chunk(c);              // row lr of this chunk at wp[(lr - c*CH) * 32]
+        uint32_t pbits = (uint32_t)(plain_rows >> (c * CH)) & ((1u << CH) - 1u);
+        while (lr < cend) {
+            // a run of lean rows (bounded by the chunk): no per-row classification, no divergent control flow
+            const uint32_t inv = ~pbits & ((1u << CH) - 1u);
+            int run = inv ? __ffs(inv) - 1 : CH;
+            run = run < cend - lr ? run : cend - lr;
+            pbits >>= run;
+            for (const int end = lr + run; lr < end; lr++, out += g.nx, wp += 32) {
+                T tot[4];
+                bool gen;
+                const T l = extL[lr], r = extR[lr];
+                plain_row_down<T>(plain_word<ENC>(*wp, gen), d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
+                store_row<AL, T>(out, tot, gc0, g.nx);
             }
-            T b[4];
+            if (lr >= cend) break;
+            {   // one generic row
+                T tot[4];
+                int k[4];
+                const int am = rows.active(lr);
+                decode_row<ENC>(rows.word(lr), am, g, gr0 + lr, gc0, border, k);
+                T ext[4] = {0, 0, 0, 0};
+                if (lr == 0) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] + ext[j] : (T)0;
-            sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
+                    for (int j = 0; j < 4; j++) ext[j] = in_t[4 * lane + j];
+                } else if (lr == th - 1) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) d[j] += 1;
-            store_row<AL, T>(out, tot, gc0, g.nx);
-            lr++; out += g.nx;
+                    for (int j = 0; j < 4; j++) ext[j] = in_t[TW + 4 * lane + j];
+                } else {
+                    if (lane == 0) ext[0] = extL[lr];
+                    if (lane == rlane && tw > 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) if (j == rj) ext[j] += extR[lr];
+                    }
+                }
+                T b[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] + ext[j] : (T)0;
+                sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
+#pragma unroll
+                for (int j = 0; j < 4; j++) d[j] += 1;
+                store_row<AL, T>(out, tot, gc0, g.nx);
+                lr++; out += g.nx; wp += 32; pbits >>= 1;
+            }
         }
     }
 }
@@ -878,19 +948,22 @@ __global__ void k_g_walk(int64_t nnodes, const int32_t *__restrict__ parent, con
     if (i >= nnodes) return;
     int32_t en = entry[i];
     if (en == -1) return;                                   // not an exit: nothing to carry
+    int32_t p = parent[i];
+    uint32_t wc = (uint32_t)w[i];
     int64_t cur = i;
     unsigned long long old = atomicAdd(&wq[cur], (unsigned long long)(-(long long)PEND1));   // own arrival
     uint32_t add = 0;
     while ((uint32_t)(old >> 32) == 1u) {                   // we took pending to zero: cur is final
-        uint32_t total = (uint32_t)old + add + (uint32_t)w[cur];
+        const uint32_t total = (uint32_t)old + add + wc;
         if (en >= 0) atomicAdd(&inflow[en], (int32_t)total);
         else if (en == -2) stripe_total[cur] = (int32_t)total;     // a stripe exit keeps its stripe-local total
-        int32_t p = parent[cur];
         if (p < 0) break;
-        en = entry[p];
+        // the parent's static data does not depend on the atomic: fetch it first so the hop costs ONE L2 round trip
+        const int32_t pp = parent[p], pen = entry[p];
+        const uint32_t pw = (uint32_t)w[p];
         old = atomicAdd(&wq[p], (unsigned long long)total - PEND1);
         add = total;
-        cur = p;
+        cur = p; p = pp; en = pen; wc = pw;
     }
 }
 
@@ -1083,8 +1156,9 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
-    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
+    const size_t smemF = (size_t)(mask ? 4 : 2) * WPB * CH * 32 * sizeof(uint32_t);
+    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
+    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -1098,8 +1172,9 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);
     const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
-    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, 0, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
+    const size_t smemF = (size_t)(mask ? 4 : 2) * WPB * CH * 32 * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T);
+    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
+    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
     k_generalC<ENC, T><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, w.inflow, w.ext_unres, acc);
     WMF_LAUNCH_CHECK();
     return 0;
