@@ -206,6 +206,16 @@ __device__ __forceinline__ void sweep_row_down(const int (&k)[4], int am, const 
 // chunk is swept the next one is in flight, so the sweeps never wait on HBM row by row and a warp
 // holds only 2 * CH rows (2 KB) of shared memory, which keeps occupancy register-bound.
 constexpr int CH = 8;
+// cp.async (LDGSTS) of one 32-bit word; raw PTX: the <cuda_pipeline.h> wrapper pads every copy with
+// three predicated-off LDS that still take issue slots in an issue-bound kernel.
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <bool AL>
 struct TileRows {
     uint32_t *wbase, *mbase;    // this lane's column of the two DIR / mask chunk buffers (stride 32 per row, CH*32 per buffer)
@@ -233,15 +243,15 @@ struct TileRows {
                 const uint8_t *sm = mask0 ? mask0 + (int64_t)r0 * nx : nullptr;
                 if (r0 + CH <= th) {
 #pragma unroll
-                    for (int r = 0; r < CH; r++, sd += nx) __pipeline_memcpy_async(dw + r * 32, sd, 4);
+                    for (int r = 0; r < CH; r++, sd += nx) cp_async4(dw + r * 32, sd);
                     if (sm) {
 #pragma unroll
-                        for (int r = 0; r < CH; r++, sm += nx) __pipeline_memcpy_async(dm + r * 32, sm, 4);
+                        for (int r = 0; r < CH; r++, sm += nx) cp_async4(dm + r * 32, sm);
                     }
                 } else {
                     for (int r = 0; r0 + r < th; r++, sd += nx) {
-                        __pipeline_memcpy_async(dw + r * 32, sd, 4);
-                        if (sm) { __pipeline_memcpy_async(dm + r * 32, sm, 4); sm += nx; }
+                        cp_async4(dw + r * 32, sd);
+                        if (sm) { cp_async4(dm + r * 32, sm); sm += nx; }
                     }
                 }
             } else {
@@ -262,12 +272,12 @@ struct TileRows {
                 if (mask0) dm[r * 32] = mm;
             }
         }
-        __pipeline_commit();
+        cp_async_commit();
     }
     // chunk c has arrived; start fetching chunk `next` (or nothing when out of range) into the other buffer
     __device__ __forceinline__ void arrive(int next, int nchunks) const
     {
-        __pipeline_wait_prior(0);
+        cp_async_wait_all();
         __syncwarp();
         if (next >= 0 && next < nchunks) prefetch(next);
     }
@@ -387,20 +397,27 @@ __device__ __forceinline__ void plain_row_down(uint32_t k, T (&d)[4], T (&tot)[4
     d[3] = tot[2] * (T)bit01<2>(m.se) + d[3] + 1;
 }
 
-// Upward (label) step of a plain row, middle rows of a full interior tile.  A plain row has no pits,
-// so an East cell's own term is 0 and "copy the chain end" is own + next * E.
-__device__ __forceinline__ void plain_row_up(uint32_t k, uint32_t (&lb)[4], int lr, int lane, uint32_t &metaL, uint32_t &metaR)
+// Upward (label) step of a plain row of a full interior tile.  A plain row has no pits, so an East
+// cell's own term is 0 and "copy the chain end" is own + next * E.  slotL / slotR: boundary slots of
+// the left- / right-column cell of this row.  BOTTOM: the tile's last row, where S / SE / SW leave the tile.
+template <bool BOTTOM>
+__device__ __forceinline__ void plain_row_up(uint32_t k, uint32_t (&lb)[4], int lane, uint32_t slotL, uint32_t slotR)
 {
     const RowBits m = row_bits(k);
-    const uint32_t lbR0 = __shfl_down_sync(FULL, lb[0], 1), lbL3 = __shfl_up_sync(FULL, lb[3], 1);
-    uint32_t own[4];
-    own[0] = lb[0] * bit01<0>(m.s) + lb[1] * bit01<0>(m.se) + lbL3 * bit01<0>(m.sw);
-    own[1] = lb[1] * bit01<1>(m.s) + lb[2] * bit01<1>(m.se) + lb[0] * bit01<1>(m.sw);
-    own[2] = lb[2] * bit01<2>(m.s) + lb[3] * bit01<2>(m.se) + lb[1] * bit01<2>(m.sw);
-    own[3] = lb[3] * bit01<3>(m.s) + lbR0 * bit01<3>(m.se) + lb[2] * bit01<3>(m.sw);
     uint32_t E0 = bit01<0>(m.e), E1 = bit01<1>(m.e), E2 = bit01<2>(m.e), E3 = bit01<3>(m.e);
-    if (lane == 31 && ((k >> 24) & 0xFFu) <= 1u) { own[3] = (uint32_t)(2 * TW + TH + lr); E3 = 0; }   // E / SE leave through the right column
-    if (lane == 0 && (k & 0xFFu) == 3u) own[0] = (uint32_t)(2 * TW + lr);                               // SW leaves through the left column
+    uint32_t own[4];
+    if (BOTTOM) {
+        const uint32_t s0 = TW + 4 * lane;
+        own[0] = (s0 + 0) * (1u - E0); own[1] = (s0 + 1) * (1u - E1); own[2] = (s0 + 2) * (1u - E2); own[3] = (s0 + 3) * (1u - E3);
+    } else {
+        const uint32_t lbR0 = __shfl_down_sync(FULL, lb[0], 1), lbL3 = __shfl_up_sync(FULL, lb[3], 1);
+        own[0] = lb[0] * bit01<0>(m.s) + lb[1] * bit01<0>(m.se) + lbL3 * bit01<0>(m.sw);
+        own[1] = lb[1] * bit01<1>(m.s) + lb[2] * bit01<1>(m.se) + lb[0] * bit01<1>(m.sw);
+        own[2] = lb[2] * bit01<2>(m.s) + lb[3] * bit01<2>(m.se) + lb[1] * bit01<2>(m.sw);
+        own[3] = lb[3] * bit01<3>(m.s) + lbR0 * bit01<3>(m.se) + lb[2] * bit01<3>(m.sw);
+    }
+    if (lane == 31 && ((k >> 24) & 0xFFu) <= 1u) { own[3] = slotR; E3 = 0; }   // E / SE leave through the right column
+    if (lane == 0 && (k & 0xFFu) == 3u) own[0] = slotL;                         // SW leaves through the left column
     uint32_t V = own[3] + LNONE * E3;                        // label at cell 0 if nothing comes from the right
     V = V * E2 + own[2];
     V = V * E1 + own[1];
@@ -410,8 +427,6 @@ __device__ __forceinline__ void plain_row_up(uint32_t k, uint32_t (&lb)[4], int 
     cur = cur * E2 + own[2]; lb[2] = cur;
     cur = cur * E1 + own[1]; lb[1] = cur;
     cur = cur * E0 + own[0]; lb[0] = cur;
-    metaL = meta_pack(lb[0], (int)(k & 0xFFu), false, true);
-    metaR = meta_pack(lb[3], (int)((k >> 24) & 0xFFu), false, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -455,10 +470,9 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
         for (int lr = c * CH; lr < cend; lr++) {
             const uint32_t w = wp[(lr - c * CH) * 32];
             int32_t tot[4];
-            const bool edge_row = lr == 0 || lr == th - 1;
             bool gen = true;
             uint32_t kw = 0;
-            if (plain_tile && !edge_row) { kw = plain_word<ENC>(w, gen); gen = __any_sync(FULL, gen); }
+            if (plain_tile) { kw = plain_word<ENC>(w, gen); gen = __any_sync(FULL, gen); }
             if (!gen) {
                 plain_rows |= 1ull << lr;
                 plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
@@ -486,7 +500,7 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
             }
         }
     }
-    __pipeline_wait_prior(0);
+    cp_async_wait_all();
     __syncwarp();
     if (complex_tile) {                              // the general solver redoes this tile
         if (lane == 0) tile_class[tile] = 1;
@@ -508,11 +522,22 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
                 int run = rest ? __clzll((long long)rest) : lr + 1;
                 run = run < lr - cbeg + 1 ? run : lr - cbeg + 1;
                 for (const int end = lr - run; lr > end; lr--) {
-                    uint32_t mL, mR;
                     bool gen;
-                    plain_row_up(plain_word<ENC>(wp[(lr - cbeg) * 32], gen), lb, lr, lane, mL, mR);
-                    if (lane == 0) { m_t[2 * TW + lr] = mL; w_t[2 * TW + lr] = BIAS; }
-                    if (lane == 31) { m_t[2 * TW + TH + lr] = mR; w_t[2 * TW + TH + lr] = BIAS; }
+                    const uint32_t kw = plain_word<ENC>(wp[(lr - cbeg) * 32], gen);
+                    if (lr == 0 || lr == TH - 1) {        // first / last row of the tile: every cell is a boundary slot
+                        if (lr == 0) plain_row_up<false>(kw, lb, lane, 0u, (uint32_t)(TW - 1));
+                        else plain_row_up<true>(kw, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1));
+                        const int base = (lr == 0 ? 0 : TW) + 4 * lane;
+                        *reinterpret_cast<uint4 *>(m_t + base) =
+                            make_uint4(meta_pack(lb[0], (int)(kw & 0xFFu), false, true), meta_pack(lb[1], (int)((kw >> 8) & 0xFFu), false, true),
+                                       meta_pack(lb[2], (int)((kw >> 16) & 0xFFu), false, true), meta_pack(lb[3], (int)(kw >> 24), false, true));
+                        *reinterpret_cast<ulonglong2 *>(w_t + base) = make_ulonglong2(BIAS, BIAS);
+                        *reinterpret_cast<ulonglong2 *>(w_t + base + 2) = make_ulonglong2(BIAS, BIAS);
+                    } else {
+                        plain_row_up<false>(kw, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
+                        if (lane == 0) { m_t[2 * TW + lr] = meta_pack(lb[0], (int)(kw & 0xFFu), false, true); w_t[2 * TW + lr] = BIAS; }
+                        if (lane == 31) { m_t[2 * TW + TH + lr] = meta_pack(lb[3], (int)(kw >> 24), false, true); w_t[2 * TW + TH + lr] = BIAS; }
+                    }
                 }
                 if (lr < cbeg) break;
             }
@@ -652,8 +677,15 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepC(const int8_t *__restrict
             for (const int end = lr + run; lr < end; lr++, out += g.nx, wp += 32) {
                 T tot[4];
                 bool gen;
-                const T l = extL[lr], r = extR[lr];
-                plain_row_down<T>(plain_word<ENC>(*wp, gen), d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
+                if (lr == 0 || lr == TH - 1) {            // first / last row: every cell is a boundary slot
+                    const T *e4 = in_t + (lr == 0 ? 0 : TW) + 4 * lane;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) d[j] += e4[j];
+                    plain_row_down<T>(plain_word<ENC>(*wp, gen), d, tot, lane, (T)0, (T)0);
+                } else {
+                    const T l = extL[lr], r = extR[lr];
+                    plain_row_down<T>(plain_word<ENC>(*wp, gen), d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
+                }
                 store_row<AL, T>(out, tot, gc0, g.nx);
             }
             if (lr >= cend) break;
@@ -923,17 +955,37 @@ constexpr unsigned long long PEND1 = 1ull << 32;
 __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__restrict__ meta, int32_t *__restrict__ parent,
                                                    int32_t *__restrict__ entry, unsigned long long *wq)
 {
+    // one block per tile, one thread per boundary slot; tile geometry is block-uniform, everything is 32-bit
     const int tile = blockIdx.x, s = threadIdx.x;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
+    const int th = ty == g.tiles_y - 1 ? last_th : TH, tw = tx == g.tiles_x - 1 ? last_tw : TW;
     const int64_t i = (int64_t)tile * NSLOT + s;
-    uint32_t me = 0;
-    int64_t e = entry_of(g, meta, tile, s, me);
-    int32_t p = -1, en = e == -2 ? -2 : -1;                 // -2: drains into a neighbouring row stripe
-    if (e >= 0 && ((me >> 21) & 1)) {                       // an exit whose receiver is active
-        en = (int32_t)e;
-        uint32_t link = me & 0xFFFFu;
-        if (link != LNONE) {
-            p = (int32_t)((e / NSLOT) * NSLOT + link);
-            atomicAdd(&wq[p], PEND1);
+    int32_t p = -1, en = -1;
+    int lr, lc;
+    if (cell_of(s, th, tw, lr, lc)) {
+        const uint32_t m = meta[i];
+        const int k = (m >> 16) & 0xF;
+        if (((m >> 21) & 1) && k != 8) {
+            const int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
+            if (rr < 0 || rr >= th || cc < 0 || cc >= tw) {          // the edge leaves the tile
+                const int ty2 = ty + (rr < 0 ? -1 : (rr >= th ? 1 : 0)), tx2 = tx + (cc < 0 ? -1 : (cc >= tw ? 1 : 0));
+                if (ty2 < 0 || ty2 >= g.tiles_y) en = -2;            // into a neighbouring row stripe
+                else {
+                    const int th2 = ty2 == g.tiles_y - 1 ? last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? last_tw : TW;
+                    const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
+                    const int e = (ty2 * g.tiles_x + tx2) * NSLOT + slot_of(lr2, lc2, th2, tw2);
+                    const uint32_t me = meta[e];
+                    if ((me >> 21) & 1) {                            // the receiver is active
+                        en = e;
+                        const uint32_t link = me & 0xFFFFu;
+                        if (link != LNONE) {
+                            p = (e / NSLOT) * NSLOT + (int)link;
+                            atomicAdd(&wq[p], PEND1);
+                        }
+                    }
+                }
+            }
         }
     }
     parent[i] = p;
@@ -1153,7 +1205,7 @@ template <int ENC, typename T>
 int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, cudaStream_t st)
 {
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
-    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);   // persistent: most tiles are skipped
+    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     const size_t smemF = (size_t)(mask ? 4 : 2) * WPB * CH * 32 * sizeof(uint32_t);
@@ -1169,7 +1221,7 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
                  cudaStream_t st)
 {
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
-    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);
     const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     const size_t smemF = (size_t)(mask ? 4 : 2) * WPB * CH * 32 * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T);
