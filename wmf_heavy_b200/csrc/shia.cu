@@ -101,11 +101,20 @@ struct Shia5Args {
     int nblk;
 };
 
-// K = 3: {entradas, salidas, S1+..+S4};  DIAG adds {S1,S2,S3,S4,h1,h2,h3} -> K = 10
-template <bool DIAG>
+// x ** 0.6 for x in [0, 1] (soil saturation): exp2(0.6 * log2 x) on the SFU.  __log2f is within 2^-22
+// absolute on [0.5, 2] and 2 ulp elsewhere, so the relative error of the power is ~1e-7 -- two orders of
+// magnitude inside the 1e-5 parity tolerance -- against ~70 instructions for the correctly rounded powf.
+__device__ __forceinline__ float pow06(float x) { return x > 0.0f ? exp2f(0.6f * __log2f(x)) : 0.0f; }
+
+// Per-step sums.  K = 2: {R, q} with q = (storage now - storage before) + (v4 + Evp_loss) per cell, so that
+// balance(t) = sum(q) - sum(R) (Modelos:533) needs ONE reduced quantity beside the rain; forming the
+// difference per cell in fp32 also avoids the catastrophic cancellation of the Fortran's two ~5N-term sums.
+// DIAG adds {S1,S2,S3,S4,h1,h2,h3} -> K = 9 (slot 0 of the series carries the constant sums of S5 and h4).
+// T2: some tank uses the kinematic-wave speed (speed_type 2); the all-type-1 kernel carries none of that code.
+template <bool DIAG, bool T2>
 __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
 {
-    constexpr int K = DIAG ? 10 : 3;
+    constexpr int K = DIAG ? 9 : 2;
     __shared__ double stage[WARPS][TB][K];
     const int64_t N = a.N, T = a.N_reg;
     const int pset = blockIdx.y;
@@ -141,31 +150,32 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
     float fl[3];                              // type-1 outflow fraction, constant in time (Modelos:462)
 #pragma unroll
     for (int i = 0; i < 3; i++) fl[i] = 1.0f - L / (hs[i] * dt + L);
-    const bool t2_0 = a.p.speed_type[0] != 1, t2_1 = a.p.speed_type[1] != 1, t2_2 = a.p.speed_type[2] != 1;
+    const bool t2_0 = T2 && a.p.speed_type[0] != 1, t2_1 = T2 && a.p.speed_type[1] != 1, t2_2 = T2 && a.p.speed_type[2] != 1;
+    const float invH1 = 1.0f / H1;
     const bool raq = a.p.retorno_aq > 0.0f, rgr = a.p.retorno_gr > 0.0f;
     const int niter = a.p.calc_niter;
     float acum = 0.0f;
 
-    {   // slot 0: initial sums.  {S5 sum, h4 sum, S1+..+S4, S1..S4, h1..h3}
+    {   // slot 0: the constant sums {S5, h4} (tank 5 and speed row 4 are never touched), then the initial S1..S4, h1..h3
         float v[K];
         v[0] = live ? S5 : 0.0f;
         v[1] = live ? hs[3] : 0.0f;
-        v[2] = live ? ((S1 + S2) + (S3 + S4)) : 0.0f;
         if (DIAG) {
-            v[3] = live ? S1 : 0.0f; v[4] = live ? S2 : 0.0f; v[5] = live ? S3 : 0.0f; v[6] = live ? S4 : 0.0f;
-            v[7] = live ? hs[0] : 0.0f; v[8] = live ? hs[1] : 0.0f; v[9] = live ? hs[2] : 0.0f;
+            v[2] = live ? S1 : 0.0f; v[3] = live ? S2 : 0.0f; v[4] = live ? S3 : 0.0f; v[5] = live ? S4 : 0.0f;
+            v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
         }
         red.add(v);
     }
+    float sto_prev = (S1 + S2) + (S3 + S4);
 
     for (int64_t t = 0; t < T; t++) {
         const int pos = a.pos[t];
         float R = 0.0f;
-        if (pos != 1) R = (float)a.rain[(int64_t)(pos - 1) * N + cc] / 1000.0f;          // :370
+        if (pos != 1) R = (float)a.rain[(int64_t)(pos - 1) * N + cc] * 0.001f;            // :370 (RainInt/1000.)
         acum = acum + R;                                                                   // :380
         float v1 = fmaxf(0.0f, (R - H1) + S1);                                             // :393
         S1 = (S1 + R) - v1;                                                                // :394
-        float evl = fminf((a.evp[t] * vs[0]) * powf(S1 / H1, 0.6f), S1);                   // :396-398
+        float evl = fminf((a.evp[t] * vs[0]) * pow06(S1 * invH1), S1);                     // :396-398
         S1 = S1 - evl;                                                                     // :407
         float v2 = fminf(v1, vs[1]); S2 = (S2 + v1) - v2;                                  // :409-412
         float v3 = fminf(v2, vs[2]); S3 = (S3 + v2) - v3;
@@ -183,13 +193,14 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
         else { ar = 0.0f; calc_speed(S4 * m3mm, coef[2], expo[2], L, dt, niter, hs[2], ar); hf = fminf(((ar * hs[2]) * dt) / m3mm, S4); }
         S4 = S4 - hf;
 
+        const float sto_now = (S1 + S2) + (S3 + S4);
         float v[K];
         v[0] = live ? R : 0.0f;
-        v[1] = live ? (v4 + evl) : 0.0f;                                                   // :459
-        v[2] = live ? ((S1 + S2) + (S3 + S4)) : 0.0f;
+        v[1] = live ? ((sto_now - sto_prev) + (v4 + evl)) : 0.0f;                          // :459, :533
+        sto_prev = sto_now;
         if (DIAG) {
-            v[3] = live ? S1 : 0.0f; v[4] = live ? S2 : 0.0f; v[5] = live ? S3 : 0.0f; v[6] = live ? S4 : 0.0f;
-            v[7] = live ? hs[0] : 0.0f; v[8] = live ? hs[1] : 0.0f; v[9] = live ? hs[2] : 0.0f;
+            v[2] = live ? S1 : 0.0f; v[3] = live ? S2 : 0.0f; v[4] = live ? S3 : 0.0f; v[5] = live ? S4 : 0.0f;
+            v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
         }
         red.add(v);
     }
@@ -215,17 +226,17 @@ __global__ void k_shia5_outputs(const double *__restrict__ totals, int K, int64_
     int64_t t = i - (int64_t)p * T;
     const double *tot = totals + (int64_t)p * (T + 1) * K;
     const double *now = tot + (t + 1) * K, *prev = tot + t * K;
-    balance[i] = (float)(((now[2] - prev[2]) - now[0]) + now[1]);
+    balance[i] = (float)(now[1] - now[0]);
     if (p == 0 && mean_rain) mean_rain[t] = (float)(now[0] / (double)N);
-    if (K == 10) {
+    if (K == 9) {
         if (mean_storage) {
             float *ms = mean_storage + (int64_t)p * 5 * T;
-            for (int k = 0; k < 4; k++) ms[k * T + t] = (float)(now[3 + k] / (double)N);
+            for (int k = 0; k < 4; k++) ms[k * T + t] = (float)(now[2 + k] / (double)N);
             ms[4 * T + t] = (float)(tot[0] / (double)N);       // tank 5 is never touched
         }
         if (mean_speed) {
             float *mv = mean_speed + (int64_t)p * 4 * T;
-            for (int k = 0; k < 3; k++) mv[k * T + t] = (float)(now[7 + k] / (double)N);
+            for (int k = 0; k < 3; k++) mv[k * T + t] = (float)(now[6 + k] / (double)N);
             mv[3 * T + t] = (float)(tot[1] / (double)N);
         }
     }
@@ -334,7 +345,7 @@ int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg,
                 WMF_E_ARG, "null pointer");
     WMF_REQUIRE(N > 0 && N_reg > 0 && n_rec > 0 && P > 0 && P <= 65535, WMF_E_ARG, "bad size");
     const bool diag = mean_storage || mean_speed;
-    const int K = diag ? 10 : 3;
+    const int K = diag ? 9 : 2;
     const int nblk = (int)((N + TH - 1) / TH);
     WsCursor cur(workspace, ws_bytes);
     double *part = cur.take<double>((size_t)P * nblk * (N_reg + 1) * K);
@@ -344,8 +355,9 @@ int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg,
     a.p = *params_host; a.N = N; a.N_reg = N_reg; a.cs = cell_static; a.rain = rain_records; a.pos = pos_evento;
     a.evp = evp; a.calib = calib; a.sto = sto; a.hspeed = hspeed; a.acum_rain = acum_rain; a.part = part; a.nblk = nblk;
     dim3 grid(nblk, P);
-    if (diag) k_shia5<true><<<grid, TH, 0, st>>>(a);
-    else k_shia5<false><<<grid, TH, 0, st>>>(a);
+    const bool t2 = a.p.speed_type[0] != 1 || a.p.speed_type[1] != 1 || a.p.speed_type[2] != 1;
+    if (diag) { if (t2) k_shia5<true, true><<<grid, TH, 0, st>>>(a); else k_shia5<true, false><<<grid, TH, 0, st>>>(a); }
+    else { if (t2) k_shia5<false, true><<<grid, TH, 0, st>>>(a); else k_shia5<false, false><<<grid, TH, 0, st>>>(a); }
     const int64_t TK = (N_reg + 1) * K;
     k_fold_blocks<<<dim3(blocks_for(TK, 256), P), 256, 0, st>>>(part, nblk, TK, totals);
     k_shia5_outputs<<<blocks_for((int64_t)P * N_reg, 256), 256, 0, st>>>(totals, K, N_reg, N, P, balance, mean_rain,
