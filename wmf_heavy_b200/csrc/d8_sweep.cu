@@ -22,13 +22,13 @@
 // Cycle semantics (basics.py:166-175): a cell is finalised only when all its donors are; others
 // keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
 // contracted forest carries this through `blocked` nodes and the `ext_unres` entry flags.
-#include <cuda_pipeline.h>
-
 #include "common.cuh"
 
 namespace {
 
-constexpr int TW = 128;                 // tile width  (one warp, 4 cells per lane)
+constexpr int NC = 8;                   // cells per lane in the fast kernels
+constexpr int NWD = NC / 4;             // 32-bit DIR words per lane per row
+constexpr int TW = 32 * NC;             // tile width  (one warp)
 constexpr int TH = 64;                  // tile height
 constexpr int NSLOT = 2 * TW + 2 * TH;  // boundary slots: top row, bottom row, left col, right col
 constexpr int WPB = 4;                  // warps (= tiles) per block in the fast kernels
@@ -144,56 +144,56 @@ __device__ __forceinline__ uint32_t label_carry_from_left(uint32_t V, bool P, in
     return lane == 0 ? LNONE : c;
 }
 
-// One row of the downward sweep.  b[] = base (own cell + inflow from above + external inflow) for
-// active cells; returns tot[] (final for this sweep) and updates d[] = contributions to the row below.
-// Sets `complex_row` when the row breaks the "simple tile" conditions.
+// One row of the downward sweep, any codes (generic path).  b[] = base (own cell + inflow from above
+// + external inflow) for active cells; returns tot[] and d[] = contributions to the row below.
+// Sets `twocycle` when the row holds an E -> W adjacent pair (the tile is then not "simple").
 template <typename T>
-__device__ __forceinline__ void sweep_row_down(const int (&k)[4], int am, const T (&b)[4], T (&tot)[4], T (&d)[4],
+__device__ __forceinline__ void sweep_row_down(const int (&k)[NC], int am, const T (&b)[NC], T (&tot)[NC], T (&d)[NC],
                                                int lane, bool &twocycle)
 {
-    // East chains: e_in[j] = inflow from the west neighbour
-    T e_in[4], w_in[4];
-    {
+    T e_in[NC], w_in[NC];
+    {   // East chains: e_in[j] = inflow from the west neighbour
         T S = 0;
         bool P = true;
 #pragma unroll
-        for (int j = 0; j < 4; j++) { bool ps = k[j] == 0; S = ps ? b[j] + S : (T)0; P = P && ps; }
-        T carry = chain_carry_from_left<T>(S, P, lane);
-        e_in[0] = carry;
+        for (int j = 0; j < NC; j++) { bool ps = k[j] == 0; S = ps ? b[j] + S : (T)0; P = P && ps; }
+        e_in[0] = chain_carry_from_left<T>(S, P, lane);
 #pragma unroll
-        for (int j = 1; j < 4; j++) e_in[j] = (k[j - 1] == 0) ? b[j - 1] + e_in[j - 1] : (T)0;
+        for (int j = 1; j < NC; j++) e_in[j] = (k[j - 1] == 0) ? b[j - 1] + e_in[j - 1] : (T)0;
     }
-    const bool anyW = __any_sync(FULL, k[0] == 4 || k[1] == 4 || k[2] == 4 || k[3] == 4);
-    if (anyW) {
+    bool hasW = false;
+#pragma unroll
+    for (int j = 0; j < NC; j++) hasW = hasW || k[j] == 4;
+    if (__any_sync(FULL, hasW)) {
         T S = 0;
         bool P = true;
 #pragma unroll
-        for (int j = 3; j >= 0; j--) { bool ps = k[j] == 4; S = ps ? b[j] + S : (T)0; P = P && ps; }
-        T carry = chain_carry_from_right<T>(S, P, lane);
-        w_in[3] = carry;
+        for (int j = NC - 1; j >= 0; j--) { bool ps = k[j] == 4; S = ps ? b[j] + S : (T)0; P = P && ps; }
+        w_in[NC - 1] = chain_carry_from_right<T>(S, P, lane);
 #pragma unroll
-        for (int j = 2; j >= 0; j--) w_in[j] = (k[j + 1] == 4) ? b[j + 1] + w_in[j + 1] : (T)0;
+        for (int j = NC - 2; j >= 0; j--) w_in[j] = (k[j + 1] == 4) ? b[j + 1] + w_in[j + 1] : (T)0;
         // E -> W adjacent pairs are two-cycles: not handled by the scans
         int k0_right = __shfl_down_sync(FULL, k[0], 1);
-        bool tc = (k[0] == 0 && k[1] == 4) || (k[1] == 0 && k[2] == 4) || (k[2] == 0 && k[3] == 4) ||
-                  (lane < 31 && k[3] == 0 && k0_right == 4);
+        bool tc = lane < 31 && k[NC - 1] == 0 && k0_right == 4;
+#pragma unroll
+        for (int j = 0; j + 1 < NC; j++) tc = tc || (k[j] == 0 && k[j + 1] == 4);
         twocycle = twocycle || __any_sync(FULL, tc);
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) w_in[j] = 0;
+        for (int j = 0; j < NC; j++) w_in[j] = 0;
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++) tot[j] = ((am >> j) & 1) ? b[j] + e_in[j] + w_in[j] : (T)0;
+    for (int j = 0; j < NC; j++) tot[j] = ((am >> j) & 1) ? b[j] + e_in[j] + w_in[j] : (T)0;
     // contributions to the row below: S from the same column, SE from the left neighbour, SW from the right one
-    T se_out = (k[3] == 1) ? tot[3] : (T)0, sw_out = (k[0] == 3) ? tot[0] : (T)0;
+    T se_out = (k[NC - 1] == 1) ? tot[NC - 1] : (T)0, sw_out = (k[0] == 3) ? tot[0] : (T)0;
     T from_left = __shfl_up_sync(FULL, se_out, 1), from_right = __shfl_down_sync(FULL, sw_out, 1);
     if (lane == 0) from_left = 0;
     if (lane == 31) from_right = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < NC; j++) {
         T v = (k[j] == 2) ? tot[j] : (T)0;
         v += (j > 0) ? ((k[j > 0 ? j - 1 : 0] == 1) ? tot[j > 0 ? j - 1 : 0] : (T)0) : from_left;
-        v += (j < 3) ? ((k[j < 3 ? j + 1 : 3] == 3) ? tot[j < 3 ? j + 1 : 3] : (T)0) : from_right;
+        v += (j < NC - 1) ? ((k[j < NC - 1 ? j + 1 : NC - 1] == 3) ? tot[j < NC - 1 ? j + 1 : NC - 1] : (T)0) : from_right;
         d[j] = v;
     }
 }
@@ -201,24 +201,24 @@ __device__ __forceinline__ void sweep_row_down(const int (&k)[4], int am, const 
 // ---------------------------------------------------------------------------------------------
 // fast solver: staging, row classification and the lean "plain row" step
 // ---------------------------------------------------------------------------------------------
-// The tile's raw DIR words (4 codes per lane per row) -- and the mask words when there is a mask --
-// stream through shared memory in chunks of CH rows, double buffered with cp.async (LDGSTS): while a
-// chunk is swept the next one is in flight, so the sweeps never wait on HBM row by row and a warp
-// holds only 2 * CH rows (2 KB) of shared memory, which keeps occupancy register-bound.
+// The tile's raw DIR words (NC codes = NWD words per lane per row) -- and the mask words when there is
+// a mask -- stream through shared memory in chunks of CH rows, double buffered with cp.async (LDGSTS):
+// while a chunk is swept the next one is in flight, so the sweeps never wait on HBM row by row and a
+// warp holds only 2 * CH rows of shared memory, which keeps occupancy register-bound.
 constexpr int CH = 8;
-// cp.async (LDGSTS) of one 32-bit word; raw PTX: the <cuda_pipeline.h> wrapper pads every copy with
-// three predicated-off LDS that still take issue slots in an issue-bound kernel.
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+constexpr int ROWW = 32 * NWD;          // 32-bit words of one staged row of one warp
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <bool AL>
 struct TileRows {
-    uint32_t *wbase, *mbase;    // this lane's column of the two DIR / mask chunk buffers (stride 32 per row, CH*32 per buffer)
+    uint32_t *wbase, *mbase;    // this lane's NWD words in the two DIR / mask chunk buffers (ROWW per row, CH*ROWW per buffer)
     const int8_t *dir0;         // &dir[gr0][gc0]
     const uint8_t *mask0;       // &mask[gr0][gc0] or nullptr
     int64_t nx, gc0;
@@ -227,15 +227,15 @@ struct TileRows {
     __device__ __forceinline__ void init(uint32_t *smem_words, int warp, int lane, const int8_t *dir, const uint8_t *mask,
                                          int64_t nx_, int64_t gr0, int64_t gc0_, int th_)
     {
-        wbase = smem_words + (size_t)warp * 2 * CH * 32 + lane;
-        mbase = smem_words + (size_t)(WPB + warp) * 2 * CH * 32 + lane;
+        wbase = smem_words + (size_t)warp * 2 * CH * ROWW + lane * NWD;
+        mbase = smem_words + (size_t)(WPB + warp) * 2 * CH * ROWW + lane * NWD;
         dir0 = dir + gr0 * nx_ + gc0_;
         mask0 = mask ? mask + gr0 * nx_ + gc0_ : nullptr;
         nx = nx_; gc0 = gc0_; th = th_;
     }
     __device__ __forceinline__ void prefetch(int c) const      // chunk c -> buffer c & 1
     {
-        uint32_t *dw = wbase + (c & 1) * CH * 32, *dm = mbase + (c & 1) * CH * 32;
+        uint32_t *dw = wbase + (c & 1) * CH * ROWW, *dm = mbase + (c & 1) * CH * ROWW;
         const int r0 = c * CH;
         if (AL) {
             if (gc0 < nx) {
@@ -243,33 +243,38 @@ struct TileRows {
                 const uint8_t *sm = mask0 ? mask0 + (int64_t)r0 * nx : nullptr;
                 if (r0 + CH <= th) {
 #pragma unroll
-                    for (int r = 0; r < CH; r++, sd += nx) cp_async4(dw + r * 32, sd);
+                    for (int r = 0; r < CH; r++, sd += nx) cp_async<4 * NWD>(dw + r * ROWW, sd);
                     if (sm) {
 #pragma unroll
-                        for (int r = 0; r < CH; r++, sm += nx) cp_async4(dm + r * 32, sm);
+                        for (int r = 0; r < CH; r++, sm += nx) cp_async<4 * NWD>(dm + r * ROWW, sm);
                     }
                 } else {
                     for (int r = 0; r0 + r < th; r++, sd += nx) {
-                        cp_async4(dw + r * 32, sd);
-                        if (sm) { cp_async4(dm + r * 32, sm); sm += nx; }
+                        cp_async<4 * NWD>(dw + r * ROWW, sd);
+                        if (sm) { cp_async<4 * NWD>(dm + r * ROWW, sm); sm += nx; }
                     }
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < CH; r++) { dw[r * 32] = 0; if (mask0) dm[r * 32] = 0; }
+                for (int r = 0; r < CH; r++)
+#pragma unroll
+                    for (int q = 0; q < NWD; q++) { dw[r * ROWW + q] = 0; if (mask0) dm[r * ROWW + q] = 0; }
             }
         } else {
             for (int r = 0; r < CH && r0 + r < th; r++) {
-                uint32_t ww = 0, mm = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (gc0 + j < nx) {
-                        const int64_t o = (int64_t)(r0 + r) * nx + j;
-                        ww |= (uint32_t)(uint8_t)dir0[o] << (8 * j);
-                        if (mask0) mm |= (uint32_t)(mask0[o] != 0) << (8 * j);
-                    }
-                dw[r * 32] = ww;
-                if (mask0) dm[r * 32] = mm;
+                for (int q = 0; q < NWD; q++) {
+                    uint32_t ww = 0, mm = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (gc0 + 4 * q + j < nx) {
+                            const int64_t o = (int64_t)(r0 + r) * nx + 4 * q + j;
+                            ww |= (uint32_t)(uint8_t)dir0[o] << (8 * j);
+                            if (mask0) mm |= (uint32_t)(mask0[o] != 0) << (8 * j);
+                        }
+                    dw[r * ROWW + q] = ww;
+                    if (mask0) dm[r * ROWW + q] = mm;
+                }
             }
         }
         cp_async_commit();
@@ -281,34 +286,32 @@ struct TileRows {
         __syncwarp();
         if (next >= 0 && next < nchunks) prefetch(next);
     }
-    // this lane's words of chunk c: row r of the chunk at [r * 32]
-    __device__ __forceinline__ const uint32_t *chunk(int c) const { return wbase + (c & 1) * CH * 32; }
-    __device__ __forceinline__ uint32_t word(int lr) const { return wbase[((lr / CH) & 1) * CH * 32 + (lr % CH) * 32]; }
-    // active nibble of the lane's 4 cells in row lr
+    // this lane's words of chunk c: word q of row r of the chunk at [r * ROWW + q]
+    __device__ __forceinline__ const uint32_t *chunk(int c) const { return wbase + (c & 1) * CH * ROWW; }
+    // active bits of the lane's NC cells in row lr
     __device__ __forceinline__ int active(int lr) const
     {
         int am = 0;
-        if (mask0) {
-            const uint32_t mw = mbase[((lr / CH) & 1) * CH * 32 + (lr % CH) * 32];
+        const uint32_t *mp = mbase + (((lr / CH) & 1) * CH + (lr % CH)) * ROWW;
 #pragma unroll
-            for (int j = 0; j < 4; j++) am |= (int)(((mw >> (8 * j)) & 0xFFu) != 0 && gc0 + j < nx) << j;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) am |= (int)(gc0 + j < nx) << j;
+        for (int j = 0; j < NC; j++) {
+            bool a = gc0 + j < nx;
+            if (mask0) a = a && ((mp[j / 4] >> (8 * (j % 4))) & 0xFFu) != 0;
+            am |= (int)a << j;
         }
         return am;
     }
 };
 
-// decode a staged word: k[4] (8 = none; inactive cells are none) ; on border tiles a code whose
+// decode staged words: k[NC] (8 = none; inactive cells are none); on border tiles a code whose
 // receiver lies outside the raster becomes none.
 template <int ENC>
-__device__ __forceinline__ void decode_row(uint32_t w, int am, const Geo &g, int64_t gr, int64_t gc0, bool border,
-                                           int (&k)[4])
+__device__ __forceinline__ void decode_row(const uint32_t *wp, int am, const Geo &g, int64_t gr, int64_t gc0, bool border,
+                                           int (&k)[NC])
 {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int kk = ((am >> j) & 1) ? d8_norm<ENC>((int)(int8_t)(w >> (8 * j))) : 8;
+    for (int j = 0; j < NC; j++) {
+        int kk = ((am >> j) & 1) ? d8_norm<ENC>((int)(int8_t)(wp[j / 4] >> (8 * (j % 4)))) : 8;
         if (border && kk != 8) {
             int64_t rr = g.gy0 + gr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
             if (rr < 0 || rr >= g.gny || cc < 0 || cc >= g.nx) kk = 8;
@@ -318,20 +321,15 @@ __device__ __forceinline__ void decode_row(uint32_t w, int am, const Geo &g, int
 }
 
 // ---- lean "plain row" machinery ---------------------------------------------------------------
-// A plain row holds only E / SE / S / SW codes (every cell active, tile interior).  Its four codes
-// per lane are turned into byte masks with two multiplies and four LOP3s, and every (cell, dir)
-// select is one PRMT (sign-replicate) + one LOP3 -- no predicates, so nothing spills to P2R.
+// A plain row holds only E / SE / S / SW codes (every cell active, tile interior).
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
-// all-ones / all-zeros from the top bit of byte j of m
-template <int J>
-__device__ __forceinline__ int32_t bmask(uint32_t m) { return (int32_t)prmt(m, 0u, 0x8888u + 0x1111u * J); }
 
-// internal-coded word of a row (E 0, SE 1, S 2, SW 3), or "needs the generic row" when any byte is
+// internal-coded word of 4 cells (E 0, SE 1, S 2, SW 3), or "needs the generic row" when any byte is
 // something else.  Keypad words are translated with a PRMT table lookup.
 template <int ENC>
 __device__ __forceinline__ uint32_t plain_word(uint32_t w, bool &generic)
@@ -348,109 +346,124 @@ __device__ __forceinline__ uint32_t plain_word(uint32_t w, bool &generic)
     generic = junk || (k & 0x04040404u) != 0;
     return k;
 }
-
-// Direction tests of the four cells as packed 0/1 bytes.  Every select below is a multiply by 0/1
-// fused into an IMAD, which runs on the FMA pipe: the kernel is ALU-pipe bound (LOP3 / PRMT / SEL),
-// so moving the selects off that pipe matters more than the instruction count.
-struct RowBits { uint32_t e, se, s, sw; };
-__device__ __forceinline__ RowBits row_bits(uint32_t k)
+template <int ENC>
+__device__ __forceinline__ bool plain_words(const uint32_t *wp, uint32_t (&kw)[NWD])
 {
-    const uint32_t x0 = k & 0x01010101u, x1 = (k >> 1) & 0x01010101u;
+    bool generic = false;
+#pragma unroll
+    for (int q = 0; q < NWD; q++) { bool g1; kw[q] = plain_word<ENC>(wp[q], g1); generic = generic || g1; }
+    return generic;
+}
+
+// Direction tests of the NC cells as 0/1 integers.  Every select below is a multiply by 0/1 fused into
+// an IMAD, which runs on the FMA pipe: the kernels are ALU-pipe bound (LOP3 / PRMT / SEL), so moving the
+// selects off that pipe matters more than the instruction count.
+struct RowBits { uint32_t e[NC], se[NC], s[NC], sw[NC]; bool all_e; };
+__device__ __forceinline__ RowBits row_bits(const uint32_t (&kw)[NWD])
+{
     RowBits m;
-    m.sw = x0 & x1; m.se = x0 ^ m.sw; m.s = x1 ^ m.sw; m.e = (x0 | x1) ^ 0x01010101u;
+    m.all_e = true;
+#pragma unroll
+    for (int q = 0; q < NWD; q++) {
+        const uint32_t x0 = kw[q] & 0x01010101u, x1 = (kw[q] >> 1) & 0x01010101u;
+        const uint32_t sw = x0 & x1, se = x0 ^ sw, s = x1 ^ sw, e = (x0 | x1) ^ 0x01010101u;
+        m.all_e = m.all_e && e == 0x01010101u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {             // byte j as a 0/1 integer
+            m.e[4 * q + j] = prmt(e, 0u, 0x4440u + j);
+            m.se[4 * q + j] = prmt(se, 0u, 0x4440u + j);
+            m.s[4 * q + j] = prmt(s, 0u, 0x4440u + j);
+            m.sw[4 * q + j] = prmt(sw, 0u, 0x4440u + j);
+        }
+    }
     return m;
 }
-// byte J of m as a 0/1 integer
-template <int J>
-__device__ __forceinline__ uint32_t bit01(uint32_t m) { return prmt(m, 0u, 0x4440u + J); }
 
 // Downward step of a plain row.  d[] holds, for each cell, 1 + the inflow from the row above (the
 // cell's own +1 is folded into the accumulate chain of the row above); tot[] out; d[] out for the
 // row below.  extL / extR: external inflow of the left- / right-column cell (phase C), else zero.
 template <typename T>
-__device__ __forceinline__ void plain_row_down(uint32_t k, T (&d)[4], T (&tot)[4], int lane, T extL, T extR)
+__device__ __forceinline__ void plain_row_down(const uint32_t (&kw)[NWD], T (&d)[NC], T (&tot)[NC], int lane, T extL, T extR)
 {
-    const RowBits m = row_bits(k);
-    const T E0 = bit01<0>(m.e), E1 = bit01<1>(m.e), E2 = bit01<2>(m.e), E3 = bit01<3>(m.e);
-    T t0 = d[0] + extL;
-    T t1 = t0 * E0 + d[1];
-    T t2 = t1 * E1 + d[2];
-    T t3 = t2 * E2 + d[3] + extR;
-    T carry = chain_carry_from_left<T>(t3 * E3, m.e == 0x01010101u, lane);
-    tot[0] = t0 + carry; carry *= E0;
-    tot[1] = t1 + carry; carry *= E1;
-    tot[2] = t2 + carry; carry *= E2;
-    tot[3] = t3 + carry;
-    T from_left = __shfl_up_sync(FULL, tot[3] * (T)bit01<3>(m.se), 1);
-    T from_right = __shfl_down_sync(FULL, tot[0] * (T)bit01<0>(m.sw), 1);
+    const RowBits m = row_bits(kw);
+    T t[NC];
+    t[0] = d[0] + extL;
+#pragma unroll
+    for (int j = 1; j < NC; j++) t[j] = t[j - 1] * (T)m.e[j - 1] + d[j];
+    t[NC - 1] += extR;
+    T carry = chain_carry_from_left<T>(t[NC - 1] * (T)m.e[NC - 1], m.all_e, lane);
+#pragma unroll
+    for (int j = 0; j < NC; j++) { tot[j] = t[j] + carry; carry *= (T)m.e[j]; }
+    T from_left = __shfl_up_sync(FULL, tot[NC - 1] * (T)m.se[NC - 1], 1);
+    T from_right = __shfl_down_sync(FULL, tot[0] * (T)m.sw[0], 1);
     from_left = lane == 0 ? (T)1 : from_left + 1;            // the "+1" of the cell below rides along
     if (lane == 31) from_right = 0;
-    d[0] = tot[0] * (T)bit01<0>(m.s) + from_left;
-    d[0] = tot[1] * (T)bit01<1>(m.sw) + d[0];
-    d[1] = tot[1] * (T)bit01<1>(m.s) + 1;
-    d[1] = tot[0] * (T)bit01<0>(m.se) + d[1];
-    d[1] = tot[2] * (T)bit01<2>(m.sw) + d[1];
-    d[2] = tot[2] * (T)bit01<2>(m.s) + 1;
-    d[2] = tot[1] * (T)bit01<1>(m.se) + d[2];
-    d[2] = tot[3] * (T)bit01<3>(m.sw) + d[2];
-    d[3] = tot[3] * (T)bit01<3>(m.s) + from_right;
-    d[3] = tot[2] * (T)bit01<2>(m.se) + d[3] + 1;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        T v = tot[j] * (T)m.s[j] + (j == 0 ? from_left : (T)1);
+        if (j > 0) v = tot[j > 0 ? j - 1 : 0] * (T)m.se[j > 0 ? j - 1 : 0] + v;
+        if (j < NC - 1) v = tot[j < NC - 1 ? j + 1 : 0] * (T)m.sw[j < NC - 1 ? j + 1 : 0] + v;
+        else v += from_right;
+        d[j] = v;
+    }
 }
 
 // Upward (label) step of a plain row of a full interior tile.  A plain row has no pits, so an East
 // cell's own term is 0 and "copy the chain end" is own + next * E.  slotL / slotR: boundary slots of
 // the left- / right-column cell of this row.  BOTTOM: the tile's last row, where S / SE / SW leave the tile.
 template <bool BOTTOM>
-__device__ __forceinline__ void plain_row_up(uint32_t k, uint32_t (&lb)[4], int lane, uint32_t slotL, uint32_t slotR)
+__device__ __forceinline__ void plain_row_up(const uint32_t (&kw)[NWD], uint32_t (&lb)[NC], int lane, uint32_t slotL, uint32_t slotR)
 {
-    const RowBits m = row_bits(k);
-    uint32_t E0 = bit01<0>(m.e), E1 = bit01<1>(m.e), E2 = bit01<2>(m.e), E3 = bit01<3>(m.e);
-    uint32_t own[4];
+    RowBits m = row_bits(kw);
+    uint32_t own[NC];
     if (BOTTOM) {
-        const uint32_t s0 = TW + 4 * lane;
-        own[0] = (s0 + 0) * (1u - E0); own[1] = (s0 + 1) * (1u - E1); own[2] = (s0 + 2) * (1u - E2); own[3] = (s0 + 3) * (1u - E3);
+#pragma unroll
+        for (int j = 0; j < NC; j++) own[j] = (uint32_t)(TW + NC * lane + j) * (1u - m.e[j]);
     } else {
-        const uint32_t lbR0 = __shfl_down_sync(FULL, lb[0], 1), lbL3 = __shfl_up_sync(FULL, lb[3], 1);
-        own[0] = lb[0] * bit01<0>(m.s) + lb[1] * bit01<0>(m.se) + lbL3 * bit01<0>(m.sw);
-        own[1] = lb[1] * bit01<1>(m.s) + lb[2] * bit01<1>(m.se) + lb[0] * bit01<1>(m.sw);
-        own[2] = lb[2] * bit01<2>(m.s) + lb[3] * bit01<2>(m.se) + lb[1] * bit01<2>(m.sw);
-        own[3] = lb[3] * bit01<3>(m.s) + lbR0 * bit01<3>(m.se) + lb[2] * bit01<3>(m.sw);
+        const uint32_t lbR0 = __shfl_down_sync(FULL, lb[0], 1), lbL = __shfl_up_sync(FULL, lb[NC - 1], 1);
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const uint32_t right = j < NC - 1 ? lb[j < NC - 1 ? j + 1 : 0] : lbR0, left = j > 0 ? lb[j > 0 ? j - 1 : 0] : lbL;
+            own[j] = lb[j] * m.s[j] + right * m.se[j] + left * m.sw[j];
+        }
     }
-    if (lane == 31 && ((k >> 24) & 0xFFu) <= 1u) { own[3] = slotR; E3 = 0; }   // E / SE leave through the right column
-    if (lane == 0 && (k & 0xFFu) == 3u) own[0] = slotL;                         // SW leaves through the left column
-    uint32_t V = own[3] + LNONE * E3;                        // label at cell 0 if nothing comes from the right
-    V = V * E2 + own[2];
-    V = V * E1 + own[1];
-    V = V * E0 + own[0];
-    uint32_t cur = label_carry_from_right(V, (E0 & E1 & E2 & E3) != 0, lane);
-    cur = cur * E3 + own[3]; lb[3] = cur;
-    cur = cur * E2 + own[2]; lb[2] = cur;
-    cur = cur * E1 + own[1]; lb[1] = cur;
-    cur = cur * E0 + own[0]; lb[0] = cur;
+    const uint32_t kR = (kw[NWD - 1] >> 24) & 0xFFu, kL = kw[0] & 0xFFu;
+    if (lane == 31 && kR <= 1u) { own[NC - 1] = slotR; m.e[NC - 1] = 0; }     // E / SE leave through the right column
+    if (lane == 0 && kL == 3u) own[0] = slotL;                                // SW leaves through the left column
+    uint32_t V = own[NC - 1] + LNONE * m.e[NC - 1];          // label at cell 0 if nothing comes from the right
+    uint32_t allE = m.e[NC - 1];
+#pragma unroll
+    for (int j = NC - 2; j >= 0; j--) { V = V * m.e[j] + own[j]; allE &= m.e[j]; }
+    uint32_t cur = label_carry_from_right(V, allE != 0, lane);
+#pragma unroll
+    for (int j = NC - 1; j >= 0; j--) { cur = cur * m.e[j] + own[j]; lb[j] = cur; }
 }
+
+// byte j of the plain (internal-coded) words
+__device__ __forceinline__ int plain_k(const uint32_t (&kw)[NWD], int j) { return (int)((kw[j / 4] >> (8 * (j % 4))) & 0xFFu); }
 
 // ---------------------------------------------------------------------------------------------
 // phase A, fast solver
 // ---------------------------------------------------------------------------------------------
 template <int ENC, bool AL>
-__global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
-                                                        Geo g, int ntiles, uint32_t *__restrict__ meta,
-                                                        int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
-                                                        unsigned long long *__restrict__ row_plain,
-                                                        unsigned long long *__restrict__ wq)
+__global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+                                                     Geo g, int ntiles, uint32_t *__restrict__ meta,
+                                                     int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
+                                                     unsigned long long *__restrict__ row_plain,
+                                                     unsigned long long *__restrict__ wq)
 {
-    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][32] DIR words (+ the same again for mask words)
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ the same again for mask words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
     int ty, tx, th, tw;
     tile_dims(g, tile, ty, tx, th, tw);
-    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + 4 * lane;
+    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
     uint32_t *m_t = meta + (int64_t)tile * NSLOT;
     int32_t *x_t = exit_acc + (int64_t)tile * NSLOT;
     unsigned long long *w_t = wq + (int64_t)tile * NSLOT;     // packed forest words: pending << 32 | sum
     constexpr unsigned long long BIAS = 1ull << 32;           // every node waits for its own walker
-    const int rlane = (tw - 1) >> 2, rj = (tw - 1) & 3;       // lane / sub-cell holding the right column
+    const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;      // lane / sub-cell holding the right column
     const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
     const bool full = th == TH && tw == TW;
     const bool plain_tile = mask == nullptr && full && !border;
@@ -458,8 +471,25 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
     rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
     const int nch = (th + CH - 1) / CH;
 
+    // boundary-row stores: NC consecutive slots per lane
+    auto store_acc_row = [&](int base, const int32_t (&tot)[NC]) {
+#pragma unroll
+        for (int q = 0; q < NC / 4; q++)
+            *reinterpret_cast<int4 *>(x_t + base + NC * lane + 4 * q) = make_int4(tot[4 * q], tot[4 * q + 1], tot[4 * q + 2], tot[4 * q + 3]);
+    };
+    auto store_meta_row = [&](int base, const uint32_t (&mw)[NC]) {
+#pragma unroll
+        for (int q = 0; q < NC / 4; q++)
+            *reinterpret_cast<uint4 *>(m_t + base + NC * lane + 4 * q) = make_uint4(mw[4 * q], mw[4 * q + 1], mw[4 * q + 2], mw[4 * q + 3]);
+#pragma unroll
+        for (int q = 0; q < NC / 2; q++)
+            *reinterpret_cast<ulonglong2 *>(w_t + base + NC * lane + 2 * q) = make_ulonglong2(BIAS, BIAS);
+    };
+
     // ---- downward sweep: local accumulation
-    int32_t d[4] = {1, 1, 1, 1};                     // 1 + inflow from the row above
+    int32_t d[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) d[j] = 1;           // 1 + inflow from the row above
     bool complex_tile = false;
     unsigned long long plain_rows = 0;               // bit lr set: row lr takes the lean path (both sweeps, phase C too)
     rows.prefetch(0);
@@ -467,36 +497,40 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
         rows.arrive(c + 1, nch);
         const int cend = th < (c + 1) * CH ? th : (c + 1) * CH;
         const uint32_t *wp = rows.chunk(c);
-        for (int lr = c * CH; lr < cend; lr++) {
-            const uint32_t w = wp[(lr - c * CH) * 32];
-            int32_t tot[4];
+        for (int lr = c * CH; lr < cend; lr++, wp += ROWW) {
+            int32_t tot[NC];
             bool gen = true;
-            uint32_t kw = 0;
-            if (plain_tile) { kw = plain_word<ENC>(w, gen); gen = __any_sync(FULL, gen); }
+            uint32_t kw[NWD];
+            if (plain_tile) gen = __any_sync(FULL, plain_words<ENC>(wp, kw));
             if (!gen) {
                 plain_rows |= 1ull << lr;
                 plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
             } else {
-                int k[4];
+                int k[NC];
                 const int am = rows.active(lr);
-                decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
+                decode_row<ENC>(wp, am, g, gr0 + lr, gc0, border, k);
                 if (lr > 0) {
-                    bool up = (k[0] >= 5 && k[0] <= 7) || (k[1] >= 5 && k[1] <= 7) || (k[2] >= 5 && k[2] <= 7) || (k[3] >= 5 && k[3] <= 7);
+                    bool up = false;
+#pragma unroll
+                    for (int j = 0; j < NC; j++) up = up || (k[j] >= 5 && k[j] <= 7);
                     complex_tile = complex_tile || __any_sync(FULL, up);
                 }
-                int32_t b[4];
+                int32_t b[NC];
 #pragma unroll
-                for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] : 0;
+                for (int j = 0; j < NC; j++) b[j] = ((am >> j) & 1) ? d[j] : 0;
                 sweep_row_down<int32_t>(k, am, b, tot, d, lane, complex_tile);
                 if (complex_tile) break;
 #pragma unroll
-                for (int j = 0; j < 4; j++) d[j] += 1;
+                for (int j = 0; j < NC; j++) d[j] += 1;
             }
-            if (lr == 0) *reinterpret_cast<int4 *>(x_t + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
-            else if (lr == th - 1) *reinterpret_cast<int4 *>(x_t + TW + 4 * lane) = make_int4(tot[0], tot[1], tot[2], tot[3]);
+            if (lr == 0) store_acc_row(0, tot);
+            else if (lr == th - 1) store_acc_row(TW, tot);
             else {
                 if (lane == 0) x_t[2 * TW + lr] = tot[0];
-                if (lane == rlane && tw > 1) x_t[2 * TW + TH + lr] = tot[rj];
+                if (lane == rlane && tw > 1) {
+#pragma unroll
+                    for (int j = 0; j < NC; j++) if (j == rj) x_t[2 * TW + TH + lr] = tot[j];
+                }
             }
         }
     }
@@ -509,12 +543,14 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
     if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
 
     // ---- upward sweep: exit labels (the chunks come back from L2 in reverse order)
-    uint32_t lb[4] = {LNONE, LNONE, LNONE, LNONE};   // labels of the row below
+    uint32_t lb[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) lb[j] = LNONE;      // labels of the row below
     rows.prefetch(nch - 1);
     for (int c = nch - 1; c >= 0; c--) {
         rows.arrive(c - 1, nch);
         const int cbeg = c * CH;
-        const uint32_t *wp = rows.chunk(c);
+        const uint32_t *wc = rows.chunk(c);
         int lr = (th < (c + 1) * CH ? th : (c + 1) * CH) - 1;
         while (lr >= cbeg) {
             {   // a run of lean rows going up (bounded by the chunk)
@@ -522,35 +558,33 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
                 int run = rest ? __clzll((long long)rest) : lr + 1;
                 run = run < lr - cbeg + 1 ? run : lr - cbeg + 1;
                 for (const int end = lr - run; lr > end; lr--) {
-                    bool gen;
-                    const uint32_t kw = plain_word<ENC>(wp[(lr - cbeg) * 32], gen);
+                    uint32_t kw[NWD];
+                    plain_words<ENC>(wc + (lr - cbeg) * ROWW, kw);
                     if (lr == 0 || lr == TH - 1) {        // first / last row of the tile: every cell is a boundary slot
                         if (lr == 0) plain_row_up<false>(kw, lb, lane, 0u, (uint32_t)(TW - 1));
                         else plain_row_up<true>(kw, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1));
-                        const int base = (lr == 0 ? 0 : TW) + 4 * lane;
-                        *reinterpret_cast<uint4 *>(m_t + base) =
-                            make_uint4(meta_pack(lb[0], (int)(kw & 0xFFu), false, true), meta_pack(lb[1], (int)((kw >> 8) & 0xFFu), false, true),
-                                       meta_pack(lb[2], (int)((kw >> 16) & 0xFFu), false, true), meta_pack(lb[3], (int)(kw >> 24), false, true));
-                        *reinterpret_cast<ulonglong2 *>(w_t + base) = make_ulonglong2(BIAS, BIAS);
-                        *reinterpret_cast<ulonglong2 *>(w_t + base + 2) = make_ulonglong2(BIAS, BIAS);
+                        uint32_t mw[NC];
+#pragma unroll
+                        for (int j = 0; j < NC; j++) mw[j] = meta_pack(lb[j], plain_k(kw, j), false, true);
+                        store_meta_row(lr == 0 ? 0 : TW, mw);
                     } else {
                         plain_row_up<false>(kw, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
-                        if (lane == 0) { m_t[2 * TW + lr] = meta_pack(lb[0], (int)(kw & 0xFFu), false, true); w_t[2 * TW + lr] = BIAS; }
-                        if (lane == 31) { m_t[2 * TW + TH + lr] = meta_pack(lb[3], (int)(kw >> 24), false, true); w_t[2 * TW + TH + lr] = BIAS; }
+                        if (lane == 0) { m_t[2 * TW + lr] = meta_pack(lb[0], plain_k(kw, 0), false, true); w_t[2 * TW + lr] = BIAS; }
+                        if (lane == 31) { m_t[2 * TW + TH + lr] = meta_pack(lb[NC - 1], plain_k(kw, NC - 1), false, true); w_t[2 * TW + TH + lr] = BIAS; }
                     }
                 }
                 if (lr < cbeg) break;
             }
-            const uint32_t w = wp[(lr - cbeg) * 32];
-            int k[4];
+            const uint32_t *wp = wc + (lr - cbeg) * ROWW;
+            int k[NC];
             const int am = rows.active(lr);
-            decode_row<ENC>(w, am, g, gr0 + lr, gc0, border, k);
-            uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left3 = __shfl_up_sync(FULL, lb[3], 1);
-            uint32_t own[4];
-            bool pe[4], pw[4];
+            decode_row<ENC>(wp, am, g, gr0 + lr, gc0, border, k);
+            const uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left = __shfl_up_sync(FULL, lb[NC - 1], 1);
+            uint32_t own[NC];
+            bool pe[NC], pw[NC];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int lc = 4 * lane + j, kk = k[j];
+            for (int j = 0; j < NC; j++) {
+                const int lc = NC * lane + j, kk = k[j];
                 const bool top = lr == 0, bot = lr == th - 1, lft = lc == 0, rgt = lc == tw - 1;
                 bool exits = (bot && kk >= 1 && kk <= 3) || (top && kk >= 5 && kk <= 7) ||
                              (rgt && (kk == 0 || kk == 1 || kk == 7)) || (lft && kk >= 3 && kk <= 5);
@@ -559,46 +593,48 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
                 if (kk != 8) {
                     if (exits) v = (uint32_t)slot_of(lr, lc, th, tw);
                     else if (kk == 2) v = lb[j];
-                    else if (kk == 1) v = (j < 3) ? lb[j < 3 ? j + 1 : 3] : lb_right0;
-                    else if (kk == 3) v = (j > 0) ? lb[j > 0 ? j - 1 : 0] : lb_left3;
+                    else if (kk == 1) v = (j < NC - 1) ? lb[j < NC - 1 ? j + 1 : 0] : lb_right0;
+                    else if (kk == 3) v = (j > 0) ? lb[j > 0 ? j - 1 : 0] : lb_left;
                     else if (kk == 0) pe[j] = true;
                     else if (kk == 4) pw[j] = true;
                 }
                 own[j] = v;
             }
-            uint32_t lab[4];
+            uint32_t lab[NC];
             {   // East cells copy the label of the chain end on their right
                 uint32_t V = LNONE;
                 bool P = true;
 #pragma unroll
-                for (int j = 3; j >= 0; j--) { V = pe[j] ? V : own[j]; P = P && pe[j]; }
+                for (int j = NC - 1; j >= 0; j--) { V = pe[j] ? V : own[j]; P = P && pe[j]; }
                 uint32_t cur = label_carry_from_right(V, P, lane);
 #pragma unroll
-                for (int j = 3; j >= 0; j--) { cur = pe[j] ? cur : own[j]; lab[j] = cur; }
+                for (int j = NC - 1; j >= 0; j--) { cur = pe[j] ? cur : own[j]; lab[j] = cur; }
             }
-            if (__any_sync(FULL, pw[0] || pw[1] || pw[2] || pw[3])) {
+            bool anyw = false;
+#pragma unroll
+            for (int j = 0; j < NC; j++) anyw = anyw || pw[j];
+            if (__any_sync(FULL, anyw)) {
                 uint32_t V = LNONE;
                 bool P = true;
 #pragma unroll
-                for (int j = 0; j < 4; j++) { V = pw[j] ? V : lab[j]; P = P && pw[j]; }
+                for (int j = 0; j < NC; j++) { V = pw[j] ? V : lab[j]; P = P && pw[j]; }
                 uint32_t cur = label_carry_from_left(V, P, lane);
 #pragma unroll
-                for (int j = 0; j < 4; j++) { cur = pw[j] ? cur : lab[j]; lab[j] = cur; }
+                for (int j = 0; j < NC; j++) { cur = pw[j] ? cur : lab[j]; lab[j] = cur; }
             }
-            uint32_t mw[4];
+            uint32_t mw[NC];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < NC; j++) {
                 lb[j] = lab[j];
                 mw[j] = meta_pack(lab[j], k[j], false, (am >> j) & 1);
             }
-            if (lr == 0 || lr == th - 1) {
-                const int base = (lr == 0 ? 0 : TW) + 4 * lane;
-                *reinterpret_cast<uint4 *>(m_t + base) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-                *reinterpret_cast<ulonglong2 *>(w_t + base) = make_ulonglong2(BIAS, BIAS);
-                *reinterpret_cast<ulonglong2 *>(w_t + base + 2) = make_ulonglong2(BIAS, BIAS);
-            } else {
+            if (lr == 0 || lr == th - 1) store_meta_row(lr == 0 ? 0 : TW, mw);
+            else {
                 if (lane == 0) { m_t[2 * TW + lr] = mw[0]; w_t[2 * TW + lr] = BIAS; }
-                if (lane == rlane && tw > 1) { m_t[2 * TW + TH + lr] = mw[rj]; w_t[2 * TW + TH + lr] = BIAS; }
+                if (lane == rlane && tw > 1) {
+#pragma unroll
+                    for (int j = 0; j < NC; j++) if (j == rj) { m_t[2 * TW + TH + lr] = mw[j]; w_t[2 * TW + TH + lr] = BIAS; }
+                }
             }
             lr--;
         }
@@ -609,113 +645,116 @@ __global__ void __launch_bounds__(WPB * 32, 8) k_sweepA(const int8_t *__restrict
 // phase C, fast solver
 // ---------------------------------------------------------------------------------------------
 template <bool AL, typename T>
-__device__ __forceinline__ void store_row(T *out, const T (&tot)[4], int64_t gc0, int64_t nx)
+__device__ __forceinline__ void store_row(T *out, const T (&tot)[NC], int64_t gc0, int64_t nx)
 {
     if (AL) {
         if (gc0 < nx) {
-            if (sizeof(T) == 4) *reinterpret_cast<int4 *>(out) = make_int4((int)tot[0], (int)tot[1], (int)tot[2], (int)tot[3]);
-            else {
-                *reinterpret_cast<longlong2 *>(out) = make_longlong2((long long)tot[0], (long long)tot[1]);
-                *reinterpret_cast<longlong2 *>(out + 2) = make_longlong2((long long)tot[2], (long long)tot[3]);
+            if (sizeof(T) == 4) {
+#pragma unroll
+                for (int q = 0; q < NC / 4; q++)
+                    *reinterpret_cast<int4 *>(out + 4 * q) = make_int4((int)tot[4 * q], (int)tot[4 * q + 1], (int)tot[4 * q + 2], (int)tot[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < NC / 2; q++)
+                    *reinterpret_cast<longlong2 *>(out + 2 * q) = make_longlong2((long long)tot[2 * q], (long long)tot[2 * q + 1]);
             }
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) if (gc0 + j < nx) out[j] = tot[j];
+        for (int j = 0; j < NC; j++) if (gc0 + j < nx) out[j] = tot[j];
     }
 }
 
-// number of consecutive set bits of `rows` starting at bit lr
-__device__ __forceinline__ int plain_run(unsigned long long rows, int lr)
-{
-    unsigned long long rest = ~(rows >> lr);            // first zero bit = first generic row
-    return rest ? __ffsll((long long)rest) - 1 : 64 - lr;
-}
-
 template <int ENC, bool AL, typename T>
-__global__ void __launch_bounds__(WPB * 32, 8) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
-                                                        Geo g, int ntiles, const T *__restrict__ inflow,
-                                                        const uint8_t *__restrict__ tile_class,
-                                                        const unsigned long long *__restrict__ row_plain, T *__restrict__ acc)
+__global__ void __launch_bounds__(WPB * 32, 6) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+                                                     Geo g, int ntiles, const T *__restrict__ inflow,
+                                                     const uint8_t *__restrict__ tile_class,
+                                                     const unsigned long long *__restrict__ row_plain, T *__restrict__ acc)
 {
-    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][32] DIR words (+ mask words) + the side inflows
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ mask words) + the side inflows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
     if (tile_class[tile] != 0) return;              // general solver
     int ty, tx, th, tw;
     tile_dims(g, tile, ty, tx, th, tw);
-    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + 4 * lane;
+    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
     const T *in_t = inflow + (int64_t)tile * NSLOT;
-    const int rlane = (tw - 1) >> 2, rj = (tw - 1) & 3;
+    const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;
     const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
     TileRows<AL> rows;
     rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
     const int nch = (th + CH - 1) / CH;
     rows.prefetch(0);
     // external inflow of the left / right column cells
-    T *extL = reinterpret_cast<T *>(s_dyn + (mask ? 4 : 2) * WPB * CH * 32) + 2 * TH * warp, *extR = extL + TH;
+    T *extL = reinterpret_cast<T *>(s_dyn + (mask ? 2 : 1) * WPB * 2 * CH * ROWW) + 2 * TH * warp, *extR = extL + TH;
     extL[lane] = in_t[2 * TW + lane]; extL[lane + 32] = in_t[2 * TW + 32 + lane];
     extR[lane] = in_t[2 * TW + TH + lane]; extR[lane + 32] = in_t[2 * TW + TH + 32 + lane];
-    T d[4] = {1, 1, 1, 1};                           // 1 + inflow from the row above
+    T d[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) d[j] = 1;           // 1 + inflow from the row above
     bool dummy = false;
     T *out = acc + gr0 * g.nx + gc0;
-    const unsigned long long plain_rows = row_plain[tile];
+    // the per-chunk lean-row masks live in shared memory: an L1TEX load (global or a register spill) issued
+    // behind the chunk prefetch would wait for the prefetch's HBM round trip (the L1TEX queue is in order)
+    unsigned char *pchunk = reinterpret_cast<unsigned char *>(extL + (size_t)2 * TH * (WPB - warp)) + 8 * warp;
+    if (lane == 0) *reinterpret_cast<unsigned long long *>(pchunk) = row_plain[tile];
     const bool is_l = lane == 0, is_r = lane == 31;
     for (int c = 0; c < nch; c++) {
         rows.arrive(c + 1, nch);
         const int cend = th < (c + 1) * CH ? th : (c + 1) * CH;
         int lr = c * CH;
-        const uint32_t *wp = rows.chunk(c);              // row lr of this chunk at wp[(lr - c*CH) * 32]
-        uint32_t pbits = (uint32_t)(plain_rows >> (c * CH)) & ((1u << CH) - 1u);
+        const uint32_t *wp = rows.chunk(c);              // row lr of this chunk at wp
+        uint32_t pbits = pchunk[c];
         while (lr < cend) {
             // a run of lean rows (bounded by the chunk): no per-row classification, no divergent control flow
             const uint32_t inv = ~pbits & ((1u << CH) - 1u);
             int run = inv ? __ffs(inv) - 1 : CH;
             run = run < cend - lr ? run : cend - lr;
             pbits >>= run;
-            for (const int end = lr + run; lr < end; lr++, out += g.nx, wp += 32) {
-                T tot[4];
-                bool gen;
+            for (const int end = lr + run; lr < end; lr++, out += g.nx, wp += ROWW) {
+                T tot[NC];
+                uint32_t kw[NWD];
+                plain_words<ENC>(wp, kw);
                 if (lr == 0 || lr == TH - 1) {            // first / last row: every cell is a boundary slot
-                    const T *e4 = in_t + (lr == 0 ? 0 : TW) + 4 * lane;
+                    const T *e4 = in_t + (lr == 0 ? 0 : TW) + NC * lane;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) d[j] += e4[j];
-                    plain_row_down<T>(plain_word<ENC>(*wp, gen), d, tot, lane, (T)0, (T)0);
+                    for (int j = 0; j < NC; j++) d[j] += e4[j];
+                    plain_row_down<T>(kw, d, tot, lane, (T)0, (T)0);
                 } else {
                     const T l = extL[lr], r = extR[lr];
-                    plain_row_down<T>(plain_word<ENC>(*wp, gen), d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
+                    plain_row_down<T>(kw, d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
                 }
                 store_row<AL, T>(out, tot, gc0, g.nx);
             }
             if (lr >= cend) break;
             {   // one generic row
-                T tot[4];
-                int k[4];
+                T tot[NC];
+                int k[NC];
                 const int am = rows.active(lr);
-                decode_row<ENC>(rows.word(lr), am, g, gr0 + lr, gc0, border, k);
-                T ext[4] = {0, 0, 0, 0};
-                if (lr == 0) {
+                decode_row<ENC>(wp, am, g, gr0 + lr, gc0, border, k);
+                T ext[NC];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) ext[j] = in_t[4 * lane + j];
-                } else if (lr == th - 1) {
+                for (int j = 0; j < NC; j++) ext[j] = 0;
+                if (lr == 0 || lr == th - 1) {
+                    const T *e4 = in_t + (lr == 0 ? 0 : TW) + NC * lane;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) ext[j] = in_t[TW + 4 * lane + j];
+                    for (int j = 0; j < NC; j++) ext[j] = e4[j];
                 } else {
                     if (lane == 0) ext[0] = extL[lr];
                     if (lane == rlane && tw > 1) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) if (j == rj) ext[j] += extR[lr];
+                        for (int j = 0; j < NC; j++) if (j == rj) ext[j] += extR[lr];
                     }
                 }
-                T b[4];
+                T b[NC];
 #pragma unroll
-                for (int j = 0; j < 4; j++) b[j] = ((am >> j) & 1) ? d[j] + ext[j] : (T)0;
+                for (int j = 0; j < NC; j++) b[j] = ((am >> j) & 1) ? d[j] + ext[j] : (T)0;
                 sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
 #pragma unroll
-                for (int j = 0; j < 4; j++) d[j] += 1;
+                for (int j = 0; j < NC; j++) d[j] += 1;
                 store_row<AL, T>(out, tot, gc0, g.nx);
-                lr++; out += g.nx; wp += 32; pbits >>= 1;
+                lr++; out += g.nx; wp += ROWW; pbits >>= 1;
             }
         }
     }
@@ -820,7 +859,13 @@ __global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir
                                                   int32_t *__restrict__ exit_acc, unsigned long long *__restrict__ wq)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // each block owns a contiguous range of tiles and looks at all their classes at once: nearly always
+  // nothing is complex and the block leaves after one coalesced load and one barrier
+  const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
+  bool any_mine = false;
+  for (int t = t_lo + threadIdx.x; t < t_hi; t += GTH) any_mine = any_mine || (tile_class[t] & 1);
+  if (!__syncthreads_or(any_mine)) return;
+  for (int tile = t_lo; tile < t_hi; tile++) {
     if (!(tile_class[tile] & 1)) continue;
     __syncthreads();                                   // previous tile of this block is done with smem
     int32_t *acc = reinterpret_cast<int32_t *>(smem);
@@ -869,7 +914,11 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
                                                   const uint8_t *__restrict__ ext_unres, T *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
+  bool any_mine = false;
+  for (int t = t_lo + threadIdx.x; t < t_hi; t += GTH) any_mine = any_mine || tile_class[t] != 0;
+  if (!__syncthreads_or(any_mine)) return;
+  for (int tile = t_lo; tile < t_hi; tile++) {
     if (tile_class[tile] == 0) continue;
     __syncthreads();
     T *acc = reinterpret_cast<T *>(smem);
@@ -1208,7 +1257,7 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    const size_t smemF = (size_t)(mask ? 4 : 2) * WPB * CH * 32 * sizeof(uint32_t);
+    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t);
     if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
     else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
@@ -1224,7 +1273,7 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);
     const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
     WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-    const size_t smemF = (size_t)(mask ? 4 : 2) * WPB * CH * 32 * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T);
+    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T) + WPB * 8;
     if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
     else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
     k_generalC<ENC, T><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, w.inflow, w.ext_unres, acc);
@@ -1247,7 +1296,7 @@ int sweep_phaseG_i64(const Geo &g, int64_t nnodes, const SweepWs<T> &w, bool use
 
 static bool aligned4(const void *dir, const void *mask, const void *acc, int64_t nx)
 {
-    return (nx % 4 == 0) && (((uintptr_t)dir & 3) == 0) && (mask == nullptr || ((uintptr_t)mask & 3) == 0) &&
+    return (nx % NC == 0) && (((uintptr_t)dir & (NC - 1)) == 0) && (mask == nullptr || ((uintptr_t)mask & (NC - 1)) == 0) &&
            (((uintptr_t)acc & 15) == 0);
 }
 
