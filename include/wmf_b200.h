@@ -152,6 +152,21 @@ int wmf_basin_2map(const int32_t *structure, int64_t stride, int64_t n, const vo
 int wmf_stream_nod(const int32_t *structure, int64_t stride, int64_t n, const int32_t *acum, int32_t umbral,
                    int32_t *cauce, int32_t *nodos, int32_t *trazado, int32_t *counts_host, void *stream);
 
+/* ---------------------------------------------------------------- N2: stream receiver / HAND
+ * wmf_stream_receiver replaces wmf_py/cu_py/metrics.py:189-268 hydro_distance_and_receiver: for every active
+ * cell the linear index of the first stream cell on its downstream path (a_quien; -1 outside the mask or when
+ * the path never meets a stream; a stream cell is its own receiver) and the path length to it (hdnd, nullable;
+ * nan where a_quien is -1; steps cost dx when the row stays, dy when the column stays, hypot(dx, dy) diagonally).
+ * wmf_hand replaces metrics.py:271-323 hand: max(dem - dem[first stream cell downstream], 0); nan outside the
+ * mask, where no stream is met, and -- like the reference's topological order -- behind a non-stream cell of a
+ * drainage cycle.  stream: uint8 raster, nonzero = stream cell.  Both sync (convergence checks).  ny*nx < 2^31. */
+size_t wmf_stream_receiver_workspace(int64_t ny, int64_t nx);
+int wmf_stream_receiver(const int8_t *dir, const uint8_t *mask, const uint8_t *stream, int64_t ny, int64_t nx, int encoding,
+                        double dx, double dy, int32_t *a_quien, double *hdnd, void *workspace, size_t ws_bytes, void *stream_);
+size_t wmf_hand_workspace(int64_t ny, int64_t nx);
+int wmf_hand(const double *dem, const int8_t *dir, const uint8_t *mask, const uint8_t *stream, int64_t ny, int64_t nx,
+             int encoding, double *hand, void *workspace, size_t ws_bytes, void *stream_);
+
 /* ---------------------------------------------------------------- S1/S2: SHIA 5-tank (Fortran semantics)
  * Replaces models.shia_v1 as shipped (wmf_heavy/Modelos_heavy.f90:169-548) incl. calc_speed
  * (:907-919): vertical cascade + lateral outflow of tanks 2..4 (discarded), fp32.

@@ -67,6 +67,10 @@ SIGNATURES = {
     "wmf_basin_map2basin": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _vp]),
     "wmf_basin_2map": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _vp]),
     "wmf_stream_nod": (_int, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "wmf_stream_receiver_workspace": (_sz, [_i64, _i64]),
+    "wmf_stream_receiver": (_int, [_vp, _vp, _vp, _i64, _i64, _int, C.c_double, C.c_double, _vp, _vp, _vp, _sz, _vp]),
+    "wmf_hand_workspace": (_sz, [_i64, _i64]),
+    "wmf_hand": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _sz, _vp]),
     "wmf_shia5_workspace": (_sz, [_i64, _i64, _i32]),
     "wmf_shia5_run": (_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),

@@ -331,3 +331,40 @@ def d8_stripe_finish(dir_t: torch.Tensor, ws: torch.Tensor, row0: int, ny_total:
     check(_lib.load().wmf_d8_stripe_finish(ptr(dir_t), ptr(mask_t), ptr(out), acc_dtype, ny, nx, int(row0), int(ny_total),
                                            encoding, ptr(ext_inflow), ptr(ext_unres), ptr(ws), ws.numel(), stream_ptr()))
     return out
+
+
+# --------------------------------------------------------------------------------------- N2: stream receiver / HAND
+def stream_receiver(dir_t: torch.Tensor, mask_t: Optional[torch.Tensor], stream_t: torch.Tensor, dx: float, dy: float,
+                    encoding: int = ENC_INTERNAL, with_distance: bool = True):
+    """First stream cell downstream of every cell (+ path length): metrics.py:189-268."""
+    require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    _chk_dev(stream_t, torch.uint8, "stream")
+    if mask_t is not None:
+        _chk_dev(mask_t, torch.uint8, "mask")
+    ny, nx = dir_t.shape
+    aq = torch.empty((ny, nx), dtype=torch.int32, device=dir_t.device)
+    hd = torch.empty((ny, nx), dtype=torch.float64, device=dir_t.device) if with_distance else None
+    lib = _lib.load()
+    ws = workspace(lib.wmf_stream_receiver_workspace(ny, nx))
+    check(lib.wmf_stream_receiver(ptr(dir_t), ptr(mask_t), ptr(stream_t), ny, nx, encoding, float(dx), float(dy), ptr(aq),
+                                  ptr(hd), ptr(ws), ws.numel(), stream_ptr()))
+    return aq, hd
+
+
+def hand(dem_t: torch.Tensor, dir_t: torch.Tensor, mask_t: Optional[torch.Tensor], stream_t: torch.Tensor,
+         encoding: int = ENC_INTERNAL) -> torch.Tensor:
+    """Height above the nearest drainage along the flow path: metrics.py:271-323."""
+    require_cuda()
+    _chk_dev(dem_t, torch.float64, "dem")
+    _chk_dev(dir_t, torch.int8, "dir")
+    _chk_dev(stream_t, torch.uint8, "stream")
+    if mask_t is not None:
+        _chk_dev(mask_t, torch.uint8, "mask")
+    ny, nx = dir_t.shape
+    out = torch.empty((ny, nx), dtype=torch.float64, device=dir_t.device)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_hand_workspace(ny, nx))
+    check(lib.wmf_hand(ptr(dem_t), ptr(dir_t), ptr(mask_t), ptr(stream_t), ny, nx, encoding, ptr(out), ptr(ws), ws.numel(),
+                       stream_ptr()))
+    return out
