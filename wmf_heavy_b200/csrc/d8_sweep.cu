@@ -466,7 +466,11 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;      // lane / sub-cell holding the right column
     const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
     const bool full = th == TH && tw == TW;
-    const bool plain_tile = mask == nullptr && full && !border;
+    // Lean rows also serve the raster's own edge tiles: a left-column SW cell or a right-column E / SE cell
+    // drains nowhere in the row arithmetic and keeps its own slot as exit label; k_g_build / entry_of give
+    // such an exit no entry.  Only the raster's last row (S / SE / SW leave the raster) stays generic.
+    const bool plain_tile = mask == nullptr && full;
+    const int last_generic = (g.gy0 + gr0 + th == g.gny) ? th - 1 : -1;
     TileRows<AL> rows;
     rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
     const int nch = (th + CH - 1) / CH;
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             int32_t tot[NC];
             bool gen = true;
             uint32_t kw[NWD];
-            if (plain_tile) gen = __any_sync(FULL, plain_words<ENC>(wp, kw));
+            if (plain_tile && lr != last_generic) gen = __any_sync(FULL, plain_words<ENC>(wp, kw));
             if (!gen) {
                 plain_rows |= 1ull << lr;
                 plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
@@ -966,7 +970,8 @@ __device__ __forceinline__ int64_t entry_of(const Geo &g, const uint32_t *__rest
     if (k == 8) return -1;
     int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
     if (rr >= 0 && rr < th && cc >= 0 && cc < tw) return -1;            // stays in the tile: not an exit
-    int64_t gr = (int64_t)ty * TH + rr, gc = (int64_t)tx * TW + cc;     // in raster by construction
+    int64_t gr = (int64_t)ty * TH + rr, gc = (int64_t)tx * TW + cc;
+    if (gc < 0 || gc >= g.nx) return -1;                                // off the raster's side: no receiver
     if (gr < 0 || gr >= g.ny) return -2;
     int ty2 = (int)(gr / TH), tx2 = (int)(gc / TW);
     int tile2 = ty2 * g.tiles_x + tx2, ty3, tx3, th2, tw2;
@@ -1019,7 +1024,8 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__rest
             const int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
             if (rr < 0 || rr >= th || cc < 0 || cc >= tw) {          // the edge leaves the tile
                 const int ty2 = ty + (rr < 0 ? -1 : (rr >= th ? 1 : 0)), tx2 = tx + (cc < 0 ? -1 : (cc >= tw ? 1 : 0));
-                if (ty2 < 0 || ty2 >= g.tiles_y) en = -2;            // into a neighbouring row stripe
+                if (tx2 < 0 || tx2 >= g.tiles_x) { }                 // off the raster's side: no receiver
+                else if (ty2 < 0 || ty2 >= g.tiles_y) en = -2;       // into a neighbouring row stripe
                 else {
                     const int th2 = ty2 == g.tiles_y - 1 ? last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? last_tw : TW;
                     const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
@@ -1153,7 +1159,8 @@ __global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restri
     const bool is_exit = active && entry[node] == -2 &&
                          ((side == 0 && k >= 5 && k <= 7) || (side == 1 && k >= 1 && k <= 3));
     const bool resolved = (uint32_t)(wq[node] >> 32) == 0u;
-    const int64_t rec_k = active ? k : 9;
+    const int64_t c_recv = col + (k < 8 ? d8_dc(k) : 0);
+    const int64_t rec_k = !active ? 9 : ((c_recv < 0 || c_recv >= g.nx) ? 8 : k);
     const int64_t rec_unres = (is_exit && !resolved) ? 1 : 0;
     recs[i] = (is_exit && resolved) ? (int64_t)stripe_total[node] : 0;       // plane 0: exit_acc
     int32_t link = -1;
