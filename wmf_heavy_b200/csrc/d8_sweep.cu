@@ -1047,43 +1047,64 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__rest
     entry[i] = en;
 }
 
-__global__ void k_g_walk(int64_t nnodes, const int32_t *__restrict__ parent, const int32_t *__restrict__ entry,
-                         const int32_t *__restrict__ w, unsigned long long *wq, int32_t *__restrict__ inflow,
-                         int32_t *__restrict__ stripe_total)
+// "Did every exit finalise?" without a host round trip: GCNT words (one 32-byte sector each, so the
+// per-warp adds spread out) hold exits << 32 | finalised; k_g_unres has work only when the halves differ.
+constexpr int GCNT = 64;                                     // power of two
+constexpr size_t GCNT_BYTES = sizeof(unsigned long long) * 4 * GCNT;
+__global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const int32_t *__restrict__ parent, const int32_t *__restrict__ entry,
+                                                const int32_t *__restrict__ w, unsigned long long *wq, int32_t *__restrict__ inflow,
+                                                int32_t *__restrict__ stripe_total, unsigned long long *__restrict__ gcnt)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnodes) return;
-    int32_t en = entry[i];
-    if (en == -1) return;                                   // not an exit: nothing to carry
-    int32_t p = parent[i];
-    uint32_t wc = (uint32_t)w[i];
-    int64_t cur = i;
-    unsigned long long old = atomicAdd(&wq[cur], (unsigned long long)(-(long long)PEND1));   // own arrival
-    uint32_t add = 0;
-    while ((uint32_t)(old >> 32) == 1u) {                   // we took pending to zero: cur is final
-        const uint32_t total = (uint32_t)old + add + wc;
-        if (en >= 0) atomicAdd(&inflow[en], (int32_t)total);
-        else if (en == -2) stripe_total[cur] = (int32_t)total;     // a stripe exit keeps its stripe-local total
-        if (p < 0) break;
-        // the parent's static data does not depend on the atomic: fetch it first so the hop costs ONE L2 round trip
-        const int32_t pp = parent[p], pen = entry[p];
-        const uint32_t pw = (uint32_t)w[p];
-        old = atomicAdd(&wq[p], (unsigned long long)total - PEND1);
-        add = total;
-        cur = p; p = pp; en = pen; wc = pw;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t en = i < nnodes ? entry[i] : -1;
+    const unsigned int nexit = __popc(__ballot_sync(FULL, en != -1));
+    unsigned int nfin = 0;
+    if (en != -1) {                                         // an exit: carry its total downstream
+        int32_t p = parent[i];
+        uint32_t wc = (uint32_t)w[i];
+        int64_t cur = i;
+        unsigned long long old = atomicAdd(&wq[cur], (unsigned long long)(-(long long)PEND1));   // own arrival
+        uint32_t add = 0;
+        while ((uint32_t)(old >> 32) == 1u) {               // we took pending to zero: cur is final
+            const uint32_t total = (uint32_t)old + add + wc;
+            nfin++;
+            if (en >= 0) atomicAdd(&inflow[en], (int32_t)total);
+            else if (en == -2) stripe_total[cur] = (int32_t)total;     // a stripe exit keeps its stripe-local total
+            if (p < 0) break;
+            // the parent's static data does not depend on the atomic: fetch it first so the hop costs ONE L2 round trip
+            const int32_t pp = parent[p], pen = entry[p];
+            const uint32_t pw = (uint32_t)w[p];
+            old = atomicAdd(&wq[p], (unsigned long long)total - PEND1);
+            add = total;
+            cur = p; p = pp; en = pen; wc = pw;
+        }
     }
+    __syncwarp();
+    nfin = __reduce_add_sync(FULL, nfin);
+    if ((threadIdx.x & 31) == 0 && nexit)
+        atomicAdd(&gcnt[4 * (blockIdx.x & (GCNT - 1))], ((unsigned long long)nexit << 32) | nfin);
 }
 
+// Exits that never finalised (cycles, or fed by one) poison the entry they drain to.  Nothing to do
+// when every exit finalised, which the two counters tell without a host round trip.
 __global__ void k_g_unres(int64_t nnodes, const int32_t *__restrict__ entry, const unsigned long long *__restrict__ wq,
-                          uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class)
+                          uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class,
+                          const unsigned long long *__restrict__ gcnt)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnodes) return;
-    int32_t en = entry[i];
-    if (en < 0) return;
-    if ((uint32_t)(wq[i] >> 32) != 0u) {                    // never finalised: the entry it feeds never finalises
-        ext_unres[en] = 1;
-        tile_class[en / NSLOT] = 2;                         // (racing writers all store non-zero)
+    {
+        const int lane = threadIdx.x & 31;
+        unsigned long long c = 0;
+        for (int q = lane; q < GCNT; q += 32) c += gcnt[4 * q];
+        const unsigned int exits = __reduce_add_sync(FULL, (unsigned int)(c >> 32)), fin = __reduce_add_sync(FULL, (unsigned int)c);
+        if (exits == fin) return;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t en = entry[i];
+        if (en < 0) continue;
+        if ((uint32_t)(wq[i] >> 32) != 0u) {                // never finalised: the entry it feeds never finalises
+            ext_unres[en] = 1;
+            tile_class[en / NSLOT] = 2;                     // (racing writers all store non-zero)
+        }
     }
 }
 
@@ -1224,7 +1245,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
 template <typename T>
 struct SweepWs {
     uint32_t *meta; int32_t *exit_acc, *parent, *cnt; T *A, *inflow; uint8_t *blocked, *ext_unres, *tile_class;
-    unsigned long long *row_plain, *wq; int64_t *w64;
+    unsigned long long *row_plain, *wq; int64_t *w64; unsigned long long *gcnt;
     bool ok;
 };
 template <typename T>
@@ -1244,6 +1265,7 @@ SweepWs<T> carve_ws(void *ws, size_t ws_bytes, int64_t nnodes, int ntiles, bool 
     w.row_plain = cur.take<unsigned long long>((size_t)ntiles);
     w.wq = cur.take<unsigned long long>((size_t)nnodes);
     w.w64 = stripe ? cur.take<int64_t>((size_t)nnodes) : nullptr;
+    w.gcnt = cur.take<unsigned long long>(GCNT_BYTES / sizeof(unsigned long long));
     w.ok = cur.ok;
     return w;
 }
@@ -1319,6 +1341,8 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
     const SweepWs<T> w = carve_ws<T>(ws, ws_bytes, nnodes, ntiles, false);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, acc, nx);
+    unsigned long long *gcnt = w.gcnt;
+    if (sizeof(T) == 4) WMF_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, GCNT_BYTES, st));
     WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(T) * nnodes, st));
     WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
     int rc = sweep_phaseA<ENC, T>(dir, mask, g, ntiles, w, al, st);
@@ -1326,8 +1350,8 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
     if (sizeof(T) == 4) {
         int32_t *entry = w.cnt;                              // reuse: the packed walk needs no counters
         k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
-        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, (int32_t *)w.inflow, nullptr);
-        k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class);
+        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, (int32_t *)w.inflow, nullptr, gcnt);
+        k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class, gcnt);
         WMF_LAUNCH_CHECK();
     } else {
         k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
@@ -1354,13 +1378,15 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, nullptr, nx);
     int32_t *inflow32 = (int32_t *)w.w64, *entry = w.cnt, *stripe_total = (int32_t *)w.A;
+    unsigned long long *gcnt = w.gcnt;
+    WMF_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, GCNT_BYTES, st));
     WMF_CUDA_CHECK(cudaMemsetAsync(inflow32, 0, sizeof(int32_t) * nnodes, st));
     WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
     int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st);
     if (rc) return rc;
     k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
-    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, inflow32, stripe_total);
-    k_g_unres<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class);
+    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, inflow32, stripe_total, gcnt);
+    k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class, gcnt);
     k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, stripe_total, w.wq, recs);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -1401,7 +1427,7 @@ size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
     int64_t ntiles = ((nx + TW - 1) / TW) * ((ny + TH - 1) / TH);
     size_t nn = (size_t)ntiles * NSLOT, tsz = acc_dtype == WMF_ACC_I32 ? 4 : 8;
     return 4 * wmf_align(nn * 4) + 2 * wmf_align(nn * 8) + 2 * wmf_align(nn * tsz) + 2 * wmf_align(nn) +
-           wmf_align((size_t)ntiles) + wmf_align((size_t)ntiles * 8) + 4096;
+           wmf_align((size_t)ntiles) + wmf_align((size_t)ntiles * 8) + wmf_align(GCNT_BYTES) + 4096;
 }
 
 int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx, int encoding,
