@@ -11,7 +11,8 @@ from wmf_heavy_b200 import _lib, ops, stripes
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case,G", [("sch", 2), ("sch", 5), ("steep", 3), ("random", 4), ("mask", 3), ("keypad", 2)])
+@pytest.mark.parametrize("case,G", [("sch", 2), ("sch", 5), ("steep", 3), ("random", 4), ("mask", 3), ("keypad", 2),
+                                    ("serpentine", 2), ("serpentine", 3)])
 def test_striped_equals_oracle(case, G):
     mask = None
     enc = _lib.ENC_INTERNAL
@@ -21,6 +22,8 @@ def test_striped_equals_oracle(case, G):
         fd = helpers.steepest(533, 390, 5)
     elif case == "random":
         fd = helpers.random_codes(300, 260, 6)
+    elif case == "serpentine":            # one path through every cell: boundary paths far longer than the recorded part
+        fd = helpers.serpentine(260, 600)
     elif case == "mask":
         fd, mask = helpers.steepest(420, 333, 7), np.random.default_rng(7).random((420, 333)) > 0.06
     else:

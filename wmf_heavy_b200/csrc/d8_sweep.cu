@@ -22,6 +22,7 @@
 // Cycle semantics (basics.py:166-175): a cell is finalised only when all its donors are; others
 // keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
 // contracted forest carries this through `blocked` nodes and the `ext_unres` entry flags.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -1160,13 +1161,108 @@ __device__ __forceinline__ int64_t first_exit(const uint32_t *__restrict__ meta,
     return l == LNONE ? -1 : (e0 / NSLOT) * NSLOT + l;
 }
 
+// Contracted path of every stripe-boundary cell (2*nx of them): the entries flow passes after entering
+// the stripe at that cell.  Only the forest (parent / entry) is needed, so the chase runs beside
+// k_g_walk on a second stream.  It is a chain of dependent loads, one per tile crossed, so it is cut
+// short with macro links: tile rows are grouped MR at a time, k_macro_links chases (in parallel, <= MR-ish
+// hops each) from every top-row entry of a group to the exit that leaves the group, and the boundary
+// chase then takes one jump per group.  A jump is recorded as one path item (JUMP flag) that the route
+// kernel expands again.  path is hop-major ([hop][2*nx]): chase and route both touch it coalesced; a
+// path longer than pcap items keeps its continuation (pce, pcx) and the route kernel finishes it serially.
+constexpr int MR = 16;
+constexpr int32_t JUMP = (int32_t)0x80000000;
+struct StripePaths { int32_t *path, *plen, *pce, *pcx, *plink, *mlink; int pcap; };
+
+// macro row of an entry node when it is a top-row cell of the first tile row of a group, else -1
+__device__ __forceinline__ int macro_top(const Geo &g, int64_t e)
+{
+    const int tile = (int)(e / NSLOT), s = (int)(e - (int64_t)tile * NSLOT);
+    const int ty = tile / g.tiles_x;
+    return (s < TW && ty % MR == 0) ? ty / MR : -1;
+}
+__device__ __forceinline__ int macro_of(const Geo &g, int64_t e) { return (int)(e / NSLOT) / g.tiles_x / MR; }
+
+// mlink[macro row][col]: the exit (node id) through which flow entering at that top-row cell leaves the
+// group of tile rows (its entry lies in another group, in another stripe, or nowhere); -1: ends inside.
+__global__ void k_macro_links(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
+                              const int32_t *__restrict__ entry, int32_t *__restrict__ mlink)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nmac = (g.tiles_y + MR - 1) / MR;
+    if (i >= (int64_t)nmac * g.nx) return;
+    const int mr = (int)(i / g.nx);
+    const int64_t col = i - (int64_t)mr * g.nx;
+    const int tile = mr * MR * g.tiles_x + (int)(col / TW);
+    const int64_t e0 = (int64_t)tile * NSLOT + (col % TW);
+    int32_t out = -1;
+    if ((meta[e0] >> 21) & 1) {
+        int64_t x = first_exit(meta, e0);
+        for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
+            const int32_t en = entry[x];
+            if (en < 0 || macro_of(g, en) != mr) { out = (int32_t)x; break; }
+            x = parent[x];
+        }
+    }
+    mlink[i] = out;
+}
+
+__global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
+                               const int32_t *__restrict__ entry, StripePaths sp)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n2 = 2 * g.nx;
+    if (i >= n2) return;
+    const int side = (int)(i / g.nx);
+    const int64_t col = i - (int64_t)side * g.nx;
+    int tile;
+    const int64_t node = boundary_node(g, side, col, tile);
+    int32_t len = 0, link = -1, ce = -1, cx = -1;
+    if ((meta[node] >> 21) & 1) {
+        int64_t e = node, x = -2, last = -1;                 // x == -2: not looked up yet
+        for (int64_t hops = 0; hops <= nnodes; hops++) {
+            const int mr = macro_top(g, e);
+            if (len >= sp.pcap) {                            // out of room: the serial tail takes over at e (no jumps there)
+                if (ce < 0) { ce = (int32_t)e; cx = (int32_t)(x == -2 ? first_exit(meta, e) : x); }
+                if (x == -2) x = first_exit(meta, e);
+            } else if (mr >= 0) {                            // one jump across the group of tile rows
+                const int64_t ecol = (int64_t)((int)(e / NSLOT) % g.tiles_x) * TW + (e % NSLOT);
+                sp.path[(int64_t)len * n2 + i] = (int32_t)e | JUMP;
+                len++;
+                x = sp.mlink[(int64_t)mr * g.nx + ecol];
+                if (x < 0) break;                            // the path ends inside the group
+                const int32_t en = entry[x];
+                if (en < 0) { last = x; break; }
+                e = en; x = -2;
+                continue;
+            } else {
+                sp.path[(int64_t)len * n2 + i] = (int32_t)e;
+                len++;
+                if (x == -2) x = first_exit(meta, e);
+            }
+            if (x < 0) break;                                // the path ends inside the stripe
+            const int32_t en = entry[x];
+            if (en < 0) { last = x; break; }                 // x leaves the stripe (-2) or has no active receiver (-1)
+            e = en;
+            x = parent[x];                                   // = first_exit(meta, en)
+        }
+        if (last >= 0 && entry[last] == -2) {                // the path leaves the stripe at exit `last`
+            const int xt = (int)(last / NSLOT);
+            int ty, tx, th, tw, lr, lc;
+            tile_dims(g, xt, ty, tx, th, tw);
+            cell_of((int)(last - (int64_t)xt * NSLOT), th, tw, lr, lc);
+            const int64_t row = (int64_t)ty * TH + lr, c2 = (int64_t)tx * TW + lc;
+            link = (int32_t)((row == 0 ? 0 : 1) * g.nx + c2);
+        }
+    }
+    sp.plen[i] = len; sp.pce[i] = ce; sp.pcx[i] = cx; sp.plink[i] = link;
+}
+
 // Packed boundary records, int64 [2][2][nx] (index side*nx + col inside a plane):
 //   plane 0  exit_acc: stripe-local total of a cell draining across the stripe edge (0 elsewhere)
 //   plane 1  link (low 32 bits: boundary index where flow ENTERING here leaves the stripe, -1 = ends inside)
 //            | k << 32 (normalised code, 8 none, 9 inactive) | unres << 40 (the exit is locally unresolved)
-__global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
-                                 const int32_t *__restrict__ entry, const int32_t *__restrict__ stripe_total,
-                                 const unsigned long long *__restrict__ wq, int64_t *__restrict__ recs)
+__global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const int32_t *__restrict__ entry,
+                                 const int32_t *__restrict__ stripe_total, const unsigned long long *__restrict__ wq,
+                                 const int32_t *__restrict__ plink, int64_t *__restrict__ recs)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * g.nx) return;
@@ -1184,24 +1280,7 @@ __global__ void k_stripe_summary(Geo g, int64_t nnodes, const uint32_t *__restri
     const int64_t rec_k = !active ? 9 : ((c_recv < 0 || c_recv >= g.nx) ? 8 : k);
     const int64_t rec_unres = (is_exit && !resolved) ? 1 : 0;
     recs[i] = (is_exit && resolved) ? (int64_t)stripe_total[node] : 0;       // plane 0: exit_acc
-    int32_t link = -1;
-    if (active) {
-        int64_t x = first_exit(meta, node);
-        for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
-            const int32_t p = parent[x];
-            if (p < 0) break;
-            x = p;
-        }
-        if (x >= 0 && entry[x] == -2) {               // the path leaves the stripe at exit x
-            const int xt = (int)(x / NSLOT);
-            int ty, tx, th, tw, lr, lc;
-            tile_dims(g, xt, ty, tx, th, tw);
-            cell_of((int)(x - (int64_t)xt * NSLOT), th, tw, lr, lc);
-            const int64_t row = (int64_t)ty * TH + lr, c2 = (int64_t)tx * TW + lc;
-            link = (int32_t)((row == 0 ? 0 : 1) * g.nx + c2);
-        }
-    }
-    recs[2 * g.nx + i] = (int64_t)(uint32_t)link | (rec_k << 32) | (rec_unres << 40);   // plane 1: link | k | unres
+    recs[2 * g.nx + i] = (int64_t)(uint32_t)plink[i] | (rec_k << 32) | (rec_unres << 40);   // plane 1: link | k | unres
 }
 
 template <typename T>
@@ -1212,33 +1291,49 @@ __global__ void k_widen(const int32_t *__restrict__ a, T *__restrict__ b, int64_
 }
 
 // Route what arrives from the other stripes along the contracted paths: every entry on the path of a
-// boundary cell gets the cell's external inflow added (linearity of the accumulation).
+// boundary cell gets the cell's external inflow added (linearity of the accumulation).  One thread per
+// (hop, boundary cell); hop 0 also finishes a path that outgrew the recorded part.
 template <typename T>
 __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
-                               const int32_t *__restrict__ entry, const int64_t *__restrict__ ext_inflow,
-                               const uint8_t *__restrict__ ext_un, T *__restrict__ inflow, uint8_t *__restrict__ ext_unres,
-                               uint8_t *__restrict__ tile_class)
+                               const int32_t *__restrict__ entry,
+                               StripePaths sp, const int64_t *__restrict__ ext_inflow, const uint8_t *__restrict__ ext_un,
+                               T *__restrict__ inflow, uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * g.nx) return;
-    const int side = (int)(i / g.nx);
-    const int64_t col = i - (int64_t)side * g.nx;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n2 = 2 * g.nx;
+    if (i >= n2) return;
+    const int plen = sp.plen[i];
+    if ((int)blockIdx.y >= plen) return;
     const int64_t v = ext_inflow[i];
     const bool u = ext_un && ext_un[i];
     if (v == 0 && !u) return;
-    int tile;
-    const int64_t node = boundary_node(g, side, col, tile);
-    if (!((meta[node] >> 21) & 1)) return;            // inactive cells take nothing
-    int64_t e = node;
-    int64_t x = first_exit(meta, node);
-    for (int64_t hops = 0; hops <= nnodes; hops++) {
+    for (int h = blockIdx.y; h < plen; h += gridDim.y) {
+        const int32_t item = sp.path[(int64_t)h * n2 + i];
+        int64_t e = item & ~JUMP;
         inflow_add<T>(&inflow[e], (T)v);
         if (u) { ext_unres[e] = 1; tile_class[e / NSLOT] = 2; }
-        if (x < 0) break;
-        const int32_t en = entry[x];
-        if (en < 0) break;                            // leaves the stripe (or ends at an inactive receiver)
-        e = en;
-        x = parent[x];                                // = first_exit(meta, en)
+        if (item & JUMP) {                                   // the entries the jump skipped inside its group of tile rows
+            const int mr = macro_of(g, e);
+            int64_t x = first_exit(meta, e);
+            for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
+                const int32_t en = entry[x];
+                if (en < 0 || macro_of(g, en) != mr) break;
+                inflow_add<T>(&inflow[en], (T)v);
+                if (u) { ext_unres[en] = 1; tile_class[en / NSLOT] = 2; }
+                x = parent[x];
+            }
+        }
+    }
+    if (blockIdx.y == 0 && sp.pce[i] >= 0) {
+        int64_t e = sp.pce[i], x = sp.pcx[i];
+        for (int64_t hops = 0; hops <= nnodes; hops++) {
+            inflow_add<T>(&inflow[e], (T)v);
+            if (u) { ext_unres[e] = 1; tile_class[e / NSLOT] = 2; }
+            if (x < 0) break;
+            const int32_t en = entry[x];
+            if (en < 0) break;
+            e = en;
+            x = parent[x];
+        }
     }
 }
 
@@ -1246,10 +1341,13 @@ template <typename T>
 struct SweepWs {
     uint32_t *meta; int32_t *exit_acc, *parent, *cnt; T *A, *inflow; uint8_t *blocked, *ext_unres, *tile_class;
     unsigned long long *row_plain, *wq; int64_t *w64; unsigned long long *gcnt;
+    StripePaths sp;
     bool ok;
 };
+static int stripe_pcap(const Geo &g) { return g.tiles_y + 32 < 1024 ? g.tiles_y + 32 : 1024; }   // recorded hops per boundary path
+
 template <typename T>
-SweepWs<T> carve_ws(void *ws, size_t ws_bytes, int64_t nnodes, int ntiles, bool stripe)
+SweepWs<T> carve_ws(void *ws, size_t ws_bytes, int64_t nnodes, int ntiles, bool stripe, const Geo *g = nullptr)
 {
     WsCursor cur(ws, ws_bytes);
     SweepWs<T> w;
@@ -1266,6 +1364,17 @@ SweepWs<T> carve_ws(void *ws, size_t ws_bytes, int64_t nnodes, int ntiles, bool 
     w.wq = cur.take<unsigned long long>((size_t)nnodes);
     w.w64 = stripe ? cur.take<int64_t>((size_t)nnodes) : nullptr;
     w.gcnt = cur.take<unsigned long long>(GCNT_BYTES / sizeof(unsigned long long));
+    w.sp = StripePaths{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    if (stripe) {
+        const size_t n2 = (size_t)(2 * g->nx);
+        w.sp.pcap = stripe_pcap(*g);
+        w.sp.path = cur.take<int32_t>(n2 * (size_t)w.sp.pcap);
+        w.sp.plen = cur.take<int32_t>(n2);
+        w.sp.pce = cur.take<int32_t>(n2);
+        w.sp.pcx = cur.take<int32_t>(n2);
+        w.sp.plink = cur.take<int32_t>(n2);
+        w.sp.mlink = cur.take<int32_t>((size_t)((g->tiles_y + MR - 1) / MR) * (size_t)g->nx);
+    }
     w.ok = cur.ok;
     return w;
 }
@@ -1365,6 +1474,24 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
 // ---- stripe entry points --------------------------------------------------------------------------
 // The stripe-local pass always runs the packed int32 forest walk (a stripe holds < 2^31 cells); only
 // the finish pass is typed by the output accumulation.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream *side_stream()
+{
+    static SideStream tab[64];
+    static bool made[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!made[dev]) {
+        int lo = 0, hi = 0;                                  // highest priority: its few blocks go ahead of the walk's many
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&tab[dev].stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&tab[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&tab[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        made[dev] = true;
+    }
+    return &tab[dev];
+}
+
 template <int ENC>
 int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
                    int64_t *recs, void *ws, size_t ws_bytes, cudaStream_t st)
@@ -1374,7 +1501,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "stripe too large for the tiled accumulation");
     const int ntiles = (int)ntiles64;
     const int64_t nnodes = ntiles64 * NSLOT;
-    const SweepWs<int64_t> w = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true);
+    const SweepWs<int64_t> w = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true, &g);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, nullptr, nx);
     int32_t *inflow32 = (int32_t *)w.w64, *entry = w.cnt, *stripe_total = (int32_t *)w.A;
@@ -1385,9 +1512,20 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st);
     if (rc) return rc;
     k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
+    // the path chase needs the forest only: it runs beside the walk (both are latency-bound chains)
+    SideStream *ss = side_stream();
+    WMF_REQUIRE(ss != nullptr, (int)cudaErrorUnknown, "cannot create the side stream");
+    WMF_CUDA_CHECK(cudaEventRecord(ss->fork, st));
+    WMF_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    static const int dbg_mode = getenv("WMF_STRIPE_DEBUG") ? atoi(getenv("WMF_STRIPE_DEBUG")) : 0;   // 1: no chase (timing only)
+    k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, w.parent, entry, w.sp.mlink);
+    if (dbg_mode != 1)
+    k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.parent, entry, w.sp);
+    WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
     k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, inflow32, stripe_total, gcnt);
     k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class, gcnt);
-    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, stripe_total, w.wq, recs);
+    WMF_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
+    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, entry, stripe_total, w.wq, w.sp.plink, recs);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1401,7 +1539,7 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, 
     const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
     const int ntiles = (int)ntiles64;
     const int64_t nnodes = ntiles64 * NSLOT;
-    const SweepWs<int64_t> w0 = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true);
+    const SweepWs<int64_t> w0 = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true, &g);
     WMF_REQUIRE(w0.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, acc, nx);
     int32_t *inflow32 = (int32_t *)w0.w64, *entry = w0.cnt;
@@ -1410,10 +1548,11 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, 
     SweepWs<T> w;
     w.meta = w0.meta; w.exit_acc = w0.exit_acc; w.parent = w0.parent; w.cnt = w0.cnt; w.A = (T *)w0.A;
     w.inflow = (T *)w0.inflow; w.blocked = w0.blocked; w.ext_unres = w0.ext_unres; w.tile_class = w0.tile_class;
-    w.row_plain = w0.row_plain; w.wq = w0.wq; w.w64 = w0.w64; w.ok = true;
-    k_widen<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(inflow32, w.inflow, nnodes);
-    k_stripe_route<T><<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, ext_inflow, ext_un, w.inflow,
-                                                             w.ext_unres, w.tile_class);
+    w.row_plain = w0.row_plain; w.wq = w0.wq; w.w64 = w0.w64; w.gcnt = w0.gcnt; w.sp = w0.sp; w.ok = true;
+    if (sizeof(T) == 4) w.inflow = (T *)inflow32;            // an int32 accumulation takes the local inflows as they are
+    else k_widen<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(inflow32, w.inflow, nnodes);
+    k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, w.sp, ext_inflow, ext_un,
+                                                                                          w.inflow, w.ext_unres, w.tile_class);
     WMF_LAUNCH_CHECK();
     return sweep_phaseC<ENC, T>(dir, mask, g, ntiles, w, al, acc, st);
 }
@@ -1447,7 +1586,13 @@ int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, i
 
 extern "C" {
 
-size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx) { return d8_sweep_workspace(ny, nx, WMF_ACC_I64); }
+size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx)
+{
+    const Geo g = make_geo(ny, nx, 0, ny);
+    const size_t n2 = (size_t)(2 * nx);
+    return d8_sweep_workspace(ny, nx, WMF_ACC_I64) + wmf_align(n2 * (size_t)stripe_pcap(g) * 4) + 4 * wmf_align(n2 * 4) +
+           wmf_align((size_t)((g.tiles_y + MR - 1) / MR) * (size_t)nx * 4);
+}
 
 int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
                         int encoding, int64_t *records, void *workspace, size_t ws_bytes, void *stream)
