@@ -22,7 +22,6 @@
 // Cycle semantics (basics.py:166-175): a cell is finalised only when all its donors are; others
 // keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
 // contracted forest carries this through `blocked` nodes and the `ext_unres` entry flags.
-#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -1394,7 +1393,15 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
     const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
-    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    {   // once per device and instantiation
+        static bool done[64];
+        int dev = 0;
+        WMF_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+    }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t);
     if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
     else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
@@ -1410,7 +1417,15 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
     const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);
     const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
-    WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    {   // once per device and instantiation
+        static bool done[64];
+        int dev = 0;
+        WMF_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+    }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T) + WPB * 8;
     if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
     else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
@@ -1517,9 +1532,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     WMF_REQUIRE(ss != nullptr, (int)cudaErrorUnknown, "cannot create the side stream");
     WMF_CUDA_CHECK(cudaEventRecord(ss->fork, st));
     WMF_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-    static const int dbg_mode = getenv("WMF_STRIPE_DEBUG") ? atoi(getenv("WMF_STRIPE_DEBUG")) : 0;   // 1: no chase (timing only)
     k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, w.parent, entry, w.sp.mlink);
-    if (dbg_mode != 1)
     k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.parent, entry, w.sp);
     WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
     k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, inflow32, stripe_total, gcnt);
