@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             *reinterpret_cast<ulonglong2 *>(w_t + base + NC * lane + 2 * q) = make_ulonglong2(BIAS, BIAS);
     };
 
+    int32_t *x_side = x_t + 2 * TW + (lane == 31 ? TH : 0);   // side-column slots of a full tile (lanes 0 / 31)
     // ---- downward sweep: local accumulation
     int32_t d[NC];
 #pragma unroll
@@ -509,6 +510,11 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             if (!gen) {
                 plain_rows |= 1ull << lr;
                 plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
+                // a lean row belongs to a full tile: the side columns sit in lanes 0 and 31
+                if (lr == 0) store_acc_row(0, tot);
+                else if (lr == TH - 1) store_acc_row(TW, tot);
+                else if (lane == 0 || lane == 31) x_side[lr] = lane ? tot[NC - 1] : tot[0];
+                continue;
             } else {
                 int k[NC];
                 const int am = rows.active(lr);
@@ -573,8 +579,11 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                         store_meta_row(lr == 0 ? 0 : TW, mw);
                     } else {
                         plain_row_up<false>(kw, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
-                        if (lane == 0) { m_t[2 * TW + lr] = meta_pack(lb[0], plain_k(kw, 0), false, true); w_t[2 * TW + lr] = BIAS; }
-                        if (lane == 31) { m_t[2 * TW + TH + lr] = meta_pack(lb[NC - 1], plain_k(kw, NC - 1), false, true); w_t[2 * TW + TH + lr] = BIAS; }
+                        if (lane == 0 || lane == 31) {
+                            const int so = 2 * TW + (lane ? TH : 0) + lr;
+                            m_t[so] = meta_pack(lane ? lb[NC - 1] : lb[0], lane ? plain_k(kw, NC - 1) : plain_k(kw, 0), false, true);
+                            w_t[so] = BIAS;
+                        }
                     }
                 }
                 if (lr < cbeg) break;
