@@ -324,8 +324,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                              "of wmf_py basin_acum (oracle/wmf_oracle.c, gcc -O2, 1 thread); "
                              f"{times[0]:.2f} s"}
         # kernels of libwmfb200.so per accumulation (profiles/*launches*.csv): walk = indegree + walk; sweep = sweepA,
-        # generalA, g_build, g_walk, g_unres, sweepC, generalC; stripes = 8 (local) + 4 (boundary forest) + 9 (finish)
-        launches_per_step = {"walk": 2, "sweep": 7, "auto": 7}[args.algo] if world == 1 else 21
+        # generalA, g_build, g_walk, g_unres, sweepC, generalC; stripes = 8 (local: + macro_links, stripe_paths,
+        # stripe_summary) + 6 (boundary forest) + 3 (route, sweepC, generalC; + widen for an int64 accumulation)
+        launches_per_step = ({"walk": 2, "sweep": 7, "auto": 7}[args.algo] if world == 1
+                             else (17 if acc.dtype == torch.int32 else 18))
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -338,7 +340,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "l2": "inputs (DIR 0.27 GB + ACC 1.07 GB) exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read+write of all kernels of one accumulation (ncu, profiles/r01_summary.md), 16384^2 int32
-                         "traffic": 2.135e9 if (world == 1 and n == 16384 and args.algo != "walk") else None,
+                         "traffic": 2.095e9 if (world == 1 and n == 16384 and args.algo != "walk") else None,
                          "peak_source": peak_src,
                          "kernel": "wmf_d8_accum, all passes of one accumulation "
                                    f"({bytes_per_cell:.0f} B/cell algorithmic)"},
