@@ -195,6 +195,17 @@ int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg,
                   float *mean_rain, float *acum_rain, float *mean_storage, float *mean_speed,
                   void *workspace, size_t ws_bytes, void *stream);
 
+/* N3: the same run with storage snapshots -- the save_storage / guarda_cond mechanism of
+ * Modelos_heavy.f90:317-328, 496-500, where the storages after selected steps go to records of a direct-access
+ * file.  snap_slot int32 [N_reg]: -1, or the slot s in [0, n_snap) that receives the five storages after that
+ * step; snap_out float [P][n_snap][5][N].  The host layer writes the slots as records (models.write_float_basin). */
+int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,
+                       const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento,
+                       const float *evp, const float *calib, float *sto, float *hspeed, float *balance,
+                       float *mean_rain, float *acum_rain, float *mean_storage, float *mean_speed,
+                       const int32_t *snap_slot, int32_t n_snap, float *snap_out,
+                       void *workspace, size_t ws_bytes, void *stream);
+
 /* ---------------------------------------------------------------- S4: SHIA 3-tank (wmf_py semantics)
  * Replaces wmf_py/models_py/core.py:64-295 shia_v1, fp64.  rain/et double [nsteps][ncell]
  * (et nullable, already multiplied by nothing: et_scale = dt/3600 or dt/86400 is applied

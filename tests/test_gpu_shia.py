@@ -198,3 +198,78 @@ def test_run_shia_object_api(tmp_path):
     np.testing.assert_allclose(pop["StoOut"][0], o["StoOut"], rtol=1e-5, atol=1e-4)
     o2 = oracle.f_shia_v1(inp, cal * 1.5, np.full((5, N), 0.001, np.float32))
     np.testing.assert_allclose(pop["StoOut"][1], o2["StoOut"], rtol=1e-5, atol=1e-4)
+
+
+def _prefix(inp, T):
+    """The same inputs cut to the first T steps (the storages after step T - 1 of the long run)."""
+    import copy
+    q = copy.copy(inp)
+    q.pos_evento, q.evp = inp.pos_evento[:T].copy(), inp.evp[:T].copy()
+    return q
+
+
+def test_shia5_storage_snapshots():
+    """N3 / save_storage (Modelos_heavy.f90:496-500): the snapshot after step t equals the final storages of an
+    oracle run over the first t + 1 steps; the run itself is unchanged by taking snapshots."""
+    N, T = 2000, 40
+    inp = helpers.shia5_inputs(oracle, N, T, 90, speed_type=(1, 2, 1))
+    cal = np.vstack([np.ones(11), np.full(11, 1.3)]).astype(np.float32)
+    sto0 = np.full((5, N), 0.001, np.float32)
+    steps = [0, 7, 8, 39]
+    slot = np.full(T, -1, np.int32)
+    slot[steps] = np.arange(len(steps))
+    cs = torch.from_numpy(helpers.cell_static(inp)).cuda()
+    args = (cs, torch.from_numpy(inp.rain_records).cuda(), torch.from_numpy(inp.pos_evento).cuda(),
+            torch.from_numpy(inp.evp).cuda(), torch.from_numpy(cal).cuda())
+    kw = dict(dt=inp.dt, calc_niter=inp.calc_niter, speed_type=inp.speed_type)
+    sto = torch.from_numpy(np.broadcast_to(sto0, (2, 5, N)).copy()).cuda()
+    out = ops.shia5_run(*args, sto, None, snap_slot=torch.from_numpy(slot).cuda(), n_snap=len(steps), **kw)
+    plain = ops.shia5_run(*args, torch.from_numpy(np.broadcast_to(sto0, (2, 5, N)).copy()).cuda(), None, **kw)
+    assert plain["snapshots"] is None and torch.equal(plain["StoOut"], out["StoOut"])
+    snaps = out["snapshots"].cpu().numpy()
+    assert snaps.shape == (2, len(steps), 5, N)
+    for p in range(2):
+        for k, t in enumerate(steps):
+            o = oracle.f_shia_v1(_prefix(inp, t + 1), cal[p], sto0)
+            np.testing.assert_allclose(snaps[p, k], o["StoOut"], rtol=1e-5, atol=1e-4)
+    assert np.array_equal(snaps[:, -1], out["StoOut"].cpu().numpy())         # the last step's snapshot is StoOut
+    with pytest.raises(ValueError):
+        ops.shia5_run(*args, sto, None, snap_slot=torch.from_numpy(slot[:5].copy()).cuda(), n_snap=2, **kw)
+
+
+def test_shia_v1_writes_storage_records(tmp_path):
+    """models.shia_v1 with save_storage = 1: records guarda_cond[t] of ruta_storage in write_float_basin's layout."""
+    N, T = 500, 24
+    inp = helpers.shia5_inputs(oracle, N, T, 91)
+    models.v_coef, models.h_coef, models.h_exp = inp.v_coef, inp.h_coef, inp.h_exp
+    models.max_capilar, models.max_gravita, models.max_aquifer = (a[None] for a in (inp.max_capilar, inp.max_gravita, inp.max_aquifer))
+    models.hill_long, models.elem_area = inp.hill_long[None], inp.elem_area[None]
+    models.speed_type, models.evpserie, models.dt = np.array([1, 1, 1]), inp.evp, inp.dt
+    models.storage, models.storage_constant, models.rain_first_point = None, 0.001, 1
+    models.retorno_gr = models.retorno_aq = 0
+    models.control, models.control_h = np.zeros((1, N), np.int32), np.zeros((1, N), np.int32)
+    path = str(tmp_path / "rain")
+    models.write_rain(path + ".bin", path + ".hdr", inp.rain_records, inp.pos_evento)
+    sto_path = str(tmp_path / "states.StObin")
+    models.save_storage = 1
+    models.guarda_cond = np.zeros(T, np.int32)
+    models.guarda_cond[[3, 10, 23]] = [1, 2, 3]
+    try:
+        res = models.shia_v1(path + ".bin", path + ".hdr", np.ones(11, np.float32), N, 1, 0, T, None, None, sto_path)
+    finally:
+        models.save_storage = 0
+    import os
+    assert os.path.getsize(sto_path) == 3 * 5 * N * 4
+    for rec, t in ((1, 3), (2, 10), (3, 23)):
+        v, rc = models.read_float_basin_ncol(sto_path, rec, N, 5)
+        o = oracle.f_shia_v1(_prefix(inp, t + 1), np.ones(11, np.float32), np.full((5, N), 0.001, np.float32))
+        assert rc == 0 and v.shape == (5, N)
+        np.testing.assert_allclose(v, o["StoOut"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_array_equal(models.read_float_basin_ncol(sto_path, 3, N, 5)[0], res[9])   # record 3 == StoOut
+    # a stored state restarts the model (StorageLoc of run_shia): steps 11.. from record 2 end where the full run ends
+    v, _ = models.read_float_basin_ncol(sto_path, 2, N, 5)
+    if v[0, 0] > 0:                                   # (StoIn is only honoured when StoIn(1,1) > 0, Modelos:229)
+        models.write_rain(path + "_b.bin", path + "_b.hdr", inp.rain_records, inp.pos_evento[11:])
+        models.evpserie = inp.evp[11:]
+        res2 = models.shia_v1(path + "_b.bin", path + "_b.hdr", np.ones(11, np.float32), N, 1, 0, T - 11, v, None, None)
+        np.testing.assert_allclose(res2[9], res[9], rtol=1e-6, atol=1e-6)  # (speed_type 1: hspeed carries no state)

@@ -93,6 +93,34 @@ def test_scheidegger_host_is_deterministic_and_windowed():
     assert np.array_equal(k, np.array([6, 3, 2], dtype=np.int8)[a])
 
 
+def test_basin_record_files(tmp_path):        # N3: Modelos_heavy.f90:552-624 (direct access, RECL = 4 * N_col * N_cel)
+    N = 11
+    f = str(tmp_path / "sto.StObin")
+    a = np.arange(5 * N, dtype=np.float32).reshape(5, N)
+    with pytest.raises(FileNotFoundError):
+        models.write_float_basin(f, a, 2, N, 5)              # status='old' for records other than 1
+    models.write_float_basin(f, a, 0, N, 5)                  # record <= 0: nothing written (f90:603)
+    assert not os.path.exists(f)
+    models.write_float_basin(f, a, 1, N, 5)
+    models.write_float_basin(f, 2 * a, 3, N, 5)              # leaves record 2 as a hole
+    assert os.path.getsize(f) == 3 * 5 * N * 4
+    raw = np.fromfile(f, dtype="<f4")
+    assert np.array_equal(raw[:5], a[:, 0]) and np.array_equal(raw[5:10], a[:, 1])   # N_col values per cell
+    v, res = models.read_float_basin_ncol(f, 3, N, 5)
+    assert res == 0 and v.shape == (5, N) and np.array_equal(v, 2 * a)
+    v, res = models.read_float_basin_ncol(f, 4, N, 5)
+    assert res != 0                                          # iostat /= 0 past the end
+    v1, res = models.read_float_basin(f, 2, N)               # same file read as N_col = 1 records
+    assert res == 0 and np.array_equal(v1, raw[N:2 * N])
+    models.write_float_basin(f, a, 1, N, 5)                  # record 1 replaces the file
+    assert os.path.getsize(f) == 5 * N * 4
+    g = str(tmp_path / "ints.bin")
+    b = (np.arange(2 * N) * 7).astype(np.int32).reshape(2, N)
+    models.write_int_basin(g, b, 1, N, 2)
+    assert np.array_equal(np.fromfile(g, dtype="<i4").reshape(N, 2).T, b)
+    assert np.array_equal(models.read_int_basin(g, 1, 2 * N), np.ascontiguousarray(b.T).reshape(-1))
+
+
 def test_rain_file_roundtrip(tmp_path):        # Modelos_heavy.f90:580-590, 631-663
     N, T = 37, 12
     rng = np.random.default_rng(1)

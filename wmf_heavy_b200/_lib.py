@@ -74,6 +74,8 @@ SIGNATURES = {
     "wmf_shia5_workspace": (_sz, [_i64, _i64, _i32]),
     "wmf_shia5_run": (_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),
+    "wmf_shia5_run_snap": (_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "wmf_shia3_workspace": (_sz, [_i64, _i64]),
     "wmf_shia3_run": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),

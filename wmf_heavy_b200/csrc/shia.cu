@@ -99,6 +99,9 @@ struct Shia5Args {
     float *acum_rain;           // [N]
     double *part;               // [P][nblk][N_reg+1][K]
     int nblk;
+    const int32_t *snap_slot;   // [N_reg] or null: slot (>= 0) that receives the storages after that step
+    float *snap_out;            // [P][n_snap][5][N]
+    int n_snap;
 };
 
 // x ** 0.6 for x in [0, 1] (soil saturation): exp2(0.6 * log2 x) on the SFU.  __log2f is within 2^-22
@@ -111,7 +114,7 @@ __device__ __forceinline__ float pow06(float x) { return x > 0.0f ? exp2f(0.6f *
 // difference per cell in fp32 also avoids the catastrophic cancellation of the Fortran's two ~5N-term sums.
 // DIAG adds {S1,S2,S3,S4,h1,h2,h3} -> K = 9 (slot 0 of the series carries the constant sums of S5 and h4).
 // T2: some tank uses the kinematic-wave speed (speed_type 2); the all-type-1 kernel carries none of that code.
-template <bool DIAG, bool T2>
+template <bool DIAG, bool T2, bool SNAP>
 __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
 {
     constexpr int K = DIAG ? 9 : 2;
@@ -203,6 +206,13 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
             v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
         }
         red.add(v);
+        if (SNAP) {                                                                        // :496-500 (save_storage)
+            const int slot = a.snap_slot[t];
+            if (slot >= 0 && live) {
+                float *o = a.snap_out + ((int64_t)pset * a.n_snap + slot) * 5 * N + c;
+                o[0] = S1; o[N] = S2; o[2 * N] = S3; o[3 * N] = S4; o[4 * N] = S5;
+            }
+        }
     }
     red.flush();
     if (live) {
@@ -340,7 +350,20 @@ int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg,
                   const float *calib, float *sto, float *hspeed, float *balance, float *mean_rain, float *acum_rain,
                   float *mean_storage, float *mean_speed, void *workspace, size_t ws_bytes, void *stream)
 {
+    return wmf_shia5_run_snap(params_host, N, N_reg, n_rec, P, cell_static, rain_records, pos_evento, evp, calib, sto, hspeed,
+                              balance, mean_rain, acum_rain, mean_storage, mean_speed, nullptr, 0, nullptr, workspace, ws_bytes,
+                              stream);
+}
+
+int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,
+                       const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento, const float *evp,
+                       const float *calib, float *sto, float *hspeed, float *balance, float *mean_rain, float *acum_rain,
+                       float *mean_storage, float *mean_speed, const int32_t *snap_slot, int32_t n_snap, float *snap_out,
+                       void *workspace, size_t ws_bytes, void *stream)
+{
     cudaStream_t st = as_stream(stream);
+    WMF_REQUIRE((snap_slot == nullptr) == (snap_out == nullptr) && n_snap >= 0 && (snap_slot == nullptr || n_snap > 0), WMF_E_ARG,
+                "snap_slot, snap_out and n_snap go together");
     WMF_REQUIRE(params_host && cell_static && rain_records && pos_evento && evp && calib && sto && hspeed && balance,
                 WMF_E_ARG, "null pointer");
     WMF_REQUIRE(N > 0 && N_reg > 0 && n_rec > 0 && P > 0 && P <= 65535, WMF_E_ARG, "bad size");
@@ -354,10 +377,20 @@ int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg,
     Shia5Args a;
     a.p = *params_host; a.N = N; a.N_reg = N_reg; a.cs = cell_static; a.rain = rain_records; a.pos = pos_evento;
     a.evp = evp; a.calib = calib; a.sto = sto; a.hspeed = hspeed; a.acum_rain = acum_rain; a.part = part; a.nblk = nblk;
+    a.snap_slot = snap_slot; a.snap_out = snap_out; a.n_snap = n_snap;
     dim3 grid(nblk, P);
     const bool t2 = a.p.speed_type[0] != 1 || a.p.speed_type[1] != 1 || a.p.speed_type[2] != 1;
-    if (diag) { if (t2) k_shia5<true, true><<<grid, TH, 0, st>>>(a); else k_shia5<true, false><<<grid, TH, 0, st>>>(a); }
-    else { if (t2) k_shia5<false, true><<<grid, TH, 0, st>>>(a); else k_shia5<false, false><<<grid, TH, 0, st>>>(a); }
+    const int variant = (diag ? 4 : 0) | (t2 ? 2 : 0) | (snap_slot ? 1 : 0);
+    switch (variant) {
+    case 0: k_shia5<false, false, false><<<grid, TH, 0, st>>>(a); break;
+    case 1: k_shia5<false, false, true><<<grid, TH, 0, st>>>(a); break;
+    case 2: k_shia5<false, true, false><<<grid, TH, 0, st>>>(a); break;
+    case 3: k_shia5<false, true, true><<<grid, TH, 0, st>>>(a); break;
+    case 4: k_shia5<true, false, false><<<grid, TH, 0, st>>>(a); break;
+    case 5: k_shia5<true, false, true><<<grid, TH, 0, st>>>(a); break;
+    case 6: k_shia5<true, true, false><<<grid, TH, 0, st>>>(a); break;
+    default: k_shia5<true, true, true><<<grid, TH, 0, st>>>(a); break;
+    }
     const int64_t TK = (N_reg + 1) * K;
     k_fold_blocks<<<dim3(blocks_for(TK, 256), P), 256, 0, st>>>(part, nblk, TK, totals);
     k_shia5_outputs<<<blocks_for((int64_t)P * N_reg, 256), 256, 0, st>>>(totals, K, N_reg, N, P, balance, mean_rain,

@@ -97,6 +97,63 @@ def read_rain_records(ruta_bin: str, n_cel: int) -> np.ndarray:
     return np.fromfile(ruta_bin, dtype="<i4", count=n_rec * n_cel).reshape(n_rec, n_cel)
 
 
+# ---- basin record files (Modelos_heavy.f90:552-624): Fortran direct-access, RECL = 4 * N_col * N_cel bytes,
+# record r at byte (r - 1) * RECL, the (N_col, N_cel) array in column-major order (N_col values per cell).
+def _read_record(ruta: str, record: int, n_cel: int, n_col: int, dtype: str):
+    res = 0
+    v = np.zeros((n_col, n_cel), dtype=dtype, order="F")
+    with open(ruta, "rb") as fh:                     # status='old': a missing file is an error, as in Fortran
+        if record < 1:
+            res = 1
+        else:
+            fh.seek((record - 1) * 4 * n_cel * n_col)
+            raw = np.fromfile(fh, dtype=dtype, count=n_cel * n_col)
+            if raw.size != n_cel * n_col:
+                res = 1
+            else:
+                v = np.asfortranarray(raw.reshape(n_cel, n_col).T)
+    if res != 0:
+        print("Error: Se ha tratado de leer un valor fuera del rango")
+    return v, res
+
+
+def read_float_basin(ruta: str, record: int, n_cel: int):
+    """(vect float32 [N_cel], Res) -- Modelos_heavy.f90:552-562.  Res != 0: record out of range."""
+    v, res = _read_record(ruta, int(record), int(n_cel), 1, "<f4")
+    return v[0].copy(), res
+
+
+def read_float_basin_ncol(ruta: str, record: int, n_cel: int, n_col: int):
+    """(vect float32 (N_col, N_cel), Res) -- Modelos_heavy.f90:566-576."""
+    return _read_record(ruta, int(record), int(n_cel), int(n_col), "<f4")
+
+
+def _write_record(ruta: str, vect, record: int, n_cel: int, n_col: int, dtype: str) -> None:
+    a = np.asarray(vect, dtype=dtype).reshape(n_col, n_cel)
+    if record == 1:
+        mode = "wb"                                  # status='replace'
+    else:
+        if not os.path.exists(ruta):                 # status='old'
+            raise FileNotFoundError(f"{ruta}: record {record} can only go to an existing file (record 1 creates it)")
+        mode = "r+b"
+    with open(ruta, mode) as fh:
+        fh.seek((record - 1) * 4 * n_cel * n_col)
+        fh.write(np.ascontiguousarray(a.T).tobytes())
+
+
+def write_float_basin(ruta: str, vect, record: int, n_cel: int, n_col: int) -> None:
+    """Modelos_heavy.f90:594-608: record 1 replaces the file, record <= 0 writes nothing."""
+    if int(record) > 0:
+        _write_record(ruta, vect, int(record), int(n_cel), int(n_col), "<f4")
+
+
+def write_int_basin(ruta: str, vect, record: int, n_cel: int, n_col: int) -> None:
+    """Modelos_heavy.f90:612-624 (no record > 0 guard there: record 0 is an error)."""
+    if int(record) < 1:
+        raise ValueError("write_int_basin: record must be >= 1")
+    _write_record(ruta, vect, int(record), int(n_cel), int(n_col), "<i4")
+
+
 def write_rain(ruta_bin: str, ruta_hdr: str, records: np.ndarray, pos_evento: np.ndarray, n_hills: int = 0) -> None:
     """Write a rain binary + header in the format the readers above (and the Fortran) expect."""
     rec = np.ascontiguousarray(records, dtype="<i4")
@@ -139,15 +196,17 @@ def cell_static_table(n: int) -> np.ndarray:
 
 
 def _reject_out_of_scope():
-    for nm in ("sim_sediments", "sim_slides", "sim_floods", "separate_rain", "save_storage", "save_speed",
+    for nm in ("sim_sediments", "sim_slides", "sim_floods", "separate_rain", "save_speed",
                "save_retorno", "save_vfluxes", "save_rc"):
         if int(globals()[nm]) == 1:
             raise NotImplementedError(f"models.{nm} = 1 is outside the B200 hot path (see DESIGN.md, out of scope)")
 
 
 def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int, sto_in=None, hspeed_in=None,
-                       device_out: bool = False):
-    """P parameter sets x one basin in one launch.  ``calibs`` (P, 11); ``sto_in`` (5, N) or (P, 5, N)."""
+                       device_out: bool = False, save_records=None):
+    """P parameter sets x one basin in one launch.  ``calibs`` (P, 11); ``sto_in`` (5, N) or (P, 5, N).
+    ``save_records`` int [N_reg] (guarda_cond): steps with a record number > 0 return their storages in
+    ``out["snapshots"]`` [P, n_snap, 5, N] together with ``out["snapshot_records"]`` (record number per slot)."""
     global mean_rain, acum_rain, mean_storage, mean_speed
     _reject_out_of_scope()
     dev = require_cuda()
@@ -185,16 +244,35 @@ def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int,
         h0 = np.broadcast_to(h0.reshape((-1, 4, n_cel)), (P, 4, n_cel))
         hs = to_dev(np.ascontiguousarray(h0))
     st = np.asarray(speed_type).astype(int).reshape(-1)[:3]
+    snap_slot, snap_recs = None, None
+    if save_records is not None:
+        g = np.asarray(save_records).astype(np.int64).reshape(-1)
+        if g.size < n_reg:
+            raise ValueError("guarda_cond is shorter than N_reg (Modelos_heavy.f90:317-328)")
+        steps = np.nonzero(g[:n_reg] > 0)[0]
+        if steps.size:
+            need = P * steps.size * 5 * n_cel * 4
+            free = torch.cuda.mem_get_info(dev)[0]
+            if need > 0.8 * free:
+                raise MemoryError(f"{steps.size} storage snapshots need {need / 2**30:.1f} GiB of device memory; "
+                                  "save fewer steps (guarda_cond / Dates2Save)")
+            slot = np.full(n_reg, -1, dtype=np.int32)
+            slot[steps] = np.arange(steps.size, dtype=np.int32)
+            snap_slot, snap_recs = to_dev(slot), g[steps].copy()
     out = ops.shia5_run(cs[1], rr, pe, ev, to_dev(cal), sto, hs, dt=float(dt), retorno_gr=float(retorno_gr),
                         retorno_aq=float(retorno_aq), calc_niter=int(calc_niter), speed_type=tuple(st),
-                        show_storage=bool(show_storage), show_mean_speed=bool(show_mean_speed))
+                        show_storage=bool(show_storage), show_mean_speed=bool(show_mean_speed), snap_slot=snap_slot,
+                        n_snap=0 if snap_recs is None else int(snap_recs.size))
+    out["snapshot_records"] = snap_recs
     mean_rain = out["mean_rain"].cpu().numpy().reshape(1, n_reg)
     acum_rain = out["acum_rain"].cpu().numpy().reshape(1, n_cel)
     if out["mean_storage"] is not None:
         mean_storage = out["mean_storage"][0].cpu().numpy()
     if out["mean_speed"] is not None:
         mean_speed = out["mean_speed"][0].cpu().numpy()
-    return out if device_out else {k: (None if v is None else v.cpu().numpy()) for k, v in out.items()}
+    if device_out:
+        return out
+    return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 
 
 def shia_v1(ruta_bin, ruta_hdr, calib, n_cel, n_cont, n_conth, n_reg, stoin=None, hspeedin=None, ruta_storage=None,
@@ -207,7 +285,15 @@ def shia_v1(ruta_bin, ruta_hdr, calib, n_cel, n_cont, n_conth, n_reg, stoin=None
     _, pos = rain_read_ascii_table(ruta_hdr, n_reg)
     records = read_rain_records(ruta_bin, n_cel)
     cal = np.asarray(calib, dtype=np.float32).reshape(-1)
-    out = shia_v1_population(cal[None, :], records, pos, n_cel, n_reg, stoin, hspeedin)
+    save = None
+    if int(save_storage) == 1:                       # Modelos_heavy.f90:317-328, 496-500
+        if not ruta_storage:
+            raise ValueError("models.save_storage = 1 needs ruta_storage")
+        save = np.zeros(n_reg, dtype=np.int64) if guarda_cond is None else np.asarray(guarda_cond)
+    out = shia_v1_population(cal[None, :], records, pos, n_cel, n_reg, stoin, hspeedin, save_records=save)
+    if out.get("snapshot_records") is not None:      # in time order, like the Fortran loop writes them
+        for k, rec in enumerate(out["snapshot_records"]):
+            write_float_basin(ruta_storage, out["snapshots"][0, k], int(rec), n_cel, 5)
     f32 = np.float32
     Q = np.zeros((n_cont, n_reg), f32, order="F")
     Qsed = np.zeros((n_cont, 3, n_reg), f32, order="F")

@@ -172,9 +172,12 @@ def stream_nod(st: torch.Tensor, acum_t: torch.Tensor, umbral: int):
 def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento: torch.Tensor, evp: torch.Tensor,
               calib: torch.Tensor, sto: torch.Tensor, hspeed: Optional[torch.Tensor] = None, *, dt: float,
               retorno_gr: float = 0.0, retorno_aq: float = 0.0, calc_niter: int = 5, speed_type=(1, 1, 1),
-              show_storage: bool = False, show_mean_speed: bool = False):
+              show_storage: bool = False, show_mean_speed: bool = False, snap_slot: Optional[torch.Tensor] = None,
+              n_snap: int = 0):
     """SHIA 5-tank update as shipped (Modelos_heavy.f90:169-548) for P parameter sets at once.
-    ``sto`` [P,5,N] and ``hspeed`` [P,4,N] are advanced IN PLACE.  Returns a dict of device tensors."""
+    ``sto`` [P,5,N] and ``hspeed`` [P,4,N] are advanced IN PLACE.  Returns a dict of device tensors.
+    ``snap_slot`` int32 [N_reg] (-1 or a slot in [0, n_snap)): the storages after those steps are returned as
+    ``snapshots`` [P, n_snap, 5, N] (save_storage / guarda_cond, Modelos_heavy.f90:496-500)."""
     require_cuda()
     _chk_dev(cell_static, torch.float32, "cell_static")
     _chk_dev(rain_records, torch.int32, "rain_records")
@@ -207,11 +210,18 @@ def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento:
                            int(given))
     lib = _lib.load()
     ws = workspace(lib.wmf_shia5_workspace(N, n_reg, P))
-    check(lib.wmf_shia5_run(C.addressof(prm), N, n_reg, n_rec, P, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
-                            ptr(evp), ptr(calib), ptr(sto), ptr(hspeed), ptr(balance), ptr(mean_rain), ptr(acum_rain),
-                            ptr(ms), ptr(mv), ptr(ws), ws.numel(), stream_ptr()))
+    snaps = None
+    if snap_slot is not None:
+        _chk_dev(snap_slot, torch.int32, "snap_slot")
+        if snap_slot.shape != (n_reg,) or int(n_snap) <= 0:
+            raise ValueError("snap_slot must be int32 [N_reg] and n_snap > 0")
+        snaps = torch.zeros((P, int(n_snap), 5, N), dtype=torch.float32, device=dev)
+    check(lib.wmf_shia5_run_snap(C.addressof(prm), N, n_reg, n_rec, P, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
+                                 ptr(evp), ptr(calib), ptr(sto), ptr(hspeed), ptr(balance), ptr(mean_rain), ptr(acum_rain),
+                                 ptr(ms), ptr(mv), ptr(snap_slot), int(n_snap) if snaps is not None else 0, ptr(snaps),
+                                 ptr(ws), ws.numel(), stream_ptr()))
     return {"StoOut": sto, "hspeed": hspeed, "balance": balance, "mean_rain": mean_rain, "acum_rain": acum_rain,
-            "mean_storage": ms, "mean_speed": mv}
+            "mean_storage": ms, "mean_speed": mv, "snapshots": snaps}
 
 
 # --------------------------------------------------------------------------------------- S4

@@ -154,10 +154,31 @@ class SimuBasin(Basin):
         N = self.ncells
         models.rain_first_point = start_point
         models.calc_niter = kinematicN
-        if path_storage is not None or path_vfluxes is not None or path_speed is not None:
-            raise NotImplementedError("per-step storage/speed/vfluxes files are outside the hot path")
-        models.save_storage = 0
+        if path_vfluxes is not None or path_speed is not None:
+            raise NotImplementedError("per-step speed / vertical-flux files are outside the hot path")
         models.save_vfluxes = 0
+        # storage records (wmfv2.py:1970-1982; Modelos_heavy.f90:496-500): the states after the chosen steps go to
+        # records 1, 2, ... of <path_storage>.StObin.  Dates2Save: step positions (0-based) of this run, None = all
+        # (set_StorageDates and the .StOhdr layout are undefined in the reference: the header here lists record, step).
+        if path_storage is not None:
+            models.save_storage = 1
+            path_sto_bin, path_sto_hdr = __Add_hdr_bin_2route__(path_storage, storage=True)
+            if Dates2Save is None:
+                print('Warning: model will save states in all time steps')
+                steps = np.arange(N_intervals)
+            else:
+                steps = np.unique(np.asarray(Dates2Save, dtype=np.int64))
+                if steps.size and (steps[0] < 0 or steps[-1] >= N_intervals):
+                    raise ValueError("Dates2Save holds step positions in [0, N_intervals)")
+            models.guarda_cond = np.zeros(N_intervals, dtype=np.int32)
+            models.guarda_cond[steps] = np.arange(1, steps.size + 1, dtype=np.int32)
+            with open(path_sto_hdr, "w") as fh:
+                fh.write(f"Numero de celdas: {N}\nNumero de registros: {steps.size}\nRecord, Step\n")
+                for r, t in enumerate(steps):
+                    fh.write(f"{r + 1}, {int(t)}\n")
+        else:
+            models.save_storage = 0
+            path_sto_bin = 'no_save.StObin'
         if EvpSerie is not None:
             models.evpserie = np.asarray(EvpSerie, dtype=np.float32)
         elif models.evpserie is None or len(models.evpserie) < N_intervals:
@@ -167,7 +188,7 @@ class SimuBasin(Basin):
             calib = np.append(calib, np.float32(1.0))
         Qsim, Qsed, Qsep, Humedad, St1, St3, Balance, Speed, Area, Alm, Qsep_byrain = models.shia_v1(
             rain_pathBin, rain_pathHdr, calib, N, np.count_nonzero(models.control) + 1,
-            np.count_nonzero(models.control_h), N_intervals, StorageLoc, HspeedLoc, 'no_save.StObin', path_speed,
+            np.count_nonzero(models.control_h), N_intervals, StorageLoc, HspeedLoc, path_sto_bin, path_speed,
             'no_save.bin', path_conv, path_stra, "", "", path_retorno, path_rc)
         Retornos = {'Qsim': Qsim, 'Balance': Balance, 'Storage': Alm, 'Rain_Acum': models.acum_rain,
                     'Rain_hietogram': models.mean_rain}
