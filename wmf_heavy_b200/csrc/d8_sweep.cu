@@ -207,6 +207,7 @@ __device__ __forceinline__ void sweep_row_down(const int (&k)[NC], int am, const
 // warp holds only 2 * CH rows of shared memory, which keeps occupancy register-bound.
 constexpr int CH = 8;
 constexpr int ROWW = 32 * NWD;          // 32-bit words of one staged row of one warp
+constexpr int HBINS = 1024;            // label histogram bins of phase A (NSLOT slots + a bin for LNONE), power of two
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc)
 {
@@ -476,11 +477,6 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     const int nch = (th + CH - 1) / CH;
 
     // boundary-row stores: NC consecutive slots per lane
-    auto store_acc_row = [&](int base, const int32_t (&tot)[NC]) {
-#pragma unroll
-        for (int q = 0; q < NC / 4; q++)
-            *reinterpret_cast<int4 *>(x_t + base + NC * lane + 4 * q) = make_int4(tot[4 * q], tot[4 * q + 1], tot[4 * q + 2], tot[4 * q + 3]);
-    };
     auto store_meta_row = [&](int base, const uint32_t (&mw)[NC]) {
 #pragma unroll
         for (int q = 0; q < NC / 4; q++)
@@ -490,108 +486,68 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             *reinterpret_cast<ulonglong2 *>(w_t + base + NC * lane + 2 * q) = make_ulonglong2(BIAS, BIAS);
     };
 
-    int32_t *x_side = x_t + 2 * TW + (lane == 31 ? TH : 0);   // side-column slots of a full tile (lanes 0 / 31)
-    // ---- downward sweep: local accumulation
-    int32_t d[NC];
+    // exit_acc without a downward sweep: the local accumulation of an exit cell is the number of tile cells whose
+    // path leaves the tile there, i.e. the histogram of the labels of ALL cells, which the label sweep visits anyway.
+    // One 1024-bin histogram per warp in shared memory (bin 1023 swallows LNONE).
+    int *hist = reinterpret_cast<int *>(s_dyn + (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW) + HBINS * warp;
 #pragma unroll
-    for (int j = 0; j < NC; j++) d[j] = 1;           // 1 + inflow from the row above
+    for (int q = 0; q < HBINS / 128; q++) *reinterpret_cast<int4 *>(hist + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    auto count_labels = [&](const uint32_t (&lab)[NC]) {
+#pragma unroll
+        for (int j = 0; j < NC; j++) atomicAdd(hist + (lab[j] & (HBINS - 1)), 1);
+    };
+
+    // ---- upward sweep: exit labels, bottom row first
     bool complex_tile = false;
-    unsigned long long plain_rows = 0;               // bit lr set: row lr takes the lean path (both sweeps, phase C too)
-    rows.prefetch(0);
-    for (int c = 0; c < nch && !complex_tile; c++) {
-        rows.arrive(c + 1, nch);
-        const int cend = th < (c + 1) * CH ? th : (c + 1) * CH;
-        const uint32_t *wp = rows.chunk(c);
-        for (int lr = c * CH; lr < cend; lr++, wp += ROWW) {
-            int32_t tot[NC];
+    unsigned long long plain_rows = 0;               // bit lr set: row lr takes the lean path (here and in phase C)
+    uint32_t lb[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) lb[j] = LNONE;      // labels of the row below
+    rows.prefetch(nch - 1);
+    for (int c = nch - 1; c >= 0 && !complex_tile; c--) {
+        rows.arrive(c - 1, nch);
+        const int cbeg = c * CH;
+        const uint32_t *wc = rows.chunk(c);
+        for (int lr = (th < (c + 1) * CH ? th : (c + 1) * CH) - 1; lr >= cbeg; lr--) {
+            const uint32_t *wp = wc + (lr - cbeg) * ROWW;
             bool gen = true;
             uint32_t kw[NWD];
             if (plain_tile && lr != last_generic) gen = __any_sync(FULL, plain_words<ENC>(wp, kw));
             if (!gen) {
                 plain_rows |= 1ull << lr;
-                plain_row_down<int32_t>(kw, d, tot, lane, 0, 0);
-                // a lean row belongs to a full tile: the side columns sit in lanes 0 and 31
-                if (lr == 0) store_acc_row(0, tot);
-                else if (lr == TH - 1) store_acc_row(TW, tot);
-                else if (lane == 0 || lane == 31) x_side[lr] = lane ? tot[NC - 1] : tot[0];
-                continue;
-            } else {
-                int k[NC];
-                const int am = rows.active(lr);
-                decode_row<ENC>(wp, am, g, gr0 + lr, gc0, border, k);
-                if (lr > 0) {
-                    bool up = false;
+                if (lr == 0 || lr == TH - 1) {        // first / last row of the tile: every cell is a boundary slot
+                    if (lr == 0) plain_row_up<false>(kw, lb, lane, 0u, (uint32_t)(TW - 1));
+                    else plain_row_up<true>(kw, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1));
+                    uint32_t mw[NC];
 #pragma unroll
-                    for (int j = 0; j < NC; j++) up = up || (k[j] >= 5 && k[j] <= 7);
-                    complex_tile = complex_tile || __any_sync(FULL, up);
-                }
-                int32_t b[NC];
-#pragma unroll
-                for (int j = 0; j < NC; j++) b[j] = ((am >> j) & 1) ? d[j] : 0;
-                sweep_row_down<int32_t>(k, am, b, tot, d, lane, complex_tile);
-                if (complex_tile) break;
-#pragma unroll
-                for (int j = 0; j < NC; j++) d[j] += 1;
-            }
-            if (lr == 0) store_acc_row(0, tot);
-            else if (lr == th - 1) store_acc_row(TW, tot);
-            else {
-                if (lane == 0) x_t[2 * TW + lr] = tot[0];
-                if (lane == rlane && tw > 1) {
-#pragma unroll
-                    for (int j = 0; j < NC; j++) if (j == rj) x_t[2 * TW + TH + lr] = tot[j];
-                }
-            }
-        }
-    }
-    cp_async_wait_all();
-    __syncwarp();
-    if (complex_tile) {                              // the general solver redoes this tile
-        if (lane == 0) tile_class[tile] = 1;
-        return;
-    }
-    if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
-
-    // ---- upward sweep: exit labels (the chunks come back from L2 in reverse order)
-    uint32_t lb[NC];
-#pragma unroll
-    for (int j = 0; j < NC; j++) lb[j] = LNONE;      // labels of the row below
-    rows.prefetch(nch - 1);
-    for (int c = nch - 1; c >= 0; c--) {
-        rows.arrive(c - 1, nch);
-        const int cbeg = c * CH;
-        const uint32_t *wc = rows.chunk(c);
-        int lr = (th < (c + 1) * CH ? th : (c + 1) * CH) - 1;
-        while (lr >= cbeg) {
-            {   // a run of lean rows going up (bounded by the chunk)
-                unsigned long long rest = ~(plain_rows << (63 - lr));
-                int run = rest ? __clzll((long long)rest) : lr + 1;
-                run = run < lr - cbeg + 1 ? run : lr - cbeg + 1;
-                for (const int end = lr - run; lr > end; lr--) {
-                    uint32_t kw[NWD];
-                    plain_words<ENC>(wc + (lr - cbeg) * ROWW, kw);
-                    if (lr == 0 || lr == TH - 1) {        // first / last row of the tile: every cell is a boundary slot
-                        if (lr == 0) plain_row_up<false>(kw, lb, lane, 0u, (uint32_t)(TW - 1));
-                        else plain_row_up<true>(kw, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1));
-                        uint32_t mw[NC];
-#pragma unroll
-                        for (int j = 0; j < NC; j++) mw[j] = meta_pack(lb[j], plain_k(kw, j), false, true);
-                        store_meta_row(lr == 0 ? 0 : TW, mw);
-                    } else {
-                        plain_row_up<false>(kw, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
-                        if (lane == 0 || lane == 31) {
-                            const int so = 2 * TW + (lane ? TH : 0) + lr;
-                            m_t[so] = meta_pack(lane ? lb[NC - 1] : lb[0], lane ? plain_k(kw, NC - 1) : plain_k(kw, 0), false, true);
-                            w_t[so] = BIAS;
-                        }
+                    for (int j = 0; j < NC; j++) mw[j] = meta_pack(lb[j], plain_k(kw, j), false, true);
+                    store_meta_row(lr == 0 ? 0 : TW, mw);
+                } else {
+                    plain_row_up<false>(kw, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
+                    if (lane == 0 || lane == 31) {
+                        const int so = 2 * TW + (lane ? TH : 0) + lr;
+                        m_t[so] = meta_pack(lane ? lb[NC - 1] : lb[0], lane ? plain_k(kw, NC - 1) : plain_k(kw, 0), false, true);
+                        w_t[so] = BIAS;
                     }
                 }
-                if (lr < cbeg) break;
+                count_labels(lb);
+                continue;
             }
-            const uint32_t *wp = wc + (lr - cbeg) * ROWW;
             int k[NC];
             const int am = rows.active(lr);
             decode_row<ENC>(wp, am, g, gr0 + lr, gc0, border, k);
+            {   // tiles the row sweeps cannot solve go to the general solver: upward flow below the first row, and
+                // E -> W adjacent pairs (two-cycles)
+                bool bad = false;
+#pragma unroll
+                for (int j = 0; j < NC; j++) bad = bad || (lr > 0 && k[j] >= 5 && k[j] <= 7);
+                const int k0_right = __shfl_down_sync(FULL, k[0], 1);
+                bad = bad || (lane < 31 && k[NC - 1] == 0 && k0_right == 4);
+#pragma unroll
+                for (int j = 0; j + 1 < NC; j++) bad = bad || (k[j] == 0 && k[j + 1] == 4);
+                if (__any_sync(FULL, bad)) { complex_tile = true; break; }
+            }
             const uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left = __shfl_up_sync(FULL, lb[NC - 1], 1);
             uint32_t own[NC];
             bool pe[NC], pw[NC];
@@ -649,9 +605,20 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                     for (int j = 0; j < NC; j++) if (j == rj) { m_t[2 * TW + TH + lr] = mw[j]; w_t[2 * TW + TH + lr] = BIAS; }
                 }
             }
-            lr--;
+            count_labels(lab);
         }
     }
+    cp_async_wait_all();
+    __syncwarp();
+    if (complex_tile) {                              // the general solver redoes this tile
+        if (lane == 0) tile_class[tile] = 1;
+        return;
+    }
+    if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
+    // exit_acc of every slot = its bin (slots that are not exits hold whatever drained to them: unused)
+#pragma unroll
+    for (int q = 0; q < NSLOT / 128; q++)
+        *reinterpret_cast<int4 *>(x_t + 128 * q + 4 * lane) = *reinterpret_cast<const int4 *>(hist + 128 * q + 4 * lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1411,7 +1378,8 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
-    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t);
+    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * HBINS * sizeof(int);
+    static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
     if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
     else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
