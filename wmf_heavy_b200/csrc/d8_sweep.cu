@@ -32,7 +32,7 @@ constexpr int TW = 32 * NC;             // tile width  (one warp)
 constexpr int TH = 64;                  // tile height
 constexpr int NSLOT = 2 * TW + 2 * TH;  // boundary slots: top row, bottom row, left col, right col
 constexpr int WPB = 4;                  // warps (= tiles) per block in the fast kernels
-constexpr uint32_t LNONE = 0xFFFFu;
+constexpr uint32_t LNONE = 1023u;       // "no exit": above every slot, and the last bin of phase A's label histogram
 constexpr uint32_t FULL = 0xffffffffu;
 
 // meta word of a boundary slot: [15:0] link, [19:16] k, [20] locally unresolved, [21] active
@@ -207,7 +207,8 @@ __device__ __forceinline__ void sweep_row_down(const int (&k)[NC], int am, const
 // warp holds only 2 * CH rows of shared memory, which keeps occupancy register-bound.
 constexpr int CH = 8;
 constexpr int ROWW = 32 * NWD;          // 32-bit words of one staged row of one warp
-constexpr int HBINS = 1024;            // label histogram bins of phase A (NSLOT slots + a bin for LNONE), power of two
+constexpr int HBINS = 1024;            // label histogram bins of phase A: NSLOT slots ... LNONE
+static_assert(NSLOT <= (int)LNONE && (int)LNONE == HBINS - 1, "every label is a histogram bin");
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc)
 {
@@ -493,10 +494,13 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
     for (int q = 0; q < HBINS / 128; q++) *reinterpret_cast<int4 *>(hist + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
     __syncwarp();
-    auto count_labels = [&](const uint32_t (&lab)[NC]) {
+    const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
+    auto count_labels = [&](const uint32_t (&lab)[NC]) {      // (a label is a bin index as it is: slot or LNONE)
 #pragma unroll
-        for (int j = 0; j < NC; j++) atomicAdd(hist + (lab[j] & (HBINS - 1)), 1);
+        for (int j = 0; j < NC; j++) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_sa + 4u * lab[j]) : "memory");
     };
+    // side-column slots of a full tile sit in lanes 0 / 31; their forest words are set in one go at the end
+    uint32_t *m_side = m_t + 2 * TW + (lane == 31 ? TH : 0);
 
     // ---- upward sweep: exit labels, bottom row first
     bool complex_tile = false;
@@ -525,11 +529,8 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                     store_meta_row(lr == 0 ? 0 : TW, mw);
                 } else {
                     plain_row_up<false>(kw, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
-                    if (lane == 0 || lane == 31) {
-                        const int so = 2 * TW + (lane ? TH : 0) + lr;
-                        m_t[so] = meta_pack(lane ? lb[NC - 1] : lb[0], lane ? plain_k(kw, NC - 1) : plain_k(kw, 0), false, true);
-                        w_t[so] = BIAS;
-                    }
+                    if (lane == 0 || lane == 31)
+                        m_side[lr] = meta_pack(lane ? lb[NC - 1] : lb[0], lane ? kw[NWD - 1] >> 24 : kw[0] & 0xFFu, false, true);
                 }
                 count_labels(lb);
                 continue;
@@ -599,10 +600,10 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             }
             if (lr == 0 || lr == th - 1) store_meta_row(lr == 0 ? 0 : TW, mw);
             else {
-                if (lane == 0) { m_t[2 * TW + lr] = mw[0]; w_t[2 * TW + lr] = BIAS; }
+                if (lane == 0) m_t[2 * TW + lr] = mw[0];
                 if (lane == rlane && tw > 1) {
 #pragma unroll
-                    for (int j = 0; j < NC; j++) if (j == rj) { m_t[2 * TW + TH + lr] = mw[j]; w_t[2 * TW + TH + lr] = BIAS; }
+                    for (int j = 0; j < NC; j++) if (j == rj) m_t[2 * TW + TH + lr] = mw[j];
                 }
             }
             count_labels(lab);
@@ -615,6 +616,10 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
         return;
     }
     if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
+    // forest words of the side-column slots (2 * TH of them; the first / last row wrote theirs with the labels)
+#pragma unroll
+    for (int q = 0; q < 2 * TH / 64; q++)
+        *reinterpret_cast<ulonglong2 *>(w_t + 2 * TW + 64 * q + 2 * lane) = make_ulonglong2(BIAS, BIAS);
     // exit_acc of every slot = its bin (slots that are not exits hold whatever drained to them: unused)
 #pragma unroll
     for (int q = 0; q < NSLOT / 128; q++)
