@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                                                      Geo g, int ntiles, uint32_t *__restrict__ meta,
                                                      int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
                                                      unsigned long long *__restrict__ row_plain,
-                                                     unsigned long long *__restrict__ wq)
+                                                     unsigned long long *__restrict__ wq, int32_t *__restrict__ inflow32,
+                                                     uint8_t *__restrict__ ext_unres)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ the same again for mask words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -482,9 +483,6 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
         for (int q = 0; q < NC / 4; q++)
             *reinterpret_cast<uint4 *>(m_t + base + NC * lane + 4 * q) = make_uint4(mw[4 * q], mw[4 * q + 1], mw[4 * q + 2], mw[4 * q + 3]);
-#pragma unroll
-        for (int q = 0; q < NC / 2; q++)
-            *reinterpret_cast<ulonglong2 *>(w_t + base + NC * lane + 2 * q) = make_ulonglong2(BIAS, BIAS);
     };
 
     // exit_acc without a downward sweep: the local accumulation of an exit cell is the number of tile cells whose
@@ -494,6 +492,15 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
     for (int q = 0; q < HBINS / 128; q++) *reinterpret_cast<int4 *>(hist + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
     __syncwarp();
+    // the forest walk adds into inflow / flags ext_unres: clear this tile's slots here (phase A has DRAM to spare)
+    if (inflow32) {
+#pragma unroll
+        for (int q = 0; q < NSLOT / 128; q++)
+            *reinterpret_cast<int4 *>(inflow32 + (int64_t)tile * NSLOT + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
+        static_assert(NSLOT % 128 == 0 && NSLOT / 16 <= 64, "tile slots in 16-byte pieces");
+        for (int q = lane; q < NSLOT / 16; q += 32)
+            *reinterpret_cast<int4 *>(ext_unres + (int64_t)tile * NSLOT + 16 * q) = make_int4(0, 0, 0, 0);
+    }
     const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
     auto count_labels = [&](const uint32_t (&lab)[NC]) {      // (a label is a bin index as it is: slot or LNONE)
 #pragma unroll
@@ -616,14 +623,16 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
         return;
     }
     if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
-    // forest words of the side-column slots (2 * TH of them; the first / last row wrote theirs with the labels)
+    // exit_acc of every slot = its bin (slots that are not exits hold whatever drained to them: unused), and the
+    // forest word of the slot: one pending arrival (its own walker) | its weight
 #pragma unroll
-    for (int q = 0; q < 2 * TH / 64; q++)
-        *reinterpret_cast<ulonglong2 *>(w_t + 2 * TW + 64 * q + 2 * lane) = make_ulonglong2(BIAS, BIAS);
-    // exit_acc of every slot = its bin (slots that are not exits hold whatever drained to them: unused)
-#pragma unroll
-    for (int q = 0; q < NSLOT / 128; q++)
-        *reinterpret_cast<int4 *>(x_t + 128 * q + 4 * lane) = *reinterpret_cast<const int4 *>(hist + 128 * q + 4 * lane);
+    for (int q = 0; q < NSLOT / 128; q++) {
+        const int4 h = *reinterpret_cast<const int4 *>(hist + 128 * q + 4 * lane);
+        *reinterpret_cast<int4 *>(x_t + 128 * q + 4 * lane) = h;
+        ulonglong2 *wp2 = reinterpret_cast<ulonglong2 *>(w_t + 128 * q + 4 * lane);
+        wp2[0] = make_ulonglong2(BIAS | (uint32_t)h.x, BIAS | (uint32_t)h.y);
+        wp2[1] = make_ulonglong2(BIAS | (uint32_t)h.z, BIAS | (uint32_t)h.w);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -888,7 +897,7 @@ __global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir
         }
         meta[(int64_t)tile * NSLOT + s] = m;
         exit_acc[(int64_t)tile * NSLOT + s] = xa;
-        wq[(int64_t)tile * NSLOT + s] = (1ull + ((m >> 20) & 1u)) << 32;      // a locally unresolved exit never finalises
+        wq[(int64_t)tile * NSLOT + s] = ((1ull + ((m >> 20) & 1u)) << 32) | (uint32_t)xa;   // pending | weight; a locally unresolved exit never finalises
     }
   }
 }
@@ -987,8 +996,8 @@ __global__ void k_build_forest(Geo g, int64_t nnodes, const uint32_t *__restrict
 // the total into the entry cell it drains to, and carries on downstream.  No fences, no leaf pass.
 constexpr unsigned long long PEND1 = 1ull << 32;
 
-__global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__restrict__ meta, int32_t *__restrict__ parent,
-                                                   int32_t *__restrict__ entry, unsigned long long *wq)
+__global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__restrict__ meta, int2 *__restrict__ pe,
+                                                   unsigned long long *wq)
 {
     // one block per tile, one thread per boundary slot; tile geometry is block-uniform, everything is 32-bit
     const int tile = blockIdx.x, s = threadIdx.x;
@@ -1024,40 +1033,39 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__rest
             }
         }
     }
-    parent[i] = p;
-    entry[i] = en;
+    pe[i] = make_int2(p, en);                        // one 8-byte record per node: {parent exit, entry cell}
 }
 
 // "Did every exit finalise?" without a host round trip: GCNT words (one 32-byte sector each, so the
 // per-warp adds spread out) hold exits << 32 | finalised; k_g_unres has work only when the halves differ.
 constexpr int GCNT = 64;                                     // power of two
 constexpr size_t GCNT_BYTES = sizeof(unsigned long long) * 4 * GCNT;
-__global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const int32_t *__restrict__ parent, const int32_t *__restrict__ entry,
-                                                const int32_t *__restrict__ w, unsigned long long *wq, int32_t *__restrict__ inflow,
-                                                int32_t *__restrict__ stripe_total, unsigned long long *__restrict__ gcnt)
+__global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const int2 *__restrict__ pe, unsigned long long *wq,
+                                                int32_t *__restrict__ inflow, int32_t *__restrict__ stripe_total,
+                                                unsigned long long *__restrict__ gcnt)
 {
+    // wq[node] = pending << 32 | (own weight + sum of finished children): phase A left the weight in the low half
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int32_t en = i < nnodes ? entry[i] : -1;
+    const int2 me = i < nnodes ? pe[i] : make_int2(-1, -1);
+    int32_t en = me.y;
     const unsigned int nexit = __popc(__ballot_sync(FULL, en != -1));
     unsigned int nfin = 0;
     if (en != -1) {                                         // an exit: carry its total downstream
-        int32_t p = parent[i];
-        uint32_t wc = (uint32_t)w[i];
+        int32_t p = me.x;
         int64_t cur = i;
         unsigned long long old = atomicAdd(&wq[cur], (unsigned long long)(-(long long)PEND1));   // own arrival
         uint32_t add = 0;
         while ((uint32_t)(old >> 32) == 1u) {               // we took pending to zero: cur is final
-            const uint32_t total = (uint32_t)old + add + wc;
+            const uint32_t total = (uint32_t)old + add;
             nfin++;
             if (en >= 0) atomicAdd(&inflow[en], (int32_t)total);
             else if (en == -2) stripe_total[cur] = (int32_t)total;     // a stripe exit keeps its stripe-local total
             if (p < 0) break;
-            // the parent's static data does not depend on the atomic: fetch it first so the hop costs ONE L2 round trip
-            const int32_t pp = parent[p], pen = entry[p];
-            const uint32_t pw = (uint32_t)w[p];
+            // the parent's record does not depend on the atomic: fetch it first so the hop costs ONE L2 round trip
+            const int2 next = pe[p];
             old = atomicAdd(&wq[p], (unsigned long long)total - PEND1);
             add = total;
-            cur = p; p = pp; en = pen; wc = pw;
+            cur = p; p = next.x; en = next.y;
         }
     }
     __syncwarp();
@@ -1068,7 +1076,7 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const int32_t *_
 
 // Exits that never finalised (cycles, or fed by one) poison the entry they drain to.  Nothing to do
 // when every exit finalised, which the two counters tell without a host round trip.
-__global__ void k_g_unres(int64_t nnodes, const int32_t *__restrict__ entry, const unsigned long long *__restrict__ wq,
+__global__ void k_g_unres(int64_t nnodes, const int2 *__restrict__ pe, const unsigned long long *__restrict__ wq,
                           uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class,
                           const unsigned long long *__restrict__ gcnt)
 {
@@ -1080,7 +1088,7 @@ __global__ void k_g_unres(int64_t nnodes, const int32_t *__restrict__ entry, con
         if (exits == fin) return;
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) {
-        int32_t en = entry[i];
+        int32_t en = pe[i].y;
         if (en < 0) continue;
         if ((uint32_t)(wq[i] >> 32) != 0u) {                // never finalised: the entry it feeds never finalises
             ext_unres[en] = 1;
@@ -1164,8 +1172,8 @@ __device__ __forceinline__ int macro_of(const Geo &g, int64_t e) { return (int)(
 
 // mlink[macro row][col]: the exit (node id) through which flow entering at that top-row cell leaves the
 // group of tile rows (its entry lies in another group, in another stripe, or nowhere); -1: ends inside.
-__global__ void k_macro_links(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
-                              const int32_t *__restrict__ entry, int32_t *__restrict__ mlink)
+__global__ void k_macro_links(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
+                              int32_t *__restrict__ mlink)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int nmac = (g.tiles_y + MR - 1) / MR;
@@ -1178,16 +1186,16 @@ __global__ void k_macro_links(Geo g, int64_t nnodes, const uint32_t *__restrict_
     if ((meta[e0] >> 21) & 1) {
         int64_t x = first_exit(meta, e0);
         for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
-            const int32_t en = entry[x];
-            if (en < 0 || macro_of(g, en) != mr) { out = (int32_t)x; break; }
-            x = parent[x];
+            const int2 r = pe[x];
+            if (r.y < 0 || macro_of(g, r.y) != mr) { out = (int32_t)x; break; }
+            x = r.x;
         }
     }
     mlink[i] = out;
 }
 
-__global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
-                               const int32_t *__restrict__ entry, StripePaths sp)
+__global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
+                               StripePaths sp)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n2 = 2 * g.nx;
     if (i >= n2) return;
@@ -1209,7 +1217,7 @@ __global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict
                 len++;
                 x = sp.mlink[(int64_t)mr * g.nx + ecol];
                 if (x < 0) break;                            // the path ends inside the group
-                const int32_t en = entry[x];
+                const int32_t en = pe[x].y;
                 if (en < 0) { last = x; break; }
                 e = en; x = -2;
                 continue;
@@ -1219,12 +1227,12 @@ __global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict
                 if (x == -2) x = first_exit(meta, e);
             }
             if (x < 0) break;                                // the path ends inside the stripe
-            const int32_t en = entry[x];
-            if (en < 0) { last = x; break; }                 // x leaves the stripe (-2) or has no active receiver (-1)
-            e = en;
-            x = parent[x];                                   // = first_exit(meta, en)
+            const int2 r = pe[x];
+            if (r.y < 0) { last = x; break; }                // x leaves the stripe (-2) or has no active receiver (-1)
+            e = r.y;
+            x = r.x;                                         // = first_exit(meta, en)
         }
-        if (last >= 0 && entry[last] == -2) {                // the path leaves the stripe at exit `last`
+        if (last >= 0 && pe[last].y == -2) {                 // the path leaves the stripe at exit `last`
             const int xt = (int)(last / NSLOT);
             int ty, tx, th, tw, lr, lc;
             tile_dims(g, xt, ty, tx, th, tw);
@@ -1240,7 +1248,7 @@ __global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict
 //   plane 0  exit_acc: stripe-local total of a cell draining across the stripe edge (0 elsewhere)
 //   plane 1  link (low 32 bits: boundary index where flow ENTERING here leaves the stripe, -1 = ends inside)
 //            | k << 32 (normalised code, 8 none, 9 inactive) | unres << 40 (the exit is locally unresolved)
-__global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const int32_t *__restrict__ entry,
+__global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
                                  const int32_t *__restrict__ stripe_total, const unsigned long long *__restrict__ wq,
                                  const int32_t *__restrict__ plink, int64_t *__restrict__ recs)
 {
@@ -1253,7 +1261,7 @@ __global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const
     const uint32_t m = meta[node];
     const bool active = (m >> 21) & 1;
     const int k = (m >> 16) & 0xF;
-    const bool is_exit = active && entry[node] == -2 &&
+    const bool is_exit = active && pe[node].y == -2 &&
                          ((side == 0 && k >= 5 && k <= 7) || (side == 1 && k >= 1 && k <= 3));
     const bool resolved = (uint32_t)(wq[node] >> 32) == 0u;
     const int64_t c_recv = col + (k < 8 ? d8_dc(k) : 0);
@@ -1274,8 +1282,7 @@ __global__ void k_widen(const int32_t *__restrict__ a, T *__restrict__ b, int64_
 // boundary cell gets the cell's external inflow added (linearity of the accumulation).  One thread per
 // (hop, boundary cell); hop 0 also finishes a path that outgrew the recorded part.
 template <typename T>
-__global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int32_t *__restrict__ parent,
-                               const int32_t *__restrict__ entry,
+__global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
                                StripePaths sp, const int64_t *__restrict__ ext_inflow, const uint8_t *__restrict__ ext_un,
                                T *__restrict__ inflow, uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class)
 {
@@ -1295,11 +1302,12 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
             const int mr = macro_of(g, e);
             int64_t x = first_exit(meta, e);
             for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
-                const int32_t en = entry[x];
+                const int2 r = pe[x];
+                const int32_t en = r.y;
                 if (en < 0 || macro_of(g, en) != mr) break;
                 inflow_add<T>(&inflow[en], (T)v);
                 if (u) { ext_unres[en] = 1; tile_class[en / NSLOT] = 2; }
-                x = parent[x];
+                x = r.x;
             }
         }
     }
@@ -1309,10 +1317,10 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
             inflow_add<T>(&inflow[e], (T)v);
             if (u) { ext_unres[e] = 1; tile_class[e / NSLOT] = 2; }
             if (x < 0) break;
-            const int32_t en = entry[x];
-            if (en < 0) break;
-            e = en;
-            x = parent[x];
+            const int2 r = pe[x];
+            if (r.y < 0) break;
+            e = r.y;
+            x = r.x;
         }
     }
 }
@@ -1359,6 +1367,12 @@ SweepWs<T> carve_ws(void *ws, size_t ws_bytes, int64_t nnodes, int ntiles, bool 
     return w;
 }
 
+// The packed (int32) forest keeps {parent, entry} as one 8-byte record per node in the parent + cnt arrays, which the
+// cursor lays out back to back (NSLOT * 4 bytes per tile is a multiple of its 256-byte alignment).
+static_assert((NSLOT * sizeof(int32_t)) % 256 == 0, "parent and cnt are contiguous");
+template <typename T>
+static int2 *pe_of(const SweepWs<T> &w) { return reinterpret_cast<int2 *>(w.parent); }
+
 static Geo make_geo(int64_t ny, int64_t nx, int64_t gy0, int64_t gny)
 {
     Geo g;
@@ -1369,7 +1383,8 @@ static Geo make_geo(int64_t ny, int64_t nx, int64_t gy0, int64_t gny)
 }
 
 template <int ENC, typename T>
-int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, cudaStream_t st)
+int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, cudaStream_t st,
+                 int32_t *zero_inflow32 = nullptr)
 {
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
     const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);   // persistent: most tiles are skipped
@@ -1385,8 +1400,8 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * HBINS * sizeof(int);
     static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
-    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
-    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq);
+    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr);
+    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr);
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -1449,15 +1464,18 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
     const bool al = aligned4(dir, mask, acc, nx);
     unsigned long long *gcnt = w.gcnt;
     if (sizeof(T) == 4) WMF_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, GCNT_BYTES, st));
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(T) * nnodes, st));
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
-    int rc = sweep_phaseA<ENC, T>(dir, mask, g, ntiles, w, al, st);
+    else {                                                   // (the int32 path has phase A clear them tile by tile)
+        WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(T) * nnodes, st));
+        WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
+    }
+    int rc = sweep_phaseA<ENC, T>(dir, mask, g, ntiles, w, al, st, sizeof(T) == 4 ? (int32_t *)w.inflow : nullptr);
     if (rc) return rc;
     if (sizeof(T) == 4) {
         int32_t *entry = w.cnt;                              // reuse: the packed walk needs no counters
-        k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
-        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, (int32_t *)w.inflow, nullptr, gcnt);
-        k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class, gcnt);
+        int2 *pe = pe_of(w);
+        k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, pe, w.wq);
+        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, pe, w.wq, (int32_t *)w.inflow, nullptr, gcnt);
+        k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
         WMF_LAUNCH_CHECK();
     } else {
         k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
@@ -1504,23 +1522,22 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     int32_t *inflow32 = (int32_t *)w.w64, *entry = w.cnt, *stripe_total = (int32_t *)w.A;
     unsigned long long *gcnt = w.gcnt;
     WMF_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, GCNT_BYTES, st));
-    WMF_CUDA_CHECK(cudaMemsetAsync(inflow32, 0, sizeof(int32_t) * nnodes, st));
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
-    int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st);
+    int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st, inflow32);
     if (rc) return rc;
-    k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, w.parent, entry, w.wq);
+    int2 *pe = pe_of(w);
+    k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, pe, w.wq);
     // the path chase needs the forest only: it runs beside the walk (both are latency-bound chains)
     SideStream *ss = side_stream();
     WMF_REQUIRE(ss != nullptr, (int)cudaErrorUnknown, "cannot create the side stream");
     WMF_CUDA_CHECK(cudaEventRecord(ss->fork, st));
     WMF_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-    k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, w.parent, entry, w.sp.mlink);
-    k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.parent, entry, w.sp);
+    k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, pe, w.sp.mlink);
+    k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, pe, w.sp);
     WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
-    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.parent, entry, w.exit_acc, w.wq, inflow32, stripe_total, gcnt);
-    k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, entry, w.wq, w.ext_unres, w.tile_class, gcnt);
+    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, pe, w.wq, inflow32, stripe_total, gcnt);
+    k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
     WMF_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
-    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, entry, stripe_total, w.wq, w.sp.plink, recs);
+    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, pe, stripe_total, w.wq, w.sp.plink, recs);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1546,7 +1563,7 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, 
     w.row_plain = w0.row_plain; w.wq = w0.wq; w.w64 = w0.w64; w.gcnt = w0.gcnt; w.sp = w0.sp; w.ok = true;
     if (sizeof(T) == 4) w.inflow = (T *)inflow32;            // an int32 accumulation takes the local inflows as they are
     else k_widen<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(inflow32, w.inflow, nnodes);
-    k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, w.parent, entry, w.sp, ext_inflow, ext_un,
+    k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, pe_of(w0), w.sp, ext_inflow, ext_un,
                                                                                           w.inflow, w.ext_unres, w.tile_class);
     WMF_LAUNCH_CHECK();
     return sweep_phaseC<ENC, T>(dir, mask, g, ntiles, w, al, acc, st);
