@@ -996,44 +996,57 @@ __global__ void k_build_forest(Geo g, int64_t nnodes, const uint32_t *__restrict
 // the total into the entry cell it drains to, and carries on downstream.  No fences, no leaf pass.
 constexpr unsigned long long PEND1 = 1ull << 32;
 
-__global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, const uint32_t *__restrict__ meta, int2 *__restrict__ pe,
-                                                   unsigned long long *wq)
+// where exit slot s of `tile` drains: the entry's node id, -2 = into a neighbouring row stripe, -1 = not an exit /
+// no receiver.  Tile geometry only; m is the slot's meta word.
+__device__ __forceinline__ int build_target(const Geo &g, int tile, int s, uint32_t m)
 {
-    // one block per tile, one thread per boundary slot; tile geometry is block-uniform, everything is 32-bit
-    const int tile = blockIdx.x, s = threadIdx.x;
     const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
     const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
     const int th = ty == g.tiles_y - 1 ? last_th : TH, tw = tx == g.tiles_x - 1 ? last_tw : TW;
-    const int64_t i = (int64_t)tile * NSLOT + s;
-    int32_t p = -1, en = -1;
     int lr, lc;
-    if (cell_of(s, th, tw, lr, lc)) {
-        const uint32_t m = meta[i];
-        const int k = (m >> 16) & 0xF;
-        if (((m >> 21) & 1) && k != 8) {
-            const int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
-            if (rr < 0 || rr >= th || cc < 0 || cc >= tw) {          // the edge leaves the tile
-                const int ty2 = ty + (rr < 0 ? -1 : (rr >= th ? 1 : 0)), tx2 = tx + (cc < 0 ? -1 : (cc >= tw ? 1 : 0));
-                if (tx2 < 0 || tx2 >= g.tiles_x) { }                 // off the raster's side: no receiver
-                else if (ty2 < 0 || ty2 >= g.tiles_y) en = -2;       // into a neighbouring row stripe
-                else {
-                    const int th2 = ty2 == g.tiles_y - 1 ? last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? last_tw : TW;
-                    const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
-                    const int e = (ty2 * g.tiles_x + tx2) * NSLOT + slot_of(lr2, lc2, th2, tw2);
-                    const uint32_t me = meta[e];
-                    if ((me >> 21) & 1) {                            // the receiver is active
-                        en = e;
-                        const uint32_t link = me & 0xFFFFu;
-                        if (link != LNONE) {
-                            p = (e / NSLOT) * NSLOT + (int)link;
-                            atomicAdd(&wq[p], PEND1);
-                        }
-                    }
+    if (!cell_of(s, th, tw, lr, lc)) return -1;
+    const int k = (m >> 16) & 0xF;
+    if (!((m >> 21) & 1) || k == 8) return -1;
+    const int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
+    if (rr >= 0 && rr < th && cc >= 0 && cc < tw) return -1;            // stays in the tile: not an exit
+    const int ty2 = ty + (rr < 0 ? -1 : (rr >= th ? 1 : 0)), tx2 = tx + (cc < 0 ? -1 : (cc >= tw ? 1 : 0));
+    if (tx2 < 0 || tx2 >= g.tiles_x) return -1;                         // off the raster's side: no receiver
+    if (ty2 < 0 || ty2 >= g.tiles_y) return -2;                         // into a neighbouring row stripe
+    const int th2 = ty2 == g.tiles_y - 1 ? last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? last_tw : TW;
+    const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
+    return (ty2 * g.tiles_x + tx2) * NSLOT + slot_of(lr2, lc2, th2, tw2);
+}
+
+// One thread per boundary slot, BU tiles per block: the kernel is two dependent gathers (the slot's meta word, then
+// the meta word of the entry it drains to) plus an atomic, so each thread keeps BU of them in flight.
+constexpr int BU = 4;
+__global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta, int2 *__restrict__ pe,
+                                                   unsigned long long *wq)
+{
+    const int tile0 = blockIdx.x * BU, s = threadIdx.x;
+    uint32_t m[BU], me[BU];
+    int e[BU];
+#pragma unroll
+    for (int u = 0; u < BU; u++) m[u] = tile0 + u < ntiles ? meta[(int64_t)(tile0 + u) * NSLOT + s] : 0u;
+#pragma unroll
+    for (int u = 0; u < BU; u++) e[u] = tile0 + u < ntiles ? build_target(g, tile0 + u, s, m[u]) : -1;
+#pragma unroll
+    for (int u = 0; u < BU; u++) me[u] = e[u] >= 0 ? meta[e[u]] : 0u;
+#pragma unroll
+    for (int u = 0; u < BU; u++) {
+        if (tile0 + u >= ntiles) break;
+        int32_t p = -1, en = e[u];
+        if (en >= 0) {
+            if ((me[u] >> 21) & 1) {                                    // the receiver is active
+                const uint32_t link = me[u] & 0xFFFFu;
+                if (link != LNONE) {
+                    p = (en / NSLOT) * NSLOT + (int)link;
+                    atomicAdd(&wq[p], PEND1);
                 }
-            }
+            } else en = -1;
         }
+        pe[(int64_t)(tile0 + u) * NSLOT + s] = make_int2(p, en);        // one 8-byte record per node: {parent exit, entry cell}
     }
-    pe[i] = make_int2(p, en);                        // one 8-byte record per node: {parent exit, entry cell}
 }
 
 // "Did every exit finalise?" without a host round trip: GCNT words (one 32-byte sector each, so the
@@ -1473,7 +1486,7 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
     if (sizeof(T) == 4) {
         int32_t *entry = w.cnt;                              // reuse: the packed walk needs no counters
         int2 *pe = pe_of(w);
-        k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, pe, w.wq);
+        k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, pe, w.wq);
         k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, pe, w.wq, (int32_t *)w.inflow, nullptr, gcnt);
         k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
         WMF_LAUNCH_CHECK();
@@ -1525,7 +1538,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st, inflow32);
     if (rc) return rc;
     int2 *pe = pe_of(w);
-    k_g_build<<<ntiles, NSLOT, 0, st>>>(g, w.meta, pe, w.wq);
+    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, pe, w.wq);
     // the path chase needs the forest only: it runs beside the walk (both are latency-bound chains)
     SideStream *ss = side_stream();
     WMF_REQUIRE(ss != nullptr, (int)cudaErrorUnknown, "cannot create the side stream");
