@@ -90,6 +90,21 @@ def test_dtypes_and_keypad(algo):
     assert np.array_equal(gk, exp.astype(np.int32))
 
 
+def test_wide_arithmetic_path(monkeypatch):
+    """64-bit outputs of rasters below 2^32 cells are accumulated in 32 bits and widened on store; WMF_ACC_WIDE=1 keeps
+    the 64-bit arithmetic (the path of larger rasters).  Both must agree with the oracle."""
+    fd, mask = CASES["random_cycles"]()
+    exp = oracle.basin_acum(fd, mask)
+    sch = ops.synth_scheidegger_host(700, 1100, seed=3)
+    exp2 = oracle.basin_acum(sch, np.ones(sch.shape, bool))
+    for wide in ("0", "1"):
+        monkeypatch.setenv("WMF_ACC_WIDE", wide)
+        assert np.array_equal(run(fd, mask, _lib.ALGO_SWEEP, _lib.ACC_I64), exp.astype(np.int64))
+        assert np.array_equal(run(fd, mask, _lib.ALGO_SWEEP, _lib.ACC_F64), exp)
+        assert np.array_equal(run(sch, None, _lib.ALGO_SWEEP, _lib.ACC_I64), exp2.astype(np.int64))
+        assert np.array_equal(run(sch, None, _lib.ALGO_SWEEP, _lib.ACC_F64), exp2)
+
+
 def test_empty_and_errors():
     assert basics.basin_acum(np.zeros((0, 5), int), np.zeros((0, 5), bool)).shape == (0, 5)
     d = torch.zeros((4, 4), dtype=torch.int8, device="cuda")

@@ -76,6 +76,16 @@ def test_striped_full_size_int64_and_f64():
     assert g32.dtype == torch.int32 and torch.equal(g32.to(torch.int64), ref)
 
 
+def test_striped_wide_arithmetic_path(monkeypatch):
+    d = ops.synth_scheidegger(1024, 1024, seed=9)
+    ref = ops.d8_accum(d, None, acc_dtype=_lib.ACC_I64)
+    for wide in ("0", "1"):
+        monkeypatch.setenv("WMF_ACC_WIDE", wide)
+        assert torch.equal(stripes.accumulate_striped_single_device(d, 3), ref)
+        gf = stripes.accumulate_striped_single_device(d, 2, acc_dtype=_lib.ACC_F64)
+        assert torch.equal(gf.to(torch.int64), ref)
+
+
 def test_forest_accum_matches_numpy():
     rng = np.random.default_rng(1)
     n = 5000

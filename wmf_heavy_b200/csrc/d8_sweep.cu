@@ -22,6 +22,7 @@
 // Cycle semantics (basics.py:166-175): a cell is finalised only when all its donors are; others
 // keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
 // contracted forest carries this through `blocked` nodes and the `ext_unres` entry flags.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -638,32 +639,51 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 // ---------------------------------------------------------------------------------------------
 // phase C, fast solver
 // ---------------------------------------------------------------------------------------------
-template <bool AL, typename T>
-__device__ __forceinline__ void store_row(T *out, const T (&tot)[NC], int64_t gc0, int64_t nx)
+// value of an accumulation computed in T, stored as TO: a 32-bit accumulation of a raster with fewer than 2^32 cells
+// never wraps as an unsigned number, so it may be stored into a wider type (int64 / float64) without 64-bit arithmetic
+template <typename TO, typename T>
+__device__ __forceinline__ TO acc_out(T v)
 {
+    if (sizeof(T) == 4 && sizeof(TO) == 8) return (TO)(uint32_t)v;
+    return (TO)v;
+}
+
+// 32-byte stores (STG.256, sm_100): a lane's piece of a row is whole 32-byte sectors, one instruction each
+__device__ __forceinline__ void st256(void *p, unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d)
+{
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+template <bool AL, typename T, typename TO>
+__device__ __forceinline__ void store_row(TO *out, const T (&tot)[NC], int64_t gc0, int64_t nx)
+{
+    static_assert(NC == 8, "a lane stores 8 cells");
     if (AL) {
         if (gc0 < nx) {
-            if (sizeof(T) == 4) {
+            if (sizeof(TO) == 4) {
+                unsigned long long w[4];
 #pragma unroll
-                for (int q = 0; q < NC / 4; q++)
-                    *reinterpret_cast<int4 *>(out + 4 * q) = make_int4((int)tot[4 * q], (int)tot[4 * q + 1], (int)tot[4 * q + 2], (int)tot[4 * q + 3]);
+                for (int q = 0; q < 4; q++) w[q] = (unsigned long long)(uint32_t)tot[2 * q] | ((unsigned long long)(uint32_t)tot[2 * q + 1] << 32);
+                st256(out, w[0], w[1], w[2], w[3]);
             } else {
+                unsigned long long w[8];
 #pragma unroll
-                for (int q = 0; q < NC / 2; q++)
-                    *reinterpret_cast<longlong2 *>(out + 2 * q) = make_longlong2((long long)tot[2 * q], (long long)tot[2 * q + 1]);
+                for (int j = 0; j < 8; j++) { TO a = acc_out<TO, T>(tot[j]); memcpy(&w[j], &a, 8); }
+                st256(out, w[0], w[1], w[2], w[3]);
+                st256(out + 4, w[4], w[5], w[6], w[7]);
             }
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < NC; j++) if (gc0 + j < nx) out[j] = tot[j];
+        for (int j = 0; j < NC; j++) if (gc0 + j < nx) out[j] = acc_out<TO, T>(tot[j]);
     }
 }
 
-template <int ENC, bool AL, typename T>
-__global__ void __launch_bounds__(WPB * 32, 6) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
+template <int ENC, bool AL, typename T, typename TO>
+__global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
                                                      Geo g, int ntiles, const T *__restrict__ inflow,
                                                      const uint8_t *__restrict__ tile_class,
-                                                     const unsigned long long *__restrict__ row_plain, T *__restrict__ acc)
+                                                     const unsigned long long *__restrict__ row_plain, TO *__restrict__ acc)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ mask words) + the side inflows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -688,7 +708,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepC(const int8_t *__restrict
 #pragma unroll
     for (int j = 0; j < NC; j++) d[j] = 1;           // 1 + inflow from the row above
     bool dummy = false;
-    T *out = acc + gr0 * g.nx + gc0;
+    TO *out = acc + gr0 * g.nx + gc0;
     // the per-chunk lean-row masks live in shared memory: an L1TEX load (global or a register spill) issued
     // behind the chunk prefetch would wait for the prefetch's HBM round trip (the L1TEX queue is in order)
     unsigned char *pchunk = reinterpret_cast<unsigned char *>(extL + (size_t)2 * TH * (WPB - warp)) + 8 * warp;
@@ -719,7 +739,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepC(const int8_t *__restrict
                     const T l = extL[lr], r = extR[lr];
                     plain_row_down<T>(kw, d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
                 }
-                store_row<AL, T>(out, tot, gc0, g.nx);
+                store_row<AL, T, TO>(out, tot, gc0, g.nx);
             }
             if (lr >= cend) break;
             {   // one generic row
@@ -747,7 +767,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepC(const int8_t *__restrict
                 sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
 #pragma unroll
                 for (int j = 0; j < NC; j++) d[j] += 1;
-                store_row<AL, T>(out, tot, gc0, g.nx);
+                store_row<AL, T, TO>(out, tot, gc0, g.nx);
                 lr++; out += g.nx; wp += ROWW; pbits >>= 1;
             }
         }
@@ -902,10 +922,10 @@ __global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir
   }
 }
 
-template <int ENC, typename T>
+template <int ENC, typename T, typename TO>
 __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
                                                   const uint8_t *__restrict__ tile_class, const T *__restrict__ inflow,
-                                                  const uint8_t *__restrict__ ext_unres, T *__restrict__ out)
+                                                  const uint8_t *__restrict__ ext_unres, TO *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem[];
   const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
@@ -938,7 +958,7 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
     __syncthreads();
     for (int idx = threadIdx.x; idx < TCELLS; idx += GTH) {
         int lr = idx / TW, lc = idx - lr * TW;
-        if (lr < th && lc < tw) out[((int64_t)ty * TH + lr) * g.nx + (int64_t)tx * TW + lc] = acc[idx];
+        if (lr < th && lc < tw) out[((int64_t)ty * TH + lr) * g.nx + (int64_t)tx * TW + lc] = acc_out<TO, T>(acc[idx]);
     }
   }
 }
@@ -996,12 +1016,10 @@ __global__ void k_build_forest(Geo g, int64_t nnodes, const uint32_t *__restrict
 // the total into the entry cell it drains to, and carries on downstream.  No fences, no leaf pass.
 constexpr unsigned long long PEND1 = 1ull << 32;
 
-// where exit slot s of `tile` drains: the entry's node id, -2 = into a neighbouring row stripe, -1 = not an exit /
-// no receiver.  Tile geometry only; m is the slot's meta word.
-__device__ __forceinline__ int build_target(const Geo &g, int tile, int s, uint32_t m)
+// where exit slot s of tile (ty, tx) drains: the tile of the entry (and its slot in s2), -2 = into a neighbouring row
+// stripe, -1 = not an exit / no receiver.  Tile geometry only; m is the slot's meta word.
+__device__ __forceinline__ int build_target(const Geo &g, int ty, int tx, int last_th, int last_tw, int s, uint32_t m, int &s2)
 {
-    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-    const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
     const int th = ty == g.tiles_y - 1 ? last_th : TH, tw = tx == g.tiles_x - 1 ? last_tw : TW;
     int lr, lc;
     if (!cell_of(s, th, tw, lr, lc)) return -1;
@@ -1014,36 +1032,45 @@ __device__ __forceinline__ int build_target(const Geo &g, int tile, int s, uint3
     if (ty2 < 0 || ty2 >= g.tiles_y) return -2;                         // into a neighbouring row stripe
     const int th2 = ty2 == g.tiles_y - 1 ? last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? last_tw : TW;
     const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
-    return (ty2 * g.tiles_x + tx2) * NSLOT + slot_of(lr2, lc2, th2, tw2);
+    s2 = slot_of(lr2, lc2, th2, tw2);
+    return ty2 * g.tiles_x + tx2;
 }
 
-// One thread per boundary slot, BU tiles per block: the kernel is two dependent gathers (the slot's meta word, then
-// the meta word of the entry it drains to) plus an atomic, so each thread keeps BU of them in flight.
+// One thread per boundary slot, BU consecutive tiles per block: the kernel is two dependent gathers (the slot's meta
+// word, then the meta word of the entry it drains to) plus an atomic, so each thread keeps BU of them in flight.
 constexpr int BU = 4;
 __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta, int2 *__restrict__ pe,
                                                    unsigned long long *wq)
 {
     const int tile0 = blockIdx.x * BU, s = threadIdx.x;
+    const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
     uint32_t m[BU], me[BU];
-    int e[BU];
+    int t2[BU], s2[BU];
 #pragma unroll
     for (int u = 0; u < BU; u++) m[u] = tile0 + u < ntiles ? meta[(int64_t)(tile0 + u) * NSLOT + s] : 0u;
+    int ty = tile0 / g.tiles_x, tx = tile0 - ty * g.tiles_x;            // block-uniform; the next tiles follow in row-major order
 #pragma unroll
-    for (int u = 0; u < BU; u++) e[u] = tile0 + u < ntiles ? build_target(g, tile0 + u, s, m[u]) : -1;
+    for (int u = 0; u < BU; u++) {
+        s2[u] = 0;
+        t2[u] = tile0 + u < ntiles ? build_target(g, ty, tx, last_th, last_tw, s, m[u], s2[u]) : -1;
+        if (++tx == g.tiles_x) { tx = 0; ty++; }
+    }
 #pragma unroll
-    for (int u = 0; u < BU; u++) me[u] = e[u] >= 0 ? meta[e[u]] : 0u;
+    for (int u = 0; u < BU; u++) me[u] = t2[u] >= 0 ? meta[t2[u] * NSLOT + s2[u]] : 0u;
 #pragma unroll
     for (int u = 0; u < BU; u++) {
         if (tile0 + u >= ntiles) break;
-        int32_t p = -1, en = e[u];
+        int32_t p = -1, en = t2[u];
         if (en >= 0) {
+            en = -1;
             if ((me[u] >> 21) & 1) {                                    // the receiver is active
+                en = t2[u] * NSLOT + s2[u];
                 const uint32_t link = me[u] & 0xFFFFu;
                 if (link != LNONE) {
-                    p = (en / NSLOT) * NSLOT + (int)link;
+                    p = t2[u] * NSLOT + (int)link;
                     atomicAdd(&wq[p], PEND1);
                 }
-            } else en = -1;
+            }
         }
         pe[(int64_t)(tile0 + u) * NSLOT + s] = make_int2(p, en);        // one 8-byte record per node: {parent exit, entry cell}
     }
@@ -1280,7 +1307,7 @@ __global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const
     const int64_t c_recv = col + (k < 8 ? d8_dc(k) : 0);
     const int64_t rec_k = !active ? 9 : ((c_recv < 0 || c_recv >= g.nx) ? 8 : k);
     const int64_t rec_unres = (is_exit && !resolved) ? 1 : 0;
-    recs[i] = (is_exit && resolved) ? (int64_t)stripe_total[node] : 0;       // plane 0: exit_acc
+    recs[i] = (is_exit && resolved) ? (int64_t)(uint32_t)stripe_total[node] : 0;       // plane 0: exit_acc
     recs[2 * g.nx + i] = (int64_t)(uint32_t)plink[i] | (rec_k << 32) | (rec_unres << 40);   // plane 1: link | k | unres
 }
 
@@ -1420,8 +1447,8 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     return 0;
 }
 
-template <int ENC, typename T>
-int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, T *acc,
+template <int ENC, typename T, typename TO>
+int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, TO *acc,
                  cudaStream_t st)
 {
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
@@ -1432,14 +1459,14 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
         int dev = 0;
         WMF_CUDA_CHECK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !done[dev]) {
-            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T) + WPB * 8;
-    if (al) k_sweepC<ENC, true, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
-    else k_sweepC<ENC, false, T><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
-    k_generalC<ENC, T><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, w.inflow, w.ext_unres, acc);
+    if (al) k_sweepC<ENC, true, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
+    else k_sweepC<ENC, false, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
+    k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, w.inflow, w.ext_unres, acc);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1460,11 +1487,12 @@ int sweep_phaseG_i64(const Geo &g, int64_t nnodes, const SweepWs<T> &w, bool use
 static bool aligned4(const void *dir, const void *mask, const void *acc, int64_t nx)
 {
     return (nx % NC == 0) && (((uintptr_t)dir & (NC - 1)) == 0) && (mask == nullptr || ((uintptr_t)mask & (NC - 1)) == 0) &&
-           (((uintptr_t)acc & 15) == 0);
+           (((uintptr_t)acc & 31) == 0);
 }
 
-template <int ENC, typename T>
-int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+// T: the type the accumulation is computed in; TO: the type it is stored as (acc_out)
+template <int ENC, typename T, typename TO>
+int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
                 cudaStream_t st)
 {
     const Geo g = make_geo(ny, nx, 0, ny);
@@ -1496,7 +1524,7 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int6
         rc = sweep_phaseG_i64<T>(g, nnodes, w, false, st);
         if (rc) return rc;
     }
-    return sweep_phaseC<ENC, T>(dir, mask, g, ntiles, w, al, acc, st);
+    return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, al, acc, st);
 }
 
 // ---- stripe entry points --------------------------------------------------------------------------
@@ -1555,8 +1583,8 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     return 0;
 }
 
-template <int ENC, typename T>
-int stripe_finish_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, int64_t nx, int64_t row0,
+template <int ENC, typename T, typename TO>
+int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int64_t nx, int64_t row0,
                     int64_t ny_total, const int64_t *ext_inflow, const uint8_t *ext_un, void *ws, size_t ws_bytes,
                     cudaStream_t st)
 {
@@ -1579,7 +1607,7 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, T *acc, int64_t ny, 
     k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, pe_of(w0), w.sp, ext_inflow, ext_un,
                                                                                           w.inflow, w.ext_unres, w.tile_class);
     WMF_LAUNCH_CHECK();
-    return sweep_phaseC<ENC, T>(dir, mask, g, ntiles, w, al, acc, st);
+    return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, al, acc, st);
 }
 
 }  // namespace
@@ -1594,19 +1622,27 @@ size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
            wmf_align((size_t)ntiles) + wmf_align((size_t)ntiles * 8) + wmf_align(GCNT_BYTES) + 4096;
 }
 
+// Dispatch on (encoding, arithmetic type, stored type).  A raster with fewer than 2^32 cells is accumulated in 32 bits
+// whatever the output type: no accumulation can reach 2^32, so the unsigned value is exact and is widened (or turned
+// into a double) only when it is stored.
+// (WMF_ACC_WIDE=1 in the environment keeps 64-bit arithmetic for 64-bit outputs: the tests use it to cover that path)
+static bool force_wide() { const char *e = getenv("WMF_ACC_WIDE"); return e && e[0] == '1'; }
+#define WMF_ENC_DISPATCH(FN, T, TO, ...)                                                                     \
+    (encoding == WMF_ENC_INTERNAL ? FN<WMF_ENC_INTERNAL, T, TO>(__VA_ARGS__) : FN<WMF_ENC_KEYPAD, T, TO>(__VA_ARGS__))
+
 int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx, int encoding,
              void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    int rc;
-    if (acc_dtype == WMF_ACC_I32)
-        rc = encoding == WMF_ENC_INTERNAL ? run_sweep_t<WMF_ENC_INTERNAL, int32_t>(dir, mask, (int32_t *)acc, ny, nx, ws, ws_bytes, st)
-                                          : run_sweep_t<WMF_ENC_KEYPAD, int32_t>(dir, mask, (int32_t *)acc, ny, nx, ws, ws_bytes, st);
-    else
-        rc = encoding == WMF_ENC_INTERNAL ? run_sweep_t<WMF_ENC_INTERNAL, int64_t>(dir, mask, (int64_t *)acc, ny, nx, ws, ws_bytes, st)
-                                          : run_sweep_t<WMF_ENC_KEYPAD, int64_t>(dir, mask, (int64_t *)acc, ny, nx, ws, ws_bytes, st);
+    const bool narrow = ny * nx <= 0xFFFFFFFFLL && !force_wide();
+    if (acc_dtype == WMF_ACC_I32) return WMF_ENC_DISPATCH(run_sweep_t, int32_t, int32_t, dir, mask, (int32_t *)acc, ny, nx, ws, ws_bytes, st);
+    if (acc_dtype == WMF_ACC_I64) {
+        if (narrow) return WMF_ENC_DISPATCH(run_sweep_t, int32_t, int64_t, dir, mask, (int64_t *)acc, ny, nx, ws, ws_bytes, st);
+        return WMF_ENC_DISPATCH(run_sweep_t, int64_t, int64_t, dir, mask, (int64_t *)acc, ny, nx, ws, ws_bytes, st);
+    }
+    if (narrow) return WMF_ENC_DISPATCH(run_sweep_t, int32_t, double, dir, mask, (double *)acc, ny, nx, ws, ws_bytes, st);
+    int rc = WMF_ENC_DISPATCH(run_sweep_t, int64_t, int64_t, dir, mask, (int64_t *)acc, ny, nx, ws, ws_bytes, st);
     if (rc) return rc;
-    if (acc_dtype == WMF_ACC_F64) return d8_convert_i64_to_f64(acc, ny * nx, st);
-    return 0;
+    return d8_convert_i64_to_f64(acc, ny * nx, st);
 }
 
 extern "C" {
@@ -1643,18 +1679,15 @@ int wmf_d8_stripe_finish(const int8_t *dir, const uint8_t *mask, void *acc, int 
     WMF_REQUIRE(ny >= 2 && nx > 0 && row0 >= 0 && row0 + ny <= ny_total, WMF_E_ARG, "bad stripe geometry (ny >= 2)");
     WMF_REQUIRE(encoding == WMF_ENC_INTERNAL || encoding == WMF_ENC_KEYPAD, WMF_E_ARG, "unknown encoding");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (acc_dtype == WMF_ACC_I32)
-        rc = encoding == WMF_ENC_INTERNAL
-                 ? stripe_finish_t<WMF_ENC_INTERNAL, int32_t>(dir, mask, (int32_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st)
-                 : stripe_finish_t<WMF_ENC_KEYPAD, int32_t>(dir, mask, (int32_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st);
-    else
-        rc = encoding == WMF_ENC_INTERNAL
-                 ? stripe_finish_t<WMF_ENC_INTERNAL, int64_t>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st)
-                 : stripe_finish_t<WMF_ENC_KEYPAD, int64_t>(dir, mask, (int64_t *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st);
+    const bool narrow = ny_total * nx <= 0xFFFFFFFFLL && !force_wide();      // see d8_sweep
+#define WMF_FINISH(T, TO) WMF_ENC_DISPATCH(stripe_finish_t, T, TO, dir, mask, (TO *)acc, ny, nx, row0, ny_total, ext_inflow, ext_unres, workspace, ws_bytes, st)
+    if (acc_dtype == WMF_ACC_I32) return WMF_FINISH(int32_t, int32_t);
+    if (acc_dtype == WMF_ACC_I64) return narrow ? WMF_FINISH(int32_t, int64_t) : WMF_FINISH(int64_t, int64_t);
+    if (narrow) return WMF_FINISH(int32_t, double);
+    int rc = WMF_FINISH(int64_t, int64_t);
+#undef WMF_FINISH
     if (rc) return rc;
-    if (acc_dtype == WMF_ACC_F64) return d8_convert_i64_to_f64(acc, ny * nx, st);
-    return 0;
+    return d8_convert_i64_to_f64(acc, ny * nx, st);
 }
 
 }  // extern "C"
