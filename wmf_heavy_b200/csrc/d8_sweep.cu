@@ -1042,7 +1042,9 @@ constexpr int BU = 4;
 __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta, int2 *__restrict__ pe,
                                                    unsigned long long *wq)
 {
-    const int tile0 = blockIdx.x * BU, s = threadIdx.x;
+    // last tiles first: what this kernel leaves in L2 (records and forest words, 168 MB against 126 MB of L2) is then
+    // weighted towards the FIRST tile rows, where the walk that follows starts its chains
+    const int tile0 = (int)(gridDim.x - 1 - blockIdx.x) * BU, s = threadIdx.x;
     const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
     uint32_t m[BU], me[BU];
     int t2[BU], s2[BU];
