@@ -327,7 +327,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # generalA, g_build, g_walk, g_unres, sweepC, generalC; stripes = 8 (local: + macro_links, stripe_paths,
         # stripe_summary) + 6 (boundary forest) + 3 (route, sweepC, generalC; + widen for an int64 accumulation)
         launches_per_step = ({"walk": 2, "sweep": 7, "auto": 7}[args.algo] if world == 1
-                             else (17 if acc.dtype == torch.int32 else 18))
+                             else (17 if world * n * n <= 0xFFFFFFFF else 18))   # (wider rasters also widen the inflows)
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

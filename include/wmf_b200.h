@@ -167,6 +167,33 @@ size_t wmf_hand_workspace(int64_t ny, int64_t nx);
 int wmf_hand(const double *dem, const int8_t *dir, const uint8_t *mask, const uint8_t *stream, int64_t ny, int64_t nx,
              int encoding, double *hand, void *workspace, size_t ws_bytes, void *stream_);
 
+/* wmf_path_sum: out[c] = sum of per-cell weights over c's downstream path, c included, the path's last cell (no
+ * receiver) excluded -- the distance pass of basin_ppalstream_find (wmf_py/cu_py/metrics.py:420-432, with
+ * active = the stream mask, w = NULL = step lengths dx / dy / hypot, cycle_nan = 0: a cell on a cycle never enters the
+ * reference's topological order and keeps distance 0) and of basin_time_to_out (:583-597, cycle_nan = 1: nan for
+ * cycle cells and everything that drains into them).  active (nullable uint8): inactive cells do not exist (nan out,
+ * never a receiver).  Sums are formed by pointer jumping, i.e. in a different order than the reference's
+ * outlet-to-source recurrence: fp64, 1e-12 relative.  wmf_time_to_out replaces basin_time_to_out (:528-599): Manning
+ * travel time per cell with unit hydraulic radius (nan when the speed is not positive), then that path sum.
+ * Both sync (convergence checks).  ny*nx < 2^31. */
+size_t wmf_path_sum_workspace(int64_t ny, int64_t nx);
+int wmf_path_sum(const int8_t *dir, const uint8_t *active, const double *w, int64_t ny, int64_t nx, int encoding, double dx,
+                 double dy, int cycle_nan, double *out, void *workspace, size_t ws_bytes, void *stream_);
+size_t wmf_time_to_out_workspace(int64_t ny, int64_t nx);
+int wmf_time_to_out(const int8_t *dir, const double *slope, const double *manning, int64_t ny, int64_t nx, int encoding,
+                    double dx, double dy, double *out, void *workspace, size_t ws_bytes, void *stream_);
+
+/* N1: network nodes and node-to-node links (wmf_py/cu_py/streams.py:282-384 basin_netxy_find / basin_netxy_cut).
+ * node[c] = 1 for stream cells whose degree (stream donors + stream receiver) differs from 2, and for the outlet
+ * (linear index; -1 for none).  For every stream cell with a stream receiver, down_node / down_steps = the first node
+ * met downstream and the number of moves to it (-1 / 0 when the path meets none: a dead end or a node-free loop);
+ * up_node / up_steps likewise along the unique stream donors of non-node cells (the upstream end of the cell's edge).
+ * The host layer numbers the nodes in row-major order and assembles the edge dictionaries.  Syncs.  ny*nx < 2^31. */
+size_t wmf_stream_nodes_workspace(int64_t ny, int64_t nx);
+int wmf_stream_nodes(const int8_t *dir, const uint8_t *stream, int64_t ny, int64_t nx, int encoding, int64_t outlet,
+                     uint8_t *node, int32_t *down_node, int32_t *down_steps, int32_t *up_node, int32_t *up_steps,
+                     void *workspace, size_t ws_bytes, void *stream_);
+
 /* ---------------------------------------------------------------- S1/S2: SHIA 5-tank (Fortran semantics)
  * Replaces models.shia_v1 as shipped (wmf_heavy/Modelos_heavy.f90:169-548) incl. calc_speed
  * (:907-919): vertical cascade + lateral outflow of tanks 2..4 (discarded), fp32.

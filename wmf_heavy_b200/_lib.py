@@ -71,6 +71,12 @@ SIGNATURES = {
     "wmf_stream_receiver": (_int, [_vp, _vp, _vp, _i64, _i64, _int, C.c_double, C.c_double, _vp, _vp, _vp, _sz, _vp]),
     "wmf_hand_workspace": (_sz, [_i64, _i64]),
     "wmf_hand": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _sz, _vp]),
+    "wmf_path_sum_workspace": (_sz, [_i64, _i64]),
+    "wmf_path_sum": (_int, [_vp, _vp, _vp, _i64, _i64, _int, C.c_double, C.c_double, _int, _vp, _vp, _sz, _vp]),
+    "wmf_time_to_out_workspace": (_sz, [_i64, _i64]),
+    "wmf_time_to_out": (_int, [_vp, _vp, _vp, _i64, _i64, _int, C.c_double, C.c_double, _vp, _vp, _sz, _vp]),
+    "wmf_stream_nodes_workspace": (_sz, [_i64, _i64]),
+    "wmf_stream_nodes": (_int, [_vp, _vp, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wmf_shia5_workspace": (_sz, [_i64, _i64, _i32]),
     "wmf_shia5_run": (_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),

@@ -224,6 +224,60 @@ def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento:
             "mean_storage": ms, "mean_speed": mv, "snapshots": snaps}
 
 
+def path_sum(dir_t: torch.Tensor, active_t: Optional[torch.Tensor], w_t: Optional[torch.Tensor], dx: float, dy: float,
+             cycle_nan: bool, encoding: int = ENC_INTERNAL) -> torch.Tensor:
+    """Sum of per-cell weights (``w_t`` float64, or the step lengths when None) down every cell's flow path:
+    metrics.py:420-432 / :583-597."""
+    require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    if active_t is not None:
+        _chk_dev(active_t, torch.uint8, "active")
+    if w_t is not None:
+        _chk_dev(w_t, torch.float64, "w")
+    ny, nx = dir_t.shape
+    out = torch.empty((ny, nx), dtype=torch.float64, device=dir_t.device)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_path_sum_workspace(ny, nx))
+    check(lib.wmf_path_sum(ptr(dir_t), ptr(active_t), ptr(w_t), ny, nx, encoding, float(dx), float(dy), int(bool(cycle_nan)),
+                           ptr(out), ptr(ws), ws.numel(), stream_ptr()))
+    return out
+
+
+def time_to_out(dir_t: torch.Tensor, slope_t: torch.Tensor, manning_t: torch.Tensor, dx: float, dy: float,
+                encoding: int = ENC_INTERNAL) -> torch.Tensor:
+    """Manning travel time to the end of every cell's flow path: metrics.py:528-599."""
+    require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    _chk_dev(slope_t, torch.float64, "slope")
+    _chk_dev(manning_t, torch.float64, "n_manning")
+    ny, nx = dir_t.shape
+    if slope_t.shape != (ny, nx) or manning_t.shape != (ny, nx):
+        raise ValueError("slope and n_manning must have the raster's shape")
+    out = torch.empty((ny, nx), dtype=torch.float64, device=dir_t.device)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_time_to_out_workspace(ny, nx))
+    check(lib.wmf_time_to_out(ptr(dir_t), ptr(slope_t), ptr(manning_t), ny, nx, encoding, float(dx), float(dy), ptr(out),
+                              ptr(ws), ws.numel(), stream_ptr()))
+    return out
+
+
+def stream_nodes(dir_t: torch.Tensor, stream_t: torch.Tensor, outlet_index: int, encoding: int = ENC_INTERNAL):
+    """Network nodes and node-to-node links (streams.py:282-384) -> (node uint8, down_node, down_steps, up_node,
+    up_steps) rasters; the node / link fields are linear indices (-1 = none)."""
+    require_cuda()
+    _chk_dev(dir_t, torch.int8, "dir")
+    _chk_dev(stream_t, torch.uint8, "stream")
+    ny, nx = dir_t.shape
+    dev = dir_t.device
+    node = torch.empty((ny, nx), dtype=torch.uint8, device=dev)
+    outs = [torch.empty((ny, nx), dtype=torch.int32, device=dev) for _ in range(4)]
+    lib = _lib.load()
+    ws = workspace(lib.wmf_stream_nodes_workspace(ny, nx))
+    check(lib.wmf_stream_nodes(ptr(dir_t), ptr(stream_t), ny, nx, encoding, int(outlet_index), ptr(node), ptr(outs[0]),
+                               ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), ptr(ws), ws.numel(), stream_ptr()))
+    return (node, *outs)
+
+
 # --------------------------------------------------------------------------------------- S4
 def shia3_run(rain: torch.Tensor, et: Optional[torch.Tensor], cap: torch.Tensor, grav: torch.Tensor,
               aqu: torch.Tensor, prm: "_lib.Shia3Params", nsteps: int, separate_fluxes: bool = False,
