@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                                                      int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
                                                      unsigned long long *__restrict__ row_plain,
                                                      unsigned long long *__restrict__ wq, int32_t *__restrict__ inflow32,
-                                                     uint8_t *__restrict__ ext_unres)
+                                                     uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_top)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ the same again for mask words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     uint32_t *m_side = m_t + 2 * TW + (lane == 31 ? TH : 0);
 
     // ---- upward sweep: exit labels, bottom row first
-    bool complex_tile = false;
+    bool complex_tile = false, top_exits = false;
     unsigned long long plain_rows = 0;               // bit lr set: row lr takes the lean path (here and in phase C)
     uint32_t lb[NC];
 #pragma unroll
@@ -556,6 +556,12 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
                 for (int j = 0; j + 1 < NC; j++) bad = bad || (k[j] == 0 && k[j + 1] == 4);
                 if (__any_sync(FULL, bad)) { complex_tile = true; break; }
+                if (lr == 0) {
+                    bool up0 = false;
+#pragma unroll
+                    for (int j = 0; j < NC; j++) up0 = up0 || (k[j] >= 5 && k[j] <= 7);
+                    top_exits = __any_sync(FULL, up0);
+                }
             }
             const uint32_t lb_right0 = __shfl_down_sync(FULL, lb[0], 1), lb_left = __shfl_up_sync(FULL, lb[NC - 1], 1);
             uint32_t own[NC];
@@ -620,10 +626,13 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     cp_async_wait_all();
     __syncwarp();
     if (complex_tile) {                              // the general solver redoes this tile
-        if (lane == 0) tile_class[tile] = 1;
+        if (lane == 0) { tile_class[tile] = 1; tile_top[tile] = 1; }
         return;
     }
-    if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; }
+    // tile_top: can an inner first-row slot of this tile be an exit?  Only through upward flow in row 0 (never in a
+    // lean row) or in a tile that is not full size (one row: first row = last row).  The forest kernels skip the
+    // first-row slots 1 .. TW-2 of the other tiles without touching their records; the corners can leave sideways.
+    if (lane == 0) { tile_class[tile] = 0; row_plain[tile] = plain_rows; tile_top[tile] = (top_exits || !full) ? 1 : 0; }
     // exit_acc of every slot = its bin (slots that are not exits hold whatever drained to them: unused), and the
     // forest word of the slot: one pending arrival (its own walker) | its weight
 #pragma unroll
@@ -1039,7 +1048,8 @@ __device__ __forceinline__ int build_target(const Geo &g, int ty, int tx, int la
 // One thread per boundary slot, BU consecutive tiles per block: the kernel is two dependent gathers (the slot's meta
 // word, then the meta word of the entry it drains to) plus an atomic, so each thread keeps BU of them in flight.
 constexpr int BU = 4;
-__global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta, int2 *__restrict__ pe,
+__global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta,
+                                                   const uint8_t *__restrict__ tile_top, int2 *__restrict__ pe,
                                                    unsigned long long *wq)
 {
     // last tiles first: what this kernel leaves in L2 (records and forest words, 168 MB against 126 MB of L2) is then
@@ -1048,20 +1058,23 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
     const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
     uint32_t m[BU], me[BU];
     int t2[BU], s2[BU];
+    bool skip[BU];                                           // an inner first-row slot of a tile that has no exit there (tile_top)
 #pragma unroll
-    for (int u = 0; u < BU; u++) m[u] = tile0 + u < ntiles ? meta[(int64_t)(tile0 + u) * NSLOT + s] : 0u;
+    for (int u = 0; u < BU; u++) skip[u] = tile0 + u >= ntiles || (s > 0 && s < TW - 1 && !tile_top[tile0 + u]);
+#pragma unroll
+    for (int u = 0; u < BU; u++) m[u] = !skip[u] ? meta[(int64_t)(tile0 + u) * NSLOT + s] : 0u;
     int ty = tile0 / g.tiles_x, tx = tile0 - ty * g.tiles_x;            // block-uniform; the next tiles follow in row-major order
 #pragma unroll
     for (int u = 0; u < BU; u++) {
         s2[u] = 0;
-        t2[u] = tile0 + u < ntiles ? build_target(g, ty, tx, last_th, last_tw, s, m[u], s2[u]) : -1;
+        t2[u] = !skip[u] ? build_target(g, ty, tx, last_th, last_tw, s, m[u], s2[u]) : -1;
         if (++tx == g.tiles_x) { tx = 0; ty++; }
     }
 #pragma unroll
     for (int u = 0; u < BU; u++) me[u] = t2[u] >= 0 ? meta[t2[u] * NSLOT + s2[u]] : 0u;
 #pragma unroll
     for (int u = 0; u < BU; u++) {
-        if (tile0 + u >= ntiles) break;
+        if (skip[u]) continue;                               // (its record is never read: see node_is_skipped)
         int32_t p = -1, en = t2[u];
         if (en >= 0) {
             en = -1;
@@ -1082,13 +1095,20 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
 // per-warp adds spread out) hold exits << 32 | finalised; k_g_unres has work only when the halves differ.
 constexpr int GCNT = 64;                                     // power of two
 constexpr size_t GCNT_BYTES = sizeof(unsigned long long) * 4 * GCNT;
-__global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const int2 *__restrict__ pe, unsigned long long *wq,
+// inner first-row slots of a full tile whose row 0 has no upward flow are never exits: k_g_build wrote no record for them
+__device__ __forceinline__ bool node_is_skipped(const uint8_t *__restrict__ tile_top, int64_t i)
+{
+    const int tile = (int)(i / NSLOT), s = (int)(i - (int64_t)tile * NSLOT);
+    return s > 0 && s < TW - 1 && !tile_top[tile];
+}
+
+__global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *__restrict__ tile_top, const int2 *__restrict__ pe, unsigned long long *wq,
                                                 int32_t *__restrict__ inflow, int32_t *__restrict__ stripe_total,
                                                 unsigned long long *__restrict__ gcnt)
 {
     // wq[node] = pending << 32 | (own weight + sum of finished children): phase A left the weight in the low half
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int2 me = i < nnodes ? pe[i] : make_int2(-1, -1);
+    const int2 me = (i < nnodes && !node_is_skipped(tile_top, i)) ? pe[i] : make_int2(-1, -1);
     int32_t en = me.y;
     const unsigned int nexit = __popc(__ballot_sync(FULL, en != -1));
     unsigned int nfin = 0;
@@ -1118,7 +1138,7 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const int2 *__re
 
 // Exits that never finalised (cycles, or fed by one) poison the entry they drain to.  Nothing to do
 // when every exit finalised, which the two counters tell without a host round trip.
-__global__ void k_g_unres(int64_t nnodes, const int2 *__restrict__ pe, const unsigned long long *__restrict__ wq,
+__global__ void k_g_unres(int64_t nnodes, const uint8_t *__restrict__ tile_top, const int2 *__restrict__ pe, const unsigned long long *__restrict__ wq,
                           uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class,
                           const unsigned long long *__restrict__ gcnt)
 {
@@ -1130,6 +1150,7 @@ __global__ void k_g_unres(int64_t nnodes, const int2 *__restrict__ pe, const uns
         if (exits == fin) return;
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) {
+        if (node_is_skipped(tile_top, i)) continue;
         int32_t en = pe[i].y;
         if (en < 0) continue;
         if ((uint32_t)(wq[i] >> 32) != 0u) {                // never finalised: the entry it feeds never finalises
@@ -1442,8 +1463,8 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * HBINS * sizeof(int);
     static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
-    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr);
-    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr);
+    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr, w.blocked);
+    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr, w.blocked);
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -1516,9 +1537,9 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int
     if (sizeof(T) == 4) {
         int32_t *entry = w.cnt;                              // reuse: the packed walk needs no counters
         int2 *pe = pe_of(w);
-        k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, pe, w.wq);
-        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, pe, w.wq, (int32_t *)w.inflow, nullptr, gcnt);
-        k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
+        k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.blocked, pe, w.wq);
+        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, (int32_t *)w.inflow, nullptr, gcnt);
+        k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
         WMF_LAUNCH_CHECK();
     } else {
         k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
@@ -1568,7 +1589,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st, inflow32);
     if (rc) return rc;
     int2 *pe = pe_of(w);
-    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, pe, w.wq);
+    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.blocked, pe, w.wq);
     // the path chase needs the forest only: it runs beside the walk (both are latency-bound chains)
     SideStream *ss = side_stream();
     WMF_REQUIRE(ss != nullptr, (int)cudaErrorUnknown, "cannot create the side stream");
@@ -1577,8 +1598,8 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, pe, w.sp.mlink);
     k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, pe, w.sp);
     WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
-    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, pe, w.wq, inflow32, stripe_total, gcnt);
-    k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
+    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, inflow32, stripe_total, gcnt);
+    k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
     WMF_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
     k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, pe, stripe_total, w.wq, w.sp.plink, recs);
     WMF_LAUNCH_CHECK();
