@@ -46,6 +46,31 @@ struct StepReducer {
         }
         if (++slot == TB) flush();
     }
+    // TB steps at once (K == 2): q[k][u] is this thread's value of quantity k at step u of the batch.  A transposed
+    // butterfly leaves the warp sum of step u in lanes 2u and 2u + 1: 16 shuffles per quantity for 16 steps instead of
+    // 5 per step.  The caller flushes.
+    __device__ __forceinline__ void add_batch(float (&q)[2][TB], int nvalid)
+    {
+        static_assert(TB == 16, "the butterfly below reduces 16 steps over 32 lanes");
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            float (&a)[TB] = q[k];
+#pragma unroll
+            for (int h = TB / 2, o = 16; h >= 1; h >>= 1, o >>= 1) {
+                const bool upper = (lane & o) != 0;          // this lane keeps the upper half of the indices
+#pragma unroll
+                for (int i = 0; i < h; i++) {
+                    const float send = upper ? a[i] : a[i + h], keep = upper ? a[i + h] : a[i];
+                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            const float tot = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+            const int u = lane >> 1;
+            if ((lane & 1) == 0 && u < nvalid) stage[warp][u][k] = (double)tot;
+        }
+        slot = nvalid;
+    }
     __device__ __forceinline__ void flush()
     {
         if (slot == 0) return;
@@ -63,15 +88,33 @@ struct StepReducer {
     }
 };
 
-// totals[g][t][k] = sum over blocks of part[g][blk][t][k]   (g = parameter set)
+// totals[g][t][k] = sum over blocks of part[g][blk][t][k]   (g = parameter set), in a fixed order and in two
+// steps so that the fold is a streaming pass, not TK threads walking nblk rows each: chunks of FOLD_CS consecutive
+// blocks are summed in place into the chunk's first row (grid.z = chunks), then the chunk rows are summed.
+constexpr int FOLD_CS = 32;
+__global__ void k_fold_chunks(double *__restrict__ part, int nblk, int64_t TK)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TK) return;
+    const int b0 = blockIdx.z * FOLD_CS, b1 = b0 + FOLD_CS < nblk ? b0 + FOLD_CS : nblk;
+    double *p = part + (int64_t)blockIdx.y * nblk * TK;
+    double a = 0.0;
+    for (int b = b0; b < b1; b++) a += p[(int64_t)b * TK + i];
+    p[(int64_t)b0 * TK + i] = a;
+}
 __global__ void k_fold_blocks(const double *__restrict__ part, int nblk, int64_t TK, double *__restrict__ totals)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= TK) return;
     const double *p = part + (int64_t)blockIdx.y * nblk * TK;
     double a = 0.0;
-    for (int b = 0; b < nblk; b++) a += p[(int64_t)b * TK + i];
+    for (int b = 0; b < nblk; b += FOLD_CS) a += p[(int64_t)b * TK + i];
     totals[(int64_t)blockIdx.y * TK + i] = a;
+}
+static void fold_blocks(double *part, int nblk, int64_t TK, int P, double *totals, cudaStream_t st)
+{
+    k_fold_chunks<<<dim3(blocks_for(TK, 256), P, (nblk + FOLD_CS - 1) / FOLD_CS), 256, 0, st>>>(part, nblk, TK);
+    k_fold_blocks<<<dim3(blocks_for(TK, 256), P), 256, 0, st>>>(part, nblk, TK, totals);
 }
 
 // ------------------------------------------------------------------------------------ SHIA 5-tank
@@ -107,7 +150,15 @@ struct Shia5Args {
 // x ** 0.6 for x in [0, 1] (soil saturation): exp2(0.6 * log2 x) on the SFU.  __log2f is within 2^-22
 // absolute on [0.5, 2] and 2 ulp elsewhere, so the relative error of the power is ~1e-7 -- two orders of
 // magnitude inside the 1e-5 parity tolerance -- against ~70 instructions for the correctly rounded powf.
-__device__ __forceinline__ float pow06(float x) { return x > 0.0f ? exp2f(0.6f * __log2f(x)) : 0.0f; }
+// The .ftz forms need no range fix-ups: lg2(0) = -inf and ex2(-inf) = 0, a denormal saturation counts as 0.
+__device__ __forceinline__ float pow06(float x)
+{
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    l = l * 0.6f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+    return r;
+}
 
 // Per-step sums.  K = 2: {R, q} with q = (storage now - storage before) + (v4 + Evp_loss) per cell, so that
 // balance(t) = sum(q) - sum(R) (Modelos:533) needs ONE reduced quantity beside the rain; forming the
@@ -171,10 +222,11 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
     }
     float sto_prev = (S1 + S2) + (S3 + S4);
 
-    for (int64_t t = 0; t < T; t++) {
+    const int32_t *rain_cc = a.rain + cc;                // this cell's column of the rain records
+    auto one_step = [&](int64_t t, float &vR, float &vq) {
         const int pos = a.pos[t];
         float R = 0.0f;
-        if (pos != 1) R = (float)a.rain[(int64_t)(pos - 1) * N + cc] * 0.001f;            // :370 (RainInt/1000.)
+        if (pos != 1) R = (float)rain_cc[(int64_t)(pos - 1) * N] * 0.001f;                 // :370 (RainInt/1000.)
         acum = acum + R;                                                                   // :380
         float v1 = fmaxf(0.0f, (R - H1) + S1);                                             // :393
         S1 = (S1 + R) - v1;                                                                // :394
@@ -197,21 +249,38 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
         S4 = S4 - hf;
 
         const float sto_now = (S1 + S2) + (S3 + S4);
-        float v[K];
-        v[0] = live ? R : 0.0f;
-        v[1] = live ? ((sto_now - sto_prev) + (v4 + evl)) : 0.0f;                          // :459, :533
+        vR = live ? R : 0.0f;
+        vq = live ? ((sto_now - sto_prev) + (v4 + evl)) : 0.0f;                            // :459, :533
         sto_prev = sto_now;
-        if (DIAG) {
-            v[2] = live ? S1 : 0.0f; v[3] = live ? S2 : 0.0f; v[4] = live ? S3 : 0.0f; v[5] = live ? S4 : 0.0f;
-            v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
-        }
-        red.add(v);
         if (SNAP) {                                                                        // :496-500 (save_storage)
             const int slot = a.snap_slot[t];
             if (slot >= 0 && live) {
                 float *o = a.snap_out + ((int64_t)pset * a.n_snap + slot) * 5 * N + c;
                 o[0] = S1; o[N] = S2; o[2 * N] = S3; o[3 * N] = S4; o[4 * N] = S5;
             }
+        }
+    };
+    if (DIAG) {
+        for (int64_t t = 0; t < T; t++) {
+            float v[K];
+            one_step(t, v[0], v[1]);
+            if (DIAG) {
+                v[2] = live ? S1 : 0.0f; v[3] = live ? S2 : 0.0f; v[4] = live ? S3 : 0.0f; v[5] = live ? S4 : 0.0f;
+                v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
+            }
+            red.add(v);
+        }
+    } else {
+        red.flush();                                      // slot 0 is out; batches of TB steps follow
+        for (int64_t tb = 0; tb < T; tb += TB) {
+            float q[2][TB];
+#pragma unroll
+            for (int u = 0; u < TB; u++) {
+                q[0][u] = 0.0f; q[1][u] = 0.0f;
+                if (tb + u < T) one_step(tb + u, q[0][u], q[1][u]);
+            }
+            red.add_batch(q, (int)(T - tb < TB ? T - tb : TB));
+            red.flush();
         }
     }
     red.flush();
@@ -392,7 +461,7 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
     default: k_shia5<true, true, true><<<grid, TH, 0, st>>>(a); break;
     }
     const int64_t TK = (N_reg + 1) * K;
-    k_fold_blocks<<<dim3(blocks_for(TK, 256), P), 256, 0, st>>>(part, nblk, TK, totals);
+    fold_blocks(part, nblk, TK, P, totals, st);
     k_shia5_outputs<<<blocks_for((int64_t)P * N_reg, 256), 256, 0, st>>>(totals, K, N_reg, N, P, balance, mean_rain,
                                                                          mean_storage, mean_speed);
     WMF_LAUNCH_CHECK();
@@ -427,7 +496,7 @@ int wmf_shia3_run(const wmf_shia3_params *params_host, int64_t nsteps, int64_t n
     a.cap_t = cap_t; a.grav_t = grav_t; a.aqu_t = aqu_t; a.part = part;
     k_shia3<<<nblk, TH, 0, st>>>(a);
     const int64_t TK = (nsteps + 1) * 6;
-    k_fold_blocks<<<dim3(blocks_for(TK, 256), 1), 256, 0, st>>>(part, nblk, TK, sums);
+    fold_blocks(part, nblk, TK, 1, sums, st);
     WMF_LAUNCH_CHECK();
     return 0;
 }
