@@ -340,7 +340,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "l2": "inputs (DIR 0.27 GB + ACC 1.07 GB) exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read+write of all kernels of one accumulation (ncu, profiles/r01_summary.md), 16384^2 int32
-                         "traffic": 2.060e9 if (world == 1 and n == 16384 and args.algo != "walk") else None,
+                         "traffic": 1.997e9 if (world == 1 and n == 16384 and args.algo != "walk") else None,
                          "peak_source": peak_src,
                          "kernel": "wmf_d8_accum, all passes of one accumulation "
                                    f"({bytes_per_cell:.0f} B/cell algorithmic)"},
