@@ -13,8 +13,9 @@
  *     asynchronous unless noted ("syncs") and re-entrant per stream;
  *   - return value: 0 ok, <0 argument/semantic error (WMF_E_*), >0 a cudaError_t;
  *     wmf_last_error() returns a thread-local message for the last failure;
- *   - the library keeps no global mutable state (the f2py-style module state of the
- *     reference lives in the Python shim, not here);
+ *   - the library keeps no data between calls (the f2py-style module state of the reference lives in the
+ *     Python shim, not here); the only lasting objects are one helper stream and two events per device that
+ *     wmf_d8_stripe_local creates on first use -- do not overlap calls of it on one device across host threads;
  *   - workspaces are caller-owned: query the size, allocate, pass in.
  */
 #ifndef WMF_B200_H

@@ -23,6 +23,7 @@
 // keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
 // contracted forest carries this through `blocked` nodes and the `ext_unres` entry flags.
 #include <cstdlib>
+#include <mutex>
 #include "common.cuh"
 
 namespace {
@@ -1553,11 +1554,16 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int
 // ---- stripe entry points --------------------------------------------------------------------------
 // The stripe-local pass always runs the packed int32 forest walk (a stripe holds < 2^31 cells); only
 // the finish pass is typed by the output accumulation.
+// The only state the library keeps between calls: one helper stream and two events per device, created on first use.
+// wmf_d8_stripe_local calls on the SAME device must not overlap in time from several host threads (they share the
+// events); everything else is re-entrant.
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 static SideStream *side_stream()
 {
     static SideStream tab[64];
     static bool made[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!made[dev]) {
