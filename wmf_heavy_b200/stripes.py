@@ -91,7 +91,11 @@ def gather_records(rec_packed: torch.Tensor, group=None) -> torch.Tensor:
     """The one exchange step: a single all-gather of the packed boundary records -> [G, 2, 2, nx]."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    bufs = [torch.empty_like(rec_packed) for _ in range(world)]
+    if rec_packed.is_cuda:                               # NCCL: one buffer, no concatenation afterwards
+        out = torch.empty((world,) + tuple(rec_packed.shape), dtype=rec_packed.dtype, device=rec_packed.device)
+        dist.all_gather_into_tensor(out, rec_packed.contiguous(), group=group)
+        return out
+    bufs = [torch.empty_like(rec_packed) for _ in range(world)]      # gloo (the CPU tests)
     dist.all_gather(bufs, rec_packed.contiguous(), group=group)
     return torch.stack(bufs)
 
