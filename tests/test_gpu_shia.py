@@ -273,3 +273,20 @@ def test_shia_v1_writes_storage_records(tmp_path):
         models.evpserie = inp.evp[11:]
         res2 = models.shia_v1(path + "_b.bin", path + "_b.hdr", np.ones(11, np.float32), N, 1, 0, T - 11, v, None, None)
         np.testing.assert_allclose(res2[9], res[9], rtol=1e-6, atol=1e-6)  # (speed_type 1: hspeed carries no state)
+
+
+def test_shia5_population_many_sets():
+    """BASELINE config 5 in small: many parameter sets in one launch (grid.y), each equal to its own oracle run."""
+    N, T, P = 3000, 37, 96
+    inp = helpers.shia5_inputs(oracle, N, T, 95, speed_type=(1, 1, 1))
+    rng = np.random.default_rng(96)
+    calibs = rng.uniform(0.5, 2.0, (P, 11)).astype(np.float32)
+    sto0 = np.full((5, N), 0.001, np.float32)
+    out = _run5(inp, calibs, sto0, show=False)
+    got = out["StoOut"].cpu().numpy()
+    bal = out["balance"].cpu().numpy()
+    for p in (0, 1, 17, 50, 95):
+        o = oracle.f_shia_v1(inp, calibs[p], sto0)
+        np.testing.assert_allclose(got[p], o["StoOut"], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(bal[p], o["balance64"], rtol=1e-4, atol=1e-6 * float(o["StoOut"].sum()))
+    assert np.isfinite(got).all()

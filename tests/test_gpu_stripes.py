@@ -97,3 +97,42 @@ def test_forest_accum_matches_numpy():
     e_acc, e_res = helpers.forest_numpy(parent, w, blocked)
     assert np.array_equal(res.cpu().numpy(), e_res)
     assert np.array_equal(acc.cpu().numpy(), e_acc)
+
+
+def _band_consistent(d, a):
+    """acc == 1 + sum of the donors' acc for the inner rows of a band of a Scheidegger raster (codes E, SE, S)."""
+    a = a.to(torch.int64)
+    tot = torch.ones_like(a)
+    tot[:, 1:] += torch.where(d[:, :-1] == 0, a[:, :-1], torch.zeros_like(a[:, :-1]))          # from the west: E
+    tot[1:, 1:] += torch.where(d[:-1, :-1] == 1, a[:-1, :-1], torch.zeros_like(a[:-1, :-1]))  # from the north-west: SE
+    tot[1:, :] += torch.where(d[:-1, :] == 2, a[:-1, :], torch.zeros_like(a[:-1, :]))         # from the north: S
+    return bool((tot[1:] == a[1:]).all())
+
+
+def test_continental_65536_striped():
+    """BASELINE config 4 at its full size, all stripes on one device: 65536^2 = 2^32 cells, eight row stripes of
+    8192 rows, int64 accumulation through the 64-bit arithmetic path (the raster is one cell too large for 32 bits).
+    Size-independent checks: a corner window against the oracle (nothing flows into it: the network only runs east and
+    south), the donor recurrence on bands across stripe and tile edges, and mass conservation at the raster's exits."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 * 2**30:
+        pytest.skip("needs ~50 GiB of device memory")
+    n = 65536
+    d = ops.synth_scheidegger(n, n, seed=20260101)
+    acc = stripes.accumulate_striped_single_device(d, 8)
+    assert acc.dtype == torch.int64 and acc.shape == (n, n)
+    w = 1536
+    sub = ops.synth_scheidegger_host(w, w, seed=20260101, nx_total=n)
+    assert np.array_equal(sub, d[:w, :w].cpu().numpy())
+    exp = oracle.basin_acum(sub, np.ones((w, w), bool)).astype(np.int64)
+    assert np.array_equal(acc[:w, :w].cpu().numpy(), exp)
+    for r0 in (8190, 32766, 57342, 65500):                 # stripe edges, and the raster's last rows
+        r1 = min(r0 + 6, n)
+        assert _band_consistent(d[r0:r1], acc[r0:r1]), f"rows {r0}..{r1}"
+    last_col = (d[:, -1] == 0) | (d[:, -1] == 1)           # E / SE leave through the last column
+    last_row = (d[-1, :] == 2) | (d[-1, :] == 1)           # S / SE leave through the last row
+    total = int(acc[:, -1][last_col].sum()) + int(acc[-1, :-1][last_row[:-1]].sum())
+    if bool(last_row[-1]) and not bool(last_col[-1]):
+        total += int(acc[-1, -1])
+    assert total == n * n
+    assert int(acc.max()) <= n * n
