@@ -122,6 +122,34 @@ def accumulate_striped(dir_stripe: torch.Tensor, row0: int, ny_total: int, group
     return ops.d8_stripe_finish(dir_stripe, ws, row0, ny_total, inflow, unres, mask_stripe, encoding, acc_dtype, out)
 
 
+def accumulate_striped_multi(dir_local: torch.Tensor, row0: int, ny_total: int, n_local: int, group=None,
+                             encoding: int = ENC_INTERNAL, mask_local: Optional[torch.Tensor] = None,
+                             acc_dtype: int = ACC_I64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Like ``accumulate_striped`` with ``n_local`` stripes per rank (the same number on every rank): a rank's rows
+    are cut into stripes that each hold fewer than 2^31 cells -- 65536^2 on two GPUs is 2 x 2^31 cells -- and still
+    ONE all-gather carries every stripe's boundary records.  Stripe index = rank * n_local + i."""
+    import torch.distributed as dist
+    ny, nx = dir_local.shape
+    rank = dist.get_rank(group)
+    rows = stripe_rows(ny, n_local)
+    recs, wss = [], []
+    for r0, n in rows:
+        m = None if mask_local is None else mask_local[r0:r0 + n].contiguous()
+        rec, ws = ops.d8_stripe_local(dir_local[r0:r0 + n].contiguous(), row0 + r0, ny_total, m, encoding)
+        recs.append(rec)
+        wss.append(ws)
+    gathered = gather_records(torch.stack(recs), group)                    # [world, n_local, 2, 2, nx]
+    recs_all = gathered.reshape((-1,) + tuple(gathered.shape[2:]))
+    if out is None:
+        out = torch.empty((ny, nx), dtype=ops._ACC_TORCH[acc_dtype], device=dir_local.device)
+    for i, (r0, n) in enumerate(rows):
+        m = None if mask_local is None else mask_local[r0:r0 + n].contiguous()
+        inflow, unres = stripe_inflow(recs_all, rank * n_local + i)
+        ops.d8_stripe_finish(dir_local[r0:r0 + n].contiguous(), wss[i], row0 + r0, ny_total, inflow, unres, m, encoding,
+                             acc_dtype, out[r0:r0 + n])
+    return out
+
+
 def accumulate_striped_single_device(dir_t: torch.Tensor, n_stripes: int, encoding: int = ENC_INTERNAL,
                                      mask_t: Optional[torch.Tensor] = None, acc_dtype: int = ACC_I64) -> torch.Tensor:
     """All stripes on ONE device, one after the other: same kernels and boundary logic as the multi-GPU
