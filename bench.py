@@ -318,9 +318,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            mc, times, _ = cpu_oracle_accum(args.ref_sample, 1)
+            cs = args.cpu_sample or n                    # the whole raster by default: ~10-30 s of one host core
+            mc, times, _ = cpu_oracle_accum(cs, 1)
             cpu = {"value": mc, "unit": "Mcells/s", "cores": 1, "kind": "port",
-                   "sample": f"{args.ref_sample}x{args.ref_sample} top-left window of the same raster, C restatement "
+                   "sample": (f"the whole {n}x{n} raster" if cs == n else f"{cs}x{cs} top-left window of the same raster")
+                             + ", C restatement "
                              "of wmf_py basin_acum (oracle/wmf_oracle.c, gcc -O2, 1 thread); "
                              f"{times[0]:.2f} s"}
         # kernels of libwmfb200.so per accumulation (profiles/*launches*.csv): walk = indegree + walk; sweep = sweepA,
@@ -363,7 +365,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--algo", default="auto", choices=["auto", "walk", "sweep"])
-    ap.add_argument("--ref-sample", type=int, default=8192, help="window edge for the CPU baseline")
+    ap.add_argument("--ref-sample", type=int, default=8192, help="window edge of one step of --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="window edge for cpu_baseline (0 = the whole raster)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--shia-cells", type=int, default=1 << 20)
     ap.add_argument("--shia-steps", type=int, default=1000)
