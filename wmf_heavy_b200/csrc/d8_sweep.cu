@@ -1,23 +1,27 @@
 // d8_sweep.cu -- full-raster D8 accumulation, tiled algorithm (WMF_ALGO_SWEEP).
 // Replaces wmf_py/cu_py/basics.py:124-177 for ANY input, bit-exact, in three device phases:
 //
-//   A  per tile (TW x TH cells), in isolation: the accumulation every boundary cell would have if
-//      nothing entered the tile (exit_acc), and for every boundary cell the boundary cell where flow
-//      entering there leaves the tile again (link).
+//   A  per tile (TW x TH cells), in isolation: for every boundary cell the boundary cell where flow
+//      entering there leaves the tile again (link), and the accumulation every exit cell would have if
+//      nothing entered the tile (exit_acc).  One upward sweep gives every cell the label of the exit its
+//      path leaves through; exit_acc is the histogram of those labels.
 //   G  the tiles' exit cells form a contracted forest (parent(x) = link(receiver(x)), weight =
-//      exit_acc(x)); it is accumulated with the in-degree chain walk of forest.cu, and every exit
-//      pushes its total into the entry cell it drains to (inflow).
-//   C  per tile again, now with the external inflow injected at its boundary cells -> final ACC.
+//      exit_acc(x)).  int32 accumulations: one 64-bit word per node (pending arrivals | weight + finished
+//      children), one L2 atomic per hop, every finalised exit pushes its total into the entry cell it
+//      drains to (inflow).  int64 accumulations of rasters of 2^32 cells and more: the generic engine of
+//      forest.cu.
+//   C  per tile again, the downward accumulation sweep with the external inflow injected at the
+//      boundary cells -> final ACC.  A raster below 2^32 cells is accumulated in 32 bits whatever the
+//      output type and widened (or converted to float64) by the store.
 //
-// Per-tile solvers.  FAST: one warp owns a tile and streams its rows top to bottom with the
-// running row held in registers -- contributions from the row above are lane-local or one shuffle
-// away, and East / West chains inside a row are segmented warp scans (shuffle); the reverse sweep
-// for `link` is the same machinery bottom to top.  No shared-memory atomics, no barriers.  It is
-// exact for tiles whose in-tile flow never points upwards and has no E<->W two-cycles ("simple"
-// tiles; a Scheidegger network is all simple).  GENERAL: every other tile (and every tile that
-// receives flow from an unresolved, i.e. cyclic, upstream) is solved by one thread block with the
-// in-degree chain walk in shared memory.  Both produce the same outputs, so the result does not
-// depend on which solver ran: integer adds, any schedule is bit-exact.
+// Per-tile solvers.  FAST: one warp owns a tile and streams its rows with the running row held in
+// registers -- contributions from the neighbouring row are lane-local or one shuffle away, and East /
+// West chains inside a row are segmented warp scans (shuffle).  It is exact for tiles whose in-tile
+// flow never points upwards and has no E<->W two-cycles ("simple" tiles; a Scheidegger network is all
+// simple).  GENERAL: every other tile (and every tile that receives flow from an unresolved, i.e.
+// cyclic, upstream) is solved by one thread block with the in-degree chain walk in shared memory.
+// Both produce the same outputs, so the result does not depend on which solver ran: integer adds,
+// any schedule is bit-exact.
 //
 // Cycle semantics (basics.py:166-175): a cell is finalised only when all its donors are; others
 // keep the partial sum of finalised inflows without their own +1 and pass nothing on.  The
