@@ -75,6 +75,49 @@ def test_stripe_exchange_gloo_world2(kind):
         np.testing.assert_allclose(mr, mr_exp, rtol=1e-6)
 
 
+def _worker_multi(rank, world, port, fd, k, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r0, n = stripes.stripe_rows(fd.shape[0], world)[rank]
+        recs = []
+        for s0, sn in stripes.stripe_rows(n, k):          # the rank's rows cut into k stripes (accumulate_striped_multi)
+            a0 = r0 + s0
+            acc_local = oracle.basin_acum(fd[a0:a0 + sn], np.ones((sn, fd.shape[1]), bool))
+            rec = {kk: torch.from_numpy(v) for kk, v in helpers.stripe_records_numpy(fd, a0, sn, acc_local).items()}
+            recs.append(stripes.pack_records(rec))
+        gathered = stripes.gather_records(torch.stack(recs))               # [world, k, 2, 2, nx]
+        recs_all = gathered.reshape((-1,) + tuple(gathered.shape[2:]))
+        out = [stripes.stripe_inflow(recs_all, rank * k + i, forest_fn=_forest_cpu)[0].numpy() for i in range(k)]
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_several_stripes_per_rank_gloo_world2():
+    """The exchange of stripes.accumulate_striped_multi: k stripes per rank behind one all-gather."""
+    fd = helpers.steepest(66, 31, 14, pit_frac=0.02)
+    world, k = 2, 3
+    port = 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_multi, args=(r, world, port, fd, k, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rows = []
+    for r0, n in stripes.stripe_rows(fd.shape[0], world):
+        rows += [(r0 + s0, sn) for s0, sn in stripes.stripe_rows(n, k)]
+    acc_full = oracle.basin_acum(fd, np.ones(fd.shape, bool))
+    exp = helpers.expected_stripe_inflow(fd, acc_full, rows)
+    for rank, out in res:
+        for i in range(k):
+            assert np.array_equal(out[i], exp[rank * k + i]), f"rank {rank} stripe {i}"
+
+
 def test_boundary_inflow_three_stripes_single_process():
     fd = helpers.steepest(61, 29, 9, pit_frac=0.01)
     rows = stripes.stripe_rows(fd.shape[0], 3)
