@@ -234,6 +234,22 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
                        const int32_t *snap_slot, int32_t n_snap, float *snap_out,
                        void *workspace, size_t ws_bytes, void *stream);
 
+/* N4 (EXTENSION: the reference has no behaviour to match here): channel routing behind the shipped 5-tank
+ * update.  Modelos_heavy.f90 declares tank 5, `drena` and the control points (:52-55, :91-92, :202-211) but never moves
+ * water between cells, so Q == 0 as shipped.  Definition (oracle/wmf_oracle.c orc_f_shia_route is its oracle): after the
+ * shipped update of a cell, the lateral outflows of tanks 2-4 enter its tank 5 together with the outflow volumes of its
+ * donors of the SAME step; tank 5 is a linear reservoir like tanks 2-4 (speed row 4, hill_long) and drains to the
+ * receiver.  Q [n_ctrl][N_reg] in m3/s: row 0 = the outlet (the structure's last cell), row j > 0 = the cell with
+ * ctrl == j.  Cells in the structure's upstream-first order; rank = max depth - depth (wmf_basin_depth_host), donors in
+ * CSR form with ascending indices.  Speed type 1 only.  N_reg + max_rank launches (a skewed level/time wavefront). */
+int32_t wmf_basin_depth_host(const int32_t *drain, int64_t n, int32_t *depth);
+size_t wmf_shia5_route_workspace(int64_t N);
+int wmf_shia5_route_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec,
+                        const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento,
+                        const float *evp, const float *calib, const int32_t *rank, int32_t max_rank,
+                        const int32_t *don_ptr, const int32_t *don_idx, const int32_t *ctrl, int32_t n_ctrl,
+                        float *sto, float *acum_rain, float *Q, void *workspace, size_t ws_bytes, void *stream);
+
 /* ---------------------------------------------------------------- S4: SHIA 3-tank (wmf_py semantics)
  * Replaces wmf_py/models_py/core.py:64-295 shia_v1, fp64.  rain/et double [nsteps][ncell]
  * (et nullable, already multiplied by nothing: et_scale = dt/3600 or dt/86400 is applied

@@ -247,3 +247,27 @@ def f_shia_v1(inp: Shia5Inputs, calib, sto_in, hspeed_in=None, show_storage=True
     assert rc == 0
     return {"StoOut": sto, "hspeed": hs, "balance": balance, "balance64": b64, "mean_rain": mean_rain, "acum_rain": acum_rain,
             "mean_storage": ms, "mean_speed": msp, "mean_retorno": mr}
+
+
+def f_shia_route(inp: Shia5Inputs, calib, sto_in, drain, ctrl, n_ctrl):
+    """Routing extension (N4; no reference behaviour): the shipped 5-tank update plus a linear-reservoir
+    channel store (tank 5) draining along ``drain``.  ``ctrl`` int32 [N]: row of Q for that cell (> 0) or 0; row 0 is
+    the outlet.  Returns StoOut (5, N), Q (n_ctrl, N_reg) [m3/s], acum_rain, totals (rain, losses, outflow) [m3]."""
+    N = inp.max_capilar.shape[0]
+    n_reg = inp.pos_evento.shape[0]
+    assert tuple(inp.speed_type) == (1, 1, 1), "the routing extension is defined for speed type 1"
+    sto = np.array(sto_in, dtype=np.float32).reshape(5, N).copy()
+    p = _Shia5Params(inp.dt, inp.retorno_gr, inp.retorno_aq, inp.calc_niter, (C.c_int32 * 3)(*inp.speed_type), 0)
+    cal = _c(calib, np.float32)
+    acum = np.zeros(N, np.float32)
+    Q = np.zeros((n_ctrl, n_reg), np.float32)
+    totals = np.zeros(3, np.float64)
+    f32 = np.float32
+    rc = lib().orc_f_shia_route(C.byref(p), C.c_int64(N), C.c_int64(n_reg), _p(cal), _p(_c(inp.v_coef, f32)),
+                                _p(_c(inp.h_coef, f32)), _p(_c(inp.max_capilar, f32)), _p(_c(inp.max_gravita, f32)),
+                                _p(_c(inp.max_aquifer, f32)), _p(_c(inp.hill_long, f32)), _p(_c(inp.elem_area, f32)),
+                                _p(_c(inp.rain_records, np.int32)), _p(_c(inp.pos_evento, np.int32)), _p(_c(inp.evp, f32)),
+                                _p(_c(drain, np.int32)), _p(_c(ctrl, np.int32)), C.c_int32(n_ctrl), _p(sto), _p(acum), _p(Q),
+                                _p(totals))
+    assert rc == 0
+    return {"StoOut": sto, "Q": Q, "acum_rain": acum, "totals": totals}

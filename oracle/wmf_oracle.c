@@ -530,3 +530,71 @@ int orc_f_shia_v1(const orc_shia5_params *p, int64_t N, int64_t N_reg, const flo
     free(vspeed); free(H); free(rain); free(retorned);
     return 0;
 }
+
+/* ------------------------------------------------------------------ N4 (extension, no reference behaviour)
+ * Channel routing behind the shipped 5-tank update.  The reference declares tank 5, `drena` and the control
+ * points but never moves water between cells (Q == 0 as shipped); this is the documented extension of
+ * per step, after the shipped vertical / lateral update of a cell (speed type 1 only),
+ *     lat   = (hflux2 + hflux3) + hflux4                         the lateral outflows the shipped code drops [mm]
+ *     S5    = (S5 + lat) + (sum over donors d, ascending index, of qout_m3(d, t)) / m3mm(c)
+ *     q5    = (1 - L / (hspeed4 * dt + L)) * S5 ;  S5 = S5 - q5     linear reservoir, like tanks 2-4
+ *     qout_m3(c, t) = q5 * m3mm(c)            goes to the receiver n - drain(c) within the same step
+ *     Q(j, t) = qout_m3 / dt  at the cells ctrl marks (row j), row 0 = the outlet (the last cell)
+ * Cells are in the structure's upstream-first order, so index order is a topological order.  PARITY UNPINNED by
+ * construction.  totals[3] (fp64) = rain volume, losses (v4 + evaporation), outflow at the outlet, all m3. */
+int orc_f_shia_route(const orc_shia5_params *p, int64_t N, int64_t N_reg, const float *calib,
+                     const float *v_coef, const float *h_coef,
+                     const float *max_capilar, const float *max_gravita, const float *max_aquifer,
+                     const float *hill_long, const float *elem_area,
+                     const int32_t *rain_records, const int32_t *pos_evento, const float *evp,
+                     const int32_t *drain, const int32_t *ctrl, int32_t n_ctrl,
+                     float *sto, float *acum_rain, float *Q, double *totals)
+{
+    float dt = p->dt;
+    float *qout = (float *)calloc(N, sizeof(float));
+    float *qin = (float *)calloc(N, sizeof(float));
+    if (!qout || !qin) return -1;
+    for (int64_t c = 0; c < N; c++) acum_rain[c] = 0.0f;
+    for (int64_t i = 0; i < (int64_t)n_ctrl * N_reg; i++) Q[i] = 0.0f;
+    totals[0] = totals[1] = totals[2] = 0.0;
+    for (int64_t t = 0; t < N_reg; t++) {
+        for (int64_t c = 0; c < N; c++) qin[c] = 0.0f;
+        for (int64_t c = 0; c < N; c++) {
+            float R = 0.0f;
+            if (pos_evento[t] != 1) R = (float)rain_records[(int64_t)(pos_evento[t] - 1) * N + c] / 1000.0f;
+            acum_rain[c] = acum_rain[c] + R;
+            float vs[4], hs[4];
+            for (int i = 0; i < 4; i++) { vs[i] = v_coef[i * N + c] * calib[i] * dt; hs[i] = h_coef[i * N + c] * calib[i + 4]; }
+            float H1 = max_capilar[c] * calib[8], H2 = max_gravita[c] * calib[9], H3 = max_aquifer[c] * calib[10];
+            float S1 = sto[0 * N + c], S2 = sto[1 * N + c], S3 = sto[2 * N + c], S4 = sto[3 * N + c], S5 = sto[4 * N + c];
+            float v1 = fmaxf(0.0f, (R - H1) + S1);
+            S1 = (S1 + R) - v1;
+            float evl = fminf((evp[t] * vs[0]) * powf(S1 / H1, 0.6f), S1);
+            S1 = S1 - evl;
+            float v2 = fminf(v1, vs[1]); S2 = (S2 + v1) - v2;
+            float v3 = fminf(v2, vs[2]); S3 = (S3 + v2) - v3;
+            float v4 = fminf(v3, vs[3]); S4 = (S4 + v3) - v4;
+            if (p->retorno_aq > 0) { float ra = fmaxf(0.0f, S4 - H3); S3 = S3 + ra; S4 = S4 - ra; }
+            if (p->retorno_gr > 0) { float rg = fmaxf(0.0f, S3 - H2); S2 = S2 + rg; S3 = S3 - rg; }
+            float L = hill_long[c], m3mm = elem_area[c] / 1000.0f;
+            float hf2 = (1.0f - L / (hs[0] * dt + L)) * S2; S2 = S2 - hf2;
+            float hf3 = (1.0f - L / (hs[1] * dt + L)) * S3; S3 = S3 - hf3;
+            float hf4 = (1.0f - L / (hs[2] * dt + L)) * S4; S4 = S4 - hf4;
+            float lat = (hf2 + hf3) + hf4;
+            S5 = (S5 + lat) + qin[c] / m3mm;
+            float q5 = (1.0f - L / (hs[3] * dt + L)) * S5;
+            S5 = S5 - q5;
+            float qm3 = q5 * m3mm;
+            qout[c] = qm3;
+            int32_t dr = drain[c];
+            if (dr != 0) qin[N - dr] = qin[N - dr] + qm3;            /* donors arrive in ascending index order */
+            else { Q[t] = qm3 / dt; totals[2] += (double)qm3; }      /* row 0: the outlet */
+            if (ctrl[c] > 0) Q[(int64_t)ctrl[c] * N_reg + t] = qm3 / dt;
+            totals[0] += (double)R * (double)m3mm;
+            totals[1] += ((double)v4 + (double)evl) * (double)m3mm;
+            sto[0 * N + c] = S1; sto[1 * N + c] = S2; sto[2 * N + c] = S3; sto[3 * N + c] = S4; sto[4 * N + c] = S5;
+        }
+    }
+    free(qout); free(qin);
+    return 0;
+}

@@ -402,6 +402,94 @@ __global__ void __launch_bounds__(TH) k_shia3(const Shia3Args a)
     }
 }
 
+
+// ------------------------------------------------------------------------------------ N4: channel routing (extension)
+// The reference declares tank 5, `drena` and the control points but never moves water between cells, so
+// this has no reference behaviour to match; its definition and its own oracle are oracle/wmf_oracle.c orc_f_shia_route.
+// Cell c needs (c, t - 1) and (its donors, t).  With rank(c) = Dmax - depth(c) (depth = links to the outlet) every donor
+// has rank(c) - 1, so on "diagonal" d = rank + t all cells can work at once, each on its own time step t = d - rank(c):
+// N_reg + Dmax launches instead of N_reg x Dmax level sweeps.  A donor's outflow of step t is written on diagonal d - 1
+// and read on diagonal d: two buffers, by the parity of d.  Donors are pulled in ascending index order (CSR), so the
+// result does not depend on the schedule.
+struct RouteArgs {
+    int64_t N, N_reg;
+    const float *ct;             // [13][N]: vs0..3, fl2..4 (lateral fractions), fl5, 1/H1, H1, H2, H3, m3mm
+    const int32_t *rain;         // [n_rec][N]
+    const int32_t *pos;          // [N_reg]
+    const float *evp;            // [N_reg]
+    const int32_t *rank;         // [N]
+    const int32_t *don_ptr;      // [N + 1]
+    const int32_t *don_idx;      // [don_ptr[N]]
+    const int32_t *ctrl;         // [N]: row of Q (> 0), 0 none; the outlet (last cell) always writes row 0
+    float *sto;                  // [5][N] in / out
+    float *acum;                 // [N]
+    float *qbuf;                 // [2][N] outflow volumes [m3]
+    float *Q;                    // [n_ctrl][N_reg]
+    float dt, retorno_gr, retorno_aq;
+};
+
+__global__ void k_route_setup(int64_t N, const float *__restrict__ cs, const float *__restrict__ calib, float dt,
+                              float *__restrict__ ct, float *__restrict__ acum)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const float L = cs[15 * N + c];
+#pragma unroll
+    for (int i = 0; i < 4; i++) ct[i * N + c] = cs[i * N + c] * calib[i] * dt;                    // vspeed (Modelos:242)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float hs = cs[(4 + i) * N + c] * calib[4 + i];
+        ct[(4 + i) * N + c] = 1.0f - L / (hs * dt + L);                                           // :462, and tank 5 alike
+    }
+    const float H1 = cs[12 * N + c] * calib[8];
+    ct[8 * N + c] = 1.0f / H1;
+    ct[9 * N + c] = H1;
+    ct[10 * N + c] = cs[13 * N + c] * calib[9];
+    ct[11 * N + c] = cs[14 * N + c] * calib[10];
+    ct[12 * N + c] = cs[16 * N + c] / 1000.0f;
+    acum[c] = 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_route_diag(const RouteArgs a, int64_t d)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, N = a.N;
+    if (c >= N) return;
+    const int64_t t = d - a.rank[c];
+    if (t < 0 || t >= a.N_reg) return;
+    const float *ct = a.ct;
+    const int pos = a.pos[t];
+    float R = 0.0f;
+    if (pos != 1) R = (float)a.rain[(int64_t)(pos - 1) * N + c] * 0.001f;
+    a.acum[c] = a.acum[c] + R;
+    float S1 = a.sto[c], S2 = a.sto[N + c], S3 = a.sto[2 * N + c], S4 = a.sto[3 * N + c], S5 = a.sto[4 * N + c];
+    const float H1 = ct[9 * N + c], H2 = ct[10 * N + c], H3 = ct[11 * N + c], m3mm = ct[12 * N + c];
+    float v1 = fmaxf(0.0f, (R - H1) + S1);
+    S1 = (S1 + R) - v1;
+    float evl = fminf((a.evp[t] * ct[c]) * pow06(S1 * ct[8 * N + c]), S1);
+    S1 = S1 - evl;
+    float v2 = fminf(v1, ct[N + c]); S2 = (S2 + v1) - v2;
+    float v3 = fminf(v2, ct[2 * N + c]); S3 = (S3 + v2) - v3;
+    float v4 = fminf(v3, ct[3 * N + c]); S4 = (S4 + v3) - v4;
+    if (a.retorno_aq > 0.0f) { float ra = fmaxf(0.0f, S4 - H3); S3 = S3 + ra; S4 = S4 - ra; }
+    if (a.retorno_gr > 0.0f) { float rg = fmaxf(0.0f, S3 - H2); S2 = S2 + rg; S3 = S3 - rg; }
+    const float hf2 = ct[4 * N + c] * S2; S2 = S2 - hf2;
+    const float hf3 = ct[5 * N + c] * S3; S3 = S3 - hf3;
+    const float hf4 = ct[6 * N + c] * S4; S4 = S4 - hf4;
+    const float lat = (hf2 + hf3) + hf4;
+    const float *qprev = a.qbuf + ((d - 1) & 1) * N;
+    float qin = 0.0f;
+    for (int32_t k = a.don_ptr[c]; k < a.don_ptr[c + 1]; k++) qin = qin + qprev[a.don_idx[k]];
+    S5 = (S5 + lat) + qin / m3mm;
+    const float q5 = ct[7 * N + c] * S5;
+    S5 = S5 - q5;
+    const float qm3 = q5 * m3mm;
+    a.qbuf[(d & 1) * N + c] = qm3;
+    if (c == N - 1) a.Q[t] = qm3 / a.dt;
+    const int32_t j = a.ctrl[c];
+    if (j > 0) a.Q[(int64_t)j * a.N_reg + t] = qm3 / a.dt;
+    a.sto[c] = S1; a.sto[N + c] = S2; a.sto[2 * N + c] = S3; a.sto[3 * N + c] = S4; a.sto[4 * N + c] = S5;
+}
+
 }  // namespace
 
 extern "C" {
@@ -497,6 +585,52 @@ int wmf_shia3_run(const wmf_shia3_params *params_host, int64_t nsteps, int64_t n
     k_shia3<<<nblk, TH, 0, st>>>(a);
     const int64_t TK = (nsteps + 1) * 6;
     fold_blocks(part, nblk, TK, 1, sums, st);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
+
+/* N4 host helper: depth[i] = number of links from cell i to the outlet, for a structure in upstream-first order
+ * (receiver of i = n - drain[i], drain 0 = outlet).  Returns the largest depth, or -1 on a malformed structure. */
+int32_t wmf_basin_depth_host(const int32_t *drain, int64_t n, int32_t *depth)
+{
+    int32_t dmax = 0;
+    for (int64_t i = n - 1; i >= 0; i--) {
+        const int32_t dr = drain[i];
+        if (dr == 0) { depth[i] = 0; continue; }
+        const int64_t j = n - dr;
+        if (j <= i || j >= n) return -1;
+        depth[i] = depth[j] + 1;
+        if (depth[i] > dmax) dmax = depth[i];
+    }
+    return dmax;
+}
+
+size_t wmf_shia5_route_workspace(int64_t N) { return wmf_align((size_t)N * 13 * 4) + wmf_align((size_t)N * 2 * 4) + 1024; }
+
+int wmf_shia5_route_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec,
+                        const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento, const float *evp,
+                        const float *calib, const int32_t *rank, int32_t max_rank, const int32_t *don_ptr,
+                        const int32_t *don_idx, const int32_t *ctrl, int32_t n_ctrl, float *sto, float *acum_rain, float *Q,
+                        void *workspace, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = as_stream(stream);
+    WMF_REQUIRE(params_host && cell_static && rain_records && pos_evento && evp && calib && rank && don_ptr && don_idx &&
+                ctrl && sto && acum_rain && Q && workspace, WMF_E_ARG, "null pointer");
+    WMF_REQUIRE(N > 0 && N_reg > 0 && n_rec > 0 && n_ctrl >= 1 && max_rank >= 0, WMF_E_ARG, "bad size");
+    WMF_REQUIRE(params_host->speed_type[0] == 1 && params_host->speed_type[1] == 1 && params_host->speed_type[2] == 1,
+                WMF_E_ARG, "the routing extension is defined for speed type 1");
+    WsCursor cur(workspace, ws_bytes);
+    float *ct = cur.take<float>((size_t)N * 13), *qbuf = cur.take<float>((size_t)N * 2);
+    WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
+    WMF_CUDA_CHECK(cudaMemsetAsync(qbuf, 0, sizeof(float) * 2 * (size_t)N, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(Q, 0, sizeof(float) * (size_t)n_ctrl * (size_t)N_reg, st));
+    k_route_setup<<<blocks_for(N, 256), 256, 0, st>>>(N, cell_static, calib, params_host->dt, ct, acum_rain);
+    RouteArgs a;
+    a.N = N; a.N_reg = N_reg; a.ct = ct; a.rain = rain_records; a.pos = pos_evento; a.evp = evp; a.rank = rank;
+    a.don_ptr = don_ptr; a.don_idx = don_idx; a.ctrl = ctrl; a.sto = sto; a.acum = acum_rain; a.qbuf = qbuf; a.Q = Q;
+    a.dt = params_host->dt; a.retorno_gr = params_host->retorno_gr; a.retorno_aq = params_host->retorno_aq;
+    for (int64_t d = 0; d < N_reg + max_rank; d++) k_route_diag<<<blocks_for(N, 256), 256, 0, st>>>(a, d);
     WMF_LAUNCH_CHECK();
     return 0;
 }

@@ -42,6 +42,7 @@ sim_sediments = sim_slides = sim_floods = 0
 save_storage = save_speed = save_retorno = save_vfluxes = save_rc = 0
 show_storage = show_speed = show_mean_speed = show_mean_retorno = show_area = 0
 separate_fluxes = separate_rain = 0
+route_channels = 0        # EXTENSION (not in the reference, whose Q is 0 as shipped): 1 routes tank 5 along `drena`
 guarda_cond = None
 # outputs
 mean_rain = None
@@ -290,6 +291,8 @@ def shia_v1(ruta_bin, ruta_hdr, calib, n_cel, n_cont, n_conth, n_reg, stoin=None
         if not ruta_storage:
             raise ValueError("models.save_storage = 1 needs ruta_storage")
         save = np.zeros(n_reg, dtype=np.int64) if guarda_cond is None else np.asarray(guarda_cond)
+    if int(route_channels) == 1:
+        return _shia_v1_routed(cal, records, pos, n_cel, n_cont, n_conth, n_reg, stoin)
     out = shia_v1_population(cal[None, :], records, pos, n_cel, n_reg, stoin, hspeedin, save_records=save)
     if out.get("snapshot_records") is not None:      # in time order, like the Fortran loop writes them
         for k, rec in enumerate(out["snapshot_records"]):
@@ -306,3 +309,42 @@ def shia_v1(ruta_bin, ruta_hdr, calib, n_cel, n_cont, n_conth, n_reg, stoin=None
     Qsep_rain = np.zeros((n_cont, 2, n_reg), f32, order="F")
     return (Q, Qsed, Qsep, Hum, St1, St3, out["balance"][0], speed, area_c, np.asfortranarray(out["StoOut"][0]),
             Qsep_rain)
+
+
+def _shia_v1_routed(cal, records, pos, n_cel, n_cont, n_conth, n_reg, stoin):
+    """``models.route_channels = 1`` -- the routing EXTENSION: same 11 outputs, with Q [n_cont, N_reg]
+    in m3/s filled at the outlet (row 0) and at the cells ``models.control`` marks (rows 1.. in cell order)."""
+    global mean_rain, acum_rain
+    _reject_out_of_scope()
+    if int(save_storage) == 1:
+        raise NotImplementedError("models.save_storage with models.route_channels")
+    if drena is None:
+        raise ValueError("models.drena (the basin structure) must be set for routing")
+    if evpserie is None:
+        raise ValueError("models.evpserie must be set (the Fortran dereferences EvpSerie(t), Modelos:396)")
+    st = np.asarray(speed_type).astype(int).reshape(-1)[:3]
+    if tuple(st) != (1, 1, 1):
+        raise NotImplementedError("the routing extension is defined for models.speed_type = (1, 1, 1)")
+    drain = np.asarray(drena, dtype=np.int32).reshape(-1, n_cel)[0]
+    marks = np.zeros(n_cel, dtype=np.int64) if control is None else np.asarray(control).reshape(-1)[:n_cel]
+    ctrl = np.where(marks != 0, np.cumsum(marks != 0), 0).astype(np.int32)
+    if int(ctrl.max(initial=0)) + 1 > n_cont:
+        raise ValueError("N_cont is smaller than the number of control points + 1")
+    if stoin is not None and float(np.asarray(stoin).reshape(-1)[0]) > 0:
+        s0 = np.asarray(stoin, dtype=np.float32).reshape(5, n_cel)
+    else:
+        base = np.zeros((5, n_cel), np.float32) if storage is None else np.asarray(storage, dtype=np.float32)
+        s0 = base + np.float32(storage_constant)
+    rr = to_dev(np.ascontiguousarray(records, dtype=np.int32))
+    pe = to_dev(np.asarray(pos, dtype=np.int32)[:n_reg])
+    out = ops.shia5_route_run(to_dev(cell_static_table(n_cel)), rr, pe, to_dev(np.asarray(evpserie, dtype=np.float32)[:n_reg]),
+                              to_dev(np.ascontiguousarray(cal, dtype=np.float32)), to_dev(np.ascontiguousarray(s0)), drain, ctrl,
+                              n_cont, dt=float(dt), retorno_gr=float(retorno_gr), retorno_aq=float(retorno_aq))
+    rec_mean = (rr.to(torch.float64).mean(dim=1) / 1000.0).cpu().numpy()
+    mean_rain = rec_mean[np.asarray(pos[:n_reg]) - 1].astype(np.float32).reshape(1, n_reg)
+    acum_rain = out["acum_rain"].cpu().numpy().reshape(1, n_cel)
+    f32 = np.float32
+    z = lambda *shape: np.zeros(shape, f32, order="F")
+    return (np.asfortranarray(out["Q"].cpu().numpy()), z(n_cont, 3, n_reg), z(n_cont, 3, n_reg), z(n_conth, n_reg),
+            z(n_conth, n_reg), z(n_conth, n_reg), np.zeros(n_reg, f32), z(n_cont, n_reg), z(n_cont, n_reg),
+            np.asfortranarray(out["StoOut"].cpu().numpy()), z(n_cont, 2, n_reg))

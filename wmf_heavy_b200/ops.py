@@ -278,6 +278,63 @@ def stream_nodes(dir_t: torch.Tensor, stream_t: torch.Tensor, outlet_index: int,
     return (node, *outs)
 
 
+def route_topology(drain: np.ndarray):
+    """Host preparation of the routing extension from the structure's drain ids (upstream-first order, receiver of
+    cell i = n - drain[i], 0 = outlet): (rank int32 [n], max_rank, don_ptr int32 [n + 1], don_idx int32 [n - roots])."""
+    dr = np.ascontiguousarray(drain, dtype=np.int32).reshape(-1)
+    n = dr.size
+    depth = np.empty(n, dtype=np.int32)
+    dmax = int(_lib.load().wmf_basin_depth_host(dr.ctypes.data, n, depth.ctypes.data))
+    if dmax < 0:
+        raise ValueError("malformed structure: a receiver does not come after its donor")
+    rank = (dmax - depth).astype(np.int32)
+    has = dr != 0
+    recv = (n - dr[has]).astype(np.int64)
+    donors = np.nonzero(has)[0].astype(np.int32)
+    order = np.argsort(recv, kind="stable")               # donors of a receiver stay in ascending index order
+    don_idx = donors[order]
+    don_ptr = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(don_ptr, recv + 1, 1)
+    don_ptr = np.cumsum(don_ptr, dtype=np.int64).astype(np.int32)
+    return rank, dmax, don_ptr, np.ascontiguousarray(don_idx, dtype=np.int32)
+
+
+def shia5_route_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento: torch.Tensor, evp: torch.Tensor,
+                    calib: torch.Tensor, sto: torch.Tensor, drain, ctrl=None, n_ctrl: int = 1, *, dt: float,
+                    retorno_gr: float = 0.0, retorno_aq: float = 0.0):
+    """Routing EXTENSION (N4; the reference has no behaviour to match): the shipped 5-tank update plus a channel
+    store (tank 5) draining along ``drain``.  ``sto`` [5, N] advanced in place; ``ctrl`` int32 [N] = row of Q (> 0) or 0.
+    Returns {"StoOut", "Q" [n_ctrl, N_reg] m3/s (row 0 = outlet), "acum_rain"}."""
+    dev = require_cuda()
+    _chk_dev(cell_static, torch.float32, "cell_static")
+    _chk_dev(rain_records, torch.int32, "rain_records")
+    _chk_dev(pos_evento, torch.int32, "pos_evento")
+    _chk_dev(evp, torch.float32, "evp")
+    _chk_dev(calib, torch.float32, "calib")
+    _chk_dev(sto, torch.float32, "sto")
+    N = cell_static.shape[1]
+    n_reg, n_rec = pos_evento.shape[0], rain_records.shape[0]
+    if cell_static.shape != (17, N) or calib.numel() != 11 or sto.shape != (5, N) or rain_records.shape != (n_rec, N):
+        raise ValueError("shape mismatch: cell_static (17,N), calib (11,), sto (5,N), rain_records (n_rec,N)")
+    rank, dmax, don_ptr, don_idx = route_topology(np.asarray(drain))
+    if rank.size != N:
+        raise ValueError("drain must have one entry per cell")
+    c = np.zeros(N, dtype=np.int32) if ctrl is None else np.ascontiguousarray(ctrl, dtype=np.int32).reshape(-1)
+    if c.size != N or c.min() < 0 or c.max() >= max(int(n_ctrl), 1):
+        raise ValueError("ctrl must hold rows in [0, n_ctrl) for every cell")
+    to = lambda a: torch.from_numpy(a).to(dev)
+    rank_t, dp_t, di_t, c_t = to(rank), to(don_ptr), to(don_idx if don_idx.size else np.zeros(1, np.int32)), to(c)
+    Q = torch.empty((int(n_ctrl), n_reg), dtype=torch.float32, device=dev)
+    acum = torch.empty(N, dtype=torch.float32, device=dev)
+    prm = _lib.Shia5Params(dt, retorno_gr, retorno_aq, 0, (C.c_int32 * 3)(1, 1, 1), 0)
+    lib = _lib.load()
+    ws = workspace(lib.wmf_shia5_route_workspace(N))
+    check(lib.wmf_shia5_route_run(C.addressof(prm), N, n_reg, n_rec, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
+                                  ptr(evp), ptr(calib), ptr(rank_t), int(dmax), ptr(dp_t), ptr(di_t), ptr(c_t), int(n_ctrl),
+                                  ptr(sto), ptr(acum), ptr(Q), ptr(ws), ws.numel(), stream_ptr()))
+    return {"StoOut": sto, "Q": Q, "acum_rain": acum}
+
+
 # --------------------------------------------------------------------------------------- S4
 def shia3_run(rain: torch.Tensor, et: Optional[torch.Tensor], cap: torch.Tensor, grav: torch.Tensor,
               aqu: torch.Tensor, prm: "_lib.Shia3Params", nsteps: int, separate_fluxes: bool = False,
