@@ -236,7 +236,7 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
 
 /* N4 (EXTENSION: the reference has no behaviour to match here): channel routing behind the shipped 5-tank
  * update.  Modelos_heavy.f90 declares tank 5, `drena` and the control points (:52-55, :91-92, :202-211) but never moves
- * water between cells, so Q == 0 as shipped.  Definition (oracle/wmf_oracle.c orc_f_shia_route is its oracle): after the
+ * water between cells, so Q == 0 as shipped.  Definition (the tests hold a CPU restatement of it): after the
  * shipped update of a cell, the lateral outflows of tanks 2-4 enter its tank 5 together with the outflow volumes of its
  * donors of the SAME step; tank 5 is a linear reservoir like tanks 2-4 (speed row 4, hill_long) and drains to the
  * receiver.  Q [n_ctrl][N_reg] in m3/s: row 0 = the outlet (the structure's last cell), row j > 0 = the cell with

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(TH) k_shia3(const Shia3Args a)
 
 // ------------------------------------------------------------------------------------ N4: channel routing (extension)
 // The reference declares tank 5, `drena` and the control points but never moves water between cells, so
-// this has no reference behaviour to match; its definition and its own oracle are oracle/wmf_oracle.c orc_f_shia_route.
+// this has no reference behaviour to match; it is defined in DESIGN.md 4.5 and checked against a CPU restatement of its own.
 // Cell c needs (c, t - 1) and (its donors, t).  With rank(c) = Dmax - depth(c) (depth = links to the outlet) every donor
 // has rank(c) - 1, so on "diagonal" d = rank + t all cells can work at once, each on its own time step t = d - rank(c):
 // N_reg + Dmax launches instead of N_reg x Dmax level sweeps.  A donor's outflow of step t is written on diagonal d - 1
