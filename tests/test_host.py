@@ -135,3 +135,24 @@ def test_rain_file_roundtrip(tmp_path):        # Modelos_heavy.f90:580-590, 631-
     assert np.array_equal(models.read_rain_records(b, N), rec)
     with pytest.raises(ValueError):
         models.rain_read_ascii_table(h, T + 5)
+
+
+def test_route_topology_host():                # N4 extension, host part: depth / rank / donor lists from the drain ids
+    from wmf_heavy_b200 import ops
+    fd = ops.synth_scheidegger_host(60, 70, seed=12)
+    acc = oracle.basin_acum(fd, np.ones(fd.shape, bool))
+    r0, c0 = np.unravel_index(np.argmax(acc), acc.shape)
+    import helpers
+    drain = oracle.f_basin_find(helpers.to_keypad(fd), int(c0) + 1, int(r0) + 1)[0].astype(np.int32)
+    n = drain.size
+    rank, dmax, ptr, idx = ops.route_topology(drain)
+    recv = np.where(drain != 0, n - drain, -1)
+    depth = np.zeros(n, int)
+    for i in range(n - 2, -1, -1):             # receivers come later in the upstream-first order
+        depth[i] = depth[recv[i]] + 1
+    assert dmax == depth.max() and np.array_equal(rank, dmax - depth)
+    assert ptr[0] == 0 and ptr[-1] == n - 1 and np.all(np.diff(ptr) >= 0)
+    for j in range(n):
+        assert list(idx[ptr[j]:ptr[j + 1]]) == list(np.nonzero(recv == j)[0])      # ascending donor indices
+    with pytest.raises(ValueError):
+        ops.route_topology(np.array([3, 0, 0], np.int32))
