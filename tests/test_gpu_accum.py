@@ -105,6 +105,28 @@ def test_wide_arithmetic_path(monkeypatch):
         assert np.array_equal(run(sch, None, _lib.ALGO_SWEEP, _lib.ACC_F64), exp2)
 
 
+def test_accumulations_beyond_int32_in_32_bit_arithmetic():
+    """A raster of 2^31 + 65536 cells that drains through ONE cell: every row runs east, the last column south.  Its
+    64-bit output is computed in 32-bit (unsigned) arithmetic because the raster has fewer than 2^32 cells; the last
+    column holds (r + 1) * nx, up to 2 147 549 184 > INT32_MAX.  Closed-form check of every cell."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2**30:
+        pytest.skip("needs ~25 GiB of device memory")
+    ny, nx = 32769, 65536
+    d = torch.zeros((ny, nx), dtype=torch.int8, device="cuda")
+    d[:, -1] = 2
+    with pytest.raises(_lib.WmfError):
+        ops.d8_accum(d, None, acc_dtype=_lib.ACC_I32)          # int32 cannot hold it: refused, not wrapped
+    acc = ops.d8_accum(d, None, acc_dtype=_lib.ACC_I64)
+    cols = torch.arange(1, nx, dtype=torch.int64, device="cuda")
+    for r0 in range(0, ny, 4096):                              # (in bands: the expectation is not materialised)
+        band = acc[r0:r0 + 4096]
+        assert bool((band[:, :-1] == cols).all()), f"rows from {r0}"
+        rows = torch.arange(r0 + 1, r0 + band.shape[0] + 1, dtype=torch.int64, device="cuda")
+        assert torch.equal(band[:, -1], rows * nx), f"last column, rows from {r0}"
+    assert int(acc[-1, -1]) == ny * nx > 2**31
+
+
 def test_empty_and_errors():
     assert basics.basin_acum(np.zeros((0, 5), int), np.zeros((0, 5), bool)).shape == (0, 5)
     d = torch.zeros((4, 4), dtype=torch.int8, device="cuda")
