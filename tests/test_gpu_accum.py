@@ -125,6 +125,8 @@ def test_accumulations_beyond_int32_in_32_bit_arithmetic():
         rows = torch.arange(r0 + 1, r0 + band.shape[0] + 1, dtype=torch.int64, device="cuda")
         assert torch.equal(band[:, -1], rows * nx), f"last column, rows from {r0}"
     assert int(acc[-1, -1]) == ny * nx > 2**31
+    from wmf_heavy_b200 import stripes                        # and across stripe boundaries (external inflow > INT32_MAX)
+    assert torch.equal(stripes.accumulate_striped_single_device(d, 3), acc)
 
 
 def test_empty_and_errors():
