@@ -129,6 +129,19 @@ def test_accumulations_beyond_int32_in_32_bit_arithmetic():
     assert torch.equal(stripes.accumulate_striped_single_device(d, 3), acc)
 
 
+def test_keypad_equals_internal_at_size():
+    """The same Scheidegger raster in both encodings (lean rows translate keypad codes with a byte-permute table)."""
+    n = 2048
+    a = ops.d8_accum(ops.synth_scheidegger(n, n, seed=77), None)
+    k = ops.d8_accum(ops.synth_scheidegger(n, n, seed=77, encoding=_lib.ENC_KEYPAD), None, encoding=_lib.ENC_KEYPAD)
+    assert torch.equal(a, k)
+    m = (torch.rand((n, n), device="cuda") > 0.02).to(torch.uint8)          # and with a mask (no lean rows)
+    am = ops.d8_accum(ops.synth_scheidegger(n, n, seed=77), m)
+    km = ops.d8_accum(ops.synth_scheidegger(n, n, seed=77, encoding=_lib.ENC_KEYPAD), m, encoding=_lib.ENC_KEYPAD)
+    assert torch.equal(am, km) and not torch.equal(am, a)
+    assert torch.equal(ops.d8_accum(ops.synth_scheidegger(n, n, seed=77), m, algo=_lib.ALGO_WALK), am)
+
+
 def test_empty_and_errors():
     assert basics.basin_acum(np.zeros((0, 5), int), np.zeros((0, 5), bool)).shape == (0, 5)
     d = torch.zeros((4, 4), dtype=torch.int8, device="cuda")
