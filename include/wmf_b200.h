@@ -270,6 +270,30 @@ int wmf_shia3_run(const wmf_shia3_params *params_host, int64_t nsteps, int64_t n
                   double *q_base_last, double *sums, double *q_super_t, double *q_base_t, double *q_total_t,
                   double *cap_t, double *grav_t, double *aqu_t, void *workspace, size_t ws_bytes, void *stream);
 
+/* ---------------------------------------------------------------- T2 / K1: direction-code reclassification
+ * Replaces wmf_py/cu_py/basics.py:73-121 (_reclass, dir_reclass_opentopo / _rwatershed -> internal 0..7) and
+ * cuencas_heavy.f90:1086-1119 (the same two conventions -> keypad).  Two passes, the decision in between is the host
+ * layer's: wmf_dir_reclass_scan reports WHICH values the raster holds (presence: 256 bits, bit v+128 of the uint32[8]
+ * array for v in -128..127; *oor = 1 when a value lies outside that range), from which the host picks "already
+ * internal", the table, or the reference's ValueError("unknown D8 codes: ..."); wmf_dir_reclass_apply maps every
+ * element through lut[v+128] (int64 [256], device) -- values beyond int8 pass through (keep_oor) or become oor_value.
+ * `in` holds n integers of elem_bytes (1, 2, 4, 8) each; out is int64 [n] (numpy's astype(int)). */
+int wmf_dir_reclass_scan(const void *in, int elem_bytes, int64_t n, uint32_t *presence, int32_t *oor, void *stream);
+int wmf_dir_reclass_apply(const void *in, int elem_bytes, int64_t n, const int64_t *lut, int keep_oor, int64_t oor_value,
+                          int64_t *out, void *stream);
+
+/* ---------------------------------------------------------------- N3: basin <-> raster by linear index
+ * Replaces wmf_py/cu_py/basics.py:251-301 (basin_2map / basin_map2basin).  wmf_index_scan sets *flag when an index lies
+ * outside [0, ncell); wmf_index_repair rewrites idx as floor(idx / 100) * nx + (idx mod 100) mod nx (the reference's
+ * "row*100 + col" repair, basics.py:273-276, Python floor semantics); wmf_scatter_last writes out[idx[i]] = vals[i] into
+ * a raster the caller has filled with nodata -- with duplicate indices the last i wins, like the reference's sequential
+ * assignment (owner: int32 [ncell] scratch); wmf_gather reads out[i] = flat[idx[i]].  Indices must be in range. */
+int wmf_index_scan(const int64_t *idx, int64_t n, int64_t ncell, int32_t *flag, void *stream);
+int wmf_index_repair(int64_t *idx, int64_t n, int64_t nx, void *stream);
+int wmf_scatter_last(const void *vals, int elem_bytes, const int64_t *idx, int64_t n, void *out, int32_t *owner,
+                     int64_t ncell, void *stream);
+int wmf_gather(const void *flat, int elem_bytes, const int64_t *idx, int64_t n, void *out, void *stream);
+
 /* ---------------------------------------------------------------- synthetic inputs
  * Scheidegger network: per cell a counter-based RNG keyed by (seed, linear index) draws
  * internal code 0 (E) / 1 (SE) / 2 (S) with p = 1/4, 1/2, 1/4 (keypad: 6 / 3 / 2).

@@ -146,3 +146,24 @@ def test_basin_object_api():
     assert b.CellCauce.sum() == (oracle.f_basin_acum(exp) > 20).sum()
     M, props = b.Transform_Basin2Map(b.CellAcum)
     assert M.shape == (nx, ny) and M[col - 1, fil - 1] == b.ncells
+
+
+def test_dir_edited_in_place_between_calls():
+    """cu.basin_find must read the caller's DIR as it is NOW: an in-place edit between two calls (same array
+    object) changes the basin (a stale device copy keyed by id(DIR) would not)."""
+    ny, nx = 90, 70
+    key, col, fil = _basin_case(ny, nx, 43)
+    wmfv2.set_map_properties(ncols=nx, nrows=ny, xll=0.0, yll=0.0, dx=30.0, dxp=30.0)
+    x, y = 30.0 * (col - 0.5), 30.0 * ((ny - fil) + 0.5)
+    DIR = np.asfortranarray(key.T.astype(np.int32))
+    n1 = cu.basin_find(x, y, DIR, nx, ny)
+    st1 = cu.basin_cut(n1)
+    assert np.array_equal(st1, oracle.f_basin_find(key, col, fil))
+    donors = np.nonzero(st1[0] == 1)[0]                        # cells draining straight into the outlet
+    cut = donors[donors != n1 - 1][0]
+    c, f = int(st1[1, cut]), int(st1[2, cut])
+    DIR[c - 1, f - 1] = 5                                      # in place: that cell (and its subtree) leaves the basin
+    key2 = key.copy()
+    key2[f - 1, c - 1] = 5
+    n2 = cu.basin_find(x, y, DIR, nx, ny)
+    assert n2 < n1 and np.array_equal(cu.basin_cut(n2), oracle.f_basin_find(key2, col, fil))

@@ -290,3 +290,41 @@ def test_shia5_population_many_sets():
         np.testing.assert_allclose(got[p], o["StoOut"], rtol=1e-5, atol=1e-4)
         np.testing.assert_allclose(bal[p], o["balance64"], rtol=1e-4, atol=1e-6 * float(o["StoOut"].sum()))
     assert np.isfinite(got).all()
+
+
+def test_tables_edited_in_place_between_runs():
+    """A calibration loop scales the module tables IN PLACE (same array object) and rebinds others between runs
+    (the f2py idiom, wmfv2.py:1872-1916): every run must see the current values (no stale device copy)."""
+    N, T = 1500, 24
+    inp = helpers.shia5_inputs(oracle, N, T, 95)
+    models.v_coef, models.h_coef, models.h_exp = inp.v_coef, inp.h_coef, inp.h_exp
+    models.max_capilar, models.max_gravita, models.max_aquifer = (a[None].copy() for a in (inp.max_capilar, inp.max_gravita, inp.max_aquifer))
+    models.hill_long, models.elem_area = inp.hill_long[None].copy(), inp.elem_area[None].copy()
+    models.speed_type, models.evpserie, models.dt = np.array([1, 1, 1]), inp.evp, inp.dt
+    models.storage, models.storage_constant = None, 0.001
+    models.retorno_gr = models.retorno_aq = 0.0
+    models.show_storage = models.show_mean_speed = models.save_storage = 0
+    cal = np.ones(11, np.float32)
+    sto0 = np.full((5, N), 0.001, np.float32)
+    a = models.shia_v1_population(cal, inp.rain_records, inp.pos_evento, N, T)["StoOut"][0]
+    np.testing.assert_allclose(a, oracle.f_shia_v1(inp, cal, sto0)["StoOut"], rtol=1e-5, atol=1e-4)
+    models.h_coef[0, :] *= 3.0                             # in place: the array object (and its id) stay the same
+    models.max_aquifer = models.max_aquifer * 0.5          # rebound: a table the old cache key ignored
+    inp.max_aquifer = models.max_aquifer[0]
+    b = models.shia_v1_population(cal, inp.rain_records, inp.pos_evento, N, T)["StoOut"][0]
+    np.testing.assert_allclose(b, oracle.f_shia_v1(inp, cal, sto0)["StoOut"], rtol=1e-5, atol=1e-4)
+    assert not np.allclose(a[1], b[1], rtol=1e-3)
+
+
+def test_rain_record_out_of_range_is_rejected():
+    """posEvento naming a record beyond the rain file: the Fortran prints 'fuera del rango' and reads garbage
+    (Modelos_heavy.f90:580-590); here the host layer raises before any launch."""
+    N, T = 300, 10
+    inp = helpers.shia5_inputs(oracle, N, T, 96)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pos = inp.pos_evento.copy()
+    for bad in (inp.rain_records.shape[0] + 1, 0, -3):
+        pos[4] = bad
+        with pytest.raises(ValueError, match="fuera del rango"):
+            ops.shia5_run(dev(helpers.cell_static(inp)), dev(inp.rain_records), dev(pos), dev(inp.evp),
+                          torch.ones((1, 11), device="cuda"), dev(np.full((1, 5, N), 0.001, np.float32)), None, dt=inp.dt)

@@ -61,27 +61,6 @@ def test_basin_find_py():                      # wmf_py/tests/test_cu_basics.py:
         basics.basin_find(1e9, 0, 0, 0, 30, 30, 3, 3)
 
 
-def test_reclass_like_reference():             # wmf_py/tests/test_cu_basics.py:19-32
-    src = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 1]])
-    res = basics.dir_reclass_opentopo(src)
-    assert set(np.unique(res)) <= set(range(8))
-    assert np.array_equal(res, basics.dir_reclass_opentopo(res))
-    with pytest.raises(ValueError):
-        basics.dir_reclass_opentopo(np.array([[9]]))
-    res = basics.dir_reclass_rwatershed(np.arange(1, 9).reshape(2, 4))
-    assert np.array_equal(res, np.array([0, 7, 6, 5, 4, 3, 2, 1]).reshape(2, 4))
-
-
-def test_transform_like_reference():           # wmf_py/tests/test_transform.py:15-37
-    idx = np.array([0, 10, 101, 555, 999, 1234, 2345, 3456, 4321, 4999])
-    values = np.arange(idx.size)
-    raster = basics.basin_2map(values, idx, (50, 50), -1.0)
-    assert np.all(raster.ravel()[idx] == values) and (raster != -1.0).sum() == values.size
-    assert np.array_equal(basics.basin_map2basin(raster, idx, (idx.size,)), values)
-    with pytest.raises(ValueError):
-        basics.basin_2map(np.array([1, 2, 3]), np.array([0, 1]), (2, 2), 0.0)
-
-
 def test_scheidegger_host_is_deterministic_and_windowed():
     a = ops.synth_scheidegger_host(64, 96, seed=7)
     assert set(np.unique(a)) <= {0, 1, 2}

@@ -46,21 +46,13 @@ def to_dev(a, dtype: torch.dtype | None = None) -> torch.Tensor:
     return t.contiguous()
 
 
-_ws_cache: dict = {}
-
-
 def workspace(nbytes: int) -> torch.Tensor:
-    """A cached uint8 scratch buffer per (device, stream) that only ever grows."""
+    """Scratch for ONE library call, from torch's caching allocator: stream-ordered (the block is handed out again
+    only to later work on the same stream) and private to the call, so operators may be used from several host
+    threads and streams at once.  After the first call of a size the allocation is a free-list lookup."""
     dev = require_cuda()
-    key = (dev.index, stream_ptr())
-    buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = None
-        _ws_cache.pop(key, None)
-        buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
-        _ws_cache[key] = buf
-    return buf
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
 
 
 def free_workspaces() -> None:
-    _ws_cache.clear()
+    torch.cuda.empty_cache()

@@ -89,6 +89,12 @@ SIGNATURES = {
     "wmf_shia3_workspace": (_sz, [_i64, _i64]),
     "wmf_shia3_run": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),
+    "wmf_dir_reclass_scan": (_int, [_vp, _int, _i64, _vp, _vp, _vp]),
+    "wmf_dir_reclass_apply": (_int, [_vp, _int, _i64, _vp, _int, _i64, _vp, _vp]),
+    "wmf_index_scan": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "wmf_index_repair": (_int, [_vp, _i64, _i64, _vp]),
+    "wmf_scatter_last": (_int, [_vp, _int, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "wmf_gather": (_int, [_vp, _int, _vp, _i64, _vp, _vp]),
     "wmf_synth_scheidegger": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, C.c_uint64, _int, _vp]),
     "wmf_synth_scheidegger_host": (None, [_vp, _i64, _i64, _i64, _i64, _i64, C.c_uint64, _int]),
 }

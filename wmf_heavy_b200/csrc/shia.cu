@@ -132,6 +132,7 @@ __device__ __forceinline__ void calc_speed(float sm, float coef, float expo, flo
 struct Shia5Args {
     wmf_shia5_params p;
     int64_t N, N_reg;
+    int32_t n_rec;              // records in `rain`: a posEvento outside 2..n_rec reads nothing (no rain)
     const float *cs;            // [17][N]
     const int32_t *rain;        // [n_rec][N]
     const int32_t *pos;         // [N_reg]
@@ -226,7 +227,9 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
     auto one_step = [&](int64_t t, float &vR, float &vq) {
         const int pos = a.pos[t];
         float R = 0.0f;
-        if (pos != 1) R = (float)rain_cc[(int64_t)(pos - 1) * N] * 0.001f;                 // :370 (RainInt/1000.)
+        // record 1 = no rain (:366-367); a record beyond the file is the Fortran's 'fuera del rango' read error, whose
+        // RainInt is undefined: defined here as no rain (the host layer rejects such headers before the launch)
+        if ((unsigned)(pos - 2) < (unsigned)(a.n_rec - 1)) R = (float)rain_cc[(int64_t)(pos - 1) * N] * 0.001f;   // :370 (RainInt/1000.)
         acum = acum + R;                                                                   // :380
         float v1 = fmaxf(0.0f, (R - H1) + S1);                                             // :393
         S1 = (S1 + R) - v1;                                                                // :394
@@ -413,6 +416,7 @@ __global__ void __launch_bounds__(TH) k_shia3(const Shia3Args a)
 // result does not depend on the schedule.
 struct RouteArgs {
     int64_t N, N_reg;
+    int32_t n_rec;
     const float *ct;             // [13][N]: vs0..3, fl2..4 (lateral fractions), fl5, 1/H1, H1, H2, H3, m3mm
     const int32_t *rain;         // [n_rec][N]
     const int32_t *pos;          // [N_reg]
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(256) k_route_diag(const RouteArgs a, int64_t d
     const float *ct = a.ct;
     const int pos = a.pos[t];
     float R = 0.0f;
-    if (pos != 1) R = (float)a.rain[(int64_t)(pos - 1) * N + c] * 0.001f;
+    if ((unsigned)(pos - 2) < (unsigned)(a.n_rec - 1)) R = (float)a.rain[(int64_t)(pos - 1) * N + c] * 0.001f;
     a.acum[c] = a.acum[c] + R;
     float S1 = a.sto[c], S2 = a.sto[N + c], S3 = a.sto[2 * N + c], S4 = a.sto[3 * N + c], S5 = a.sto[4 * N + c];
     const float H1 = ct[9 * N + c], H2 = ct[10 * N + c], H3 = ct[11 * N + c], m3mm = ct[12 * N + c];
@@ -532,7 +536,8 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
     double *totals = cur.take<double>((size_t)P * (N_reg + 1) * K);
     WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
     Shia5Args a;
-    a.p = *params_host; a.N = N; a.N_reg = N_reg; a.cs = cell_static; a.rain = rain_records; a.pos = pos_evento;
+    WMF_REQUIRE(n_rec < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "more than 2^31-1 rain records");
+    a.p = *params_host; a.N = N; a.N_reg = N_reg; a.n_rec = (int32_t)n_rec; a.cs = cell_static; a.rain = rain_records; a.pos = pos_evento;
     a.evp = evp; a.calib = calib; a.sto = sto; a.hspeed = hspeed; a.acum_rain = acum_rain; a.part = part; a.nblk = nblk;
     a.snap_slot = snap_slot; a.snap_out = snap_out; a.n_snap = n_snap;
     dim3 grid(nblk, P);
@@ -627,7 +632,7 @@ int wmf_shia5_route_run(const wmf_shia5_params *params_host, int64_t N, int64_t 
     WMF_CUDA_CHECK(cudaMemsetAsync(Q, 0, sizeof(float) * (size_t)n_ctrl * (size_t)N_reg, st));
     k_route_setup<<<blocks_for(N, 256), 256, 0, st>>>(N, cell_static, calib, params_host->dt, ct, acum_rain);
     RouteArgs a;
-    a.N = N; a.N_reg = N_reg; a.ct = ct; a.rain = rain_records; a.pos = pos_evento; a.evp = evp; a.rank = rank;
+    a.N = N; a.N_reg = N_reg; a.n_rec = (int32_t)(n_rec < 0x7fffffff ? n_rec : 0x7fffffff); a.ct = ct; a.rain = rain_records; a.pos = pos_evento; a.evp = evp; a.rank = rank;
     a.don_ptr = don_ptr; a.don_idx = don_idx; a.ctrl = ctrl; a.sto = sto; a.acum = acum_rain; a.qbuf = qbuf; a.Q = Q;
     a.dt = params_host->dt; a.retorno_gr = params_host->retorno_gr; a.retorno_aq = params_host->retorno_aq;
     for (int64_t d = 0; d < N_reg + max_rank; d++) k_route_diag<<<blocks_for(N, 256), 256, 0, st>>>(a, d);

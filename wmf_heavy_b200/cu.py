@@ -16,8 +16,6 @@ import torch
 from . import ops
 from ._dev import require_cuda, to_dev
 from ._lib import ENC_KEYPAD, WmfError
-from .cu_py.basics import (basin_2map as _py_basin_2map, basin_map2basin as _py_basin_map2basin,  # noqa: F401
-                           dir_reclass_opentopo as _py_reclass_opentopo, dir_reclass_rwatershed as _py_reclass_rw)
 
 # ---- module state (f2py lower-cases Fortran names) : cuencas_heavy.f90:30-60
 ncols = 0
@@ -36,23 +34,17 @@ centrox = 0.0
 centroy = 0.0
 
 _basin_temp = None        # device structure of the last basin_find (Fortran: basin_temp)
-_dir_dev_cache = None     # (id(DIR), device int8 raster) so Basin + SimuBasin do not re-upload
 
 
 def _dir_to_dev(DIR) -> torch.Tensor:
-    """DIR(col, fil) keypad codes -> GIS-oriented int8 device raster [nrows][ncols]."""
-    global _dir_dev_cache
+    """DIR(col, fil) keypad codes -> GIS-oriented int8 device raster [nrows][ncols].  Uploaded on every call: the
+    caller owns DIR and may edit it in place between calls (pass a CUDA int8 tensor to keep it resident)."""
     if isinstance(DIR, torch.Tensor) and DIR.is_cuda and DIR.dtype == torch.int8:
         return DIR.t().contiguous()
-    key = id(DIR)
-    if _dir_dev_cache is not None and _dir_dev_cache[0] == key:
-        return _dir_dev_cache[1]
     a = np.asarray(DIR)
     g = np.ascontiguousarray(a.T)                       # (nrows, ncols), row = fil
     g = np.where((g >= 1) & (g <= 9), g, 0).astype(np.int8)   # nodata / <=0 -> no receiver
-    t = to_dev(g)
-    _dir_dev_cache = (key, t)
-    return t
+    return to_dev(g)
 
 
 def coord2fil_col(x, y):
@@ -153,10 +145,33 @@ def basin_2map(structure, BasinVar, map_ncols=None, map_nrows=None, nceldas=None
     return np.asfortranarray(M.cpu().numpy().T), xll, yll
 
 
+# external code -> keypad code of the two conventions (cuencas_heavy.f90:1086-1119); everything else becomes cu.nodata
+_EXT_TO_KEYPAD = {"opentopo": {3: 8, 2: 9, 1: 6, 8: 3, 7: 2, 6: 1, 5: 4, 4: 7},
+                  "rwatershed": {3: 7, 2: 8, 1: 9, 8: 6, 7: 3, 6: 2, 5: 1, 4: 4}}
+
+
+def _reclass_keypad(Mapa, convention: str) -> np.ndarray:
+    """Mat_out(nc, nr) int32, Fortran-ordered: a 256-entry lookup table applied on the device."""
+    a = np.asarray(Mapa)
+    if a.dtype.kind not in "iu" or a.dtype == np.uint64:
+        a = a.astype(np.int64)
+    elif a.dtype.kind == "u":
+        a = a.astype({1: np.int16, 2: np.int32, 4: np.int64}[a.dtype.itemsize])
+    if a.size == 0:
+        return np.zeros(a.shape, dtype=np.int32, order="F")
+    nd = int(nodata)
+    lut = np.full(256, nd, dtype=np.int64)
+    for ext, key in _EXT_TO_KEYPAD[convention].items():
+        lut[ext + 128] = key
+    out = ops.dir_reclass_apply(to_dev(a), lut, keep_oor=False, oor_value=nd)
+    return np.asfortranarray(out.to(torch.int32).cpu().numpy())
+
+
 def dir_reclass_opentopo(Mapa, nc=None, nr=None):
-    """opentopo 1..8 -> keypad is done on the wmf_py convention by the reference shim (wmfv2.py:58-59)."""
-    return _py_reclass_opentopo(np.asarray(Mapa))
+    """cu.dir_reclass_opentopo(Mapa.T, cu.ncols, cu.nrows) -> keypad codes, cu.nodata elsewhere (wmfv2.py:250; f90:1105-1119)."""
+    return _reclass_keypad(Mapa, "opentopo")
 
 
 def dir_reclass_rwatershed(Mapa, nc=None, nr=None):
-    return _py_reclass_rw(np.asarray(Mapa))
+    """cu.dir_reclass_rwatershed(Mapa.T, cu.ncols, cu.nrows) -> keypad codes (wmfv2.py:246; f90:1089-1103)."""
+    return _reclass_keypad(Mapa, "rwatershed")

@@ -22,8 +22,9 @@ from .. import ops
 from .._dev import require_cuda, to_dev
 from .._lib import ACC_F64, ENC_INTERNAL, WmfError, E_OUTLET_MASK, E_OUTLET_RANGE
 
-_RECLASS_OPENTOPO = {1: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5, 7: 6, 8: 7}          # basics.py:50-59
-_RECLASS_RWATERSHED = {1: 0, 2: 7, 3: 6, 4: 5, 5: 4, 6: 3, 7: 2, 8: 1}        # basics.py:61-70
+# external code (1..8) -> internal code (0..7) of the two conventions the reference knows (basics.py:50-70):
+# OpenTopo numbers the eight neighbours clockwise from East starting at 1, r.watershed counter-clockwise.
+_EXT_TO_INTERNAL = {"opentopo": lambda e: e - 1, "rwatershed": lambda e: (9 - e) % 8}
 
 
 def _flowdir_to_dev(flowdir) -> torch.Tensor:
@@ -107,56 +108,83 @@ def basin_cut(dem, outlet_rc: Tuple[int, int], flowdir, mask) -> Dict[str, np.nd
     return {"dem": dem_cut, "flowdir": flowdir_cut, "mask": mask_basin}
 
 
+_STORE = {1: np.uint8, 2: np.int16, 4: np.int32, 8: np.int64}     # torch-copyable integer type of the same width
+
+
+def _vec_to_dev(a) -> torch.Tensor:
+    """Flattened (C order) device copy of a host array, moved as same-width integers (bit pattern preserved)."""
+    a = np.ascontiguousarray(a).reshape(-1)
+    if a.dtype.kind not in "iufb" or a.dtype.itemsize not in _STORE:
+        raise TypeError(f"unsupported dtype {a.dtype}")
+    return to_dev(a.view(_STORE[a.dtype.itemsize]))
+
+
 def basin_2map(values, idx_basin_to_map, map_shape: Tuple[int, int], nodata: float) -> np.ndarray:
-    """Scatter basin values into a raster by linear index (basics.py:251-287).  Host-side: the
-    data are a few MB and the reference mutates ``idx_basin_to_map`` in place."""
-    vals = np.asarray(values).ravel(order="C")
-    idx = np.asarray(idx_basin_to_map).ravel(order="C")
-    if vals.size != idx.size:
+    """Basin vector -> raster by linear index (replaces basics.py:251-287): a raster of ``nodata`` with
+    ``values`` written at ``idx_basin_to_map`` (device scatter; the last of duplicate indices wins).  Like the
+    reference, indices that do not fit the raster are first re-read as ``row*100 + col`` and the repaired indices
+    are written back into the caller's array."""
+    vals = np.asarray(values)
+    idx_in = np.asarray(idx_basin_to_map)
+    if vals.size != idx_in.size:
         raise ValueError("size of values and indices must match")
-    ny, nx = map_shape
+    ny, nx = (int(v) for v in map_shape)
     ncell = ny * nx
-    if (idx >= ncell).any() or (idx < 0).any():
-        rows = idx // 100
-        cols = idx % 100
-        idx[:] = rows * nx + cols % nx
-    if (idx < 0).any() or (idx >= ncell).any():
-        raise ValueError("indices out of range")
-    out = np.full(ncell, nodata, dtype=vals.dtype)
-    out[idx] = vals
-    idx_basin_to_map[:] = idx
-    return out.reshape(map_shape)
+    if vals.size == 0:
+        return np.full(ncell, nodata, dtype=vals.dtype).reshape(ny, nx)
+    idx = to_dev(np.ascontiguousarray(idx_in, dtype=np.int64).reshape(-1))
+    if ops.index_out_of_range(idx, ncell):
+        idx = idx.clone()
+        ops.index_repair(idx, nx)
+        if ops.index_out_of_range(idx, ncell):
+            raise ValueError("indices out of range")
+        if isinstance(idx_basin_to_map, np.ndarray) and idx_basin_to_map.flags.writeable:
+            idx_basin_to_map[...] = idx.cpu().numpy().reshape(idx_basin_to_map.shape)
+    fill_bits = int(np.array([nodata]).astype(vals.dtype).view(_STORE[vals.dtype.itemsize])[0])
+    out = ops.scatter_last(_vec_to_dev(vals), idx, ncell, fill_bits)
+    return out.cpu().numpy().view(vals.dtype).reshape(ny, nx)
 
 
 def basin_map2basin(values_map, idx_basin_to_map, basin_shape) -> np.ndarray:
-    """Gather basin values from a raster by linear index (basics.py:290-301)."""
-    flat = np.asarray(values_map).ravel(order="C")
-    if np.max(idx_basin_to_map) >= flat.size or np.min(idx_basin_to_map) < 0:
+    """Raster -> basin vector by linear index (replaces basics.py:290-301), a device gather."""
+    m = np.asarray(values_map)
+    idx = to_dev(np.ascontiguousarray(idx_basin_to_map).reshape(-1).astype(np.int64, copy=False), torch.int64)
+    if idx.numel() == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    if ops.index_out_of_range(idx, m.size):
         raise ValueError("indices out of range")
-    return flat[idx_basin_to_map].reshape(basin_shape)
+    return ops.gather(_vec_to_dev(m), idx).cpu().numpy().view(m.dtype).reshape(basin_shape)
 
 
-def _reclass(flowdir: np.ndarray, table: Dict[int, int]) -> np.ndarray:
-    """basics.py:73-108: pass internal codes through, map external ones, reject unknown >= 0."""
-    if flowdir.size == 0:
-        return flowdir.astype(int)
-    vals = np.unique(flowdir)
-    valid_ext = set(table.keys())
-    valid_internal = set(range(8))
-    if set(int(v) for v in vals).issubset(valid_internal):
-        return flowdir.astype(int, copy=True)
-    unknown = {int(v) for v in vals if int(v) not in valid_ext | valid_internal and int(v) >= 0}
+def _reclass(flowdir, convention: str) -> np.ndarray:
+    """External D8 codes -> internal 0..7 with a 256-entry lookup table on the device (replaces basics.py:73-108).
+    A raster that already holds only 0..7 passes through; codes >= 0 that neither convention knows raise."""
+    a = np.asarray(flowdir)
+    if a.size == 0:
+        return a.astype(int)
+    if a.dtype.kind not in "iu" or a.dtype == np.uint64:
+        a = a.astype(np.int64)                                # (non-integral floats are truncated first)
+    elif a.dtype.kind == "u":
+        a = a.astype({1: np.int16, 2: np.int32, 4: np.int64}[a.dtype.itemsize])
+    t = to_dev(a)
+    present, beyond = ops.dir_reclass_scan(t)
+    lut = np.arange(-128, 128, dtype=np.int64)
+    if not (beyond or any(v < 0 or v > 7 for v in present)):
+        return ops.dir_reclass_apply(t, lut).cpu().numpy().astype(int, copy=False)     # already internal
+    unknown = [v for v in present if v > 8]
+    if beyond:                                                # error path only: name the far-away codes too
+        unknown += [int(v) for v in np.unique(a[a > 127])]
     if unknown:
         raise ValueError(f"unknown D8 codes: {sorted(unknown)}")
-    out = flowdir.astype(int, copy=True)
-    for k, v in table.items():
-        out[flowdir == k] = v
-    return out
+    f = _EXT_TO_INTERNAL[convention]
+    for e in range(1, 9):
+        lut[e + 128] = f(e)
+    return ops.dir_reclass_apply(t, lut).cpu().numpy().astype(int, copy=False)
 
 
 def dir_reclass_opentopo(flowdir: np.ndarray) -> np.ndarray:
-    return _reclass(np.asarray(flowdir), _RECLASS_OPENTOPO)
+    return _reclass(flowdir, "opentopo")
 
 
 def dir_reclass_rwatershed(flowdir: np.ndarray) -> np.ndarray:
-    return _reclass(np.asarray(flowdir), _RECLASS_RWATERSHED)
+    return _reclass(flowdir, "rwatershed")

@@ -63,14 +63,20 @@ def shia5_run_population_sharded(cell_static, rain_records, pos_evento, evp, cal
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     P = calibs.shape[0]
+    if P < 1:                                             # the same test on every rank: all raise together
+        raise ValueError("the population is empty")
     lo, hi = shard_range(P, rank, world)
     n = cell_static.shape[1]
-    sto = sto0.expand(hi - lo, 5, n).contiguous() if sto0.dim() == 2 else sto0[lo:hi].contiguous()
-    local = ops.shia5_run(cell_static, rain_records, pos_evento, evp, calibs[lo:hi].contiguous(), sto, None, **kw)
+    n_reg = pos_evento.shape[0]
+    local = None
+    if hi > lo:                                           # (P < world leaves some ranks without a set: they only join the gather)
+        sto = sto0.expand(hi - lo, 5, n).contiguous() if sto0.dim() == 2 else sto0[lo:hi].contiguous()
+        local = ops.shia5_run(cell_static, rain_records, pos_evento, evp, calibs[lo:hi].contiguous(), sto, None, **kw)
     sizes = [shard_range(P, r, world) for r in range(world)]
     pmax = max(h - l for l, h in sizes)
-    pad = torch.zeros((pmax, local["balance"].shape[1]), dtype=torch.float32, device=sto.device)
-    pad[: hi - lo] = local["balance"]
+    pad = torch.zeros((pmax, n_reg), dtype=torch.float32, device=cell_static.device)
+    if local is not None:
+        pad[: hi - lo] = local["balance"]
     gathered = _all_gather(pad, group)
     balance = torch.cat([gathered[r][: h - l] for r, (l, h) in enumerate(sizes)])
     return balance, local

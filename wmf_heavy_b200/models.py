@@ -52,7 +52,6 @@ mean_speed = None
 idevento = None
 posevento = None
 
-_dev_cache = {}
 
 
 # ---- rain record formats (Modelos_heavy.f90:580-590, 631-663) -----------------------------------
@@ -215,11 +214,9 @@ def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int,
     if cal.shape[1] != 11:
         raise ValueError("calib must have 11 entries (Modelos_heavy.f90:177)")
     P = cal.shape[0]
-    key = (id(v_coef), id(h_coef), id(max_capilar), id(elem_area), n_cel)
-    cs = _dev_cache.get("cs")
-    if cs is None or cs[0] != key:
-        cs = (key, to_dev(cell_static_table(n_cel)))
-        _dev_cache["cs"] = cs
+    # packed and uploaded on every call: the tables are module state the caller edits in place between runs (a
+    # calibration loop scales h_coef / max_capilar ...), and 68 B/cell is small next to the run itself
+    cs = (None, to_dev(cell_static_table(n_cel)))
     rr = rain_records if isinstance(rain_records, torch.Tensor) else to_dev(np.ascontiguousarray(rain_records, dtype=np.int32))
     pe = pos_evento if isinstance(pos_evento, torch.Tensor) else to_dev(np.asarray(pos_evento, dtype=np.int32)[:n_reg])
     if evpserie is None:

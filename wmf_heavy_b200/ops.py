@@ -169,11 +169,20 @@ def stream_nod(st: torch.Tensor, acum_t: torch.Tensor, umbral: int):
 
 
 # --------------------------------------------------------------------------------------- S1/S2
+def _check_pos_evento(pos_evento: torch.Tensor, n_rec: int) -> None:
+    """Every step must name a record of the rain file (1 = no rain).  The Fortran prints 'Se ha tratado de leer un
+    valor fuera del rango' and carries on with an undefined RainInt (Modelos_heavy.f90:580-590); here it is an error."""
+    lo, hi = (int(v) for v in torch.aminmax(pos_evento))
+    if lo < 1 or hi > n_rec:
+        raise ValueError(f"posEvento names record {lo if lo < 1 else hi}, the rain file holds records 1..{n_rec} "
+                         "(Se ha tratado de leer un valor fuera del rango)")
+
+
 def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento: torch.Tensor, evp: torch.Tensor,
               calib: torch.Tensor, sto: torch.Tensor, hspeed: Optional[torch.Tensor] = None, *, dt: float,
               retorno_gr: float = 0.0, retorno_aq: float = 0.0, calc_niter: int = 5, speed_type=(1, 1, 1),
               show_storage: bool = False, show_mean_speed: bool = False, snap_slot: Optional[torch.Tensor] = None,
-              n_snap: int = 0):
+              n_snap: int = 0, validate: bool = True):
     """SHIA 5-tank update as shipped (Modelos_heavy.f90:169-548) for P parameter sets at once.
     ``sto`` [P,5,N] and ``hspeed`` [P,4,N] are advanced IN PLACE.  Returns a dict of device tensors.
     ``snap_slot`` int32 [N_reg] (-1 or a slot in [0, n_snap)): the storages after those steps are returned as
@@ -193,6 +202,8 @@ def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento:
         raise ValueError("shape mismatch: cell_static (17,N), calib (P,11), sto (P,5,N), rain_records (n_rec,N)")
     if evp.shape[0] < n_reg:
         raise ValueError("evp must have at least N_reg entries")
+    if validate:
+        _check_pos_evento(pos_evento, n_rec)
     dev = sto.device
     given = hspeed is not None
     if given:
@@ -316,6 +327,7 @@ def shia5_route_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_e
     n_reg, n_rec = pos_evento.shape[0], rain_records.shape[0]
     if cell_static.shape != (17, N) or calib.numel() != 11 or sto.shape != (5, N) or rain_records.shape != (n_rec, N):
         raise ValueError("shape mismatch: cell_static (17,N), calib (11,), sto (5,N), rain_records (n_rec,N)")
+    _check_pos_evento(pos_evento, n_rec)
     rank, dmax, don_ptr, don_idx = route_topology(np.asarray(drain))
     if rank.size != N:
         raise ValueError("drain must have one entry per cell")
@@ -367,6 +379,74 @@ def shia3_run(rain: torch.Tensor, et: Optional[torch.Tensor], cap: torch.Tensor,
                             stream_ptr()))
     out = {"q_super_last": qsl, "q_base_last": qbl, "sums": sums}
     out.update(ser)
+    return out
+
+
+# --------------------------------------------------------------------------------------- T2 / K1, N3
+def _int_elem(t: torch.Tensor, name: str) -> int:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and
+            t.dtype in (torch.int8, torch.int16, torch.int32, torch.int64)):
+        raise TypeError(f"{name} must be a contiguous CUDA tensor of a signed integer dtype")
+    return t.element_size()
+
+
+def dir_reclass_scan(codes: torch.Tensor):
+    """Which values does the raster hold?  -> (sorted list of the values in -128..127, flag: values beyond that)."""
+    require_cuda()
+    eb = _int_elem(codes, "codes")
+    res = torch.empty(9, dtype=torch.int32, device=codes.device)         # presence uint32[8] + the flag
+    check(_lib.load().wmf_dir_reclass_scan(ptr(codes), eb, codes.numel(), ptr(res), ptr(res) + 32, stream_ptr()))
+    r = res.cpu().numpy()
+    bits = np.unpackbits(r[:8].view(np.uint8), bitorder="little")
+    return [int(v) - 128 for v in np.flatnonzero(bits)], bool(r[8])
+
+
+def dir_reclass_apply(codes: torch.Tensor, lut, keep_oor: bool = True, oor_value: int = 0) -> torch.Tensor:
+    """out[i] = lut[codes[i] + 128] (lut: 256 integers for the values -128..127) -> int64, the raster's shape."""
+    require_cuda()
+    eb = _int_elem(codes, "codes")
+    lut_t = torch.from_numpy(np.ascontiguousarray(lut, dtype=np.int64).reshape(256)).to(codes.device)
+    out = torch.empty(codes.shape, dtype=torch.int64, device=codes.device)
+    check(_lib.load().wmf_dir_reclass_apply(ptr(codes), eb, codes.numel(), ptr(lut_t), int(bool(keep_oor)), int(oor_value),
+                                            ptr(out), stream_ptr()))
+    return out
+
+
+def index_out_of_range(idx: torch.Tensor, ncell: int) -> bool:
+    require_cuda()
+    _chk_dev(idx, torch.int64, "idx")
+    flag = torch.empty(1, dtype=torch.int32, device=idx.device)
+    check(_lib.load().wmf_index_scan(ptr(idx), idx.numel(), int(ncell), ptr(flag), stream_ptr()))
+    return bool(flag.item())
+
+
+def index_repair(idx: torch.Tensor, nx: int) -> None:
+    """In place: idx = (idx // 100) * nx + (idx % 100) % nx (basics.py:273-276)."""
+    require_cuda()
+    _chk_dev(idx, torch.int64, "idx")
+    check(_lib.load().wmf_index_repair(ptr(idx), idx.numel(), int(nx), stream_ptr()))
+
+
+def scatter_last(vals: torch.Tensor, idx: torch.Tensor, ncell: int, nodata) -> torch.Tensor:
+    """Raster (flat, ncell) filled with nodata, then out[idx[i]] = vals[i]; the last duplicate wins."""
+    require_cuda()
+    _chk_dev(idx, torch.int64, "idx")
+    if not (vals.is_cuda and vals.is_contiguous() and vals.numel() == idx.numel() and vals.element_size() in (1, 2, 4, 8)):
+        raise TypeError("vals must be a contiguous CUDA tensor with as many elements as idx")
+    out = torch.full((int(ncell),), nodata, dtype=vals.dtype, device=vals.device)
+    owner = torch.empty(int(ncell), dtype=torch.int32, device=vals.device)
+    check(_lib.load().wmf_scatter_last(ptr(vals), vals.element_size(), ptr(idx), idx.numel(), ptr(out), ptr(owner),
+                                       int(ncell), stream_ptr()))
+    return out
+
+
+def gather(flat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    require_cuda()
+    _chk_dev(idx, torch.int64, "idx")
+    if not (flat.is_cuda and flat.is_contiguous() and flat.element_size() in (1, 2, 4, 8)):
+        raise TypeError("flat must be a contiguous CUDA tensor")
+    out = torch.empty(idx.numel(), dtype=flat.dtype, device=flat.device)
+    check(_lib.load().wmf_gather(ptr(flat), flat.element_size(), ptr(idx), idx.numel(), ptr(out), stream_ptr()))
     return out
 
 

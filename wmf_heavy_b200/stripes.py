@@ -116,7 +116,13 @@ def accumulate_striped(dir_stripe: torch.Tensor, row0: int, ny_total: int, group
     """One rank's part of the striped accumulation (torch.distributed must be initialised, backend nccl).
     Ranks must own the stripes in rank order."""
     import torch.distributed as dist
-    rec, ws = ops.d8_stripe_local(dir_stripe, row0, ny_total, mask_stripe, encoding)
+    try:
+        rec, ws = ops.d8_stripe_local(dir_stripe, row0, ny_total, mask_stripe, encoding)
+    except Exception:
+        # a stripe the library rejects (e.g. fewer than 2 rows) must not leave the other ranks waiting in the
+        # collective: join it with an empty record, then fail here (the launcher takes the job down)
+        gather_records(torch.zeros((2, 2, dir_stripe.shape[1]), dtype=torch.int64, device=dir_stripe.device), group)
+        raise
     recs_all = gather_records(rec, group)
     inflow, unres = stripe_inflow(recs_all, dist.get_rank(group))
     return ops.d8_stripe_finish(dir_stripe, ws, row0, ny_total, inflow, unres, mask_stripe, encoding, acc_dtype, out)
@@ -131,13 +137,20 @@ def accumulate_striped_multi(dir_local: torch.Tensor, row0: int, ny_total: int, 
     import torch.distributed as dist
     ny, nx = dir_local.shape
     rank = dist.get_rank(group)
+    if n_local < 1:
+        raise ValueError("n_local must be >= 1")
     rows = stripe_rows(ny, n_local)
     recs, wss = [], []
-    for r0, n in rows:
-        m = None if mask_local is None else mask_local[r0:r0 + n].contiguous()
-        rec, ws = ops.d8_stripe_local(dir_local[r0:r0 + n].contiguous(), row0 + r0, ny_total, m, encoding)
-        recs.append(rec)
-        wss.append(ws)
+    try:
+        for r0, n in rows:
+            m = None if mask_local is None else mask_local[r0:r0 + n].contiguous()
+            rec, ws = ops.d8_stripe_local(dir_local[r0:r0 + n].contiguous(), row0 + r0, ny_total, m, encoding)
+            recs.append(rec)
+            wss.append(ws)
+    except Exception:
+        # (see accumulate_striped) join the collective the other ranks are heading for, then fail
+        gather_records(torch.zeros((n_local, 2, 2, nx), dtype=torch.int64, device=dir_local.device), group)
+        raise
     gathered = gather_records(torch.stack(recs), group)                    # [world, n_local, 2, 2, nx]
     recs_all = gathered.reshape((-1,) + tuple(gathered.shape[2:]))
     if out is None:
