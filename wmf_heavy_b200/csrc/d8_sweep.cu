@@ -296,6 +296,7 @@ struct TileRows {
     }
     // this lane's words of chunk c: word q of row r of the chunk at [r * ROWW + q]
     __device__ __forceinline__ const uint32_t *chunk(int c) const { return wbase + (c & 1) * CH * ROWW; }
+    __device__ __forceinline__ const uint32_t *mchunk(int c) const { return mbase + (c & 1) * CH * ROWW; }   // ... of the mask
     // active bits of the lane's NC cells in row lr
     __device__ __forceinline__ int active(int lr) const
     {
@@ -363,6 +364,42 @@ __device__ __forceinline__ bool plain_words(const uint32_t *wp, uint32_t (&kw)[N
     return generic;
 }
 
+// exact per-byte tests of a word -> 0x01 per byte
+__device__ __forceinline__ uint32_t byte_nonzero(uint32_t w) { return ((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7) & 0x01010101u; }
+__device__ __forceinline__ uint32_t byte_zero(uint32_t w) { return byte_nonzero(w) ^ 0x01010101u; }
+
+// Lean rows of a raster WITH a mask (MK): a row qualifies when no ACTIVE cell holds a W / NW / N / NE code.  Inactive
+// cells and active cells without a receiver code (pits, nodata codes) ride along: av = 0x01 per active cell, dv = 0x01
+// per active cell with a lean direction (E / SE / S / SW).  Flow into an inactive cell needs no test of its own -- in
+// the label sweep an inactive cell carries "no exit", which is what its donors must copy; in the accumulation sweep
+// whatever arrives at a cell is multiplied by the cell's own activity.
+template <int ENC>
+__device__ __forceinline__ bool lean_words_mk(const uint32_t *wp, const uint32_t *mp, uint32_t (&kw)[NWD], uint32_t (&dv)[NWD],
+                                              uint32_t (&av)[NWD])
+{
+    bool reject = false;
+#pragma unroll
+    for (int q = 0; q < NWD; q++) {
+        const uint32_t w = wp[q];
+        uint32_t ki;                                  // per byte: 0..3 lean direction, 4..7 another direction, else none
+        if (ENC == WMF_ENC_INTERNAL) ki = w;
+        else {
+            // keypad 1 SW, 2 S, 3 SE, 6 E -> 3, 2, 1, 0; 4 W, 7 NW, 8 N, 9 NE -> 4; 0, 5, negatives, > 9 -> 8 (none)
+            const uint32_t t = (w & 0x00070007u) | ((w & 0x07000700u) >> 4);
+            const uint32_t sel = (t & 0xFFu) | ((t >> 8) & 0xFF00u);
+            const uint32_t low = prmt(0x01020308u, 0x04000804u, sel);     // table[code & 7]
+            const uint32_t hb = byte_nonzero(w & 0xF8F8F8F8u), is89 = byte_zero((w & 0xFEFEFEFEu) ^ 0x08080808u);
+            ki = (low & ~(hb * 0xFFu)) | ((hb << 3) - (is89 << 2));
+        }
+        av[q] = byte_nonzero(mp[q]);
+        const uint32_t t = ki & 0xFCFCFCFCu;
+        dv[q] = byte_zero(t) & av[q];
+        reject = reject || (byte_zero(t ^ 0x04040404u) & av[q]) != 0;
+        kw[q] = ki;
+    }
+    return reject;
+}
+
 // Direction tests of the NC cells as 0/1 integers.  Every select below is a multiply by 0/1 fused into
 // an IMAD, which runs on the FMA pipe: the kernels are ALU-pipe bound (LOP3 / PRMT / SEL), so moving the
 // selects off that pipe matters more than the instruction count.
@@ -386,14 +423,49 @@ __device__ __forceinline__ RowBits row_bits(const uint32_t (&kw)[NWD])
     }
     return m;
 }
+// the same with a mask: a cell has a direction only where dv is set; egate (nullable) also cuts an East link whose
+// receiver is inactive (accumulation sweep).  act[] = the cells' activity as 0/1 integers.
+__device__ __forceinline__ RowBits row_bits_mk(const uint32_t (&kw)[NWD], const uint32_t (&dv)[NWD], const uint32_t *egate)
+{
+    RowBits m;
+    m.all_e = true;
+#pragma unroll
+    for (int q = 0; q < NWD; q++) {
+        const uint32_t x0 = kw[q] & dv[q], x1 = (kw[q] >> 1) & dv[q];
+        const uint32_t sw = x0 & x1, se = x0 ^ sw, s = x1 ^ sw;
+        uint32_t e = (x0 | x1) ^ dv[q];
+        if (egate) e &= egate[q];
+        m.all_e = m.all_e && e == 0x01010101u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            m.e[4 * q + j] = prmt(e, 0u, 0x4440u + j);
+            m.se[4 * q + j] = prmt(se, 0u, 0x4440u + j);
+            m.s[4 * q + j] = prmt(s, 0u, 0x4440u + j);
+            m.sw[4 * q + j] = prmt(sw, 0u, 0x4440u + j);
+        }
+    }
+    return m;
+}
+__device__ __forceinline__ void byte_flags(const uint32_t (&f)[NWD], uint32_t (&out)[NC])
+{
+#pragma unroll
+    for (int j = 0; j < NC; j++) out[j] = prmt(f[j / 4], 0u, 0x4440u + (j % 4));
+}
+// activity of the cell to the right of each cell (the next lane's first cell for the last one; none beyond lane 31)
+__device__ __forceinline__ void right_neighbour_flags(const uint32_t (&av)[NWD], int lane, uint32_t (&out)[NWD])
+{
+    uint32_t nxt = __shfl_down_sync(FULL, av[0], 1);
+    if (lane == 31) nxt = 0;
+#pragma unroll
+    for (int q = 0; q < NWD; q++) out[q] = __funnelshift_r(av[q], q + 1 < NWD ? av[q + 1 < NWD ? q + 1 : 0] : nxt, 8);
+}
 
 // Downward step of a plain row.  d[] holds, for each cell, 1 + the inflow from the row above (the
 // cell's own +1 is folded into the accumulate chain of the row above); tot[] out; d[] out for the
 // row below.  extL / extR: external inflow of the left- / right-column cell (phase C), else zero.
 template <typename T>
-__device__ __forceinline__ void plain_row_down(const uint32_t (&kw)[NWD], T (&d)[NC], T (&tot)[NC], int lane, T extL, T extR)
+__device__ __forceinline__ void plain_row_down_m(const RowBits &m, T (&d)[NC], T (&tot)[NC], int lane, T extL, T extR)
 {
-    const RowBits m = row_bits(kw);
     T t[NC];
     t[0] = d[0] + extL;
 #pragma unroll
@@ -415,18 +487,39 @@ __device__ __forceinline__ void plain_row_down(const uint32_t (&kw)[NWD], T (&d)
         d[j] = v;
     }
 }
+template <typename T>
+__device__ __forceinline__ void plain_row_down(const uint32_t (&kw)[NWD], T (&d)[NC], T (&tot)[NC], int lane, T extL, T extR)
+{
+    plain_row_down_m<T>(row_bits(kw), d, tot, lane, extL, extR);
+}
+// With a mask: what has arrived at a cell (from above, and the external inflow the caller has added to d) counts only
+// if the cell is active, and an East link into an inactive cell is cut; everything else is the plain step.
+template <typename T>
+__device__ __forceinline__ void plain_row_down_mk(const uint32_t (&kw)[NWD], const uint32_t (&dv)[NWD], const uint32_t (&av)[NWD],
+                                                  T (&d)[NC], T (&tot)[NC], int lane, T extL, T extR)
+{
+    uint32_t act[NC], rgt[NWD];
+    byte_flags(av, act);
+    right_neighbour_flags(av, lane, rgt);
+    d[0] += extL; d[NC - 1] += extR;
+#pragma unroll
+    for (int j = 0; j < NC; j++) d[j] *= (T)act[j];
+    plain_row_down_m<T>(row_bits_mk(kw, dv, rgt), d, tot, lane, (T)0, (T)0);
+}
 
 // Upward (label) step of a plain row of a full interior tile.  A plain row has no pits, so an East
 // cell's own term is 0 and "copy the chain end" is own + next * E.  slotL / slotR: boundary slots of
 // the left- / right-column cell of this row.  BOTTOM: the tile's last row, where S / SE / SW leave the tile.
-template <bool BOTTOM>
-__device__ __forceinline__ void plain_row_up(const uint32_t (&kw)[NWD], uint32_t (&lb)[NC], int lane, uint32_t slotL, uint32_t slotR)
+template <bool BOTTOM, bool MK>
+__device__ __forceinline__ void plain_row_up(const uint32_t (&kw)[NWD], const uint32_t (&dv)[NWD], uint32_t (&lb)[NC], int lane,
+                                             uint32_t slotL, uint32_t slotR)
 {
-    RowBits m = row_bits(kw);
+    RowBits m = MK ? row_bits_mk(kw, dv, nullptr) : row_bits(kw);
     uint32_t own[NC];
     if (BOTTOM) {
 #pragma unroll
-        for (int j = 0; j < NC; j++) own[j] = (uint32_t)(TW + NC * lane + j) * (1u - m.e[j]);
+        for (int j = 0; j < NC; j++)
+            own[j] = MK ? (uint32_t)(TW + NC * lane + j) * (m.se[j] + m.s[j] + m.sw[j]) : (uint32_t)(TW + NC * lane + j) * (1u - m.e[j]);
     } else {
         const uint32_t lbR0 = __shfl_down_sync(FULL, lb[0], 1), lbL = __shfl_up_sync(FULL, lb[NC - 1], 1);
 #pragma unroll
@@ -435,9 +528,16 @@ __device__ __forceinline__ void plain_row_up(const uint32_t (&kw)[NWD], uint32_t
             own[j] = lb[j] * m.s[j] + right * m.se[j] + left * m.sw[j];
         }
     }
+    if (MK) {                                                  // no direction (inactive, pit, nodata code): no exit
+        uint32_t has[NC];
+        byte_flags(dv, has);
+#pragma unroll
+        for (int j = 0; j < NC; j++) own[j] += LNONE * (1u - has[j]);
+    }
     const uint32_t kR = (kw[NWD - 1] >> 24) & 0xFFu, kL = kw[0] & 0xFFu;
-    if (lane == 31 && kR <= 1u) { own[NC - 1] = slotR; m.e[NC - 1] = 0; }     // E / SE leave through the right column
-    if (lane == 0 && kL == 3u) own[0] = slotL;                                // SW leaves through the left column
+    const bool dR = !MK || (dv[NWD - 1] >> 24) != 0, dL = !MK || (dv[0] & 0xFFu) != 0;
+    if (lane == 31 && dR && kR <= 1u) { own[NC - 1] = slotR; m.e[NC - 1] = 0; }   // E / SE leave through the right column
+    if (lane == 0 && dL && kL == 3u) own[0] = slotL;                              // SW leaves through the left column
     uint32_t V = own[NC - 1] + LNONE * m.e[NC - 1];          // label at cell 0 if nothing comes from the right
     uint32_t allE = m.e[NC - 1];
 #pragma unroll
@@ -449,11 +549,17 @@ __device__ __forceinline__ void plain_row_up(const uint32_t (&kw)[NWD], uint32_t
 
 // byte j of the plain (internal-coded) words
 __device__ __forceinline__ int plain_k(const uint32_t (&kw)[NWD], int j) { return (int)((kw[j / 4] >> (8 * (j % 4))) & 0xFFu); }
+// ... of a masked lean row: the normalised code (8 = none) and the activity of cell j
+__device__ __forceinline__ int plain_k_mk(const uint32_t (&kw)[NWD], const uint32_t (&dv)[NWD], int j)
+{
+    return ((dv[j / 4] >> (8 * (j % 4))) & 1u) ? (int)((kw[j / 4] >> (8 * (j % 4))) & 3u) : 8;
+}
+__device__ __forceinline__ bool flag_of(const uint32_t (&f)[NWD], int j) { return ((f[j / 4] >> (8 * (j % 4))) & 1u) != 0; }
 
 // ---------------------------------------------------------------------------------------------
 // phase A, fast solver
 // ---------------------------------------------------------------------------------------------
-template <int ENC, bool AL>
+template <int ENC, bool AL, bool MK>
 __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
                                                      Geo g, int ntiles, uint32_t *__restrict__ meta,
                                                      int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
@@ -478,7 +584,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     // Lean rows also serve the raster's own edge tiles: a left-column SW cell or a right-column E / SE cell
     // drains nowhere in the row arithmetic and keeps its own slot as exit label; k_g_build / entry_of give
     // such an exit no entry.  Only the raster's last row (S / SE / SW leave the raster) stays generic.
-    const bool plain_tile = mask == nullptr && full;
+    const bool plain_tile = full;                            // (MK: the raster has a mask)
     const int last_generic = (g.gy0 + gr0 + th == g.gny) ? th - 1 : -1;
     TileRows<AL> rows;
     rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
@@ -529,21 +635,28 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
         for (int lr = (th < (c + 1) * CH ? th : (c + 1) * CH) - 1; lr >= cbeg; lr--) {
             const uint32_t *wp = wc + (lr - cbeg) * ROWW;
             bool gen = true;
-            uint32_t kw[NWD];
-            if (plain_tile && lr != last_generic) gen = __any_sync(FULL, plain_words<ENC>(wp, kw));
+            uint32_t kw[NWD], dv[NWD], av[NWD];
+            if (plain_tile && lr != last_generic) {
+                if (MK) gen = __any_sync(FULL, lean_words_mk<ENC>(wp, rows.mchunk(c) + (lr - cbeg) * ROWW, kw, dv, av));
+                else gen = __any_sync(FULL, plain_words<ENC>(wp, kw));
+            }
             if (!gen) {
                 plain_rows |= 1ull << lr;
                 if (lr == 0 || lr == TH - 1) {        // first / last row of the tile: every cell is a boundary slot
-                    if (lr == 0) plain_row_up<false>(kw, lb, lane, 0u, (uint32_t)(TW - 1));
-                    else plain_row_up<true>(kw, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1));
+                    if (lr == 0) plain_row_up<false, MK>(kw, dv, lb, lane, 0u, (uint32_t)(TW - 1));
+                    else plain_row_up<true, MK>(kw, dv, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1));
                     uint32_t mw[NC];
 #pragma unroll
-                    for (int j = 0; j < NC; j++) mw[j] = meta_pack(lb[j], plain_k(kw, j), false, true);
+                    for (int j = 0; j < NC; j++)
+                        mw[j] = MK ? meta_pack(lb[j], plain_k_mk(kw, dv, j), false, flag_of(av, j)) : meta_pack(lb[j], plain_k(kw, j), false, true);
                     store_meta_row(lr == 0 ? 0 : TW, mw);
                 } else {
-                    plain_row_up<false>(kw, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
-                    if (lane == 0 || lane == 31)
-                        m_side[lr] = meta_pack(lane ? lb[NC - 1] : lb[0], lane ? kw[NWD - 1] >> 24 : kw[0] & 0xFFu, false, true);
+                    plain_row_up<false, MK>(kw, dv, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
+                    if (lane == 0 || lane == 31) {
+                        const int js = lane ? NC - 1 : 0;
+                        m_side[lr] = MK ? meta_pack(lane ? lb[NC - 1] : lb[0], plain_k_mk(kw, dv, js), false, flag_of(av, js))
+                                        : meta_pack(lane ? lb[NC - 1] : lb[0], plain_k(kw, js), false, true);
+                    }
                 }
                 count_labels(lb);
                 continue;
@@ -693,7 +806,7 @@ __device__ __forceinline__ void store_row(TO *out, const T (&tot)[NC], int64_t g
     }
 }
 
-template <int ENC, bool AL, typename T, typename TO>
+template <int ENC, bool AL, bool MK, typename T, typename TO>
 __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
                                                      Geo g, int ntiles, const T *__restrict__ inflow,
                                                      const uint8_t *__restrict__ tile_class,
@@ -742,17 +855,19 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
             pbits >>= run;
             for (const int end = lr + run; lr < end; lr++, out += g.nx, wp += ROWW) {
                 T tot[NC];
-                uint32_t kw[NWD];
-                plain_words<ENC>(wp, kw);
+                uint32_t kw[NWD], dv[NWD], av[NWD];
+                if (MK) lean_words_mk<ENC>(wp, rows.mchunk(c) + (lr - c * CH) * ROWW, kw, dv, av);
+                else plain_words<ENC>(wp, kw);
+                T l = 0, r = 0;
                 if (lr == 0 || lr == TH - 1) {            // first / last row: every cell is a boundary slot
                     const T *e4 = in_t + (lr == 0 ? 0 : TW) + NC * lane;
 #pragma unroll
                     for (int j = 0; j < NC; j++) d[j] += e4[j];
-                    plain_row_down<T>(kw, d, tot, lane, (T)0, (T)0);
                 } else {
-                    const T l = extL[lr], r = extR[lr];
-                    plain_row_down<T>(kw, d, tot, lane, is_l ? l : (T)0, is_r ? r : (T)0);
+                    l = is_l ? extL[lr] : (T)0; r = is_r ? extR[lr] : (T)0;
                 }
+                if (MK) plain_row_down_mk<T>(kw, dv, av, d, tot, lane, l, r);
+                else plain_row_down<T>(kw, d, tot, lane, l, r);
                 store_row<AL, T, TO>(out, tot, gc0, g.nx);
             }
             if (lr >= cend) break;
@@ -1468,8 +1583,12 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * HBINS * sizeof(int);
     static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
-    if (al) k_sweepA<ENC, true><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr, w.blocked);
-    else k_sweepA<ENC, false><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr, w.blocked);
+#define WMF_LAUNCH_A(AL_, MK_)                                                                                                   \
+    k_sweepA<ENC, AL_, MK_><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, \
+                                                                  w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr, w.blocked)
+    if (mask) { if (al) WMF_LAUNCH_A(true, true); else WMF_LAUNCH_A(false, true); }
+    else { if (al) WMF_LAUNCH_A(true, false); else WMF_LAUNCH_A(false, false); }
+#undef WMF_LAUNCH_A
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -1492,8 +1611,11 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
         }
     }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T) + WPB * 8;
-    if (al) k_sweepC<ENC, true, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
-    else k_sweepC<ENC, false, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc);
+#define WMF_LAUNCH_C(AL_, MK_) \
+    k_sweepC<ENC, AL_, MK_, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc)
+    if (mask) { if (al) WMF_LAUNCH_C(true, true); else WMF_LAUNCH_C(false, true); }
+    else { if (al) WMF_LAUNCH_C(true, false); else WMF_LAUNCH_C(false, false); }
+#undef WMF_LAUNCH_C
     k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, w.inflow, w.ext_unres, acc);
     WMF_LAUNCH_CHECK();
     return 0;
