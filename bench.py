@@ -372,6 +372,7 @@ def main():
     ap.add_argument("--shia-steps", type=int, default=1000)
     ap.add_argument("--no-shia", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -150,6 +150,162 @@ __device__ __forceinline__ uint32_t label_carry_from_left(uint32_t V, bool P, in
     return lane == 0 ? LNONE : c;
 }
 
+// ---- packed variant for int32 accumulations -----------------------------------------------------
+// ONE 64-bit word per boundary slot:
+//   [31:0]  sum: own weight + totals of finished children (the node's total once it is finalised)
+//   [43:32] pending arrivals: children + 1 for the node's own walker (+ 1 more when the node is blocked)
+//   [57:54] the cell's normalised D8 code (phase A writes it beside the weight)
+// k_g_build counts the children into the parents' words (atomics) and writes the 4-byte parent pointer of every exit.
+// A walker brings its total and its "-1 pending" in ONE atomic; whoever takes pending to zero finalises the node and
+// carries on downstream (the parent's parent is fetched before the atomic, so a hop is one L2 round trip).  Nothing is
+// pushed into the tiles: phase C PULLS the inflow of its boundary cells from the words of the (at most five) cells
+// across the tile edge -- a word whose code points at the cell and whose pending field is zero is a finalised donor
+// (slots that are not exits are never walked and keep their pending arrival).
+constexpr unsigned long long PEND1 = 1ull << 32;
+constexpr int W_K = 54;
+constexpr int32_t PAR_ROOT = -1, PAR_NONE = -2, PAR_STRIPE = -3;   // values of the parent array beside a parent (>= 0)
+__device__ __forceinline__ uint32_t w_pending(unsigned long long w) { return (uint32_t)(w >> 32) & 0xFFFu; }
+__device__ __forceinline__ int w_k(unsigned long long w) { return (int)(w >> W_K) & 0xF; }
+static_assert(3 * NSLOT + 2 < 0xFFF, "the children count fits its field");
+
+struct TileGeo { int last_th, last_tw; };
+__device__ __forceinline__ TileGeo tile_geo(const Geo &g)
+{
+    return TileGeo{(int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW)};
+}
+
+// where exit slot s of tile (ty, tx) drains: the tile of the entry (and its slot in s2), -2 = into a neighbouring row
+// stripe, -1 = not an exit / no receiver.  Tile geometry only; k is the slot's normalised code, active its activity.
+__device__ __forceinline__ int exit_target(const Geo &g, const TileGeo &tg, int ty, int tx, int s, int k, bool active, int &s2)
+{
+    const int th = ty == g.tiles_y - 1 ? tg.last_th : TH, tw = tx == g.tiles_x - 1 ? tg.last_tw : TW;
+    int lr, lc;
+    if (!cell_of(s, th, tw, lr, lc)) return -1;
+    if (!active || k == 8) return -1;
+    const int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
+    if (rr >= 0 && rr < th && cc >= 0 && cc < tw) return -1;            // stays in the tile: not an exit
+    const int ty2 = ty + (rr < 0 ? -1 : (rr >= th ? 1 : 0)), tx2 = tx + (cc < 0 ? -1 : (cc >= tw ? 1 : 0));
+    if (tx2 < 0 || tx2 >= g.tiles_x) return -1;                         // off the raster's side: no receiver
+    if (ty2 < 0 || ty2 >= g.tiles_y) return -2;                         // into a neighbouring row stripe
+    const int th2 = ty2 == g.tiles_y - 1 ? tg.last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? tg.last_tw : TW;
+    const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
+    s2 = slot_of(lr2, lc2, th2, tw2);
+    return ty2 * g.tiles_x + tx2;
+}
+__device__ __forceinline__ int build_target(const Geo &g, int ty, int tx, int last_th, int last_tw, int s, uint32_t m, int &s2)
+{
+    return exit_target(g, TileGeo{last_th, last_tw}, ty, tx, s, (int)((m >> 16) & 0xF), ((m >> 21) & 1) != 0, s2);
+}
+
+// ---- phase C's side of the packed forest: the inflow of a boundary cell, pulled from the donors across the tile edge
+// value a neighbour's word contributes when that neighbour is an exit with code kexp: its total once finalised
+__device__ __forceinline__ uint32_t donor_val(unsigned long long w, int kexp)
+{
+    const uint32_t hi = (uint32_t)(w >> 32);                // [11:0] pending, [25:22] k
+    return (hi & (0xFFFu | (0xFu << 22))) == ((uint32_t)kexp << 22) ? (uint32_t)w : 0u;
+}
+// any tile, any slot: the sum over the (up to five) cells outside the tile that drain into slot s; `unres` is set when
+// one of them is an exit that never finalised
+template <typename WalkedFn>
+__device__ __forceinline__ uint32_t pull_slot(const Geo &g, const TileGeo &tg, const unsigned long long *__restrict__ wq, int ty,
+                                              int tx, int th, int tw, int s, bool &unres, WalkedFn walked)
+{
+    int lr, lc;
+    if (!cell_of(s, th, tw, lr, lc)) return 0u;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                           // the neighbour that reaches (lr, lc) with code k
+        const int rr = lr - d8_dr(k), cc = lc - d8_dc(k);
+        if (rr >= 0 && rr < th && cc >= 0 && cc < tw) continue;
+        const int ty2 = ty + (rr < 0 ? -1 : (rr >= th ? 1 : 0)), tx2 = tx + (cc < 0 ? -1 : (cc >= tw ? 1 : 0));
+        if (ty2 < 0 || ty2 >= g.tiles_y || tx2 < 0 || tx2 >= g.tiles_x) continue;
+        const int th2 = ty2 == g.tiles_y - 1 ? tg.last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? tg.last_tw : TW;
+        const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
+        const unsigned long long w = __ldcg(&wq[(int64_t)(ty2 * g.tiles_x + tx2) * NSLOT + slot_of(lr2, lc2, th2, tw2)]);
+        const uint32_t hi = (uint32_t)(w >> 32);
+        if (((hi >> 22) & 0xFu) == (uint32_t)k) {          // a donor: finalised, never finalising (unresolved), or not an
+            if ((hi & 0xFFFu) == 0u) sum += (uint32_t)w;    // exit at all (`walked` tells the last two apart)
+            else if (walked((int64_t)(ty2 * g.tiles_x + tx2) * NSLOT + slot_of(lr2, lc2, th2, tw2))) unres = true;
+        }
+    }
+    return sum;
+}
+
+// A FULL tile's 640 inflows by one warp, vectorised: ext[] in shared memory (slot order).  Its neighbours above and to
+// the left are full tiles too; the ones below / to the right may be ragged, which does not move their first row / column.
+__device__ __forceinline__ void pull_full_tile(const Geo &g, const unsigned long long *__restrict__ wq, const uint8_t *__restrict__ tile_top,
+                                               int tile, int ty, int tx, int lane, uint32_t *ext)
+{
+    const bool up = ty > 0, dn = ty + 1 < g.tiles_y, lf = tx > 0, rt = tx + 1 < g.tiles_x;
+    auto word = [&](int t, int s) { return __ldcg(&wq[(int64_t)t * NSLOT + s]); };
+    // ---- first row (donors: last row of the tile above, codes SE / S / SW) and last row (first row of the tile below,
+    // codes NE / N / NW); the corner cells' diagonal donors live in the diagonal tiles
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const bool have = side == 0 ? up : dn;
+        const int t = side == 0 ? tile - g.tiles_x : tile + g.tiles_x;
+        const int kl = side == 0 ? 1 : 7, km = side == 0 ? 2 : 6, kr = side == 0 ? 3 : 5;   // donor at c-1 / c / c+1
+        uint32_t v[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) v[j] = 0;
+        uint32_t to_right = 0, to_left = 0;                 // what this lane's last / first donor sends to the next / previous lane
+        if (have && (side == 0 || tile_top[t])) {           // (a tile without upward flow in its first row feeds nothing upwards)
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(wq + (int64_t)t * NSLOT + (side == 0 ? TW : 0) + NC * lane);
+            unsigned long long w[NC];
+#pragma unroll
+            for (int q = 0; q < NC / 2; q++) { const ulonglong2 x = __ldcg(src + q); w[2 * q] = x.x; w[2 * q + 1] = x.y; }
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                v[j] += donor_val(w[j], km);
+                if (j + 1 < NC) v[j + 1 < NC ? j + 1 : 0] += donor_val(w[j], kl);
+                if (j > 0) v[j > 0 ? j - 1 : 0] += donor_val(w[j], kr);
+            }
+            to_right = donor_val(w[NC - 1], kl);
+            to_left = donor_val(w[0], kr);
+        }
+        const uint32_t from_left = __shfl_up_sync(FULL, to_right, 1), from_right = __shfl_down_sync(FULL, to_left, 1);
+        if (lane > 0) v[0] += from_left;
+        if (lane < 31) v[NC - 1] += from_right;
+        if (have && lane == 0 && lf) v[0] += donor_val(word(t - 1, side == 0 ? 2 * TW - 1 : TW - 1), kl);
+        if (have && lane == 31 && rt) v[NC - 1] += donor_val(word(t + 1, side == 0 ? TW : 0), kr);
+        uint32_t *dst = ext + (side == 0 ? 0 : TW) + NC * lane;
+#pragma unroll
+        for (int j = 0; j < NC; j++) dst[j] = v[j];
+    }
+    __syncwarp();
+    // ---- first column (donors: last column of the tile to the left, codes SE / E / NE from the rows r-1 / r / r+1) and
+    // last column (first column of the tile to the right, codes SW / W / NW).  Rows 0 and TH-1 are corner cells: their
+    // slots belong to the first / last row, the side donors are ADDED there.
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const bool have = side == 0 ? lf : rt;
+        const int t = side == 0 ? tile - 1 : tile + 1;
+        const int ku = side == 0 ? 1 : 3, km = side == 0 ? 0 : 4, kd = side == 0 ? 7 : 5;   // donor in row r-1 / r / r+1
+        uint32_t a_mid = 0, a_dn = 0, a_up = 0, b_mid = 0, b_dn = 0, b_up = 0;   // by the DONOR's row: lane (a) and lane + 32 (b)
+        if (have) {
+            // the donor column's slot in row r: corners sit in the first / last row's slot range
+            const int ra = lane, rb = lane + 32;
+            const int sa = ra == 0 ? (side == 0 ? TW - 1 : 0) : (side == 0 ? 2 * TW + TH : 2 * TW) + ra;
+            const int sb = rb == TH - 1 ? (side == 0 ? 2 * TW - 1 : TW) : (side == 0 ? 2 * TW + TH : 2 * TW) + rb;
+            const unsigned long long wa = word(t, sa), wb = word(t, sb);
+            a_mid = donor_val(wa, km); a_dn = donor_val(wa, ku); a_up = donor_val(wa, kd);   // to row r / r+1 / r-1
+            b_mid = donor_val(wb, km); b_dn = donor_val(wb, ku); b_up = donor_val(wb, kd);
+        }
+        const uint32_t a_from_above = __shfl_up_sync(FULL, a_dn, 1), a_from_below = __shfl_down_sync(FULL, a_up, 1);
+        const uint32_t b_from_above = __shfl_up_sync(FULL, b_dn, 1), b_from_below = __shfl_down_sync(FULL, b_up, 1);
+        const uint32_t a31_dn = __shfl_sync(FULL, a_dn, 31), b0_up = __shfl_sync(FULL, b_up, 0);
+        const uint32_t va = a_mid + (lane > 0 ? a_from_above : 0u) + (lane < 31 ? a_from_below : b0_up);
+        const uint32_t vb = b_mid + (lane > 0 ? b_from_above : a31_dn) + (lane < 31 ? b_from_below : 0u);
+        // rows lane and lane + 32 of this tile's first / last column
+        const int col_base = side == 0 ? 2 * TW : 2 * TW + TH;
+        if (lane == 0) ext[side == 0 ? 0 : TW - 1] += va;                       // row 0: the first row's corner slot
+        else ext[col_base + lane] = va;
+        if (lane == 31) ext[side == 0 ? TW : 2 * TW - 1] += vb;                 // row TH-1: the last row's corner slot
+        else ext[col_base + 32 + lane] = vb;
+    }
+    __syncwarp();
+}
+
 // One row of the downward sweep, any codes (generic path).  b[] = base (own cell + inflow from above
 // + external inflow) for active cells; returns tot[] and d[] = contributions to the row below.
 // Sets `twocycle` when the row holds an E -> W adjacent pair (the tile is then not "simple").
@@ -564,8 +720,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                                                      Geo g, int ntiles, uint32_t *__restrict__ meta,
                                                      int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
                                                      unsigned long long *__restrict__ row_plain,
-                                                     unsigned long long *__restrict__ wq, int32_t *__restrict__ inflow32,
-                                                     uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_top)
+                                                     unsigned long long *__restrict__ wq, uint8_t *__restrict__ tile_top)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ the same again for mask words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -575,7 +730,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     tile_dims(g, tile, ty, tx, th, tw);
     const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
     uint32_t *m_t = meta + (int64_t)tile * NSLOT;
-    int32_t *x_t = exit_acc + (int64_t)tile * NSLOT;
+    int32_t *x_t = exit_acc ? exit_acc + (int64_t)tile * NSLOT : nullptr;
     unsigned long long *w_t = wq + (int64_t)tile * NSLOT;     // packed forest words: pending << 32 | sum
     constexpr unsigned long long BIAS = 1ull << 32;           // every node waits for its own walker
     const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;      // lane / sub-cell holding the right column
@@ -604,15 +759,6 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
     for (int q = 0; q < HBINS / 128; q++) *reinterpret_cast<int4 *>(hist + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
     __syncwarp();
-    // the forest walk adds into inflow / flags ext_unres: clear this tile's slots here (phase A has DRAM to spare)
-    if (inflow32) {
-#pragma unroll
-        for (int q = 0; q < NSLOT / 128; q++)
-            *reinterpret_cast<int4 *>(inflow32 + (int64_t)tile * NSLOT + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
-        static_assert(NSLOT % 128 == 0 && NSLOT / 16 <= 64, "tile slots in 16-byte pieces");
-        for (int q = lane; q < NSLOT / 16; q += 32)
-            *reinterpret_cast<int4 *>(ext_unres + (int64_t)tile * NSLOT + 16 * q) = make_int4(0, 0, 0, 0);
-    }
     const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
     auto count_labels = [&](const uint32_t (&lab)[NC]) {      // (a label is a bin index as it is: slot or LNONE)
 #pragma unroll
@@ -756,10 +902,13 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
     for (int q = 0; q < NSLOT / 128; q++) {
         const int4 h = *reinterpret_cast<const int4 *>(hist + 128 * q + 4 * lane);
-        *reinterpret_cast<int4 *>(x_t + 128 * q + 4 * lane) = h;
+        if (exit_acc) *reinterpret_cast<int4 *>(x_t + 128 * q + 4 * lane) = h;     // (only the 64-bit forest engine reads it)
+        // (the slots' meta words, written by this warp a moment ago, come back from L2: their code goes into the word)
+        const uint4 mq = __ldcg(reinterpret_cast<const uint4 *>(m_t + 128 * q + 4 * lane));
+        auto word = [&](uint32_t m, int hh) { return BIAS | ((unsigned long long)((m >> 16) & 0xFu) << W_K) | (uint32_t)hh; };
         ulonglong2 *wp2 = reinterpret_cast<ulonglong2 *>(w_t + 128 * q + 4 * lane);
-        wp2[0] = make_ulonglong2(BIAS | (uint32_t)h.x, BIAS | (uint32_t)h.y);
-        wp2[1] = make_ulonglong2(BIAS | (uint32_t)h.z, BIAS | (uint32_t)h.w);
+        wp2[0] = make_ulonglong2(word(mq.x, h.x), word(mq.y, h.y));
+        wp2[1] = make_ulonglong2(word(mq.z, h.z), word(mq.w, h.w));
     }
 }
 
@@ -806,13 +955,49 @@ __device__ __forceinline__ void store_row(TO *out, const T (&tot)[NC], int64_t g
     }
 }
 
+// The external inflow of the tile's 640 boundary slots, in shared memory (slot order): pulled from the packed forest
+// words of the neighbouring tiles (wq; int32 accumulations), plus an optional per-slot array `extra` (what the other row
+// stripes send in; or, for the 64-bit forest engine, everything).
+template <typename T>
+__device__ __forceinline__ void tile_inflow(const Geo &g, const unsigned long long *__restrict__ wq, const uint8_t *__restrict__ tile_top,
+                                            const T *__restrict__ extra, int tile, int ty, int tx, int th, int tw, int lane, T *ext)
+{
+    if (wq) {
+        uint32_t *e32 = reinterpret_cast<uint32_t *>(ext);
+        if (th == TH && tw == TW) {
+            pull_full_tile(g, wq, tile_top, tile, ty, tx, lane, e32);
+        } else {
+            const TileGeo tg = tile_geo(g);
+            bool un = false;                                // (tiles with an unresolved feeder never come here: class 2)
+            for (int s = lane; s < NSLOT; s += 32) e32[s] = pull_slot(g, tg, wq, ty, tx, th, tw, s, un, [](int64_t) { return false; });
+            __syncwarp();
+        }
+        if (sizeof(T) == 8) {                               // widen in place, last slots first (a lane's reads precede its writes
+            for (int q = NSLOT / 32 - 1; q >= 0; q--) {     // of higher addresses; lanes are in step)
+                const uint32_t v = e32[32 * q + lane];
+                __syncwarp();
+                ext[32 * q + lane] = (T)v;
+                __syncwarp();
+            }
+        }
+    } else {
+        for (int s = lane; s < NSLOT; s += 32) ext[s] = 0;
+    }
+    if (extra) {
+        const T *x = extra + (int64_t)tile * NSLOT;
+        for (int s = lane; s < NSLOT; s += 32) ext[s] += x[s];
+    }
+    __syncwarp();
+}
+
 template <int ENC, bool AL, bool MK, typename T, typename TO>
 __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
-                                                     Geo g, int ntiles, const T *__restrict__ inflow,
+                                                     Geo g, int ntiles, const unsigned long long *__restrict__ wq,
+                                                     const uint8_t *__restrict__ tile_top, const T *__restrict__ extra,
                                                      const uint8_t *__restrict__ tile_class,
                                                      const unsigned long long *__restrict__ row_plain, TO *__restrict__ acc)
 {
-    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ mask words) + the side inflows
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ mask words) + the boundary inflows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
@@ -820,17 +1005,16 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
     int ty, tx, th, tw;
     tile_dims(g, tile, ty, tx, th, tw);
     const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
-    const T *in_t = inflow + (int64_t)tile * NSLOT;
     const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;
     const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
     TileRows<AL> rows;
     rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
     const int nch = (th + CH - 1) / CH;
     rows.prefetch(0);
-    // external inflow of the left / right column cells
-    T *extL = reinterpret_cast<T *>(s_dyn + (mask ? 2 : 1) * WPB * 2 * CH * ROWW) + 2 * TH * warp, *extR = extL + TH;
-    extL[lane] = in_t[2 * TW + lane]; extL[lane + 32] = in_t[2 * TW + 32 + lane];
-    extR[lane] = in_t[2 * TW + TH + lane]; extR[lane + 32] = in_t[2 * TW + TH + 32 + lane];
+    // external inflow of the boundary cells: first row, last row, first column, last column
+    T *ext = reinterpret_cast<T *>(s_dyn + (mask ? 2 : 1) * WPB * 2 * CH * ROWW) + NSLOT * warp;
+    const T *extL = ext + 2 * TW, *extR = ext + 2 * TW + TH;
+    tile_inflow<T>(g, wq, tile_top, extra, tile, ty, tx, th, tw, lane, ext);
     T d[NC];
 #pragma unroll
     for (int j = 0; j < NC; j++) d[j] = 1;           // 1 + inflow from the row above
@@ -838,7 +1022,7 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
     TO *out = acc + gr0 * g.nx + gc0;
     // the per-chunk lean-row masks live in shared memory: an L1TEX load (global or a register spill) issued
     // behind the chunk prefetch would wait for the prefetch's HBM round trip (the L1TEX queue is in order)
-    unsigned char *pchunk = reinterpret_cast<unsigned char *>(extL + (size_t)2 * TH * (WPB - warp)) + 8 * warp;
+    unsigned char *pchunk = reinterpret_cast<unsigned char *>(ext + (size_t)NSLOT * (WPB - warp)) + 8 * warp;
     if (lane == 0) *reinterpret_cast<unsigned long long *>(pchunk) = row_plain[tile];
     const bool is_l = lane == 0, is_r = lane == 31;
     for (int c = 0; c < nch; c++) {
@@ -860,7 +1044,7 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
                 else plain_words<ENC>(wp, kw);
                 T l = 0, r = 0;
                 if (lr == 0 || lr == TH - 1) {            // first / last row: every cell is a boundary slot
-                    const T *e4 = in_t + (lr == 0 ? 0 : TW) + NC * lane;
+                    const T *e4 = ext + (lr == 0 ? 0 : TW) + NC * lane;
 #pragma unroll
                     for (int j = 0; j < NC; j++) d[j] += e4[j];
                 } else {
@@ -876,23 +1060,23 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
                 int k[NC];
                 const int am = rows.active(lr);
                 decode_row<ENC>(wp, am, g, gr0 + lr, gc0, border, k);
-                T ext[NC];
+                T ex[NC];
 #pragma unroll
-                for (int j = 0; j < NC; j++) ext[j] = 0;
+                for (int j = 0; j < NC; j++) ex[j] = 0;
                 if (lr == 0 || lr == th - 1) {
-                    const T *e4 = in_t + (lr == 0 ? 0 : TW) + NC * lane;
+                    const T *e4 = ext + (lr == 0 ? 0 : TW) + NC * lane;
 #pragma unroll
-                    for (int j = 0; j < NC; j++) ext[j] = e4[j];
+                    for (int j = 0; j < NC; j++) ex[j] = e4[j];
                 } else {
-                    if (lane == 0) ext[0] = extL[lr];
+                    if (lane == 0) ex[0] = extL[lr];
                     if (lane == rlane && tw > 1) {
 #pragma unroll
-                        for (int j = 0; j < NC; j++) if (j == rj) ext[j] += extR[lr];
+                        for (int j = 0; j < NC; j++) if (j == rj) ex[j] += extR[lr];
                     }
                 }
                 T b[NC];
 #pragma unroll
-                for (int j = 0; j < NC; j++) b[j] = ((am >> j) & 1) ? d[j] + ext[j] : (T)0;
+                for (int j = 0; j < NC; j++) b[j] = ((am >> j) & 1) ? d[j] + ex[j] : (T)0;
                 sweep_row_down<T>(k, am, b, tot, d, lane, dummy);
 #pragma unroll
                 for (int j = 0; j < NC; j++) d[j] += 1;
@@ -1045,22 +1229,25 @@ __global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir
             }
         }
         meta[(int64_t)tile * NSLOT + s] = m;
-        exit_acc[(int64_t)tile * NSLOT + s] = xa;
-        wq[(int64_t)tile * NSLOT + s] = ((1ull + ((m >> 20) & 1u)) << 32) | (uint32_t)xa;   // pending | weight; a locally unresolved exit never finalises
+        if (exit_acc) exit_acc[(int64_t)tile * NSLOT + s] = xa;
+        // pending | code | weight; a locally unresolved exit never finalises
+        wq[(int64_t)tile * NSLOT + s] = ((1ull + ((m >> 20) & 1u)) << 32) | ((unsigned long long)((m >> 16) & 0xFu) << W_K) | (uint32_t)xa;
     }
   }
 }
 
 template <int ENC, typename T, typename TO>
 __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
-                                                  const uint8_t *__restrict__ tile_class, const T *__restrict__ inflow,
-                                                  const uint8_t *__restrict__ ext_unres, TO *__restrict__ out)
+                                                  const uint8_t *__restrict__ tile_class, const unsigned long long *__restrict__ wq,
+                                                  const int32_t *__restrict__ par, const T *__restrict__ extra,
+                                                  const uint8_t *__restrict__ extra_unres, TO *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem[];
   const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
   bool any_mine = false;
   for (int t = t_lo + threadIdx.x; t < t_hi; t += GTH) any_mine = any_mine || tile_class[t] != 0;
   if (!__syncthreads_or(any_mine)) return;
+  const TileGeo tg = tile_geo(g);
   for (int tile = t_lo; tile < t_hi; tile++) {
     if (tile_class[tile] == 0) continue;
     __syncthreads();
@@ -1079,8 +1266,12 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
         if (!cell_of(s, th, tw, lr, lc)) continue;
         int idx = lr * TW + lc;
         if (!(kk[idx] & 16)) continue;
-        acc[idx] = inflow[(int64_t)tile * NSLOT + s];
-        if (ext_unres[(int64_t)tile * NSLOT + s]) cnt[idx] = cnt[idx] == 0xFF ? 1 : cnt[idx] + 1;   // phantom donor
+        bool un = false;
+        T v = wq ? (T)pull_slot(g, tg, wq, ty, tx, th, tw, s, un, [&](int64_t node) { return par[node] != PAR_NONE; }) : (T)0;
+        if (extra) v += extra[(int64_t)tile * NSLOT + s];
+        if (extra_unres && extra_unres[(int64_t)tile * NSLOT + s]) un = true;
+        acc[idx] = v;
+        if (un) cnt[idx] = cnt[idx] == 0xFF ? 1 : cnt[idx] + 1;   // phantom donor: an unresolved upstream never arrives
     }
     __syncthreads();
     general_walk<T>(kk, cnt, acc, th, tw);
@@ -1138,42 +1329,18 @@ __global__ void k_build_forest(Geo g, int64_t nnodes, const uint32_t *__restrict
     blocked[i] = (uint8_t)((meta[i] >> 20) & 1);
 }
 
-// ---- packed variant for int32 accumulations -----------------------------------------------------
-// One 64-bit word per node: pending children (+1 for the node's own walker, +1 more when the node is
-// blocked) in the high half, the sum of finished children in the low half.  A walker brings its
-// total and its "-1 pending" in ONE atomic; whoever takes pending to zero finalises the node, pushes
-// the total into the entry cell it drains to, and carries on downstream.  No fences, no leaf pass.
-constexpr unsigned long long PEND1 = 1ull << 32;
-
-// where exit slot s of tile (ty, tx) drains: the tile of the entry (and its slot in s2), -2 = into a neighbouring row
-// stripe, -1 = not an exit / no receiver.  Tile geometry only; m is the slot's meta word.
-__device__ __forceinline__ int build_target(const Geo &g, int ty, int tx, int last_th, int last_tw, int s, uint32_t m, int &s2)
-{
-    const int th = ty == g.tiles_y - 1 ? last_th : TH, tw = tx == g.tiles_x - 1 ? last_tw : TW;
-    int lr, lc;
-    if (!cell_of(s, th, tw, lr, lc)) return -1;
-    const int k = (m >> 16) & 0xF;
-    if (!((m >> 21) & 1) || k == 8) return -1;
-    const int rr = lr + d8_dr(k), cc = lc + d8_dc(k);
-    if (rr >= 0 && rr < th && cc >= 0 && cc < tw) return -1;            // stays in the tile: not an exit
-    const int ty2 = ty + (rr < 0 ? -1 : (rr >= th ? 1 : 0)), tx2 = tx + (cc < 0 ? -1 : (cc >= tw ? 1 : 0));
-    if (tx2 < 0 || tx2 >= g.tiles_x) return -1;                         // off the raster's side: no receiver
-    if (ty2 < 0 || ty2 >= g.tiles_y) return -2;                         // into a neighbouring row stripe
-    const int th2 = ty2 == g.tiles_y - 1 ? last_th : TH, tw2 = tx2 == g.tiles_x - 1 ? last_tw : TW;
-    const int lr2 = rr < 0 ? th2 - 1 : (rr >= th ? 0 : rr), lc2 = cc < 0 ? tw2 - 1 : (cc >= tw ? 0 : cc);
-    s2 = slot_of(lr2, lc2, th2, tw2);
-    return ty2 * g.tiles_x + tx2;
-}
-
 // One thread per boundary slot, BU consecutive tiles per block: the kernel is two dependent gathers (the slot's meta
-// word, then the meta word of the entry it drains to) plus an atomic, so each thread keeps BU of them in flight.
+// word, then the meta word of the entry it drains to) plus two reductions, so each thread keeps BU of them in flight.
+// par: the parent exit of every slot (>= 0), or PAR_ROOT (an exit whose flow ends in the next tile), PAR_STRIPE (an exit
+// into a neighbouring row stripe), PAR_NONE (not an exit, or its receiver is inactive: never walked).
+// pe (nullable; the stripe kernels chase it): one 8-byte record {parent exit, entry cell} per node.
 constexpr int BU = 4;
 __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta,
-                                                   const uint8_t *__restrict__ tile_top, int2 *__restrict__ pe,
-                                                   unsigned long long *wq)
+                                                   const uint8_t *__restrict__ tile_top, int32_t *__restrict__ par,
+                                                   int2 *__restrict__ pe, unsigned long long *wq)
 {
-    // last tiles first: what this kernel leaves in L2 (records and forest words, 168 MB against 126 MB of L2) is then
-    // weighted towards the FIRST tile rows, where the walk that follows starts its chains
+    // last tiles first: what this kernel leaves in L2 is then weighted towards the FIRST tile rows, where the walk
+    // that follows starts its chains
     const int tile0 = (int)(gridDim.x - 1 - blockIdx.x) * BU, s = threadIdx.x;
     const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
     uint32_t m[BU], me[BU];
@@ -1194,7 +1361,7 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
     for (int u = 0; u < BU; u++) me[u] = t2[u] >= 0 ? meta[t2[u] * NSLOT + s2[u]] : 0u;
 #pragma unroll
     for (int u = 0; u < BU; u++) {
-        if (skip[u]) continue;                               // (its record is never read: see node_is_skipped)
+        if (skip[u]) continue;                               // (its slot is never walked: see node_is_skipped)
         int32_t p = -1, en = t2[u];
         if (en >= 0) {
             en = -1;
@@ -1207,7 +1374,8 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
                 }
             }
         }
-        pe[(int64_t)(tile0 + u) * NSLOT + s] = make_int2(p, en);        // one 8-byte record per node: {parent exit, entry cell}
+        par[(int64_t)(tile0 + u) * NSLOT + s] = p >= 0 ? p : (en >= 0 ? PAR_ROOT : (en == -2 ? PAR_STRIPE : PAR_NONE));
+        if (pe) pe[(int64_t)(tile0 + u) * NSLOT + s] = make_int2(p, en);
     }
 }
 
@@ -1215,39 +1383,34 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
 // per-warp adds spread out) hold exits << 32 | finalised; k_g_unres has work only when the halves differ.
 constexpr int GCNT = 64;                                     // power of two
 constexpr size_t GCNT_BYTES = sizeof(unsigned long long) * 4 * GCNT;
-// inner first-row slots of a full tile whose row 0 has no upward flow are never exits: k_g_build wrote no record for them
+// inner first-row slots of a full tile whose row 0 has no upward flow are never exits: k_g_build left their words alone
 __device__ __forceinline__ bool node_is_skipped(const uint8_t *__restrict__ tile_top, int64_t i)
 {
     const int tile = (int)(i / NSLOT), s = (int)(i - (int64_t)tile * NSLOT);
     return s > 0 && s < TW - 1 && !tile_top[tile];
 }
 
-__global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *__restrict__ tile_top, const int2 *__restrict__ pe, unsigned long long *wq,
-                                                int32_t *__restrict__ inflow, int32_t *__restrict__ stripe_total,
-                                                unsigned long long *__restrict__ gcnt)
+
+__global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *__restrict__ tile_top, const int32_t *__restrict__ par,
+                                                unsigned long long *wq, unsigned long long *__restrict__ gcnt)
 {
-    // wq[node] = pending << 32 | (own weight + sum of finished children): phase A left the weight in the low half
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int2 me = (i < nnodes && !node_is_skipped(tile_top, i)) ? pe[i] : make_int2(-1, -1);
-    int32_t en = me.y;
-    const unsigned int nexit = __popc(__ballot_sync(FULL, en != -1));
+    int32_t p = (i < nnodes && !node_is_skipped(tile_top, i)) ? par[i] : PAR_NONE;
+    const bool walk = p != PAR_NONE;
+    const unsigned int nexit = __popc(__ballot_sync(FULL, walk));
     unsigned int nfin = 0;
-    if (en != -1) {                                         // an exit: carry its total downstream
-        int32_t p = me.x;
-        int64_t cur = i;
-        unsigned long long old = atomicAdd(&wq[cur], (unsigned long long)(-(long long)PEND1));   // own arrival
+    if (walk) {                                             // an exit: carry its total downstream
+        unsigned long long old = atomicAdd(&wq[i], (unsigned long long)(-(long long)PEND1));   // own arrival
         uint32_t add = 0;
-        while ((uint32_t)(old >> 32) == 1u) {               // we took pending to zero: cur is final
+        while (w_pending(old) == 1u) {                      // we took pending to zero: the node is final, its word holds the total
             const uint32_t total = (uint32_t)old + add;
             nfin++;
-            if (en >= 0) atomicAdd(&inflow[en], (int32_t)total);
-            else if (en == -2) stripe_total[cur] = (int32_t)total;     // a stripe exit keeps its stripe-local total
-            if (p < 0) break;
-            // the parent's record does not depend on the atomic: fetch it first so the hop costs ONE L2 round trip
-            const int2 next = pe[p];
+            if (p < 0) break;                               // the chain ends here: a root, or a stripe exit
+            // the parent's parent does not depend on the atomic: fetch it first so the hop costs ONE L2 round trip
+            const int32_t nxt = par[p];
             old = atomicAdd(&wq[p], (unsigned long long)total - PEND1);
             add = total;
-            cur = p; p = next.x; en = next.y;
+            p = nxt;
         }
     }
     __syncwarp();
@@ -1256,10 +1419,11 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *_
         atomicAdd(&gcnt[4 * (blockIdx.x & (GCNT - 1))], ((unsigned long long)nexit << 32) | nfin);
 }
 
-// Exits that never finalised (cycles, or fed by one) poison the entry they drain to.  Nothing to do
-// when every exit finalised, which the two counters tell without a host round trip.
-__global__ void k_g_unres(int64_t nnodes, const uint8_t *__restrict__ tile_top, const int2 *__restrict__ pe, const unsigned long long *__restrict__ wq,
-                          uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class,
+// Exits that never finalised (cycles, or fed by one) poison the tile they drain into: it goes to the general solver,
+// which sees the unresolved donors when it pulls.  Nothing to do when every exit finalised, which the two counters
+// tell without a host round trip.
+__global__ void k_g_unres(Geo g, int64_t nnodes, const uint8_t *__restrict__ tile_top, const int32_t *__restrict__ par,
+                          const unsigned long long *__restrict__ wq, uint8_t *__restrict__ tile_class,
                           const unsigned long long *__restrict__ gcnt)
 {
     {
@@ -1269,14 +1433,17 @@ __global__ void k_g_unres(int64_t nnodes, const uint8_t *__restrict__ tile_top, 
         const unsigned int exits = __reduce_add_sync(FULL, (unsigned int)(c >> 32)), fin = __reduce_add_sync(FULL, (unsigned int)c);
         if (exits == fin) return;
     }
+    const TileGeo tg = tile_geo(g);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) {
         if (node_is_skipped(tile_top, i)) continue;
-        int32_t en = pe[i].y;
-        if (en < 0) continue;
-        if ((uint32_t)(wq[i] >> 32) != 0u) {                // never finalised: the entry it feeds never finalises
-            ext_unres[en] = 1;
-            tile_class[en / NSLOT] = 2;                     // (racing writers all store non-zero)
-        }
+        const int32_t pp = par[i];
+        if (pp == PAR_NONE || pp == PAR_STRIPE) continue;
+        const unsigned long long w = wq[i];
+        if (w_pending(w) == 0u) continue;
+        const int tile = (int)(i / NSLOT), ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+        int s2;
+        const int te = exit_target(g, tg, ty, tx, (int)(i - (int64_t)tile * NSLOT), w_k(w), true, s2);
+        if (te >= 0) tile_class[te] = 2;                    // (racing writers all store the same value)
     }
 }
 
@@ -1431,9 +1598,9 @@ __global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict
 //   plane 0  exit_acc: stripe-local total of a cell draining across the stripe edge (0 elsewhere)
 //   plane 1  link (low 32 bits: boundary index where flow ENTERING here leaves the stripe, -1 = ends inside)
 //            | k << 32 (normalised code, 8 none, 9 inactive) | unres << 40 (the exit is locally unresolved)
-__global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
-                                 const int32_t *__restrict__ stripe_total, const unsigned long long *__restrict__ wq,
-                                 const int32_t *__restrict__ plink, int64_t *__restrict__ recs)
+__global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const int32_t *__restrict__ par,
+                                 const unsigned long long *__restrict__ wq, const int32_t *__restrict__ plink,
+                                 int64_t *__restrict__ recs)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * g.nx) return;
@@ -1444,13 +1611,14 @@ __global__ void k_stripe_summary(Geo g, const uint32_t *__restrict__ meta, const
     const uint32_t m = meta[node];
     const bool active = (m >> 21) & 1;
     const int k = (m >> 16) & 0xF;
-    const bool is_exit = active && pe[node].y == -2 &&
+    const unsigned long long w = wq[node];
+    const bool is_exit = active && par[node] == PAR_STRIPE &&
                          ((side == 0 && k >= 5 && k <= 7) || (side == 1 && k >= 1 && k <= 3));
-    const bool resolved = (uint32_t)(wq[node] >> 32) == 0u;
+    const bool resolved = w_pending(w) == 0u;
     const int64_t c_recv = col + (k < 8 ? d8_dc(k) : 0);
     const int64_t rec_k = !active ? 9 : ((c_recv < 0 || c_recv >= g.nx) ? 8 : k);
     const int64_t rec_unres = (is_exit && !resolved) ? 1 : 0;
-    recs[i] = (is_exit && resolved) ? (int64_t)(uint32_t)stripe_total[node] : 0;       // plane 0: exit_acc
+    recs[i] = (is_exit && resolved) ? (int64_t)(uint32_t)w : 0;                        // plane 0: exit_acc (the finalised total)
     recs[2 * g.nx + i] = (int64_t)(uint32_t)plink[i] | (rec_k << 32) | (rec_unres << 40);   // plane 1: link | k | unres
 }
 
@@ -1467,7 +1635,7 @@ __global__ void k_widen(const int32_t *__restrict__ a, T *__restrict__ b, int64_
 template <typename T>
 __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
                                StripePaths sp, const int64_t *__restrict__ ext_inflow, const uint8_t *__restrict__ ext_un,
-                               T *__restrict__ inflow, uint8_t *__restrict__ ext_unres, uint8_t *__restrict__ tile_class)
+                               T *__restrict__ extra, uint8_t *__restrict__ extra_unres, uint8_t *__restrict__ tile_class)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n2 = 2 * g.nx;
     if (i >= n2) return;
@@ -1479,8 +1647,8 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
     for (int h = blockIdx.y; h < plen; h += gridDim.y) {
         const int32_t item = sp.path[(int64_t)h * n2 + i];
         int64_t e = item & ~JUMP;
-        inflow_add<T>(&inflow[e], (T)v);
-        if (u) { ext_unres[e] = 1; tile_class[e / NSLOT] = 2; }
+        inflow_add<T>(&extra[e], (T)v);
+        if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; }
         if (item & JUMP) {                                   // the entries the jump skipped inside its group of tile rows
             const int mr = macro_of(g, e);
             int64_t x = first_exit(meta, e);
@@ -1488,8 +1656,8 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
                 const int2 r = pe[x];
                 const int32_t en = r.y;
                 if (en < 0 || macro_of(g, en) != mr) break;
-                inflow_add<T>(&inflow[en], (T)v);
-                if (u) { ext_unres[en] = 1; tile_class[en / NSLOT] = 2; }
+                inflow_add<T>(&extra[en], (T)v);
+                if (u) { extra_unres[en] = 1; tile_class[en / NSLOT] = 2; }
                 x = r.x;
             }
         }
@@ -1497,8 +1665,8 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
     if (blockIdx.y == 0 && sp.pce[i] >= 0) {
         int64_t e = sp.pce[i], x = sp.pcx[i];
         for (int64_t hops = 0; hops <= nnodes; hops++) {
-            inflow_add<T>(&inflow[e], (T)v);
-            if (u) { ext_unres[e] = 1; tile_class[e / NSLOT] = 2; }
+            inflow_add<T>(&extra[e], (T)v);
+            if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; }
             if (x < 0) break;
             const int2 r = pe[x];
             if (r.y < 0) break;
@@ -1508,53 +1676,58 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
     }
 }
 
-template <typename T>
+// Workspace layout.  Always: meta, the packed forest words, the per-tile arrays.  `wide` adds the arrays of the 64-bit
+// forest engine (rasters of 2^32 cells and more), `stripe` the records the stripe kernels chase and the inflow that
+// arrives from the other stripes.
 struct SweepWs {
-    uint32_t *meta; int32_t *exit_acc, *parent, *cnt; T *A, *inflow; uint8_t *blocked, *ext_unres, *tile_class;
-    unsigned long long *row_plain, *wq; int64_t *w64; unsigned long long *gcnt;
+    uint32_t *meta; unsigned long long *wq; int32_t *par; uint8_t *tile_class, *tile_top; unsigned long long *row_plain, *gcnt;
+    int32_t *exit_acc, *parent, *cnt; int64_t *A, *inflow; uint8_t *blocked, *ext_unres;   // wide
+    int2 *pe; void *extra; uint8_t *extra_unres;                              // stripe
     StripePaths sp;
+    size_t used;
     bool ok;
 };
 static int stripe_pcap(const Geo &g) { return g.tiles_y + 32 < 1024 ? g.tiles_y + 32 : 1024; }   // recorded hops per boundary path
 
-template <typename T>
-SweepWs<T> carve_ws(void *ws, size_t ws_bytes, int64_t nnodes, int ntiles, bool stripe, const Geo *g = nullptr)
+static SweepWs carve_ws(void *ws, size_t ws_bytes, const Geo &g, bool wide, bool stripe)
 {
+    const size_t nt = (size_t)g.tiles_x * (size_t)g.tiles_y, nn = nt * NSLOT;
     WsCursor cur(ws, ws_bytes);
-    SweepWs<T> w;
-    w.meta = cur.take<uint32_t>((size_t)nnodes);
-    w.exit_acc = cur.take<int32_t>((size_t)nnodes);
-    w.parent = cur.take<int32_t>((size_t)nnodes);
-    w.cnt = cur.take<int32_t>((size_t)nnodes);
-    w.A = cur.take<T>((size_t)nnodes);
-    w.inflow = cur.take<T>((size_t)nnodes);
-    w.blocked = cur.take<uint8_t>((size_t)nnodes);
-    w.ext_unres = cur.take<uint8_t>((size_t)nnodes);
-    w.tile_class = cur.take<uint8_t>((size_t)ntiles);
-    w.row_plain = cur.take<unsigned long long>((size_t)ntiles);
-    w.wq = cur.take<unsigned long long>((size_t)nnodes);
-    w.w64 = stripe ? cur.take<int64_t>((size_t)nnodes) : nullptr;
+    SweepWs w{};
+    w.meta = cur.take<uint32_t>(nn);
+    w.wq = cur.take<unsigned long long>(nn);
+    w.par = cur.take<int32_t>(nn);
+    w.tile_class = cur.take<uint8_t>(nt);
+    w.tile_top = cur.take<uint8_t>(nt);
+    w.row_plain = cur.take<unsigned long long>(nt);
     w.gcnt = cur.take<unsigned long long>(GCNT_BYTES / sizeof(unsigned long long));
+    if (wide) {
+        w.exit_acc = cur.take<int32_t>(nn);
+        w.parent = cur.take<int32_t>(nn);
+        w.cnt = cur.take<int32_t>(nn);
+        w.A = cur.take<int64_t>(nn);
+        w.inflow = cur.take<int64_t>(nn);
+        w.blocked = cur.take<uint8_t>(nn);
+        w.ext_unres = cur.take<uint8_t>(nn);
+    }
     w.sp = StripePaths{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     if (stripe) {
-        const size_t n2 = (size_t)(2 * g->nx);
-        w.sp.pcap = stripe_pcap(*g);
+        w.pe = cur.take<int2>(nn);
+        w.extra = cur.take<int64_t>(nn);
+        w.extra_unres = cur.take<uint8_t>(nn);
+        const size_t n2 = (size_t)(2 * g.nx);
+        w.sp.pcap = stripe_pcap(g);
         w.sp.path = cur.take<int32_t>(n2 * (size_t)w.sp.pcap);
         w.sp.plen = cur.take<int32_t>(n2);
         w.sp.pce = cur.take<int32_t>(n2);
         w.sp.pcx = cur.take<int32_t>(n2);
         w.sp.plink = cur.take<int32_t>(n2);
-        w.sp.mlink = cur.take<int32_t>((size_t)((g->tiles_y + MR - 1) / MR) * (size_t)g->nx);
+        w.sp.mlink = cur.take<int32_t>((size_t)((g.tiles_y + MR - 1) / MR) * (size_t)g.nx);
     }
+    w.used = cur.off;
     w.ok = cur.ok;
     return w;
 }
-
-// The packed (int32) forest keeps {parent, entry} as one 8-byte record per node in the parent + cnt arrays, which the
-// cursor lays out back to back (NSLOT * 4 bytes per tile is a multiple of its 256-byte alignment).
-static_assert((NSLOT * sizeof(int32_t)) % 256 == 0, "parent and cnt are contiguous");
-template <typename T>
-static int2 *pe_of(const SweepWs<T> &w) { return reinterpret_cast<int2 *>(w.parent); }
 
 static Geo make_geo(int64_t ny, int64_t nx, int64_t gy0, int64_t gny)
 {
@@ -1565,12 +1738,24 @@ static Geo make_geo(int64_t ny, int64_t nx, int64_t gy0, int64_t gny)
     return g;
 }
 
-template <int ENC, typename T>
-int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, cudaStream_t st,
-                 int32_t *zero_inflow32 = nullptr)
+static int sm_count()
+{
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <int ENC>
+int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs &w, bool al, cudaStream_t st)
 {
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
-    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);   // persistent: most tiles are skipped
+    const unsigned gen_blocks = (unsigned)(ntiles < sm_count() * 4 ? ntiles : sm_count() * 4);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
     {   // once per device and instantiation
         static bool done[64];
@@ -1585,7 +1770,7 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
 #define WMF_LAUNCH_A(AL_, MK_)                                                                                                   \
     k_sweepA<ENC, AL_, MK_><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, \
-                                                                  w.wq, zero_inflow32, zero_inflow32 ? w.ext_unres : nullptr, w.blocked)
+                                                                  w.wq, w.tile_top)
     if (mask) { if (al) WMF_LAUNCH_A(true, true); else WMF_LAUNCH_A(false, true); }
     else { if (al) WMF_LAUNCH_A(true, false); else WMF_LAUNCH_A(false, false); }
 #undef WMF_LAUNCH_A
@@ -1594,42 +1779,44 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     return 0;
 }
 
+// wq: the packed forest words phase C pulls from (nullptr: everything comes from `extra`)
 template <int ENC, typename T, typename TO>
-int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs<T> &w, bool al, TO *acc,
-                 cudaStream_t st)
+int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs &w, const unsigned long long *wq,
+                 const T *extra, const uint8_t *extra_unres, bool al, TO *acc, cudaStream_t st)
 {
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
-    const unsigned gen_blocks = (unsigned)(ntiles < 148 * 4 ? ntiles : 148 * 4);
+    const unsigned gen_blocks = (unsigned)(ntiles < sm_count() * 4 ? ntiles : sm_count() * 4);
     const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
+    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * NSLOT * sizeof(T) + WPB * 8;
     {   // once per device and instantiation
         static bool done[64];
         int dev = 0;
         WMF_CUDA_CHECK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !done[dev]) {
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
-    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * 2 * TH * sizeof(T) + WPB * 8;
 #define WMF_LAUNCH_C(AL_, MK_) \
-    k_sweepC<ENC, AL_, MK_, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.inflow, w.tile_class, w.row_plain, acc)
+    k_sweepC<ENC, AL_, MK_, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, wq, w.tile_top, extra, w.tile_class, w.row_plain, acc)
     if (mask) { if (al) WMF_LAUNCH_C(true, true); else WMF_LAUNCH_C(false, true); }
     else { if (al) WMF_LAUNCH_C(true, false); else WMF_LAUNCH_C(false, false); }
 #undef WMF_LAUNCH_C
-    k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, w.inflow, w.ext_unres, acc);
+    k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, wq, w.par, extra, extra_unres, acc);
     WMF_LAUNCH_CHECK();
     return 0;
 }
 
-// forest walk of the int64 path: weights int32 (first pass) or the int64 copy with stripe inflow added
-template <typename T>
-int sweep_phaseG_i64(const Geo &g, int64_t nnodes, const SweepWs<T> &w, bool use_w64, cudaStream_t st)
+// the packed forest (int32 sums): build, walk, flag what never finalised
+static int sweep_phaseG_packed(const Geo &g, int ntiles, int64_t nnodes, const SweepWs &w, int2 *pe, cudaStream_t st)
 {
-    int rc = use_w64 ? forest_accum_i64w(w.parent, w.w64, (int64_t *)w.A, w.cnt, nnodes, st, w.blocked)
-                     : forest_accum_i64(w.parent, w.exit_acc, (int64_t *)w.A, w.cnt, nnodes, st, w.blocked);
-    if (rc) return rc;
-    k_push_inflow<int64_t><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, (int64_t *)w.A, w.cnt, (int64_t *)w.inflow,
-                                                                    w.ext_unres, w.tile_class);
+    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, pe, w.wq);
+    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
+    k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1640,50 +1827,9 @@ static bool aligned4(const void *dir, const void *mask, const void *acc, int64_t
            (((uintptr_t)acc & 31) == 0);
 }
 
-// T: the type the accumulation is computed in; TO: the type it is stored as (acc_out)
-template <int ENC, typename T, typename TO>
-int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
-                cudaStream_t st)
-{
-    const Geo g = make_geo(ny, nx, 0, ny);
-    const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
-    WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "raster too large for the tiled accumulation");
-    const int ntiles = (int)ntiles64;
-    const int64_t nnodes = ntiles64 * NSLOT;
-    const SweepWs<T> w = carve_ws<T>(ws, ws_bytes, nnodes, ntiles, false);
-    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
-    const bool al = aligned4(dir, mask, acc, nx);
-    unsigned long long *gcnt = w.gcnt;
-    if (sizeof(T) == 4) WMF_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, GCNT_BYTES, st));
-    else {                                                   // (the int32 path has phase A clear them tile by tile)
-        WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(T) * nnodes, st));
-        WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
-    }
-    int rc = sweep_phaseA<ENC, T>(dir, mask, g, ntiles, w, al, st, sizeof(T) == 4 ? (int32_t *)w.inflow : nullptr);
-    if (rc) return rc;
-    if (sizeof(T) == 4) {
-        int32_t *entry = w.cnt;                              // reuse: the packed walk needs no counters
-        int2 *pe = pe_of(w);
-        k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.blocked, pe, w.wq);
-        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, (int32_t *)w.inflow, nullptr, gcnt);
-        k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
-        WMF_LAUNCH_CHECK();
-    } else {
-        k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
-        WMF_LAUNCH_CHECK();
-        rc = sweep_phaseG_i64<T>(g, nnodes, w, false, st);
-        if (rc) return rc;
-    }
-    return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, al, acc, st);
-}
-
-// ---- stripe entry points --------------------------------------------------------------------------
-// The stripe-local pass always runs the packed int32 forest walk (a stripe holds < 2^31 cells); only
-// the finish pass is typed by the output accumulation.
-// The only state the library keeps between calls: one helper stream and two events per device, created on first use.
-// wmf_d8_stripe_local calls on the SAME device must not overlap in time from several host threads (they share the
-// events); everything else is re-entrant.
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+// The only state the library keeps between calls: one helper stream and two events per device, created on first use;
+// a per-device lock serialises the enqueue of wmf_d8_stripe_local calls from several host threads (they share the events).
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; std::mutex busy; };
 static SideStream *side_stream()
 {
     static SideStream tab[64];
@@ -1703,6 +1849,44 @@ static SideStream *side_stream()
     return &tab[dev];
 }
 
+// T: the type the accumulation is computed in; TO: the type it is stored as (acc_out)
+template <int ENC, typename T, typename TO>
+int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
+                cudaStream_t st)
+{
+    const Geo g = make_geo(ny, nx, 0, ny);
+    const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
+    WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "raster too large for the tiled accumulation");
+    const int ntiles = (int)ntiles64;
+    const int64_t nnodes = ntiles64 * NSLOT;
+    const bool wide = sizeof(T) == 8;
+    const SweepWs w = carve_ws(ws, ws_bytes, g, wide, false);
+    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
+    const bool al = aligned4(dir, mask, acc, nx);
+    if (!wide) {
+        WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, GCNT_BYTES, st));
+        int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
+        if (rc) return rc;
+        rc = sweep_phaseG_packed(g, ntiles, nnodes, w, nullptr, st);
+        if (rc) return rc;
+        return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, w.wq, (const T *)nullptr, nullptr, al, acc, st);
+    }
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.inflow, 0, sizeof(int64_t) * nnodes, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.ext_unres, 0, (size_t)nnodes, st));
+    int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
+    if (rc) return rc;
+    k_build_forest<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.parent, w.blocked);
+    WMF_LAUNCH_CHECK();
+    rc = forest_accum_i64(w.parent, w.exit_acc, w.A, w.cnt, nnodes, st, w.blocked);
+    if (rc) return rc;
+    k_push_inflow<int64_t><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.A, w.cnt, w.inflow, w.ext_unres, w.tile_class);
+    WMF_LAUNCH_CHECK();
+    return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, nullptr, (const T *)w.inflow, w.ext_unres, al, acc, st);
+}
+
+// ---- stripe entry points --------------------------------------------------------------------------
+// The stripe-local pass always runs the packed int32 forest walk (a stripe holds < 2^31 cells); only
+// the finish pass is typed by the output accumulation.
 template <int ENC>
 int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
                    int64_t *recs, void *ws, size_t ws_bytes, cudaStream_t st)
@@ -1712,28 +1896,28 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "stripe too large for the tiled accumulation");
     const int ntiles = (int)ntiles64;
     const int64_t nnodes = ntiles64 * NSLOT;
-    const SweepWs<int64_t> w = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true, &g);
+    const SweepWs w = carve_ws(ws, ws_bytes, g, false, true);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, nullptr, nx);
-    int32_t *inflow32 = (int32_t *)w.w64, *entry = w.cnt, *stripe_total = (int32_t *)w.A;
-    unsigned long long *gcnt = w.gcnt;
-    WMF_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, GCNT_BYTES, st));
-    int rc = sweep_phaseA<ENC, int64_t>(dir, mask, g, ntiles, w, al, st, inflow32);
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, GCNT_BYTES, st));
+    int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
     if (rc) return rc;
-    int2 *pe = pe_of(w);
-    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.blocked, pe, w.wq);
+    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, w.pe, w.wq);
     // the path chase needs the forest only: it runs beside the walk (both are latency-bound chains)
     SideStream *ss = side_stream();
     WMF_REQUIRE(ss != nullptr, (int)cudaErrorUnknown, "cannot create the side stream");
-    WMF_CUDA_CHECK(cudaEventRecord(ss->fork, st));
-    WMF_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-    k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, pe, w.sp.mlink);
-    k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, pe, w.sp);
-    WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
-    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, inflow32, stripe_total, gcnt);
-    k_g_unres<<<148 * 8, 256, 0, st>>>(nnodes, w.blocked, pe, w.wq, w.ext_unres, w.tile_class, gcnt);
-    WMF_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
-    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, pe, stripe_total, w.wq, w.sp.plink, recs);
+    {
+        std::lock_guard<std::mutex> lock(ss->busy);
+        WMF_CUDA_CHECK(cudaEventRecord(ss->fork, st));
+        WMF_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+        k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp.mlink);
+        k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp);
+        WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
+        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
+        k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt);
+        WMF_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
+    }
+    k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, w.par, w.wq, w.sp.plink, recs);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1747,22 +1931,18 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny,
     const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
     const int ntiles = (int)ntiles64;
     const int64_t nnodes = ntiles64 * NSLOT;
-    const SweepWs<int64_t> w0 = carve_ws<int64_t>(ws, ws_bytes, nnodes, ntiles, true, &g);
-    WMF_REQUIRE(w0.ok, WMF_E_WORKSPACE, "workspace too small");
+    const SweepWs w = carve_ws(ws, ws_bytes, g, false, true);
+    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, acc, nx);
-    int32_t *inflow32 = (int32_t *)w0.w64, *entry = w0.cnt;
-    // phase-A state, the forest (parent / entry) and the stripe-local inflows are still in the workspace:
-    // widen the inflows to the output type, add what the other stripes send, run phase C.
-    SweepWs<T> w;
-    w.meta = w0.meta; w.exit_acc = w0.exit_acc; w.parent = w0.parent; w.cnt = w0.cnt; w.A = (T *)w0.A;
-    w.inflow = (T *)w0.inflow; w.blocked = w0.blocked; w.ext_unres = w0.ext_unres; w.tile_class = w0.tile_class;
-    w.row_plain = w0.row_plain; w.wq = w0.wq; w.w64 = w0.w64; w.gcnt = w0.gcnt; w.sp = w0.sp; w.ok = true;
-    if (sizeof(T) == 4) w.inflow = (T *)inflow32;            // an int32 accumulation takes the local inflows as they are
-    else k_widen<T><<<blocks_for(nnodes, 256), 256, 0, st>>>(inflow32, w.inflow, nnodes);
-    k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, pe_of(w0), w.sp, ext_inflow, ext_un,
-                                                                                          w.inflow, w.ext_unres, w.tile_class);
+    // phase-A state and the finalised forest words of the stripe-local pass are still in the workspace: what the other
+    // stripes send is routed along the contracted paths into `extra`, and phase C adds it to what it pulls.
+    T *extra = (T *)w.extra;
+    WMF_CUDA_CHECK(cudaMemsetAsync(extra, 0, sizeof(T) * nnodes, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.extra_unres, 0, (size_t)nnodes, st));
+    k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, w.pe, w.sp, ext_inflow, ext_un,
+                                                                                          extra, w.extra_unres, w.tile_class);
     WMF_LAUNCH_CHECK();
-    return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, al, acc, st);
+    return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, w.wq, (const T *)extra, w.extra_unres, al, acc, st);
 }
 
 }  // namespace
@@ -1771,10 +1951,8 @@ int d8_convert_i64_to_f64(void *buf, int64_t n, cudaStream_t st);
 
 size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
 {
-    int64_t ntiles = ((nx + TW - 1) / TW) * ((ny + TH - 1) / TH);
-    size_t nn = (size_t)ntiles * NSLOT, tsz = acc_dtype == WMF_ACC_I32 ? 4 : 8;
-    return 4 * wmf_align(nn * 4) + 2 * wmf_align(nn * 8) + 2 * wmf_align(nn * tsz) + 2 * wmf_align(nn) +
-           wmf_align((size_t)ntiles) + wmf_align((size_t)ntiles * 8) + wmf_align(GCNT_BYTES) + 4096;
+    // (64-bit outputs may take the wide engine: rasters of 2^32 cells and more, or WMF_ACC_WIDE)
+    return carve_ws(nullptr, (size_t)-1, make_geo(ny, nx, 0, ny), acc_dtype != WMF_ACC_I32, false).used + 4096;
 }
 
 // Dispatch on (encoding, arithmetic type, stored type).  A raster with fewer than 2^32 cells is accumulated in 32 bits
@@ -1804,10 +1982,7 @@ extern "C" {
 
 size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx)
 {
-    const Geo g = make_geo(ny, nx, 0, ny);
-    const size_t n2 = (size_t)(2 * nx);
-    return d8_sweep_workspace(ny, nx, WMF_ACC_I64) + wmf_align(n2 * (size_t)stripe_pcap(g) * 4) + 4 * wmf_align(n2 * 4) +
-           wmf_align((size_t)((g.tiles_y + MR - 1) / MR) * (size_t)nx * 4);
+    return carve_ws(nullptr, (size_t)-1, make_geo(ny, nx, 0, ny), false, true).used + 4096;
 }
 
 int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
