@@ -32,4 +32,6 @@ m95 = synth.nodata_mask(n, n, 0.05)
 for name, d, m in (("scheidegger", sch, None), ("scheidegger+all-true mask", sch, m1), ("scheidegger+5% nodata", sch, m95),
                    ("terrain", ter, None), ("terrain+5% nodata", ter, m95)):
     ms, acc = timed(d, m)
-    print(json.dumps({"input": name, "ms": ms, "mcells_s": n * n / ms / 1e3, "acc_sum": int(acc.sum(dtype=torch.int64))}), flush=True)
+    st = {}
+    ops.d8_accum(d, m, out=acc, stats=st)
+    print(json.dumps({"input": name, "tiles": st.get("tile_classes"), "sweeps": st.get("multi_sweeps"), "ms": ms, "mcells_s": n * n / ms / 1e3, "acc_sum": int(acc.sum(dtype=torch.int64))}), flush=True)

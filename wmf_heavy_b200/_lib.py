@@ -48,6 +48,7 @@ SIGNATURES = {
     "wmf_device_info": (_int, [_vp]),
     "wmf_d8_accum_workspace": (_sz, [_i64, _i64, _int, _int]),
     "wmf_d8_accum": (_int, [_vp, _vp, _vp, _int, _i64, _i64, _int, _int, _vp, _sz, _vp]),
+    "wmf_d8_accum_tile_classes": (_int, [_vp, _sz, _i64, _i64, _vp, _vp]),
     "wmf_d8_stripe_workspace": (_sz, [_i64, _i64]),
     "wmf_d8_stripe_local": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _sz, _vp]),
     "wmf_stripe_boundary_workspace": (_sz, [_int, _i64]),

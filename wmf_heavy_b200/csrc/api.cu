@@ -13,6 +13,8 @@ size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype);
 int d8_sweep(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtype, int64_t ny, int64_t nx, int encoding,
              void *ws, size_t ws_bytes, cudaStream_t st);
 
+int d8_sweep_tile_classes(const void *ws, size_t ws_bytes, int64_t ny, int64_t nx, int64_t *counts8, cudaStream_t st);
+
 static thread_local char g_err[512] = "";
 
 void wmf_set_error(const char *fmt, ...)
@@ -90,6 +92,12 @@ int wmf_d8_accum(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtyp
     if (algo == WMF_ALGO_WALK)
         return d8_walk(dir, mask, acc, acc_dtype, ny, nx, encoding, workspace, ws_bytes, as_stream(stream));
     return d8_sweep(dir, mask, acc, acc_dtype, ny, nx, encoding, workspace, ws_bytes, as_stream(stream));
+}
+
+int wmf_d8_accum_tile_classes(const void *workspace, size_t ws_bytes, int64_t ny, int64_t nx, int64_t *counts8_host, void *stream)
+{
+    WMF_REQUIRE(workspace && counts8_host && ny > 0 && nx > 0, WMF_E_ARG, "bad argument");
+    return d8_sweep_tile_classes(workspace, ws_bytes, ny, nx, counts8_host, as_stream(stream));
 }
 
 int wmf_synth_scheidegger(int8_t *dir, int64_t ny, int64_t nx, int64_t row0, int64_t col0, int64_t nx_total,

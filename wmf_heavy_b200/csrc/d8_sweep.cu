@@ -1088,6 +1088,398 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
 }
 
 // ---------------------------------------------------------------------------------------------
+// multi-sweep solver: tiles with in-tile upward flow (every tile of a real DEM)
+// ---------------------------------------------------------------------------------------------
+// A row sweep follows a path as long as it moves with the sweep (or sideways); flow against the sweep waits for the
+// next sweep in the opposite direction.  A path with r vertical runs is settled after r (+1) sweeps -- typically 3-5 on
+// terrain at this tile height -- and a tile whose sweeps stop making progress holds a cycle and goes to the chain-walk
+// solver.  One warp per tile as in the one-pass solver; the tile's decoded codes (a nibble per cell: 0..7, 8 none,
+// 9 inactive) stay in shared memory for all sweeps and are handed to phase C; the state that crosses sweeps lives in a
+// scratch raster (labels in phase A, waiting flow in phase C).
+//   phase A  label[c] = label[receiver(c)]: a sweep takes the labels of the row it has just left from registers and
+//            those of the row it has not reached yet from the previous sweep (LUNK until known).  The histogram of the
+//            last sweep is exit_acc.
+//   phase C  flow in transit: acc[c] counts what has arrived at c so far, wait[c] what has arrived but could not
+//            move on because c drains against the sweep.  A sweep moves everything it meets as far as it can; integer
+//            adds, so the order in which the flow arrives does not matter.  Done when nothing waits.
+// Up-sweeps run the down-sweep's row arithmetic on mirrored codes (NE<->SE, N<->S, NW<->SW).
+constexpr uint32_t LUNK = 1022u;            // label not known yet (a histogram bin no slot uses)
+constexpr int MAX_SWEEPS = 24;
+static_assert(NSLOT <= (int)LUNK, "LUNK is not a slot");
+constexpr int MWPB = 4;                     // warps (tiles) per block of the multi-sweep kernels
+
+__device__ __forceinline__ int mirror_k(int k) { return k < 8 ? ((8 - k) & 7) : k; }
+
+// decode the whole tile into nibbles: codes[lr * 32 + lane] holds the lane's NC cells of row lr.  Returns false when the
+// tile has an adjacent E -> W pair (a two-cycle: not for the sweeps); top_up: upward flow in the first row.
+template <int ENC>
+__device__ __forceinline__ bool multi_decode(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, const Geo &g, int ty, int tx,
+                                             int th, int tw, int lane, uint32_t *codes, bool &top_up)
+{
+    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
+    const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
+    bool two = false, up0 = false;
+    for (int lr = 0; lr < TH; lr++) {
+        uint32_t cw = 0x99999999u;
+        if (lr < th) {
+            cw = 0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                int kk = 9;
+                if (gc0 + j < g.nx) {
+                    const int64_t gi = (gr0 + lr) * g.nx + gc0 + j;
+                    if (mask == nullptr || mask[gi] != 0) {
+                        kk = d8_norm<ENC>((int)dir[gi]);
+                        if (border && kk != 8) {
+                            const int64_t rr = g.gy0 + gr0 + lr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
+                            if (rr < 0 || rr >= g.gny || cc < 0 || cc >= g.nx) kk = 8;
+                        }
+                    }
+                }
+                cw |= (uint32_t)kk << (4 * j);
+            }
+            // E -> W adjacent pairs, inside the lane and across lanes
+            const uint32_t first_right = __shfl_down_sync(FULL, cw & 15u, 1);
+            bool tc = lane < 31 && (cw >> 28) == 0u && first_right == 4u;
+#pragma unroll
+            for (int j = 0; j + 1 < NC; j++) tc = tc || (((cw >> (4 * j)) & 15u) == 0u && ((cw >> (4 * j + 4)) & 15u) == 4u);
+            two = two || tc;
+            if (lr == 0) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) { const uint32_t kk = (cw >> (4 * j)) & 15u; up0 = up0 || (kk >= 5u && kk <= 7u); }
+            }
+        }
+        codes[lr * 32 + lane] = cw;
+    }
+    top_up = __any_sync(FULL, up0);
+    return !__any_sync(FULL, two);
+}
+
+// Label row, branch-free.  The candidate labels of a row are staged in a small per-lane table in shared memory --
+// [0..9] the row behind with one cell of halo on either side, [10..19] the row ahead likewise, then eight copies each of
+// "no exit", the East marker and the West marker -- and a cell fetches entry j + OFF[code]: OFF is a 6-bit-per-code
+// lookup word, mirrored for the sweeps that run top -> bottom.
+constexpr int LTAB = 45;                    // words per lane (44 used; odd stride: no bank conflicts)
+constexpr uint32_t MARK_E = 0x10000u, MARK_W = 0x20000u;
+__host__ __device__ constexpr unsigned long long off_lut(bool mirrored)
+{
+    // code (real orientation) -> table offset; behind = the row below for a bottom -> top sweep
+    //   bottom -> top: SE 1 -> 2, S 2 -> 1, SW 3 -> 0 (behind); NW 5 -> 10, N 6 -> 11, NE 7 -> 12 (ahead)
+    //   top -> bottom: the roles of the two rows swap: NE 7 -> 2, N 6 -> 1, NW 5 -> 0; SW 3 -> 10, S 2 -> 11, SE 1 -> 12
+    const int nat[10] = {28, 2, 1, 0, 36, 10, 11, 12, 20, 20}, mir[10] = {28, 12, 11, 10, 36, 0, 1, 2, 20, 20};
+    unsigned long long v = 0;
+    for (int k = 0; k < 10; k++) v |= (unsigned long long)(mirrored ? mir[k] : nat[k]) << (6 * k);
+    return v;
+}
+
+template <int ENC>
+__global__ void __launch_bounds__(MWPB * 32) k_multiA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
+                                                      uint32_t *__restrict__ meta, int32_t *__restrict__ exit_acc,
+                                                      uint8_t *__restrict__ tile_class, unsigned long long *__restrict__ wq,
+                                                      uint8_t *__restrict__ tile_top, uint32_t *__restrict__ codes4,
+                                                      uint16_t *__restrict__ labels, unsigned long long *__restrict__ sweeps_of)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [MWPB][TH * 32] codes + [MWPB][HBINS] histogram + [MWPB][32 * LTAB] tables
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * MWPB + warp;
+    if (tile >= ntiles || tile_class[tile] != 1) return;
+    int ty, tx, th, tw;
+    tile_dims(g, tile, ty, tx, th, tw);
+    uint32_t *codes = s_dyn + (size_t)warp * TH * 32;
+    int *hist = reinterpret_cast<int *>(s_dyn + (size_t)MWPB * TH * 32) + HBINS * warp;
+    uint32_t *tab = s_dyn + (size_t)MWPB * (TH * 32 + HBINS) + (size_t)warp * 32 * LTAB + lane * LTAB;
+    const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
+    uint32_t *m_t = meta + (int64_t)tile * NSLOT;
+    uint16_t *lab_t = labels + (int64_t)tile * TH * TW + NC * lane;
+    const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;
+    bool top_up = false;
+    bool ok = multi_decode<ENC>(dir, mask, g, ty, tx, th, tw, lane, codes, top_up);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { tab[20 + j] = LNONE; tab[28 + j] = MARK_E; tab[36 + j] = MARK_W; }
+    __syncwarp();
+    {   // phase C of this tile starts from the decoded codes
+        uint32_t *c4 = codes4 + (int64_t)tile * TH * 32;
+        for (int lr = 0; lr < TH; lr++) c4[lr * 32 + lane] = codes[lr * 32 + lane];
+    }
+    int prev_unknown = TH * TW + 1, nsweeps = 0;
+    for (int sweep = 0; ok; sweep++) {
+        nsweeps = sweep + 1;
+        const bool up = (sweep & 1) == 0;           // sweep 0 runs bottom -> top: it settles every path that only descends
+        const unsigned long long lut = up ? off_lut(false) : off_lut(true);
+#pragma unroll
+        for (int q = 0; q < HBINS / 128; q++) *reinterpret_cast<int4 *>(hist + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
+        __syncwarp();
+        uint32_t lbB[NC];                            // labels of the row the sweep has just left ("behind")
+#pragma unroll
+        for (int j = 0; j < NC; j++) lbB[j] = LNONE;
+        int unknown;
+        for (int step = 0; step < th; step++) {
+            const int lr = up ? th - 1 - step : step;
+            const uint32_t cw = codes[lr * 32 + lane];
+            uint32_t lbA[NC];                        // labels of the row ahead, as the previous sweep left them
+            if (sweep > 0 && step + 1 < th) {
+                const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(lab_t + (int64_t)(up ? lr - 1 : lr + 1) * TW));
+                lbA[0] = q.x & 0xFFFFu; lbA[1] = q.x >> 16; lbA[2] = q.y & 0xFFFFu; lbA[3] = q.y >> 16;
+                lbA[4] = q.z & 0xFFFFu; lbA[5] = q.z >> 16; lbA[6] = q.w & 0xFFFFu; lbA[7] = q.w >> 16;
+            } else {
+#pragma unroll
+                for (int j = 0; j < NC; j++) lbA[j] = LUNK;
+            }
+            // candidate table of this lane
+            tab[0] = __shfl_up_sync(FULL, lbB[NC - 1], 1);
+            tab[9] = __shfl_down_sync(FULL, lbB[0], 1);
+            tab[10] = __shfl_up_sync(FULL, lbA[NC - 1], 1);
+            tab[19] = __shfl_down_sync(FULL, lbA[0], 1);
+#pragma unroll
+            for (int j = 0; j < NC; j++) { tab[1 + j] = lbB[j]; tab[11 + j] = lbA[j]; }
+            __syncwarp();
+            uint32_t own[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const uint32_t kr = (cw >> (4 * j)) & 15u;
+                own[j] = tab[j + ((uint32_t)(lut >> (6u * kr)) & 63u)];
+            }
+            __syncwarp();
+            // cells whose receiver lies outside the tile carry their own slot: the first / last row of the sweep entirely,
+            // otherwise only the two side columns (codes SW / W / NW on the left, NE / E / SE on the right: the same sets
+            // in either sweep direction)
+            if (step == 0 || step == th - 1 || tw != TW) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const int lc = NC * lane + j, kr = (int)((cw >> (4 * j)) & 15u);
+                    const int kk = up ? kr : mirror_k(kr);       // sweep coordinates: 1..3 drain behind, 5..7 ahead
+                    const bool exits = (step == 0 && kk >= 1 && kk <= 3) || (step == th - 1 && kk >= 5 && kk <= 7) ||
+                                       (lc == tw - 1 && (kk == 0 || kk == 1 || kk == 7)) || (lc == 0 && kk >= 3 && kk <= 5);
+                    if (exits) own[j] = (uint32_t)slot_of(lr, lc, th, tw);
+                }
+            } else {
+                const uint32_t k0 = cw & 15u, k7 = cw >> 28;
+                if (lane == 0 && k0 >= 3u && k0 <= 5u) own[0] = (uint32_t)(2 * TW + lr);
+                if (lane == 31 && (k7 <= 1u || k7 == 7u)) own[NC - 1] = (uint32_t)(2 * TW + TH + lr);
+            }
+            uint32_t lab[NC];
+            {   // East cells copy the label of the chain end on their right
+                uint32_t V = LNONE;
+                bool P = true;
+#pragma unroll
+                for (int j = NC - 1; j >= 0; j--) { const bool e = own[j] == MARK_E; V = e ? V : own[j]; P = P && e; }
+                uint32_t cur = label_carry_from_right(V, P, lane);
+#pragma unroll
+                for (int j = NC - 1; j >= 0; j--) { cur = own[j] == MARK_E ? cur : own[j]; lab[j] = cur; }
+            }
+            bool anyw = false;
+#pragma unroll
+            for (int j = 0; j < NC; j++) anyw = anyw || own[j] == MARK_W;
+            if (__any_sync(FULL, anyw)) {
+                uint32_t V = LNONE;
+                bool P = true;
+#pragma unroll
+                for (int j = 0; j < NC; j++) { const bool ww = own[j] == MARK_W; V = ww ? V : lab[j]; P = P && ww; }
+                uint32_t cur = label_carry_from_left(V, P, lane);
+#pragma unroll
+                for (int j = 0; j < NC; j++) { cur = own[j] == MARK_W ? cur : lab[j]; lab[j] = cur; }
+            }
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                lbB[j] = lab[j];
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_sa + 4u * lab[j]) : "memory");
+            }
+            *reinterpret_cast<uint4 *>(lab_t + (int64_t)lr * TW) =
+                make_uint4(lab[0] | (lab[1] << 16), lab[2] | (lab[3] << 16), lab[4] | (lab[5] << 16), lab[6] | (lab[7] << 16));
+            // boundary slots (the last sweep's values stand)
+            if (lr == 0 || lr == th - 1) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const int kr = (int)((cw >> (4 * j)) & 15u);
+                    if (NC * lane + j < tw) m_t[(lr == 0 ? 0 : TW) + NC * lane + j] = meta_pack(lab[j], kr < 8 ? kr : 8, false, kr != 9);
+                }
+            } else {
+                if (lane == 0) { const int kr = (int)(cw & 15u); m_t[2 * TW + lr] = meta_pack(lab[0], kr < 8 ? kr : 8, false, kr != 9); }
+                if (lane == rlane && tw > 1) {
+#pragma unroll
+                    for (int j = 0; j < NC; j++) {
+                        const int kr = (int)((cw >> (4 * j)) & 15u);
+                        if (j == rj) m_t[2 * TW + TH + lr] = meta_pack(lab[j], kr < 8 ? kr : 8, false, kr != 9);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        unknown = hist[LUNK];                        // the labels still unknown are one of the bins
+        if (unknown == 0) break;
+        if (unknown >= prev_unknown || sweep + 1 >= MAX_SWEEPS) { ok = false; break; }   // no progress: a cycle
+        prev_unknown = unknown;
+    }
+    if (!ok) {                                       // the chain-walk solver redoes this tile
+        if (lane == 0) { tile_class[tile] = 3; tile_top[tile] = 1; }
+        return;
+    }
+    if (lane == 0) { tile_class[tile] = 4; tile_top[tile] = (top_up || th != TH || tw != TW) ? 1 : 0; sweeps_of[tile] = (unsigned long long)nsweeps; }
+    // unused slots of a ragged tile: inactive
+    if (th != TH || tw != TW) {
+        for (int s = lane; s < NSLOT; s += 32) { int lr, lc; if (!cell_of(s, th, tw, lr, lc)) m_t[s] = 0u; }
+    }
+    __syncwarp();
+    // exit_acc of every slot = its bin; the forest word = one pending arrival | code | weight
+    int32_t *x_t = exit_acc ? exit_acc + (int64_t)tile * NSLOT : nullptr;
+    unsigned long long *w_t = wq + (int64_t)tile * NSLOT;
+    for (int s = lane; s < NSLOT; s += 32) {
+        const uint32_t m = __ldcg(m_t + s);
+        const int h = hist[s];
+        if (x_t) x_t[s] = h;
+        w_t[s] = PEND1 | ((unsigned long long)((m >> 16) & 0xFu) << W_K) | (uint32_t)h;
+    }
+}
+
+template <typename TO, typename T>
+__device__ __forceinline__ T acc_in(TO v)
+{
+    if (sizeof(T) == 4 && sizeof(TO) == 8) return (T)(uint32_t)v;          // (see acc_out)
+    return (T)v;
+}
+
+// NC consecutive values of the scratch raster (16-byte pieces; the tile rows are 16-byte aligned)
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, T (&v)[NC])
+{
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int q = 0; q < NC / PER; q++) {
+        const uint4 x = __ldcg(reinterpret_cast<const uint4 *>(p) + q);
+        memcpy(&v[PER * q], &x, 16);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T *p, const T (&v)[NC])
+{
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int q = 0; q < NC / PER; q++) {
+        uint4 x;
+        memcpy(&x, &v[PER * q], 16);
+        reinterpret_cast<uint4 *>(p)[q] = x;
+    }
+}
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(MWPB * 32) k_multiC(Geo g, int ntiles, const uint32_t *__restrict__ codes4,
+                                                      const unsigned long long *__restrict__ wq, const uint8_t *__restrict__ tile_top,
+                                                      const T *__restrict__ extra, const uint8_t *__restrict__ tile_class,
+                                                      T *__restrict__ wait, TO *__restrict__ acc, unsigned long long *__restrict__ sweeps_of)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [MWPB][TH * 32] codes + [MWPB][NSLOT] boundary inflows (T)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * MWPB + warp;
+    if (tile >= ntiles || tile_class[tile] != 4) return;
+    int ty, tx, th, tw;
+    tile_dims(g, tile, ty, tx, th, tw);
+    uint32_t *codes = s_dyn + (size_t)warp * TH * 32;
+    T *ext = reinterpret_cast<T *>(s_dyn + (size_t)MWPB * TH * 32) + NSLOT * warp;
+    {
+        const uint32_t *c4 = codes4 + (int64_t)tile * TH * 32;
+        for (int lr = 0; lr < TH; lr++) codes[lr * 32 + lane] = __ldcg(c4 + lr * 32 + lane);
+    }
+    tile_inflow<T>(g, wq, tile_top, extra, tile, ty, tx, th, tw, lane, ext);
+    const T *extL = ext + 2 * TW, *extR = ext + 2 * TW + TH;
+    const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;
+    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
+    const bool al = (g.nx % NC == 0) && ((reinterpret_cast<uintptr_t>(acc) & 31) == 0);
+    TO *acc_t = acc + gr0 * g.nx + gc0;
+    T *wait_t = wait + (int64_t)tile * TH * TW + NC * lane;
+    bool dummy = false;
+    unsigned long long rows_waiting = 0;             // rows that hold waiting flow (warp-uniform)
+    for (int sweep = 0; sweep < MAX_SWEEPS + 2; sweep++) {
+        const bool down = (sweep & 1) == 0;
+        unsigned long long next_waiting = 0;
+        T d[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) d[j] = 0;
+        bool d_any = false;
+        for (int step = 0; step < th; step++) {
+            const int lr = down ? step : th - 1 - step;
+            // later sweeps touch a row only when something waits in it or arrives from the row behind
+            if (sweep > 0 && !d_any && !((rows_waiting >> lr) & 1ull)) continue;
+            const uint32_t cw = codes[lr * 32 + lane];
+            int k[NC], am = 0;
+            bool holds[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const int kr = (int)((cw >> (4 * j)) & 15u);
+                am |= (kr != 9) << j;
+                k[j] = kr >= 8 ? 8 : (down ? kr : mirror_k(kr));  // sweep coordinates: 1..3 drain ahead, 5..7 behind
+                holds[j] = k[j] >= 5 && k[j] <= 7;
+            }
+            T a[NC], w[NC], b[NC];
+            if (sweep == 0) {                        // everything starts as "arrived, not moved on": 1 + the external inflow
+                T ex[NC];
+#pragma unroll
+                for (int j = 0; j < NC; j++) ex[j] = 0;
+                if (lr == 0 || lr == th - 1) {
+                    const T *e4 = ext + (lr == 0 ? 0 : TW) + NC * lane;
+#pragma unroll
+                    for (int j = 0; j < NC; j++) ex[j] = e4[j];
+                } else {
+                    if (lane == 0) ex[0] = extL[lr];
+                    if (lane == rlane && tw > 1) {
+#pragma unroll
+                        for (int j = 0; j < NC; j++) if (j == rj) ex[j] += extR[lr];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NC; j++) { w[j] = ((am >> j) & 1) ? (T)1 + ex[j] : (T)0; a[j] = w[j]; }
+            } else {
+                if (al && gc0 < g.nx) {
+                    TO av[NC];
+                    if (sizeof(TO) == 4) {
+                        const uint4 *p = reinterpret_cast<const uint4 *>(acc_t + (int64_t)lr * g.nx);
+                        const uint4 x = __ldcg(p), y = __ldcg(p + 1);
+                        uint32_t u[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int j = 0; j < NC; j++) memcpy(&av[j], &u[j], 4);
+                    } else {
+                        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(acc_t + (int64_t)lr * g.nx);
+#pragma unroll
+                        for (int q = 0; q < NC / 2; q++) { const ulonglong2 x = __ldcg(p + q); memcpy(&av[2 * q], &x.x, 8); memcpy(&av[2 * q + 1], &x.y, 8); }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NC; j++) a[j] = acc_in<TO, T>(av[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC; j++) a[j] = gc0 + j < g.nx ? acc_in<TO, T>(__ldcg(acc_t + (int64_t)lr * g.nx + j)) : (T)0;
+                }
+                load8<T>(wait_t + (int64_t)lr * TW, w);
+            }
+            // cells that do not drain against the sweep release what waits in them
+            T rel[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) { rel[j] = holds[j] ? (T)0 : w[j]; b[j] = ((am >> j) & 1) ? d[j] + rel[j] : (T)0; }
+            T tot[NC];
+            sweep_row_down<T>(k, am, b, tot, d, lane, dummy);      // d: what moves on into the row ahead
+            bool wany = false, dn = false;
+            T tt[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const T arrived = tot[j] - rel[j];                 // new at this cell in this sweep
+                tt[j] = a[j] + arrived;
+                w[j] = holds[j] ? w[j] + arrived : (T)0;
+                wany = wany || w[j] != 0;
+                dn = dn || d[j] != 0;
+            }
+            store_row<true, T, TO>(acc_t + (int64_t)lr * g.nx, tt, al ? gc0 : g.nx, g.nx);
+            if (!al) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) if (gc0 + j < g.nx) acc_t[(int64_t)lr * g.nx + j] = acc_out<TO, T>(tt[j]);
+            }
+            store8<T>(wait_t + (int64_t)lr * TW, w);
+            if (__any_sync(FULL, wany)) next_waiting |= 1ull << lr;
+            d_any = __any_sync(FULL, dn);
+        }
+        rows_waiting = next_waiting;
+        if (rows_waiting == 0) { if (lane == 0) sweeps_of[tile] |= (unsigned long long)(sweep + 1) << 32; break; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // general tile solver (one block per tile, chain walk in shared memory), phases A and C
 // ---------------------------------------------------------------------------------------------
 constexpr int GTH = 256;   // threads per block
@@ -1245,11 +1637,13 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
     extern __shared__ __align__(16) unsigned char smem[];
   const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
   bool any_mine = false;
-  for (int t = t_lo + threadIdx.x; t < t_hi; t += GTH) any_mine = any_mine || tile_class[t] != 0;
+  // classes: 0 one-pass sweeps, 4 multi-sweep; everything else (1 / 3: the sweeps cannot solve it, 2: fed by an unresolved
+  // upstream) is solved here
+  for (int t = t_lo + threadIdx.x; t < t_hi; t += GTH) any_mine = any_mine || (tile_class[t] != 0 && tile_class[t] != 4);
   if (!__syncthreads_or(any_mine)) return;
   const TileGeo tg = tile_geo(g);
   for (int tile = t_lo; tile < t_hi; tile++) {
-    if (tile_class[tile] == 0) continue;
+    if (tile_class[tile] == 0 || tile_class[tile] == 4) continue;
     __syncthreads();
     T *acc = reinterpret_cast<T *>(smem);
     uint8_t *kk = smem + sizeof(T) * TCELLS;
@@ -1681,6 +2075,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
 // arrives from the other stripes.
 struct SweepWs {
     uint32_t *meta; unsigned long long *wq; int32_t *par; uint8_t *tile_class, *tile_top; unsigned long long *row_plain, *gcnt;
+    uint32_t *codes4; void *scratch;                                          // multi-sweep solver: decoded tiles, state across sweeps
     int32_t *exit_acc, *parent, *cnt; int64_t *A, *inflow; uint8_t *blocked, *ext_unres;   // wide
     int2 *pe; void *extra; uint8_t *extra_unres;                              // stripe
     StripePaths sp;
@@ -1701,6 +2096,10 @@ static SweepWs carve_ws(void *ws, size_t ws_bytes, const Geo &g, bool wide, bool
     w.tile_top = cur.take<uint8_t>(nt);
     w.row_plain = cur.take<unsigned long long>(nt);
     w.gcnt = cur.take<unsigned long long>(GCNT_BYTES / sizeof(unsigned long long));
+    if (!wide) {                                              // (the 64-bit forest engine keeps the chain-walk solver for such tiles)
+        w.codes4 = cur.take<uint32_t>(nt * TH * 32);
+        w.scratch = stripe ? (void *)cur.take<int64_t>(nt * TH * TW) : (void *)cur.take<int32_t>(nt * TH * TW);
+    }
     if (wide) {
         w.exit_acc = cur.take<int32_t>(nn);
         w.parent = cur.take<int32_t>(nn);
@@ -1774,6 +2173,20 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     if (mask) { if (al) WMF_LAUNCH_A(true, true); else WMF_LAUNCH_A(false, true); }
     else { if (al) WMF_LAUNCH_A(true, false); else WMF_LAUNCH_A(false, false); }
 #undef WMF_LAUNCH_A
+    if (w.codes4) {                                          // tiles with upward flow: alternating sweeps
+        const size_t smemM = (size_t)MWPB * (TH * 32 * sizeof(uint32_t) + HBINS * sizeof(int) + 32 * LTAB * sizeof(uint32_t));
+        {
+            static bool done[64];
+            int dev = 0;
+            WMF_CUDA_CHECK(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= 64 || !done[dev]) {
+                WMF_CUDA_CHECK(cudaFuncSetAttribute(k_multiA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemM));
+                if (dev >= 0 && dev < 64) done[dev] = true;
+            }
+        }
+        k_multiA<ENC><<<(ntiles + MWPB - 1) / MWPB, MWPB * 32, smemM, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.wq,
+                                                                            w.tile_top, w.codes4, (uint16_t *)w.scratch, w.row_plain);
+    }
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -1794,6 +2207,7 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
         WMF_CUDA_CHECK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !done[dev]) {
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_multiC<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -1806,6 +2220,11 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     if (mask) { if (al) WMF_LAUNCH_C(true, true); else WMF_LAUNCH_C(false, true); }
     else { if (al) WMF_LAUNCH_C(true, false); else WMF_LAUNCH_C(false, false); }
 #undef WMF_LAUNCH_C
+    if (w.codes4 && wq) {
+        const size_t smemM = (size_t)MWPB * (TH * 32 * sizeof(uint32_t) + NSLOT * sizeof(T));
+        k_multiC<T, TO><<<(ntiles + MWPB - 1) / MWPB, MWPB * 32, smemM, st>>>(g, ntiles, w.codes4, wq, w.tile_top, extra, w.tile_class,
+                                                                              (T *)w.scratch, acc, w.row_plain);
+    }
     k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, wq, w.par, extra, extra_unres, acc);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -1952,7 +2371,41 @@ int d8_convert_i64_to_f64(void *buf, int64_t n, cudaStream_t st);
 size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
 {
     // (64-bit outputs may take the wide engine: rasters of 2^32 cells and more, or WMF_ACC_WIDE)
-    return carve_ws(nullptr, (size_t)-1, make_geo(ny, nx, 0, ny), acc_dtype != WMF_ACC_I32, false).used + 4096;
+    const Geo g = make_geo(ny, nx, 0, ny);
+    const size_t narrow = carve_ws(nullptr, (size_t)-1, g, false, false).used;
+    const size_t wide = acc_dtype != WMF_ACC_I32 ? carve_ws(nullptr, (size_t)-1, g, true, false).used : 0;
+    return (narrow > wide ? narrow : wide) + 4096;
+}
+
+// How the tiles of the last accumulation that used this workspace were solved: counts[c] = tiles of class c
+// (0 one-pass sweeps, 4 multi-sweep, 1 / 3 chain walk, 2 chain walk because of an unresolved upstream).  Syncs.
+int d8_sweep_tile_classes(const void *ws, size_t ws_bytes, int64_t ny, int64_t nx, int64_t *counts8, cudaStream_t st)
+{
+    const Geo g = make_geo(ny, nx, 0, ny);
+    const SweepWs w = carve_ws(const_cast<void *>(ws), ws_bytes, g, false, false);
+    WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
+    const size_t nt = (size_t)g.tiles_x * (size_t)g.tiles_y;
+    uint8_t *h = (uint8_t *)malloc(nt);
+    WMF_REQUIRE(h != nullptr, WMF_E_ARG, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(h, w.tile_class, nt, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { free(h); wmf_set_error("d8_sweep_tile_classes: %s", cudaGetErrorString(e)); return (int)e; }
+    for (int c = 0; c < 8; c++) counts8[c] = 0;
+    for (size_t t = 0; t < nt; t++) counts8[h[t] & 7]++;
+    // sweeps the multi-sweep tiles took: [5] phase A total, [6] phase C total, [7] the largest of either
+    unsigned long long *sw = (unsigned long long *)malloc(nt * 8);
+    if (sw && cudaMemcpy(sw, w.row_plain, nt * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        for (size_t t = 0; t < nt; t++)
+            if (h[t] == 4) {
+                const int64_t a = (int64_t)(sw[t] & 0xFFFFFFFFu), c = (int64_t)(sw[t] >> 32);
+                counts8[5] += a; counts8[6] += c;
+                if (a > counts8[7]) counts8[7] = a;
+                if (c > counts8[7]) counts8[7] = c;
+            }
+    }
+    free(sw);
+    free(h);
+    return 0;
 }
 
 // Dispatch on (encoding, arithmetic type, stored type).  A raster with fewer than 2^32 cells is accumulated in 32 bits

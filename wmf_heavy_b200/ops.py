@@ -24,8 +24,10 @@ def _chk_dev(t: torch.Tensor, dtype, name: str):
 
 # --------------------------------------------------------------------------------------- D1
 def d8_accum(dir_t: torch.Tensor, mask_t: Optional[torch.Tensor] = None, acc_dtype: int = ACC_I32,
-             encoding: int = ENC_INTERNAL, algo: int = ALGO_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Full-raster D8 accumulation (replaces wmf_py/cu_py/basics.py:124-177)."""
+             encoding: int = ENC_INTERNAL, algo: int = ALGO_AUTO, out: Optional[torch.Tensor] = None,
+             stats: Optional[dict] = None) -> torch.Tensor:
+    """Full-raster D8 accumulation (replaces wmf_py/cu_py/basics.py:124-177).  ``stats`` (a dict) receives
+    ``tile_classes``: how many tiles each solver took (diagnostic, synchronises)."""
     require_cuda()
     _chk_dev(dir_t, torch.int8, "dir")
     ny, nx = dir_t.shape
@@ -40,6 +42,13 @@ def d8_accum(dir_t: torch.Tensor, mask_t: Optional[torch.Tensor] = None, acc_dty
     ws = workspace(nb)
     check(lib.wmf_d8_accum(ptr(dir_t), ptr(mask_t), ptr(out), acc_dtype, ny, nx, encoding, algo, ptr(ws), ws.numel(),
                            stream_ptr()))
+    if stats is not None and algo != ALGO_WALK and ny * nx <= 0xFFFFFFFF:
+        cnt = (C.c_int64 * 8)()
+        check(lib.wmf_d8_accum_tile_classes(ptr(ws), ws.numel(), ny, nx, C.addressof(cnt), stream_ptr()))
+        c = list(cnt)
+        stats["tile_classes"] = {"one_pass": c[0], "multi_sweep": c[4], "chain_walk": c[1] + c[3], "chain_walk_unresolved_upstream": c[2]}
+        if c[4]:
+            stats["multi_sweeps"] = {"phase_a_mean": c[5] / c[4], "phase_c_mean": c[6] / c[4], "max": c[7]}
     return out
 
 
