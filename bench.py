@@ -6,16 +6,22 @@
 Primary metric (BASELINE.json): D8 flow-accumulation throughput in Mcells/s on a synthetic
 16384 x 16384 Scheidegger DIR raster (int8 DIR resident in HBM -> int32 ACC resident in HBM; every
 pass of the accumulation inside the timed region).  A "step" is one full accumulation of the raster.
-Secondary (reported in the same line under "shia"): SHIA cell-timesteps/s on a synthetic 1 Mi-cell
-basin x 1000 intervals (BASELINE config 3).
+The same JSON line carries
+  parity_checked  the GPU accumulation of the benchmark raster equals the CPU oracle's, cell for cell (N = 1);
+  secondary       the same accumulation, same size, on the other input classes of SURVEY 8(d): steepest-descent
+                  terrain with all eight directions and pits, Scheidegger with an explicit all-true mask (what every
+                  reference call passes) and with 5 % nodata -- with the share of tiles each tile solver took;
+  shia            SHIA cell-timesteps/s (BASELINE configs 3 and 5): the Fortran 5-tank update with type-1 and type-2
+                  speeds, the wmf_py 3-tank fp64 update, a population of 512 parameter sets, each with its roofline
+                  figure, and the CPU restatement timed beside it.
 
-N > 1 (torchrun, one rank per GPU): the raster is (N*size) x size, row-striped, one stripe per rank
-(weak scaling); see DESIGN.md "Multi-GPU".  Timing: CUDA events on the launching stream, barrier +
-synchronize on both sides, max over ranks.  Inputs (268 MB DIR + 1 GB ACC) exceed the 126 MB L2, so no
-explicit flush is needed between iterations (stated in config.l2).
+N > 1 (torchrun, one rank per GPU): the raster is (N*size) x size, row-striped, one stripe per rank (weak scaling);
+SHIA cells and parameter sets are sharded across the ranks with their gather inside the timed region.
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Inputs (268 MB DIR +
+1 GB ACC) exceed the 126 MB L2, so no explicit flush is needed between iterations (stated in config.l2).
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/, gcc -O2, 1 thread: the
-reference is single-threaded by construction) on a bounded window of the same workload.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, gcc -O2, 1 thread: the reference is
+single-threaded by construction) on a bounded window of the same raster; it imports nothing of the product.
 """
 from __future__ import annotations
 
@@ -23,7 +29,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -35,7 +40,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "D8 flow-accum Mcells/s (16k² raster); SHIA cell-timesteps/s at 1/2/4/8 B200"
 SEED = 20260101
-ALGO_BYTES_PER_CELL = 5.0      # 1 B int8 DIR read + 4 B int32 ACC write
+
+
+def workload_config(n: int, world: int, acc_name: str, algo: str = "auto") -> dict:
+    """`config` of the JSON line: the same for both arms (the reference arm names its bounded sample in cpu_baseline)."""
+    return {"workload": f"D8 flow accumulation, synthetic Scheidegger DIR {n}x{n} per GPU (seed {SEED}), "
+                        f"int8 DIR -> {acc_name} ACC, mask = all valid", "algo": algo,
+            "parallelism": "1 GPU" if world == 1 else
+            f"{world} row stripes of {n} rows of one {world * n}x{n} raster, one NCCL all-gather of the "
+            "boundary records per accumulation",
+            "l2": "inputs (DIR 0.27 GB + ACC 1.07 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 def measured_peaks():
@@ -46,6 +60,16 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled(key: str):
+    """Figures that only a profiler can give (DRAM bytes per accumulation, issue-slot utilisation), taken from the
+    committed ncu captures of THIS build by tools/profile_figures.py -> profiles/r02_figures.json; None when absent."""
+    p = os.path.join(ROOT, "profiles", "r02_figures.json")
+    try:
+        return json.load(open(p)).get(key)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -111,47 +135,72 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_oracle_accum(sample: int, steps: int = 1):
-    """Time the CPU restatement (oracle, 1 thread) on the top-left sample x sample window of the workload."""
+# ------------------------------------------------------------------------------------------ CPU legs (oracle only)
+def cpu_oracle_accum(rows: int, n: int, steps: int = 1):
+    """Time the CPU restatement (oracle, 1 thread) on the first `rows` rows of the n x n benchmark raster (a true
+    window of it: same generator, same keys).  Returns (Mcells/s, times, the accumulation of the window)."""
     import oracle
-    from wmf_heavy_b200 import ops
-    fd = ops.synth_scheidegger_host(sample, sample, seed=SEED, nx_total=sample)
-    mask = np.ones((sample, sample), dtype=bool)
+    fd = oracle.synth_scheidegger(rows, n, seed=SEED, nx_total=n)
+    mask = np.ones((rows, n), dtype=bool)
     oracle.basin_acum(fd[:64, :64], mask[:64, :64])           # build/load outside the timed region
-    times = []
+    times, acc = [], None
     for _ in range(steps):
         t0 = time.perf_counter()
         acc = oracle.basin_acum(fd, mask)
         times.append(time.perf_counter() - t0)
-    return sample * sample / 1e6 / statistics.median(times), times, acc
+    return rows * n / 1e6 / statistics.median(times), times, acc
 
 
 def run_reference(args, rank: int, world: int):
+    """The reference arm: the reference's algorithm (wmf_py basin_acum, a sequential in-degree queue) as its C
+    restatement, on the box's host cores.  The algorithm is single-threaded by construction, so it uses one."""
     if rank != 0:
         return
-    sample = args.ref_sample
-    for _ in range(args.warmup and 1):
-        cpu_oracle_accum(min(sample, 1024), 1)
+    n, rows = args.size, min(args.ref_rows, args.size)
+    for _ in range(1 if args.warmup else 0):
+        cpu_oracle_accum(min(rows, 512), n, 1)
     t0 = time.perf_counter()
-    mcells, times, _ = cpu_oracle_accum(sample, args.steps)
+    mcells, times, _ = cpu_oracle_accum(rows, n, args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": mcells, "unit": "Mcells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"D8 accumulation, Scheidegger DIR (seed {SEED}), {sample}x{sample} window of the "
-                               f"{args.size}x{args.size} raster", "sample_cells": sample * sample},
+        "config": workload_config(n, max(args.gpus, 1), "int32" if max(args.gpus, 1) * n * n <= 2**31 - 1 else "int64"),
         "cpu_baseline": {"value": mcells, "unit": "Mcells/s", "cores": 1, "kind": "port",
-                         "sample": f"{sample}x{sample} top-left window, C restatement of wmf_py basin_acum "
-                                   "(oracle/wmf_oracle.c, gcc -O2), the Python reference cannot travel to this box"},
+                         "sample": f"per step: the first {rows} rows x {n} columns of the benchmark raster ({rows * n} cells); "
+                                   "C restatement of wmf_py basin_acum (oracle/wmf_oracle.c, gcc -O2, 1 thread; the algorithm is "
+                                   "a sequential queue), ~150x faster than the pure-Python reference, which cannot travel to this box"},
         "e2e": {"value": mcells, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
 
 
-def bench_shia(torch, ops, dev, n_cells: int, n_reg: int, steps: int, warmup: int):
-    """SHIA 5-tank (Fortran semantics, as shipped), BASELINE config 3: ~1 Mi cells x 1000 intervals."""
-    g = torch.Generator(device=dev).manual_seed(7)
+def cpu_oracle_shia(n_cells: int, n_reg: int):
+    """The Fortran 5-tank update as its C restatement, 1 thread, on a bounded sample (cells x steps)."""
+    import oracle
+    rng = np.random.default_rng(7)
+    f32 = np.float32
+    n_rec = 31
+    rec = np.vstack([np.zeros((1, n_cells), np.int32), (1000 * rng.gamma(2.0, 2.0, (n_rec - 1, n_cells))).astype(np.int32)])
+    pos = np.where(rng.random(n_reg) < 0.7, 1, rng.integers(2, n_rec + 1, n_reg)).astype(np.int32)
+    inp = oracle.Shia5Inputs(
+        v_coef=(rng.uniform(0.5, 1.5, (4, n_cells)) * np.array([[1e-2], [3e-3], [1e-3], [1e-4]])).astype(f32),
+        h_coef=(rng.uniform(0.5, 1.5, (4, n_cells)) * np.array([[0.5], [0.05], [0.005], [1.0]])).astype(f32),
+        h_exp=np.ones((4, n_cells), f32), max_capilar=rng.uniform(50, 150, n_cells).astype(f32),
+        max_gravita=rng.uniform(10, 50, n_cells).astype(f32), max_aquifer=rng.uniform(200, 800, n_cells).astype(f32),
+        hill_long=np.full(n_cells, 30.0, f32), elem_area=np.full(n_cells, 900.0, f32), rain_records=rec, pos_evento=pos,
+        evp=(0.1 + 0.1 * np.sin(np.arange(n_reg) / 7.0)).astype(f32), dt=300.0, speed_type=(1, 1, 1))
+    sto = np.full((5, n_cells), 0.001, f32)
+    t0 = time.perf_counter()
+    oracle.f_shia_v1(inp, np.ones(11, f32), sto, show_storage=False, show_mean_speed=False)
+    dt = time.perf_counter() - t0
+    return n_cells * n_reg / dt, dt
+
+
+# ------------------------------------------------------------------------------------------ SHIA (config 3 / 5)
+def shia_inputs(torch, dev, n_cells: int, n_reg: int, seed: int = 7):
+    g = torch.Generator(device=dev).manual_seed(seed)
     u = lambda lo, hi, *s: lo + (hi - lo) * torch.rand(*s, device=dev, generator=g)
     cs = torch.empty((17, n_cells), device=dev)
     cs[0:4] = u(0.5, 1.5, 4, n_cells) * torch.tensor([[1e-2], [3e-3], [1e-3], [1e-4]], device=dev)
@@ -167,29 +216,101 @@ def bench_shia(torch, ops, dev, n_cells: int, n_reg: int, steps: int, warmup: in
     pos = torch.where(torch.rand(n_reg, generator=gp) < 0.7, torch.ones(n_reg, dtype=torch.int64),
                       torch.randint(2, n_rec + 1, (n_reg,), generator=gp)).to(torch.int32).to(dev)
     evp = (0.1 + 0.1 * torch.sin(torch.arange(n_reg) / 7.0)).to(dev)
-    calib = torch.ones((1, 11), device=dev)
-    f_rain = float((pos != 1).float().mean())
+    return cs, rec, pos, evp, float((pos != 1).float().mean())
+
+
+def timed_runs(torch, fn, setup, steps: int, warmup: int, world: int, dist):
+    """Median CUDA-event time [ms] of fn(state) over `steps` runs; max over ranks."""
     times = []
     for it in range(warmup + steps):
-        sto = torch.full((1, 5, n_cells), 0.001, device=dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        state = setup()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.shia5_run(cs, rec, pos, evp, calib, sto, None, dt=300.0, speed_type=(1, 1, 1))
+        fn(state)
         e1.record()
         torch.cuda.synchronize()
         if it >= warmup:
             times.append(e0.elapsed_time(e1))
     ms = statistics.median(times)
-    return {"value": n_cells * n_reg / (ms * 1e-3), "unit": "cell-timesteps/s", "ms_per_run": ms, "cells": n_cells,
-            "intervals": n_reg, "mode": "Fortran 5-tank as shipped, fp32, time-fused, speed_type (1,1,1)",
-            "algorithmic_bytes_per_cell_step": 4.0 * f_rain + 108.0 / n_reg, "f_rain": f_rain}
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
+def bench_shia(torch, ops, dev, args, rank: int, world: int, peak: float):
+    """SHIA cell-timesteps/s.  N = 1: the runs of BASELINE config 3 (type-1 speeds, type-2 speeds, the fp64 3-tank model)
+    and config 5 (512 parameter sets x 250 k cells).  N > 1: config 3 with the basin's cells sharded across the ranks
+    (distinct cell ranges, per-step diagnostics gathered in rank order inside the timed region) and config 5 with the
+    parameter sets sharded (balance series all-gathered inside the timed region)."""
+    import torch.distributed as dist
+    from wmf_heavy_b200 import _lib
+    from wmf_heavy_b200 import dist as wdist
+    out = {}
+    n_cells, n_reg = args.shia_cells, args.shia_steps
+    # ---- config 3: this rank's cells (the whole basin at N = 1)
+    cs, rec, pos, evp, f_rain = shia_inputs(torch, dev, n_cells, n_reg, seed=7 + rank)
+    calib = torch.ones((1, 11), device=dev)
+    algo_bytes = 4.0 * f_rain + 108.0 / n_reg
+    new_sto = lambda: torch.full((1, 5, n_cells), 0.001, device=dev)
+    for name, st in (("c3_type1", (1, 1, 1)), ("c3_type2", (2, 2, 2))):
+        if world == 1:
+            run = lambda sto, st=st: ops.shia5_run(cs, rec, pos, evp, calib, sto, None, dt=300.0, speed_type=st, calc_niter=5)
+        else:
+            run = lambda sto, st=st: wdist.shia5_run_cell_sharded(cs, rec, pos, evp, calib, sto, None, dt=300.0, speed_type=st,
+                                                                  calc_niter=5)
+        ms = timed_runs(torch, run, new_sto, 3, 1, world, dist)
+        v = world * n_cells * n_reg / (ms * 1e-3)
+        gbs = algo_bytes * n_cells * n_reg / (ms * 1e-3) / 1e9
+        out[name] = {"value": v, "unit": "cell-timesteps/s", "ms_per_run": ms, "cells": world * n_cells, "intervals": n_reg,
+                     "mode": f"Fortran 5-tank as shipped, fp32, time-fused, speed_type {st}, calc_niter 5" +
+                             ("" if world == 1 else f"; cells sharded over {world} ranks, diagnostics gathered (NCCL) in the timed region"),
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                  "algorithmic_bytes_per_cell_step": algo_bytes, "f_rain": f_rain,
+                                  "issue_slot_utilisation": profiled(f"shia_{name}_issue_util"),
+                                  "note": "off the HBM roof by construction: the time loop is fused (unfused: 112 B/cell-step); "
+                                          "the kernel is instruction-issue bound"}}
+    del cs, rec, pos, evp
+    # ---- S4: the wmf_py 3-tank model, fp64, 8 B/cell-step of rain
+    if world == 1:
+        nt3 = 200
+        rain = torch.rand((nt3, n_cells), device=dev, dtype=torch.float64) * 20.0
+        prm = _lib.Shia3Params(300.0, 100.0, 30.0, 500.0, 0.0, 0.01, 0.02, 0.01, 0.005, 1.0e6, 300.0 / 3600.0, 0, 0)
+        mk = lambda: tuple(torch.full((n_cells,), v, device=dev, dtype=torch.float64) for v in (10.0, 5.0, 50.0))
+        ms = timed_runs(torch, lambda s: ops.shia3_run(rain, None, s[0], s[1], s[2], prm, nt3), mk, 3, 1, world, dist)
+        gbs = 8.0 * n_cells * nt3 / (ms * 1e-3) / 1e9
+        out["s4_fp64"] = {"value": n_cells * nt3 / (ms * 1e-3), "unit": "cell-timesteps/s", "ms_per_run": ms, "cells": n_cells,
+                          "intervals": nt3, "mode": "wmf_py 3-tank balance, fp64, time-fused",
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                       "algorithmic_bytes_per_cell_step": 8.0}}
+        del rain
+    # ---- config 5: NSGA-II population, 512 parameter sets x 250 k cells (sets sharded across the ranks)
+    P, n5 = args.pop_sets, args.pop_cells
+    cs, rec, pos, evp, f_rain = shia_inputs(torch, dev, n5, n_reg, seed=11)
+    gc = torch.Generator(device=dev).manual_seed(11)
+    calibs = 0.5 + torch.rand((P, 11), device=dev, generator=gc)
+    sto0 = torch.full((5, n5), 0.001, device=dev)
+    if world == 1:
+        run = lambda _s: ops.shia5_run(cs, rec, pos, evp, calibs, sto0.expand(P, 5, n5).contiguous(), None, dt=300.0)
+    else:
+        run = lambda _s: wdist.shia5_run_population_sharded(cs, rec, pos, evp, calibs, sto0, dt=300.0)
+    ms = timed_runs(torch, run, lambda: None, 2, 1, world, dist)
+    out["c5_population"] = {"value": P * n5 * n_reg / (ms * 1e-3), "unit": "cell-timesteps/s", "ms_per_run": ms, "sets": P,
+                            "cells": n5, "intervals": n_reg,
+                            "mode": f"{P} parameter sets x one basin, sets sharded over {world} rank(s)" +
+                                    ("" if world == 1 else ", balance series all-gathered (NCCL) in the timed region")}
+    return out
+
+
+# ------------------------------------------------------------------------------------------ the GPU arm
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
-    from wmf_heavy_b200 import _lib, ops
+    from wmf_heavy_b200 import _lib, ops, synth
     from wmf_heavy_b200.cu_py import basics
 
     torch.cuda.set_device(local_rank)
@@ -213,8 +334,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         def step():
             ops.d8_accum(d, None, algo=algo, out=acc)
     else:
-        # row stripes with one boundary exchange (all-gather over NCCL); int64 ACC: the whole raster can
-        # exceed 2^31 cells
+        # row stripes with one boundary exchange (all-gather over NCCL); int64 ACC when the whole raster can
+        # exceed 2^31 - 1 cells
         from wmf_heavy_b200 import stripes
         wide = world * n * n > 2**31 - 1
         acc = torch.empty((n, n), dtype=torch.int64 if wide else torch.int32, device=dev)
@@ -248,6 +369,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     cells_total = float(n) * n * world
     value = cells_total / (ms_per_step * 1e-3) / 1e6
     op_ms = statistics.mean(per)
+    acc_name = str(acc.dtype).replace("torch.", "")
     bytes_per_cell = 1.0 + acc.element_size()                       # int8 DIR read + ACC write
     achieved = bytes_per_cell * n * n / (op_ms * 1e-3) / 1e9
 
@@ -266,14 +388,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             basics.basin_acum(fd_np, mk_np, out=out_np)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
         assert float(out_np[-1, -1]) == float(acc[-1, -1].item())
         e2e = {"value": cells_total / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 2 * n * n,
                "d2h_bytes_per_step": 8 * n * n, "ms_per_step": 1e3 * e2e_s,
-               "api": "wmf_heavy_b200.cu_py.basics.basin_acum(flowdir int8, mask bool) -> float64"}
+               "api": "wmf_heavy_b200.cu_py.basics.basin_acum(flowdir int8, mask bool, out=pinned float64 buffer) -> float64; "
+                      "`out=` is an extension of the reference signature (without it the result lands in pageable memory)"}
         del h_dir, h_mask, h_out
 
     if args.e2e_steps > 0 and world > 1:
@@ -299,55 +418,85 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e2e_s = float(t.item())
         e2e = {"value": cells_total / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": n * n,
                "d2h_bytes_per_step": acc.element_size() * n * n, "ms_per_step": 1e3 * e2e_s,
-               "api": "wmf_heavy_b200.stripes.accumulate_striped(host int8 stripe) -> host int64 stripe, per rank"}
+               "api": "wmf_heavy_b200.stripes.accumulate_striped(host int8 stripe) -> host stripe, per rank"}
         del h_dir, h_out
+
+    # ---- the other input classes, same size (N = 1)
+    secondary = None
+    if not args.no_secondary and world == 1:
+        secondary = {}
+        ter = synth.terrain_dir(n, n, seed=5)
+        m1 = torch.ones((n, n), dtype=torch.uint8, device=dev)
+        m95 = synth.nodata_mask(n, n, 0.05, seed=9)
+        for name, dd, mm, desc in (
+                ("terrain", ter, None, "steepest descent of a tilted plane + smooth multi-scale noise: all 8 directions, pits"),
+                ("scheidegger_all_true_mask", d, m1, "the benchmark raster with an explicit all-true mask (what basin_acum(flowdir, mask) passes)"),
+                ("scheidegger_5pct_nodata", d, m95, "the benchmark raster with 5 % of the cells masked out at random"),
+                ("terrain_5pct_nodata", ter, m95, "the terrain raster with 5 % of the cells masked out")):
+            st = {}
+            for _ in range(2):
+                ops.d8_accum(dd, mm, algo=algo, out=acc)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.d8_accum(dd, mm, algo=algo, out=acc)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            ops.d8_accum(dd, mm, algo=algo, out=acc, stats=st)
+            bpc = 5.0 + (1.0 if mm is not None else 0.0)
+            gbs = bpc * n * n / (ms * 1e-3) / 1e9
+            secondary[name] = {"input": desc, "value": n * n / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms,
+                               "vs_primary": (n * n / (ms * 1e-3) / 1e6) / value,
+                               "roofline_frac": gbs / peak, "algorithmic_bytes_per_cell": bpc,
+                               "tiles": st.get("tile_classes"), "sweeps": st.get("multi_sweeps")}
+        del ter, m1, m95
+        ops.d8_accum(d, None, algo=algo, out=acc)           # (the parity check below looks at the benchmark raster)
 
     shia = None
     if not args.no_shia:
         try:
-            shia = bench_shia(torch, ops, dev, args.shia_cells, args.shia_steps, 3, 1)
-            if world > 1:
-                t = torch.tensor([shia["ms_per_run"]], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                shia["ms_per_run"] = float(t.item())
-                shia["value"] = world * shia["cells"] * shia["intervals"] / (shia["ms_per_run"] * 1e-3)
-                shia["cells"] *= world
+            shia = bench_shia(torch, ops, dev, args, rank, world, peak)
         except Exception as e:           # the primary metric must still print
             shia = {"error": repr(e)}
 
     if rank == 0:
-        cpu = None
+        cpu, parity = None, None
         if not args.no_cpu_baseline and world == 1:
-            cs = args.cpu_sample or n                    # the whole raster by default: ~10-30 s of one host core
-            mc, times, _ = cpu_oracle_accum(cs, 1)
+            rows = args.cpu_rows or n                    # the whole raster by default: ~10 s of one host core
+            mc, times, ref = cpu_oracle_accum(rows, n, 1)
+            got = acc[:rows].cpu().numpy()
+            parity = bool(np.array_equal(got, ref.astype(np.int32)))      # (the window's accumulation is exact: Scheidegger flow never runs upwards)
             cpu = {"value": mc, "unit": "Mcells/s", "cores": 1, "kind": "port",
-                   "sample": (f"the whole {n}x{n} raster" if cs == n else f"{cs}x{cs} top-left window of the same raster")
-                             + ", C restatement "
-                             "of wmf_py basin_acum (oracle/wmf_oracle.c, gcc -O2, 1 thread); "
+                   "sample": (f"the whole {n}x{n} raster" if rows == n else f"the first {rows} rows of the same raster")
+                             + ", C restatement of wmf_py basin_acum (oracle/wmf_oracle.c, gcc -O2, 1 thread); "
                              f"{times[0]:.2f} s"}
-        # kernels of libwmfb200.so per accumulation (profiles/*launches*.csv): walk = indegree + walk; sweep = sweepA,
-        # generalA, g_build, g_walk, g_unres, sweepC, generalC; stripes = 8 (local: + macro_links, stripe_paths,
-        # stripe_summary) + 6 (boundary forest) + 3 (route, sweepC, generalC; + widen for an int64 accumulation)
-        launches_per_step = ({"walk": 2, "sweep": 7, "auto": 7}[args.algo] if world == 1
-                             else (17 if world * n * n <= 0xFFFFFFFF else 18))   # (wider rasters also widen the inflows)
+            del ref, got
+            if shia is not None and "error" not in shia:
+                v, dt_s = cpu_oracle_shia(1 << 20, 50)
+                shia["cpu_baseline"] = {"value": v, "unit": "cell-timesteps/s", "cores": 1, "kind": "port",
+                                        "sample": f"1 Mi cells x 50 intervals, C restatement of Modelos_heavy.f90 shia_v1 "
+                                                  f"(oracle/wmf_oracle.c, 1 thread); {dt_s:.2f} s"}
+        # kernels of libwmfb200.so per accumulation: sweepA, multiA, generalA, g_build, g_walk, g_unres, sweepC, multiC,
+        # generalC; stripes = local (those six of phases A + G, macro_links, stripe_paths, stripe_summary) + boundary forest
+        # (6) + finish (route, sweepC, multiC, generalC)
+        launches_per_step = ({"walk": 2, "sweep": 9, "auto": 9}[args.algo] if world == 1 else 19)
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": str(acc.dtype).replace("torch.", ""), "data": "synthetic",
-            "config": {"workload": f"D8 flow accumulation, synthetic Scheidegger DIR {n}x{n} per GPU (seed {SEED}), "
-                                   f"int8 DIR -> {str(acc.dtype).replace('torch.', '')} ACC, mask = all valid", "algo": args.algo,
-                       "parallelism": "1 GPU" if world == 1 else
-                       f"{world} row stripes of {n} rows of one {world * n}x{n} raster, one NCCL all-gather of the "
-                       "boundary records per accumulation",
-                       "l2": "inputs (DIR 0.27 GB + ACC 1.07 GB) exceed the 126 MB L2; no explicit flush"},
+            "vs_baseline": None, "dtype": acc_name, "data": "synthetic",
+            "config": workload_config(n, world, acc_name, args.algo),
+            "parity_checked": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read+write of all kernels of one accumulation (ncu, profiles/r01_summary.md), 16384^2 int32
-                         "traffic": 1.997e9 if (world == 1 and n == 16384 and args.algo != "walk") else None,
+                         # dram__bytes_read + write over the kernels of one accumulation, from the ncu launch list of this
+                         # build (profiles/r02_figures.json); None when that file does not match this size / algorithm
+                         "traffic": profiled("d8_traffic_bytes") if (world == 1 and n == 16384 and args.algo != "walk") else None,
                          "peak_source": peak_src,
                          "kernel": "wmf_d8_accum, all passes of one accumulation "
                                    f"({bytes_per_cell:.0f} B/cell algorithmic)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "clocks": clk.summary(), "shia": shia,
+            "clocks": clk.summary(), "secondary": secondary, "shia": shia,
         }
         if saved_stdout is not None:
             sys.stdout.flush()
@@ -365,11 +514,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--algo", default="auto", choices=["auto", "walk", "sweep"])
-    ap.add_argument("--ref-sample", type=int, default=8192, help="window edge of one step of --impl reference")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="window edge for cpu_baseline (0 = the whole raster)")
+    ap.add_argument("--ref-rows", type=int, default=4096, help="rows of the raster one step of --impl reference accumulates")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows for cpu_baseline (0 = the whole raster)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--shia-cells", type=int, default=1 << 20)
     ap.add_argument("--shia-steps", type=int, default=1000)
+    ap.add_argument("--pop-sets", type=int, default=512)
+    ap.add_argument("--pop-cells", type=int, default=250000)
     ap.add_argument("--no-shia", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")

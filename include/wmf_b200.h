@@ -220,6 +220,8 @@ typedef struct {
     int32_t calc_niter;
     int32_t speed_type[3];
     int32_t hspeed_given;
+    int32_t strict;       /* 1: the Fortran's own operations (RainInt / 1000., (S1 / H1) ** 0.6 through powf) instead of the
+                           * fast forms (x * 0.001f, S1 * (1 / H1), exp2(0.6 * log2 x) on the SFU): ~2x slower, bit-level parity */
 } wmf_shia5_params;
 size_t wmf_shia5_workspace(int64_t N, int64_t N_reg, int32_t P);
 int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,

@@ -52,6 +52,16 @@ def basin_acum(flowdir: np.ndarray, mask: np.ndarray) -> np.ndarray:
     return acc
 
 
+def synth_scheidegger(ny: int, nx: int, seed: int = 20260101, row0: int = 0, col0: int = 0, nx_total=None) -> np.ndarray:
+    """The benchmark's Scheidegger DIR raster (internal codes), any window of it."""
+    out = np.empty((ny, nx), dtype=np.int8)
+    f = lib().orc_synth_scheidegger
+    f.restype = None
+    f(_p(out), C.c_int64(ny), C.c_int64(nx), C.c_int64(row0), C.c_int64(col0), C.c_int64(nx if nx_total is None else nx_total),
+      C.c_uint64(seed))
+    return out
+
+
 def basin_cut(dem, outlet_rc, flowdir, mask):
     """wmf_py/cu_py/basics.py:206-248 -> dict(dem, flowdir, mask)."""
     flowdir = np.asarray(flowdir)

@@ -598,3 +598,23 @@ int orc_f_shia_route(const orc_shia5_params *p, int64_t N, int64_t N_reg, const 
     free(qout); free(qin);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic workload of SURVEY 8(d) on the host, so that the CPU-baseline legs of bench.py need nothing but this
+ * library: the Scheidegger DIR raster of the headline benchmark.  Per cell a counter-based generator keyed by
+ * (seed, global linear index) -- the splitmix64 finaliser, top two bits: 0 -> E, 1 or 2 -> SE, 3 -> S -- exactly the
+ * generator the device uses (wmf_synth_scheidegger), so any window of the raster can be produced on either side.
+ * (tests/test_oracle.py checks the two against each other.) */
+void orc_synth_scheidegger(int8_t *dir, int64_t ny, int64_t nx, int64_t row0, int64_t col0, int64_t nx_total,
+                           uint64_t seed)
+{
+    for (int64_t r = 0; r < ny; r++)
+        for (int64_t c = 0; c < nx; c++) {
+            uint64_t x = seed ^ ((uint64_t)((row0 + r) * nx_total + col0 + c) * 0x9E3779B97F4A7C15ull);
+            x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+            x ^= x >> 27; x *= 0x94D049BB133111EBull;
+            x ^= x >> 31;
+            const int u = (int)(x >> 62);
+            dir[r * nx + c] = (int8_t)(u == 0 ? 0 : (u == 3 ? 2 : 1));
+        }
+}

@@ -40,7 +40,7 @@ def test_route_vs_oracle(ret):
                               torch.from_numpy(inp.pos_evento).cuda(), torch.from_numpy(inp.evp).cuda(),
                               torch.from_numpy(cal).cuda(), torch.from_numpy(sto0.copy()).cuda(), drain, ctrl, 6, dt=inp.dt,
                               retorno_gr=ret[0], retorno_aq=ret[1])
-    np.testing.assert_allclose(out["StoOut"].cpu().numpy(), o["StoOut"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(out["StoOut"].cpu().numpy(), o["StoOut"], rtol=1e-5, atol=8e-5)
     q, eq = out["Q"].cpu().numpy(), o["Q"]
     assert eq[0].max() > 0                                   # water does reach the outlet
     np.testing.assert_allclose(q, eq, rtol=1e-4, atol=1e-6 * float(eq.max()))
@@ -100,7 +100,7 @@ def test_run_shia_routed_object_api(tmp_path):
     o = oracle.f_shia_route(inp, cal, np.full((5, N), 0.001, np.float32), np.asarray(sb.structure[0], np.int32), ctrl, 3)
     assert ret["Qsim"].shape == (3, T) and ret["Qsim"][0].max() > 0
     np.testing.assert_allclose(ret["Qsim"], o["Q"], rtol=1e-4, atol=1e-6 * float(o["Q"].max()))
-    np.testing.assert_allclose(ret["Storage"], o["StoOut"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(ret["Storage"], o["StoOut"], rtol=1e-5, atol=8e-5)
     assert list(qdf.columns) == ["7", "9"] and len(qdf) == T
     ret0, _ = sb.run_shia(cal, path, T, EvpSerie=inp.evp)
     assert not ret0["Qsim"].any()

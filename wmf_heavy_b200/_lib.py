@@ -28,7 +28,8 @@ class WmfError(RuntimeError):
 
 class Shia5Params(C.Structure):
     _fields_ = [("dt", C.c_float), ("retorno_gr", C.c_float), ("retorno_aq", C.c_float),
-                ("calc_niter", C.c_int32), ("speed_type", C.c_int32 * 3), ("hspeed_given", C.c_int32)]
+                ("calc_niter", C.c_int32), ("speed_type", C.c_int32 * 3), ("hspeed_given", C.c_int32),
+                ("strict", C.c_int32)]
 
 
 class Shia3Params(C.Structure):

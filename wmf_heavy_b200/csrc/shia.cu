@@ -118,13 +118,23 @@ static void fold_blocks(double *part, int nblk, int64_t TK, int P, double *total
 }
 
 // ------------------------------------------------------------------------------------ SHIA 5-tank
-// Modelos_heavy.f90:907-919
+// Modelos_heavy.f90:907-919.  FAST: area ** expo as exp2(expo * log2(area)) on the SFU (see pow06) instead of powf.
+template <bool FAST>
 __device__ __forceinline__ void calc_speed(float sm, float coef, float expo, float L, float dt, int niter, float &sp,
                                            float &area)
 {
     for (int i = 0; i < niter; i++) {
         area = sm / (L + sp * dt);
-        float nw = coef * powf(area, expo);
+        float pw;
+        if (FAST) {
+            float l;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(area));
+            l = l * expo;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(l));
+        } else {
+            pw = powf(area, expo);
+        }
+        float nw = coef * pw;
         sp = (2.0f * nw + sp) / 3.0f;
     }
 }
@@ -166,7 +176,7 @@ __device__ __forceinline__ float pow06(float x)
 // difference per cell in fp32 also avoids the catastrophic cancellation of the Fortran's two ~5N-term sums.
 // DIAG adds {S1,S2,S3,S4,h1,h2,h3} -> K = 9 (slot 0 of the series carries the constant sums of S5 and h4).
 // T2: some tank uses the kinematic-wave speed (speed_type 2); the all-type-1 kernel carries none of that code.
-template <bool DIAG, bool T2, bool SNAP>
+template <bool DIAG, bool T2, bool SNAP, bool STRICT>
 __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
 {
     constexpr int K = DIAG ? 9 : 2;
@@ -229,11 +239,14 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
         float R = 0.0f;
         // record 1 = no rain (:366-367); a record beyond the file is the Fortran's 'fuera del rango' read error, whose
         // RainInt is undefined: defined here as no rain (the host layer rejects such headers before the launch)
-        if ((unsigned)(pos - 2) < (unsigned)(a.n_rec - 1)) R = (float)rain_cc[(int64_t)(pos - 1) * N] * 0.001f;   // :370 (RainInt/1000.)
+        if ((unsigned)(pos - 2) < (unsigned)(a.n_rec - 1)) {                                // :370 (RainInt/1000.)
+            const float ri = (float)rain_cc[(int64_t)(pos - 1) * N];
+            R = STRICT ? ri / 1000.0f : ri * 0.001f;
+        }
         acum = acum + R;                                                                   // :380
         float v1 = fmaxf(0.0f, (R - H1) + S1);                                             // :393
         S1 = (S1 + R) - v1;                                                                // :394
-        float evl = fminf((a.evp[t] * vs[0]) * pow06(S1 * invH1), S1);                     // :396-398
+        float evl = fminf((a.evp[t] * vs[0]) * (STRICT ? powf(S1 / H1, 0.6f) : pow06(S1 * invH1)), S1);   // :396-398
         S1 = S1 - evl;                                                                     // :407
         float v2 = fminf(v1, vs[1]); S2 = (S2 + v1) - v2;                                  // :409-412
         float v3 = fminf(v2, vs[2]); S3 = (S3 + v2) - v3;
@@ -242,13 +255,13 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
         if (rgr) { float rg = fmaxf(0.0f, S3 - H2); S2 = S2 + rg; S3 = S3 - rg; }          // :420-427
         float hf, ar;
         if (!t2_0) hf = fl[0] * S2;                                                        // :461-491
-        else { ar = 0.0f; calc_speed(S2 * m3mm, coef[0], expo[0], L, dt, niter, hs[0], ar); hf = fminf(((ar * hs[0]) * dt) / m3mm, S2); }
+        else { ar = 0.0f; calc_speed<!STRICT>(S2 * m3mm, coef[0], expo[0], L, dt, niter, hs[0], ar); hf = fminf(((ar * hs[0]) * dt) / m3mm, S2); }
         S2 = S2 - hf;
         if (!t2_1) hf = fl[1] * S3;
-        else { ar = 0.0f; calc_speed(S3 * m3mm, coef[1], expo[1], L, dt, niter, hs[1], ar); hf = fminf(((ar * hs[1]) * dt) / m3mm, S3); }
+        else { ar = 0.0f; calc_speed<!STRICT>(S3 * m3mm, coef[1], expo[1], L, dt, niter, hs[1], ar); hf = fminf(((ar * hs[1]) * dt) / m3mm, S3); }
         S3 = S3 - hf;
         if (!t2_2) hf = fl[2] * S4;
-        else { ar = 0.0f; calc_speed(S4 * m3mm, coef[2], expo[2], L, dt, niter, hs[2], ar); hf = fminf(((ar * hs[2]) * dt) / m3mm, S4); }
+        else { ar = 0.0f; calc_speed<!STRICT>(S4 * m3mm, coef[2], expo[2], L, dt, niter, hs[2], ar); hf = fminf(((ar * hs[2]) * dt) / m3mm, S4); }
         S4 = S4 - hf;
 
         const float sto_now = (S1 + S2) + (S3 + S4);
@@ -543,16 +556,19 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
     dim3 grid(nblk, P);
     const bool t2 = a.p.speed_type[0] != 1 || a.p.speed_type[1] != 1 || a.p.speed_type[2] != 1;
     const int variant = (diag ? 4 : 0) | (t2 ? 2 : 0) | (snap_slot ? 1 : 0);
+#define WMF_SHIA5(D_, T_, S_) \
+    do { if (a.p.strict) k_shia5<D_, T_, S_, true><<<grid, TH, 0, st>>>(a); else k_shia5<D_, T_, S_, false><<<grid, TH, 0, st>>>(a); } while (0)
     switch (variant) {
-    case 0: k_shia5<false, false, false><<<grid, TH, 0, st>>>(a); break;
-    case 1: k_shia5<false, false, true><<<grid, TH, 0, st>>>(a); break;
-    case 2: k_shia5<false, true, false><<<grid, TH, 0, st>>>(a); break;
-    case 3: k_shia5<false, true, true><<<grid, TH, 0, st>>>(a); break;
-    case 4: k_shia5<true, false, false><<<grid, TH, 0, st>>>(a); break;
-    case 5: k_shia5<true, false, true><<<grid, TH, 0, st>>>(a); break;
-    case 6: k_shia5<true, true, false><<<grid, TH, 0, st>>>(a); break;
-    default: k_shia5<true, true, true><<<grid, TH, 0, st>>>(a); break;
+    case 0: WMF_SHIA5(false, false, false); break;
+    case 1: WMF_SHIA5(false, false, true); break;
+    case 2: WMF_SHIA5(false, true, false); break;
+    case 3: WMF_SHIA5(false, true, true); break;
+    case 4: WMF_SHIA5(true, false, false); break;
+    case 5: WMF_SHIA5(true, false, true); break;
+    case 6: WMF_SHIA5(true, true, false); break;
+    default: WMF_SHIA5(true, true, true); break;
     }
+#undef WMF_SHIA5
     const int64_t TK = (N_reg + 1) * K;
     fold_blocks(part, nblk, TK, P, totals, st);
     k_shia5_outputs<<<blocks_for((int64_t)P * N_reg, 256), 256, 0, st>>>(totals, K, N_reg, N, P, balance, mean_rain,

@@ -191,11 +191,12 @@ def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento:
               calib: torch.Tensor, sto: torch.Tensor, hspeed: Optional[torch.Tensor] = None, *, dt: float,
               retorno_gr: float = 0.0, retorno_aq: float = 0.0, calc_niter: int = 5, speed_type=(1, 1, 1),
               show_storage: bool = False, show_mean_speed: bool = False, snap_slot: Optional[torch.Tensor] = None,
-              n_snap: int = 0, validate: bool = True):
+              n_snap: int = 0, validate: bool = True, strict: bool = False):
     """SHIA 5-tank update as shipped (Modelos_heavy.f90:169-548) for P parameter sets at once.
     ``sto`` [P,5,N] and ``hspeed`` [P,4,N] are advanced IN PLACE.  Returns a dict of device tensors.
     ``snap_slot`` int32 [N_reg] (-1 or a slot in [0, n_snap)): the storages after those steps are returned as
-    ``snapshots`` [P, n_snap, 5, N] (save_storage / guarda_cond, Modelos_heavy.f90:496-500)."""
+    ``snapshots`` [P, n_snap, 5, N] (save_storage / guarda_cond, Modelos_heavy.f90:496-500).
+    ``strict``: the Fortran's own operation forms (true division, powf) instead of the fast ones; see the header."""
     require_cuda()
     _chk_dev(cell_static, torch.float32, "cell_static")
     _chk_dev(rain_records, torch.int32, "rain_records")
@@ -227,7 +228,7 @@ def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento:
     ms = torch.empty((P, 5, n_reg), dtype=torch.float32, device=dev) if show_storage else None
     mv = torch.empty((P, 4, n_reg), dtype=torch.float32, device=dev) if show_mean_speed else None
     prm = _lib.Shia5Params(dt, retorno_gr, retorno_aq, int(calc_niter), (C.c_int32 * 3)(*[int(s) for s in speed_type]),
-                           int(given))
+                           int(given), int(bool(strict)))
     lib = _lib.load()
     ws = workspace(lib.wmf_shia5_workspace(N, n_reg, P))
     snaps = None
@@ -347,7 +348,7 @@ def shia5_route_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_e
     rank_t, dp_t, di_t, c_t = to(rank), to(don_ptr), to(don_idx if don_idx.size else np.zeros(1, np.int32)), to(c)
     Q = torch.empty((int(n_ctrl), n_reg), dtype=torch.float32, device=dev)
     acum = torch.empty(N, dtype=torch.float32, device=dev)
-    prm = _lib.Shia5Params(dt, retorno_gr, retorno_aq, 0, (C.c_int32 * 3)(1, 1, 1), 0)
+    prm = _lib.Shia5Params(dt, retorno_gr, retorno_aq, 0, (C.c_int32 * 3)(1, 1, 1), 0, 0)
     lib = _lib.load()
     ws = workspace(lib.wmf_shia5_route_workspace(N))
     check(lib.wmf_shia5_route_run(C.addressof(prm), N, n_reg, n_rec, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
