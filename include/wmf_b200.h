@@ -89,7 +89,8 @@ int wmf_d8_accum_tile_classes(const void *workspace, size_t ws_bytes, int64_t ny
  *                        ext_inflow int64 [2][nx], ext_unres uint8 [2][nx]
  *   wmf_d8_stripe_finish injects that inflow and writes the final acc [ny][nx] (WMF_ACC_I32 only when
  *                        ny_total*nx < 2^31, WMF_ACC_I64, WMF_ACC_F64).
- * The SAME workspace must be passed to stripe_local and stripe_finish (phase-A state lives in it). */
+ * The SAME workspace must be passed to stripe_local and stripe_finish (phase-A state lives in it).  * wmf_d8_stripe_finish CONSUMES the workspace of the local pass (it adds the routed inflow into arrays that pass cleared):
+ * one finish per local. */
 size_t wmf_d8_stripe_workspace(int64_t ny, int64_t nx);
 int wmf_d8_stripe_local(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t row0, int64_t ny_total,
                         int encoding, int64_t *records, void *workspace, size_t ws_bytes, void *stream);

@@ -26,7 +26,13 @@ t_pack = 0.0
 t_bound, (inflow, unres) = timed(lambda: stripes.stripe_inflow(recs, 0))
 wide = G * n * n > 2**31 - 1
 out = torch.empty((n, n), dtype=torch.int64 if wide else torch.int32, device="cuda")
-t_fin, _ = timed(lambda: ops.d8_stripe_finish(d, ws, 0, ny_total, inflow, unres, acc_dtype=_lib.ACC_I64 if wide else _lib.ACC_I32, out=out))
+def both():                                   # (a finish consumes the workspace of its local pass: time the pair)
+    r, w = ops.d8_stripe_local(d, 0, ny_total)
+    return ops.d8_stripe_finish(d, w, 0, ny_total, inflow, unres, acc_dtype=_lib.ACC_I64 if wide else _lib.ACC_I32, out=out)
+
+
+t_pair, _ = timed(both)
+t_fin = t_pair - t_local
 out32 = torch.empty((n, n), dtype=torch.int32, device="cuda")
 t_whole, _ = timed(lambda: ops.d8_accum(d, None, out=out32))
 print(f"n={n} G={G}: local {t_local:.3f} ms, pack/unpack {t_pack:.3f}, boundary forest {t_bound:.3f}, finish {t_fin:.3f}; unstriped accumulate {t_whole:.3f}")

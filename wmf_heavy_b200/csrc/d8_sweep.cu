@@ -2329,6 +2329,9 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
         std::lock_guard<std::mutex> lock(ss->busy);
         WMF_CUDA_CHECK(cudaEventRecord(ss->fork, st));
         WMF_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+        // (the finish pass adds what the other stripes send into `extra`: cleared here, beside the walk, where DRAM idles)
+        WMF_CUDA_CHECK(cudaMemsetAsync(w.extra, 0, sizeof(int64_t) * (size_t)nnodes, ss->stream));
+        WMF_CUDA_CHECK(cudaMemsetAsync(w.extra_unres, 0, (size_t)nnodes, ss->stream));
         k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp.mlink);
         k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp);
         WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
@@ -2355,9 +2358,7 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny,
     const bool al = aligned4(dir, mask, acc, nx);
     // phase-A state and the finalised forest words of the stripe-local pass are still in the workspace: what the other
     // stripes send is routed along the contracted paths into `extra`, and phase C adds it to what it pulls.
-    T *extra = (T *)w.extra;
-    WMF_CUDA_CHECK(cudaMemsetAsync(extra, 0, sizeof(T) * nnodes, st));
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.extra_unres, 0, (size_t)nnodes, st));
+    T *extra = (T *)w.extra;                                 // (cleared by the local pass)
     k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, w.pe, w.sp, ext_inflow, ext_un,
                                                                                           extra, w.extra_unres, w.tile_class);
     WMF_LAUNCH_CHECK();

@@ -3,8 +3,8 @@
 //   recs int64 [G][2][2][nx]: plane 0 = exit_acc; plane 1 = link (low 32 bits) | k << 32 | unres << 40
 // (k: normalised D8 code, 8 none, 9 inactive; link: boundary index side*nx+col where flow entering at
 // the cell leaves its stripe again, -1 if it ends inside).  Node id = (g*2 + side)*nx + col.
-//   k_boundary_build  parent of every stripe exit = link of the cell it drains to in the next stripe
-//   forest engine     totals of all stripe exits (2*G*nx nodes; redundant on every rank, it is tiny)
+//   k_boundary_build  parent of every stripe exit = link of the cell it drains to in the next stripe; arrival counters
+//   k_boundary_walk   totals of all stripe exits (2*G*nx nodes; redundant on every rank, it is tiny)
 //   k_boundary_pull   what enters each boundary cell of stripe `me` = sum over its <= 3 donors across
 //                     the stripe edge (pull: deterministic, no atomics)
 #include "common.cuh"
@@ -23,8 +23,10 @@ __device__ __forceinline__ bool exit_dir(int g, int side, int k, int G, int &g2)
     return false;
 }
 
+// parent of every node + the arrival counters: one token for the node's own walker (a blocked node gets one more,
+// which never arrives), one per child
 __global__ void k_boundary_build(const int64_t *__restrict__ recs, int G, int64_t nx, int32_t *__restrict__ parent,
-                                 int64_t *__restrict__ weight, uint8_t *__restrict__ blocked)
+                                 int32_t *cnt)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)G * 2 * nx) return;
@@ -32,8 +34,6 @@ __global__ void k_boundary_build(const int64_t *__restrict__ recs, int G, int64_
     const int64_t col = i % nx;
     const int64_t *rg = recs + (int64_t)g * 4 * nx;
     const int64_t m = rg[(2 + side) * nx + col];
-    weight[i] = rg[side * nx + col];
-    blocked[i] = rec_unres(m) ? 1 : 0;
     int32_t p = -1;
     int g2;
     const int k = rec_k(m);
@@ -46,10 +46,34 @@ __global__ void k_boundary_build(const int64_t *__restrict__ recs, int G, int64_
         }
     }
     parent[i] = p;
+    atomicAdd(&cnt[i], rec_unres(m) ? 2 : 1);
+    if (p >= 0) atomicAdd(&cnt[p], 1);
+}
+
+// every node brings its own weight and token; whoever takes a counter to zero carries the node's total downstream
+__global__ void k_boundary_walk(const int64_t *__restrict__ recs, int G, int64_t nx, const int32_t *__restrict__ parent,
+                                unsigned long long *acc, int32_t *cnt)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)G * 2 * nx) return;
+    const int g = (int)(i / (2 * nx)), side = (int)((i / nx) & 1);
+    const int64_t w = recs[(int64_t)g * 4 * nx + side * nx + i % nx];
+    int64_t cur = i;
+    atomicAdd(&acc[cur], (unsigned long long)w);
+    __threadfence();
+    while (atomicSub(&cnt[cur], 1) == 1) {                  // the last arrival: cur is final
+        __threadfence();
+        const unsigned long long total = atomicAdd(&acc[cur], 0ull);
+        const int32_t p = parent[cur];
+        if (p < 0) break;
+        atomicAdd(&acc[p], total);
+        __threadfence();
+        cur = p;
+    }
 }
 
 __global__ void k_boundary_pull(const int64_t *__restrict__ recs, int G, int64_t nx, int me, const int64_t *__restrict__ acc,
-                                const uint8_t *__restrict__ resolved, int64_t *__restrict__ ext_inflow,
+                                const int32_t *__restrict__ cnt, int64_t *__restrict__ ext_inflow,
                                 uint8_t *__restrict__ ext_unres)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,7 +93,7 @@ __global__ void k_boundary_pull(const int64_t *__restrict__ recs, int G, int64_t
             int gg;
             if (!exit_dir(g2, s2, k2, G, gg) || gg != me || d8_dc(k2) != dc) continue;
             const int64_t node = ((int64_t)g2 * 2 + s2) * nx + c2;
-            if (resolved[node]) sum += acc[node];
+            if (cnt[node] == 0) sum += acc[node];     // resolved: every arrival came
             else un = 1;
         }
     }
@@ -84,7 +108,7 @@ extern "C" {
 size_t wmf_stripe_boundary_workspace(int G, int64_t nx)
 {
     size_t n = (size_t)G * 2 * nx;
-    return wmf_align(n * 4) * 2 + wmf_align(n * 8) * 2 + wmf_align(n) * 2 + 1024;
+    return wmf_align(n * 4) * 2 + wmf_align(n * 8) + 1024;
 }
 
 int wmf_stripe_boundary_inflow(const int64_t *recs, int G, int64_t nx, int me, int64_t *ext_inflow, uint8_t *ext_unres,
@@ -96,15 +120,14 @@ int wmf_stripe_boundary_inflow(const int64_t *recs, int G, int64_t nx, int me, i
     const int64_t n = (int64_t)G * 2 * nx;
     WMF_REQUIRE(n < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "boundary forest too large");
     WsCursor cur(workspace, ws_bytes);
-    int32_t *parent = cur.take<int32_t>((size_t)n), *cnt = cur.take<int32_t>((size_t)n);
-    int64_t *weight = cur.take<int64_t>((size_t)n), *acc = cur.take<int64_t>((size_t)n);
-    uint8_t *blocked = cur.take<uint8_t>((size_t)n), *resolved = cur.take<uint8_t>((size_t)n);
+    int32_t *parent = cur.take<int32_t>((size_t)n);
+    int32_t *cnt = cur.take<int32_t>((size_t)n);             // (cnt and acc are adjacent: one memset clears both)
+    int64_t *acc = cur.take<int64_t>((size_t)n);
     WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
-    k_boundary_build<<<blocks_for(n, 256), 256, 0, st>>>(recs, G, nx, parent, weight, blocked);
-    WMF_LAUNCH_CHECK();
-    int rc = wmf_forest_accum(parent, weight, blocked, n, acc, resolved, cnt, wmf_align((size_t)n * 4), stream);
-    if (rc) return rc;
-    k_boundary_pull<<<blocks_for(2 * nx, 256), 256, 0, st>>>(recs, G, nx, me, acc, resolved, ext_inflow, ext_unres);
+    WMF_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)((char *)(acc + n) - (char *)cnt), st));
+    k_boundary_build<<<blocks_for(n, 256), 256, 0, st>>>(recs, G, nx, parent, cnt);
+    k_boundary_walk<<<blocks_for(n, 256), 256, 0, st>>>(recs, G, nx, parent, (unsigned long long *)acc, cnt);
+    k_boundary_pull<<<blocks_for(2 * nx, 256), 256, 0, st>>>(recs, G, nx, me, acc, cnt, ext_inflow, ext_unres);
     WMF_LAUNCH_CHECK();
     return 0;
 }
