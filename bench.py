@@ -306,6 +306,48 @@ def bench_shia(torch, ops, dev, args, rank: int, world: int, peak: float):
     return out
 
 
+# ------------------------------------------------------------------------------------------ basin path (D2-D5)
+def bench_basin(torch, ops, dev, peak: float, n: int = 2048):
+    """Basin delineation and the vector-form routines at the size of BASELINE configs 1 / 3 / 5: the largest basin of a
+    n x n Scheidegger raster (keypad codes), outlet at the cell of largest accumulation.  Algorithmic bytes:
+    1 B per raster cell + 16 B per basin cell (12 B structure + 4 B acum)."""
+    from wmf_heavy_b200 import _lib
+    d = ops.synth_scheidegger(n, n, seed=SEED + 1)
+    acc = ops.d8_accum(d, None)
+    flat = int(torch.argmax(acc.view(-1)))
+    r0, c0 = flat // n, flat % n
+    key = ops.synth_scheidegger(n, n, seed=SEED + 1, encoding=_lib.ENC_KEYPAD)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+
+    t_mask, (mask, nb) = timed(lambda: ops.basin_mask(d, None, (r0, c0)))
+    t_st, st = timed(lambda: ops.basin_structure(key, c0 + 1, r0 + 1))
+    nb = int(st.shape[1])
+    dem = torch.rand((n, n), device=dev) + 100.0
+    demv = ops.basin_map2basin(st, dem)
+    dirv = ops.basin_map2basin(st, key).to(torch.int32)
+    t_bas, bas = timed(lambda: ops.basin_basics(st, demv, dirv, 30.0, 0.0, 0.0, 30.0, n))
+    t_nod, _ = timed(lambda: ops.stream_nod(st, bas[0], 100))
+    by = 1.0 * n * n + 16.0 * nb
+    gbs = by / (t_st * 1e-3) / 1e9
+    return {"raster": f"{n}x{n} Scheidegger (keypad codes)", "basin_cells": nb,
+            "basin_mask_ms": t_mask, "basin_structure_ms": t_st, "basin_basics_ms": t_bas, "stream_nod_ms": t_nod,
+            "structure_basin_cells_per_s": nb / (t_st * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes": by,
+                         "note": "basin_find + basin_cut (BFS-ordered structure): membership by pointer jumping, order by one "
+                                 "radix sort; includes the host round trips of the call (cell count, convergence tests)"}}
+
+
 # ------------------------------------------------------------------------------------------ the GPU arm
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
@@ -461,6 +503,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         except Exception as e:           # the primary metric must still print
             shia = {"error": repr(e)}
 
+    basin = None
+    if not args.no_secondary and world == 1:
+        try:
+            basin = bench_basin(torch, ops, dev, peak)
+        except Exception as e:
+            basin = {"error": repr(e)}
+
     if rank == 0:
         cpu, parity = None, None
         if not args.no_cpu_baseline and world == 1:
@@ -496,7 +545,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "kernel": "wmf_d8_accum, all passes of one accumulation "
                                    f"({bytes_per_cell:.0f} B/cell algorithmic)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "clocks": clk.summary(), "secondary": secondary, "shia": shia,
+            "clocks": clk.summary(), "secondary": secondary, "basin": basin, "shia": shia,
         }
         if saved_stdout is not None:
             sys.stdout.flush()

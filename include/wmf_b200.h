@@ -249,14 +249,25 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
  * donors of the SAME step; tank 5 is a linear reservoir like tanks 2-4 (speed row 4, hill_long) and drains to the
  * receiver.  Q [n_ctrl][N_reg] in m3/s: row 0 = the outlet (the structure's last cell), row j > 0 = the cell with
  * ctrl == j.  Cells in the structure's upstream-first order; rank = max depth - depth (wmf_basin_depth_host), donors in
- * CSR form with ascending indices.  Speed type 1 only.  N_reg + max_rank launches (a skewed level/time wavefront). */
+ * CSR form with ascending indices.  Speed type 1 only.  A skewed level/time wavefront of N_reg + max_rank diagonals:
+ * with level_start (int32 [max_rank + 2], nullable: first cell of every rank -- the ranks ascend with the cell index in the
+ * structure's BFS order) ONE cooperative launch walks them all, the blocks meeting at a barrier between diagonals; without
+ * it, one launch per diagonal. */
 int32_t wmf_basin_depth_host(const int32_t *drain, int64_t n, int32_t *depth);
 size_t wmf_shia5_route_workspace(int64_t N);
 int wmf_shia5_route_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec,
                         const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento,
                         const float *evp, const float *calib, const int32_t *rank, int32_t max_rank,
                         const int32_t *don_ptr, const int32_t *don_idx, const int32_t *ctrl, int32_t n_ctrl,
-                        float *sto, float *acum_rain, float *Q, void *workspace, size_t ws_bytes, void *stream);
+                        const int32_t *level_start, float *sto, float *acum_rain, float *Q, void *workspace,
+                        size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------- C1: fitness of a calibration population
+ * The two objectives nsgaii_element.__evalfunc__ applies to every individual's hydrograph (wmf_heavy/wmfv2.py:2194-2198;
+ * the bodies of __eval_nash__ / __eval_q_pico__ are not in the reference, so they take their standard form): qsim float
+ * [P][T] (one row per parameter set), qobs float [T] (non-finite entries are skipped), fitness double [P][2] =
+ * {Nash-Sutcliffe efficiency, |max qsim - max qobs| / max qobs}. */
+int wmf_fitness_nash_peak(const float *qsim, const float *qobs, int32_t P, int64_t T, double *fitness, void *stream);
 
 /* ---------------------------------------------------------------- S4: SHIA 3-tank (wmf_py semantics)
  * Replaces wmf_py/models_py/core.py:64-295 shia_v1, fp64.  rain/et double [nsteps][ncell]

@@ -104,3 +104,66 @@ def test_run_shia_routed_object_api(tmp_path):
     assert list(qdf.columns) == ["7", "9"] and len(qdf) == T
     ret0, _ = sb.run_shia(cal, path, T, EvpSerie=inp.evp)
     assert not ret0["Qsim"].any()
+
+
+def test_fitness_reduction_vs_numpy():
+    """ops.fitness_nash_peak: Nash-Sutcliffe efficiency and peak-flow error of P hydrographs, NaN gaps in the observation
+    skipped (fp64 sums on the device; numpy in fp64 as the check)."""
+    import torch
+    rng = np.random.default_rng(5)
+    P, T = 37, 1000
+    qobs = (5 + 3 * np.sin(np.arange(T) / 40.0) + rng.random(T)).astype(np.float32)
+    qobs[rng.random(T) < 0.05] = np.nan
+    qsim = (qobs[None] * rng.uniform(0.5, 1.5, (P, 1)) + rng.normal(0, 0.3, (P, T))).astype(np.float32)
+    qsim = np.nan_to_num(qsim, nan=1.0).astype(np.float32)
+    got = ops.fitness_nash_peak(torch.from_numpy(qsim).cuda(), torch.from_numpy(qobs).cuda()).cpu().numpy()
+    ok = np.isfinite(qobs)
+    o, s = qobs[ok].astype(np.float64), qsim[:, ok].astype(np.float64)
+    nash = 1 - ((o - s) ** 2).sum(1) / ((o - o.mean()) ** 2).sum()
+    peak = np.abs(s.max(1) - o.max()) / o.max()
+    np.testing.assert_allclose(got[:, 0], nash, rtol=1e-12)
+    np.testing.assert_allclose(got[:, 1], peak, rtol=1e-12)
+
+
+def test_calib_nsgaii_object_api(tmp_path):
+    """SimuBasin.Calib_NSGAII(nsga_el, nodo_eval, ...) with the reference's signature (wmfv2.py:2060-2106): population
+    rounded up to a multiple of 4, every generation evaluated in one go, (pop, QsimPar, fitness (2, pop)) returned.  On
+    the routed extension the hydrographs depend on the genes, so the best Nash of the last population is at least the
+    best of a random one; as shipped (no routing) every hydrograph is zero and the run still completes."""
+    from wmf_heavy_b200 import wmfv2
+    ny, nx = 60, 70
+    fd = ops.synth_scheidegger_host(ny, nx, seed=23)
+    acc = oracle.basin_acum(fd, np.ones(fd.shape, bool))
+    r0, c0 = np.unravel_index(np.argmax(acc), acc.shape)
+    key = helpers.to_keypad(fd)
+    wmfv2.set_map_properties(ncols=nx, nrows=ny, xll=0.0, yll=0.0, dx=30.0, dxp=30.0)
+    x, y = 30.0 * (c0 + 0.5), 30.0 * ((ny - (r0 + 1)) + 0.5)
+    DIR = np.asfortranarray(key.T.astype(np.int32))
+    DEM = np.asfortranarray((1000 - 0.3 * np.add.outer(np.arange(nx), np.arange(ny))).astype(np.float32))
+    sb = wmfv2.SimuBasin(x, y, DEM, DIR, dt=300, threshold=30)
+    N, T = sb.ncells, 30
+    inp = helpers.shia5_inputs(oracle, N, T, 24)
+    models.v_coef, models.h_coef, models.h_exp = inp.v_coef, inp.h_coef, inp.h_exp
+    models.max_capilar, models.max_gravita, models.max_aquifer = (a[None] for a in (inp.max_capilar, inp.max_gravita, inp.max_aquifer))
+    models.speed_type = np.array([1, 1, 1])
+    models.control = np.zeros((1, N), np.int32)
+    models.show_storage = models.show_mean_speed = models.save_storage = 0
+    path = str(tmp_path / "lluvia")
+    models.write_rain(path + ".bin", path + ".hdr", inp.rain_records, inp.pos_evento)
+    np.random.seed(3)
+    try:
+        models.route_channels = 1
+        truth = np.array([0.8, 1.2, 1.1, 0.9, 0.7, 0.6, 0.9, 0.8, 0.9, 1.1], np.float32)
+        qobs = sb.run_shia(truth, path, T, EvpSerie=inp.evp, QsimDataFrame=False)["Qsim"][0]
+        el = wmfv2.nsgaii_element(path, qobs, T, 1, sb, evp=[0.5, 1.5], infil=[0.5, 1.5], perco=[0.5, 1.5], losses=[0.5, 1.5],
+                                  velRun=[0.5, 1.5], velSub=[0.5, 1.5], velSup=[0.5, 1.5], velStream=[0.5, 1.5],
+                                  Hu=[0.5, 1.5], Hg=[0.5, 1.5])
+        assert np.allclose(el.__evalfunc__(qobs), (1.0, 0.0))
+        pop, qsim, fit = sb.Calib_NSGAII(el, 0, pop_size=6, NGEN=2)
+        assert len(pop) == 8 and fit.shape == (2, 8) and len(qsim) == 8 and qsim[0].shape == (T,)
+        assert np.isfinite(fit).all() and fit[0].max() <= 1.0 and fit[1].min() >= 0.0
+        assert all(len(ind) == 1 and len(ind[0]) == 10 for ind in pop)
+    finally:
+        models.route_channels = 0
+    pop0, q0, fit0 = sb.Calib_NSGAII(el, 0, pop_size=4, NGEN=1)
+    assert len(pop0) == 4 and not np.asarray(q0).any() and fit0.shape == (2, 4)

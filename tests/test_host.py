@@ -135,3 +135,23 @@ def test_route_topology_host():                # N4 extension, host part: depth 
         assert list(idx[ptr[j]:ptr[j + 1]]) == list(np.nonzero(recv == j)[0])      # ascending donor indices
     with pytest.raises(ValueError):
         ops.route_topology(np.array([3, 0, 0], np.int32))
+
+
+def test_nsga2_selection_helpers():
+    """The numpy stand-ins for DEAP's selNSGA2 / selTournamentDCD behind Calib_NSGAII: non-dominated fronts, crowding."""
+    from wmf_heavy_b200 import wmfv2
+    w = (1.0, -1.0)                                      # maximise the first objective, minimise the second
+    vals = [(0.9, 0.1), (0.8, 0.05), (0.7, 0.2), (0.5, 0.5), (0.95, 0.3), (0.2, 0.9)]
+    pop = []
+    for v in vals:
+        ind = wmfv2.Individual([[np.array([0.0])] * 10])
+        ind.fitness.values = v
+        pop.append(ind)
+    fronts = wmfv2._fronts(pop, w)
+    assert sorted(i.fitness.values for i in fronts[0]) == [(0.8, 0.05), (0.9, 0.1), (0.95, 0.3)]
+    assert [i.fitness.values for i in fronts[-1]] == [(0.2, 0.9)]
+    sel = wmfv2._sel_nsga2(pop, 4, w)
+    assert len(sel) == 4 and {(0.9, 0.1), (0.8, 0.05), (0.95, 0.3), (0.7, 0.2)} == {i.fitness.values for i in sel}
+    np.random.seed(0)
+    t = wmfv2._sel_tournament_dcd(pop[:4], 4, w)
+    assert len(t) == 4 and all(i in pop[:4] for i in t)

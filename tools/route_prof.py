@@ -34,16 +34,21 @@ rec[0] = 0
 pos = torch.where(torch.rand(T) < 0.7, torch.ones(T, dtype=torch.int64), torch.randint(2, n_rec + 1, (T,))).to(torch.int32).to(dev)
 evp = torch.full((T,), 0.1, device=dev)
 cal = torch.ones(11, device=dev)
-times = []
-for it in range(3):
-    sto = torch.full((5, N), 0.001, device=dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    out = ops.shia5_route_run(cs, rec, pos, evp, cal, sto, drain, None, 1, dt=300.0)
-    e1.record()
-    torch.cuda.synchronize()
-    times.append(e0.elapsed_time(e1))
-ms = sorted(times)[1]
-print(f"routing extension: basin of {N} cells (depth {dmax}), {T} steps: {ms:.2f} ms = {N * T / ms / 1e6:.1f} G cell-steps/s, "
-      f"{T + dmax} launches; peak Q at the outlet {float(out['Q'][0].max()):.1f} m3/s")
+ref = None
+for persistent in (True, False):
+    times = []
+    for it in range(3):
+        sto = torch.full((5, N), 0.001, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        out = ops.shia5_route_run(cs, rec, pos, evp, cal, sto, drain, None, 1, dt=300.0, persistent=persistent)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[1]
+    same = "" if ref is None else f"; identical to the cooperative run: {bool(torch.equal(ref[0], out['Q']) and torch.equal(ref[1], out['StoOut']))}"
+    ref = ref or (out["Q"].clone(), out["StoOut"].clone())
+    print(f"routing extension ({'one cooperative launch' if persistent else str(T + dmax) + ' launches'}): basin of {N} cells "
+          f"(depth {dmax}), {T} steps: {ms:.2f} ms = {N * T / ms / 1e6:.1f} G cell-steps/s; peak Q at the outlet "
+          f"{float(out['Q'][0].max()):.1f} m3/s{same}")

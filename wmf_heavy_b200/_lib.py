@@ -86,8 +86,9 @@ SIGNATURES = {
                                   _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "wmf_basin_depth_host": (_i32, [_vp, _i64, _vp]),
     "wmf_shia5_route_workspace": (_sz, [_i64]),
-    "wmf_shia5_route_run": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp,
+    "wmf_shia5_route_run": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                    _vp, _vp, _sz, _vp]),
+    "wmf_fitness_nash_peak": (_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "wmf_shia3_workspace": (_sz, [_i64, _i64]),
     "wmf_shia3_run": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),

@@ -467,10 +467,10 @@ __global__ void k_route_setup(int64_t N, const float *__restrict__ cs, const flo
     acum[c] = 0.0f;
 }
 
-__global__ void __launch_bounds__(256) k_route_diag(const RouteArgs a, int64_t d)
+// one cell on one diagonal: time step t = d - rank(c)
+__device__ __forceinline__ void route_cell(const RouteArgs &a, int64_t c, int64_t d)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, N = a.N;
-    if (c >= N) return;
+    const int64_t N = a.N;
     const int64_t t = d - a.rank[c];
     if (t < 0 || t >= a.N_reg) return;
     const float *ct = a.ct;
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256) k_route_diag(const RouteArgs a, int64_t d
     const float lat = (hf2 + hf3) + hf4;
     const float *qprev = a.qbuf + ((d - 1) & 1) * N;
     float qin = 0.0f;
-    for (int32_t k = a.don_ptr[c]; k < a.don_ptr[c + 1]; k++) qin = qin + qprev[a.don_idx[k]];
+    for (int32_t k = a.don_ptr[c]; k < a.don_ptr[c + 1]; k++) qin = qin + __ldcg(qprev + a.don_idx[k]);   // (written by other blocks)
     S5 = (S5 + lat) + qin / m3mm;
     const float q5 = ct[7 * N + c] * S5;
     S5 = S5 - q5;
@@ -505,6 +505,48 @@ __global__ void __launch_bounds__(256) k_route_diag(const RouteArgs a, int64_t d
     const int32_t j = a.ctrl[c];
     if (j > 0) a.Q[(int64_t)j * a.N_reg + t] = qm3 / a.dt;
     a.sto[c] = S1; a.sto[N + c] = S2; a.sto[2 * N + c] = S3; a.sto[3 * N + c] = S4; a.sto[4 * N + c] = S5;
+}
+
+__global__ void __launch_bounds__(256) k_route_diag(const RouteArgs a, int64_t d)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < a.N) route_cell(a, c, d);
+}
+
+// All diagonals in ONE cooperative launch: the blocks meet at a barrier between diagonals instead of the host launching
+// N_reg + max_rank kernels.  The structure is in upstream-first BFS order, so the cells of one rank are contiguous
+// (level_start[r] = first cell of rank r) and a diagonal touches only the ranks whose time step is in range; a cell is
+// always served by the same thread (its index modulo the grid size), so only the outflow buffer crosses threads.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nblocks)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int *gen = bar + 1;
+        const unsigned int g = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblocks - 1) {
+            *bar = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) {}
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_route_persistent(const RouteArgs a, const int32_t *__restrict__ level_start, int max_rank,
+                                                          unsigned int *bar)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, me = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t d = 0; d < a.N_reg + max_rank; d++) {
+        const int64_t r_lo = d - a.N_reg + 1 > 0 ? d - a.N_reg + 1 : 0, r_hi = d < max_rank ? d : max_rank;
+        const int64_t c_lo = level_start[r_lo], c_hi = level_start[r_hi + 1];
+        for (int64_t c = c_lo / stride * stride + me; c < c_hi; c += stride)
+            if (c >= c_lo) route_cell(a, c, d);
+        grid_barrier(bar, gridDim.x);
+    }
 }
 
 }  // namespace
@@ -627,13 +669,13 @@ int32_t wmf_basin_depth_host(const int32_t *drain, int64_t n, int32_t *depth)
     return dmax;
 }
 
-size_t wmf_shia5_route_workspace(int64_t N) { return wmf_align((size_t)N * 13 * 4) + wmf_align((size_t)N * 2 * 4) + 1024; }
+size_t wmf_shia5_route_workspace(int64_t N) { return wmf_align((size_t)N * 13 * 4) + wmf_align((size_t)N * 2 * 4) + 2048; }
 
 int wmf_shia5_route_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec,
                         const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento, const float *evp,
                         const float *calib, const int32_t *rank, int32_t max_rank, const int32_t *don_ptr,
-                        const int32_t *don_idx, const int32_t *ctrl, int32_t n_ctrl, float *sto, float *acum_rain, float *Q,
-                        void *workspace, size_t ws_bytes, void *stream)
+                        const int32_t *don_idx, const int32_t *ctrl, int32_t n_ctrl, const int32_t *level_start, float *sto,
+                        float *acum_rain, float *Q, void *workspace, size_t ws_bytes, void *stream)
 {
     cudaStream_t st = as_stream(stream);
     WMF_REQUIRE(params_host && cell_static && rain_records && pos_evento && evp && calib && rank && don_ptr && don_idx &&
@@ -651,7 +693,29 @@ int wmf_shia5_route_run(const wmf_shia5_params *params_host, int64_t N, int64_t 
     a.N = N; a.N_reg = N_reg; a.n_rec = (int32_t)(n_rec < 0x7fffffff ? n_rec : 0x7fffffff); a.ct = ct; a.rain = rain_records; a.pos = pos_evento; a.evp = evp; a.rank = rank;
     a.don_ptr = don_ptr; a.don_idx = don_idx; a.ctrl = ctrl; a.sto = sto; a.acum = acum_rain; a.qbuf = qbuf; a.Q = Q;
     a.dt = params_host->dt; a.retorno_gr = params_host->retorno_gr; a.retorno_aq = params_host->retorno_aq;
-    for (int64_t d = 0; d < N_reg + max_rank; d++) k_route_diag<<<blocks_for(N, 256), 256, 0, st>>>(a, d);
+    // ranks in ascending cell order (the structure's BFS order): one cooperative launch walks all diagonals; otherwise
+    // (a caller's own ordering) one launch per diagonal
+    bool persistent = level_start != nullptr;
+    int dev = 0, coop = 0, per_sm = 0, sms = 0;
+    if (persistent) {
+        WMF_CUDA_CHECK(cudaGetDevice(&dev));
+        WMF_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        WMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        WMF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_persistent, 256, 0));
+        persistent = coop && per_sm > 0;
+    }
+    if (persistent) {
+        unsigned int *bar = cur.take<unsigned int>(64);
+        WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
+        WMF_CUDA_CHECK(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
+        int64_t want = (N + 255) / 256;                      // no more blocks than the basin has work for
+        int grid = (int)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
+        int mr = (int)max_rank;
+        void *args[] = {(void *)&a, (void *)&level_start, (void *)&mr, (void *)&bar};
+        WMF_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k_route_persistent, dim3(grid), dim3(256), args, 0, st));
+    } else {
+        for (int64_t d = 0; d < N_reg + max_rank; d++) k_route_diag<<<blocks_for(N, 256), 256, 0, st>>>(a, d);
+    }
     WMF_LAUNCH_CHECK();
     return 0;
 }

@@ -322,7 +322,7 @@ def route_topology(drain: np.ndarray):
 
 def shia5_route_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento: torch.Tensor, evp: torch.Tensor,
                     calib: torch.Tensor, sto: torch.Tensor, drain, ctrl=None, n_ctrl: int = 1, *, dt: float,
-                    retorno_gr: float = 0.0, retorno_aq: float = 0.0):
+                    retorno_gr: float = 0.0, retorno_aq: float = 0.0, persistent: bool = True):
     """Routing EXTENSION (N4; the reference has no behaviour to match): the shipped 5-tank update plus a channel
     store (tank 5) draining along ``drain``.  ``sto`` [5, N] advanced in place; ``ctrl`` int32 [N] = row of Q (> 0) or 0.
     Returns {"StoOut", "Q" [n_ctrl, N_reg] m3/s (row 0 = outlet), "acum_rain"}."""
@@ -346,6 +346,10 @@ def shia5_route_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_e
         raise ValueError("ctrl must hold rows in [0, n_ctrl) for every cell")
     to = lambda a: torch.from_numpy(a).to(dev)
     rank_t, dp_t, di_t, c_t = to(rank), to(don_ptr), to(don_idx if don_idx.size else np.zeros(1, np.int32)), to(c)
+    # the structure's BFS order lists the ranks in ascending order: one cooperative launch can then walk all diagonals
+    ls_t = None
+    if persistent and (np.diff(rank) >= 0).all():
+        ls_t = to(np.searchsorted(rank, np.arange(dmax + 2)).astype(np.int32))
     Q = torch.empty((int(n_ctrl), n_reg), dtype=torch.float32, device=dev)
     acum = torch.empty(N, dtype=torch.float32, device=dev)
     prm = _lib.Shia5Params(dt, retorno_gr, retorno_aq, 0, (C.c_int32 * 3)(1, 1, 1), 0, 0)
@@ -353,8 +357,21 @@ def shia5_route_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_e
     ws = workspace(lib.wmf_shia5_route_workspace(N))
     check(lib.wmf_shia5_route_run(C.addressof(prm), N, n_reg, n_rec, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
                                   ptr(evp), ptr(calib), ptr(rank_t), int(dmax), ptr(dp_t), ptr(di_t), ptr(c_t), int(n_ctrl),
-                                  ptr(sto), ptr(acum), ptr(Q), ptr(ws), ws.numel(), stream_ptr()))
+                                  ptr(ls_t), ptr(sto), ptr(acum), ptr(Q), ptr(ws), ws.numel(), stream_ptr()))
     return {"StoOut": sto, "Q": Q, "acum_rain": acum}
+
+
+def fitness_nash_peak(qsim: torch.Tensor, qobs: torch.Tensor) -> torch.Tensor:
+    """Nash-Sutcliffe efficiency and peak-flow error of P hydrographs (qsim float32 [P, T]) against qobs [T] -> float64 [P, 2]."""
+    require_cuda()
+    _chk_dev(qsim, torch.float32, "qsim")
+    _chk_dev(qobs, torch.float32, "qobs")
+    P, T = qsim.shape
+    if qobs.shape != (T,):
+        raise ValueError("qobs must have one entry per step of qsim")
+    out = torch.empty((P, 2), dtype=torch.float64, device=qsim.device)
+    check(_lib.load().wmf_fitness_nash_peak(ptr(qsim), ptr(qobs), P, T, ptr(out), stream_ptr()))
+    return out
 
 
 # --------------------------------------------------------------------------------------- S4
