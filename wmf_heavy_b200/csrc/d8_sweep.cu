@@ -40,6 +40,10 @@ constexpr int NSLOT = 2 * TW + 2 * TH;  // boundary slots: top row, bottom row, 
 constexpr int WPB = 4;                  // warps (= tiles) per block in the fast kernels
 constexpr uint32_t LNONE = 1023u;       // "no exit": above every slot, and the last bin of phase A's label histogram
 constexpr uint32_t FULL = 0xffffffffu;
+// work flags (one 32-bit word each, cleared before every accumulation): do the rarely needed tile solvers have anything to do?
+constexpr int F_COMPLEX = 0, F_CHAIN = 1, F_UNRES = 2;   // tiles for the multi-sweep solver / for the chain walk / fed by an unresolved upstream
+constexpr int F_NEXT_A = 4, F_NEXT_C = 5;                // work counters of the multi-sweep kernels
+constexpr int NFLAGS = 8;
 
 // meta word of a boundary slot: [15:0] link, [19:16] k, [20] locally unresolved, [21] active
 __host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t link, int k, bool unres, bool active)
@@ -720,7 +724,8 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                                                      Geo g, int ntiles, uint32_t *__restrict__ meta,
                                                      int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
                                                      unsigned long long *__restrict__ row_plain,
-                                                     unsigned long long *__restrict__ wq, uint8_t *__restrict__ tile_top)
+                                                     unsigned long long *__restrict__ wq, uint8_t *__restrict__ tile_top,
+                                                     uint32_t *__restrict__ flags, bool has_multi)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ the same again for mask words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -890,7 +895,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     cp_async_wait_all();
     __syncwarp();
     if (complex_tile) {                              // the general solver redoes this tile
-        if (lane == 0) { tile_class[tile] = 1; tile_top[tile] = 1; }
+        if (lane == 0) { tile_class[tile] = 1; tile_top[tile] = 1; flags[has_multi ? F_COMPLEX : F_CHAIN] = 1u; }
         return;
     }
     // tile_top: can an inner first-row slot of this tile be an exit?  Only through upward flow in row 0 (never in a
@@ -1177,12 +1182,19 @@ __global__ void __launch_bounds__(MWPB * 32) k_multiA(const int8_t *__restrict__
                                                       uint32_t *__restrict__ meta, int32_t *__restrict__ exit_acc,
                                                       uint8_t *__restrict__ tile_class, unsigned long long *__restrict__ wq,
                                                       uint8_t *__restrict__ tile_top, uint32_t *__restrict__ codes4,
-                                                      uint16_t *__restrict__ labels, unsigned long long *__restrict__ sweeps_of)
+                                                      uint16_t *__restrict__ labels, unsigned long long *__restrict__ sweeps_of,
+                                                      uint32_t *__restrict__ flags)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [MWPB][TH * 32] codes + [MWPB][HBINS] histogram + [MWPB][32 * LTAB] tables
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * MWPB + warp;
-    if (tile >= ntiles || tile_class[tile] != 1) return;
+    if (flags[F_COMPLEX] == 0u) return;               // (nearly always: no tile has upward flow, e.g. a Scheidegger network)
+  // the warps take tiles from a counter: tiles differ in the number of sweeps they need
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = (int)atomicAdd(&flags[F_NEXT_A], 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile >= ntiles) return;
+    if (tile_class[tile] != 1) continue;
     int ty, tx, th, tw;
     tile_dims(g, tile, ty, tx, th, tw);
     uint32_t *codes = s_dyn + (size_t)warp * TH * 32;
@@ -1311,8 +1323,9 @@ __global__ void __launch_bounds__(MWPB * 32) k_multiA(const int8_t *__restrict__
         prev_unknown = unknown;
     }
     if (!ok) {                                       // the chain-walk solver redoes this tile
-        if (lane == 0) { tile_class[tile] = 3; tile_top[tile] = 1; }
-        return;
+        if (lane == 0) { tile_class[tile] = 3; tile_top[tile] = 1; flags[F_CHAIN] = 1u; }
+        __syncwarp();
+        continue;
     }
     if (lane == 0) { tile_class[tile] = 4; tile_top[tile] = (top_up || th != TH || tw != TW) ? 1 : 0; sweeps_of[tile] = (unsigned long long)nsweeps; }
     // unused slots of a ragged tile: inactive
@@ -1329,6 +1342,8 @@ __global__ void __launch_bounds__(MWPB * 32) k_multiA(const int8_t *__restrict__
         if (x_t) x_t[s] = h;
         w_t[s] = PEND1 | ((unsigned long long)((m >> 16) & 0xFu) << W_K) | (uint32_t)h;
     }
+    __syncwarp();
+  }
 }
 
 template <typename TO, typename T>
@@ -1365,12 +1380,18 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(MWPB * 32) k_multiC(Geo g, int ntiles, const uint32_t *__restrict__ codes4,
                                                       const unsigned long long *__restrict__ wq, const uint8_t *__restrict__ tile_top,
                                                       const T *__restrict__ extra, const uint8_t *__restrict__ tile_class,
-                                                      T *__restrict__ wait, TO *__restrict__ acc, unsigned long long *__restrict__ sweeps_of)
+                                                      T *__restrict__ wait, TO *__restrict__ acc, unsigned long long *__restrict__ sweeps_of,
+                                                      uint32_t *__restrict__ flags)
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [MWPB][TH * 32] codes + [MWPB][NSLOT] boundary inflows (T)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * MWPB + warp;
-    if (tile >= ntiles || tile_class[tile] != 4) return;
+    if (flags[F_COMPLEX] == 0u) return;
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = (int)atomicAdd(&flags[F_NEXT_C], 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile >= ntiles) return;
+    if (tile_class[tile] != 4) continue;
     int ty, tx, th, tw;
     tile_dims(g, tile, ty, tx, th, tw);
     uint32_t *codes = s_dyn + (size_t)warp * TH * 32;
@@ -1477,6 +1498,8 @@ __global__ void __launch_bounds__(MWPB * 32) k_multiC(Geo g, int ntiles, const u
         rows_waiting = next_waiting;
         if (rows_waiting == 0) { if (lane == 0) sweeps_of[tile] |= (unsigned long long)(sweep + 1) << 32; break; }
     }
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1575,9 +1598,11 @@ __device__ __forceinline__ void general_walk(const uint8_t *kk, uint8_t *cnt, T 
 template <int ENC>
 __global__ void __launch_bounds__(GTH) k_generalA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
                                                   const uint8_t *__restrict__ tile_class, uint32_t *__restrict__ meta,
-                                                  int32_t *__restrict__ exit_acc, unsigned long long *__restrict__ wq)
+                                                  int32_t *__restrict__ exit_acc, unsigned long long *__restrict__ wq,
+                                                  const uint32_t *__restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+  if (flags[F_CHAIN] == 0u) return;
   // each block owns a contiguous range of tiles and looks at all their classes at once: nearly always
   // nothing is complex and the block leaves after one coalesced load and one barrier
   const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
@@ -1632,9 +1657,11 @@ template <int ENC, typename T, typename TO>
 __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
                                                   const uint8_t *__restrict__ tile_class, const unsigned long long *__restrict__ wq,
                                                   const int32_t *__restrict__ par, const T *__restrict__ extra,
-                                                  const uint8_t *__restrict__ extra_unres, TO *__restrict__ out)
+                                                  const uint8_t *__restrict__ extra_unres, TO *__restrict__ out,
+                                                  const uint32_t *__restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+  if (flags[F_CHAIN] == 0u && flags[F_UNRES] == 0u) return;
   const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
   bool any_mine = false;
   // classes: 0 one-pass sweeps, 4 multi-sweep; everything else (1 / 3: the sweeps cannot solve it, 2: fed by an unresolved
@@ -1818,7 +1845,7 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *_
 // tell without a host round trip.
 __global__ void k_g_unres(Geo g, int64_t nnodes, const uint8_t *__restrict__ tile_top, const int32_t *__restrict__ par,
                           const unsigned long long *__restrict__ wq, uint8_t *__restrict__ tile_class,
-                          const unsigned long long *__restrict__ gcnt)
+                          const unsigned long long *__restrict__ gcnt, uint32_t *__restrict__ flags)
 {
     {
         const int lane = threadIdx.x & 31;
@@ -1837,7 +1864,7 @@ __global__ void k_g_unres(Geo g, int64_t nnodes, const uint8_t *__restrict__ til
         const int tile = (int)(i / NSLOT), ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
         int s2;
         const int te = exit_target(g, tg, ty, tx, (int)(i - (int64_t)tile * NSLOT), w_k(w), true, s2);
-        if (te >= 0) tile_class[te] = 2;                    // (racing writers all store the same value)
+        if (te >= 0) { tile_class[te] = 2; flags[F_UNRES] = 1u; }   // (racing writers all store the same values)
     }
 }
 
@@ -1854,7 +1881,7 @@ __device__ __forceinline__ void inflow_add<int64_t>(int64_t *p, int64_t v)
 template <typename T>
 __global__ void k_push_inflow(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const T *__restrict__ A,
                               const int32_t *__restrict__ cnt, T *__restrict__ inflow, uint8_t *__restrict__ ext_unres,
-                              uint8_t *__restrict__ tile_class)
+                              uint8_t *__restrict__ tile_class, uint32_t *__restrict__ flags)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnodes) return;
@@ -1866,6 +1893,7 @@ __global__ void k_push_inflow(Geo g, int64_t nnodes, const uint32_t *__restrict_
     else {                                                            // unresolved upstream: the entry never finalises
         ext_unres[e] = 1;
         tile_class[e / NSLOT] = 2;                                    // (racing writers all store non-zero)
+        flags[F_UNRES] = 1u;
     }
 }
 
@@ -2029,7 +2057,8 @@ __global__ void k_widen(const int32_t *__restrict__ a, T *__restrict__ b, int64_
 template <typename T>
 __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
                                StripePaths sp, const int64_t *__restrict__ ext_inflow, const uint8_t *__restrict__ ext_un,
-                               T *__restrict__ extra, uint8_t *__restrict__ extra_unres, uint8_t *__restrict__ tile_class)
+                               T *__restrict__ extra, uint8_t *__restrict__ extra_unres, uint8_t *__restrict__ tile_class,
+                               uint32_t *__restrict__ flags)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n2 = 2 * g.nx;
     if (i >= n2) return;
@@ -2042,7 +2071,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
         const int32_t item = sp.path[(int64_t)h * n2 + i];
         int64_t e = item & ~JUMP;
         inflow_add<T>(&extra[e], (T)v);
-        if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; }
+        if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
         if (item & JUMP) {                                   // the entries the jump skipped inside its group of tile rows
             const int mr = macro_of(g, e);
             int64_t x = first_exit(meta, e);
@@ -2051,7 +2080,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
                 const int32_t en = r.y;
                 if (en < 0 || macro_of(g, en) != mr) break;
                 inflow_add<T>(&extra[en], (T)v);
-                if (u) { extra_unres[en] = 1; tile_class[en / NSLOT] = 2; }
+                if (u) { extra_unres[en] = 1; tile_class[en / NSLOT] = 2; flags[F_UNRES] = 1u; }
                 x = r.x;
             }
         }
@@ -2060,7 +2089,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
         int64_t e = sp.pce[i], x = sp.pcx[i];
         for (int64_t hops = 0; hops <= nnodes; hops++) {
             inflow_add<T>(&extra[e], (T)v);
-            if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; }
+            if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
             if (x < 0) break;
             const int2 r = pe[x];
             if (r.y < 0) break;
@@ -2075,7 +2104,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
 // arrives from the other stripes.
 struct SweepWs {
     uint32_t *meta; unsigned long long *wq; int32_t *par; uint8_t *tile_class, *tile_top; unsigned long long *row_plain, *gcnt;
-    uint32_t *codes4; void *scratch;                                          // multi-sweep solver: decoded tiles, state across sweeps
+    uint32_t *flags; uint32_t *codes4; void *scratch;                                          // multi-sweep solver: decoded tiles, state across sweeps
     int32_t *exit_acc, *parent, *cnt; int64_t *A, *inflow; uint8_t *blocked, *ext_unres;   // wide
     int2 *pe; void *extra; uint8_t *extra_unres;                              // stripe
     StripePaths sp;
@@ -2096,6 +2125,7 @@ static SweepWs carve_ws(void *ws, size_t ws_bytes, const Geo &g, bool wide, bool
     w.tile_top = cur.take<uint8_t>(nt);
     w.row_plain = cur.take<unsigned long long>(nt);
     w.gcnt = cur.take<unsigned long long>(GCNT_BYTES / sizeof(unsigned long long));
+    w.flags = cur.take<uint32_t>(NFLAGS);                     // (right behind the counters: one memset clears both)
     if (!wide) {                                              // (the 64-bit forest engine keeps the chain-walk solver for such tiles)
         w.codes4 = cur.take<uint32_t>(nt * TH * 32);
         w.scratch = stripe ? (void *)cur.take<int64_t>(nt * TH * TW) : (void *)cur.take<int32_t>(nt * TH * TW);
@@ -2169,7 +2199,7 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
 #define WMF_LAUNCH_A(AL_, MK_)                                                                                                   \
     k_sweepA<ENC, AL_, MK_><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, \
-                                                                  w.wq, w.tile_top)
+                                                                  w.wq, w.tile_top, w.flags, w.codes4 != nullptr)
     if (mask) { if (al) WMF_LAUNCH_A(true, true); else WMF_LAUNCH_A(false, true); }
     else { if (al) WMF_LAUNCH_A(true, false); else WMF_LAUNCH_A(false, false); }
 #undef WMF_LAUNCH_A
@@ -2184,10 +2214,11 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
                 if (dev >= 0 && dev < 64) done[dev] = true;
             }
         }
-        k_multiA<ENC><<<(ntiles + MWPB - 1) / MWPB, MWPB * 32, smemM, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.wq,
-                                                                            w.tile_top, w.codes4, (uint16_t *)w.scratch, w.row_plain);
+        const int want = (ntiles + MWPB - 1) / MWPB, cap = sm_count() * 3;      // three blocks per SM fit (shared memory)
+        k_multiA<ENC><<<want < cap ? want : cap, MWPB * 32, smemM, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.wq,
+                                                                         w.tile_top, w.codes4, (uint16_t *)w.scratch, w.row_plain, w.flags);
     }
-    k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq);
+    k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq, w.flags);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -2222,10 +2253,11 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
 #undef WMF_LAUNCH_C
     if (w.codes4 && wq) {
         const size_t smemM = (size_t)MWPB * (TH * 32 * sizeof(uint32_t) + NSLOT * sizeof(T));
-        k_multiC<T, TO><<<(ntiles + MWPB - 1) / MWPB, MWPB * 32, smemM, st>>>(g, ntiles, w.codes4, wq, w.tile_top, extra, w.tile_class,
-                                                                              (T *)w.scratch, acc, w.row_plain);
+        const int want = (ntiles + MWPB - 1) / MWPB, cap = sm_count() * 4;
+        k_multiC<T, TO><<<want < cap ? want : cap, MWPB * 32, smemM, st>>>(g, ntiles, w.codes4, wq, w.tile_top, extra, w.tile_class,
+                                                                           (T *)w.scratch, acc, w.row_plain, w.flags);
     }
-    k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, wq, w.par, extra, extra_unres, acc);
+    k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, wq, w.par, extra, extra_unres, acc, w.flags);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -2235,7 +2267,7 @@ static int sweep_phaseG_packed(const Geo &g, int ntiles, int64_t nnodes, const S
 {
     k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, pe, w.wq);
     k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
-    k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt);
+    k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt, w.flags);
     WMF_LAUNCH_CHECK();
     return 0;
 }
@@ -2283,7 +2315,7 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, acc, nx);
     if (!wide) {
-        WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, GCNT_BYTES, st));
+        WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, (size_t)((char *)(w.flags + NFLAGS) - (char *)w.gcnt), st));
         int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
         if (rc) return rc;
         rc = sweep_phaseG_packed(g, ntiles, nnodes, w, nullptr, st);
@@ -2298,7 +2330,7 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int
     WMF_LAUNCH_CHECK();
     rc = forest_accum_i64(w.parent, w.exit_acc, w.A, w.cnt, nnodes, st, w.blocked);
     if (rc) return rc;
-    k_push_inflow<int64_t><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.A, w.cnt, w.inflow, w.ext_unres, w.tile_class);
+    k_push_inflow<int64_t><<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, w.meta, w.A, w.cnt, w.inflow, w.ext_unres, w.tile_class, w.flags);
     WMF_LAUNCH_CHECK();
     return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, nullptr, (const T *)w.inflow, w.ext_unres, al, acc, st);
 }
@@ -2318,7 +2350,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     const SweepWs w = carve_ws(ws, ws_bytes, g, false, true);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const bool al = aligned4(dir, mask, nullptr, nx);
-    WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, GCNT_BYTES, st));
+    WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, (size_t)((char *)(w.flags + NFLAGS) - (char *)w.gcnt), st));
     int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
     if (rc) return rc;
     k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, w.pe, w.wq);
@@ -2336,7 +2368,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
         k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp);
         WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
         k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
-        k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt);
+        k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt, w.flags);
         WMF_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
     }
     k_stripe_summary<<<blocks_for(2 * nx, 128), 128, 0, st>>>(g, w.meta, w.par, w.wq, w.sp.plink, recs);
@@ -2360,7 +2392,7 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny,
     // stripes send is routed along the contracted paths into `extra`, and phase C adds it to what it pulls.
     T *extra = (T *)w.extra;                                 // (cleared by the local pass)
     k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, w.pe, w.sp, ext_inflow, ext_un,
-                                                                                          extra, w.extra_unres, w.tile_class);
+                                                                                          extra, w.extra_unres, w.tile_class, w.flags);
     WMF_LAUNCH_CHECK();
     return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, w.wq, (const T *)extra, w.extra_unres, al, acc, st);
 }
