@@ -224,7 +224,9 @@ typedef struct {
     int32_t strict;       /* 1: the Fortran's own operations (RainInt / 1000., (S1 / H1) ** 0.6 through powf) instead of the
                            * fast forms (x * 0.001f, S1 * (1 / H1), exp2(0.6 * log2 x) on the SFU): ~2x slower, bit-level parity */
 } wmf_shia5_params;
-size_t wmf_shia5_workspace(int64_t N, int64_t N_reg, int32_t P);
+/* diagnostics != 0: any of the optional per-step series / per-cell accumulators is requested (mean_storage, mean_speed,
+ * mean_retorno, mean_vfluxes, vfluxes, rc_coef, retorned) */
+size_t wmf_shia5_workspace(int64_t N, int64_t N_reg, int32_t P, int32_t diagnostics);
 int wmf_shia5_run(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,
                   const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento,
                   const float *evp, const float *calib, float *sto, float *hspeed, float *balance,
@@ -241,6 +243,19 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
                        float *mean_rain, float *acum_rain, float *mean_storage, float *mean_speed,
                        const int32_t *snap_slot, int32_t n_snap, float *snap_out,
                        void *workspace, size_t ws_bytes, void *stream);
+
+/* The same run with the optional outputs of the shipped shia_v1 (all nullable): mean_retorno float [P][N_reg]
+ * (show_mean_retorno, Modelos_heavy.f90:525-527), mean_vfluxes float [P][4][N_reg] and vfluxes float [P][4][N] of the last
+ * step (save_vfluxes, :429-433, 502-507), rc_coef float [P][2][N] (save_rc, :435-438, 543-544: accumulated vflux2 - vflux3
+ * capped by the accumulated rain; the accumulated rain), retorned float [P][N] (Retorned, :424; retorned_per_step = 1: the
+ * array is cleared after every step, as show_mean_retorno / save_retorno make the Fortran do, so it ends as zeros). */
+int wmf_shia5_run_ext(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,
+                      const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento,
+                      const float *evp, const float *calib, float *sto, float *hspeed, float *balance,
+                      float *mean_rain, float *acum_rain, float *mean_storage, float *mean_speed,
+                      const int32_t *snap_slot, int32_t n_snap, float *snap_out,
+                      float *mean_retorno, float *mean_vfluxes, float *vfluxes, float *rc_coef, float *retorned,
+                      int32_t retorned_per_step, void *workspace, size_t ws_bytes, void *stream);
 
 /* N4 (EXTENSION: the reference has no behaviour to match here): channel routing behind the shipped 5-tank
  * update.  Modelos_heavy.f90 declares tank 5, `drena` and the control points (:52-55, :91-92, :202-211) but never moves

@@ -375,3 +375,31 @@ def test_shia5_vs_fortran_transliteration(name, strict):
     np.testing.assert_allclose(out["mean_rain"].cpu().numpy(), FG[q + "Mean_Rain"], rtol=2e-5, atol=1e-7)
     np.testing.assert_allclose(out["mean_storage"][0].cpu().numpy(), FG[q + "mean_storage"], rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(out["mean_speed"][0].cpu().numpy(), FG[q + "mean_speed"], rtol=1e-4, atol=1e-9)
+
+
+def test_shia5_optional_outputs_vs_transliteration():
+    """The optional outputs of the shipped shia_v1 -- mean_retorno, mean_vfluxes, the last step's vfluxes, rc_coef
+    (Modelos_heavy.f90:424-438, 502-507, 525-531, 543-544) -- against the literal transliteration's vectors (the C oracle
+    does not carry them): the case runs with show_mean_retorno, save_vfluxes and save_rc set."""
+    from test_oracle import _fortran_shia_case
+    inp, calib, sto, hs = _fortran_shia_case("mixed_flags")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    q = "shia/mixed_flags/out/"
+    for strict, atol in ((True, ATOL_STRICT), (False, ATOL_FAST)):
+        out = ops.shia5_run(dev(helpers.cell_static(inp)), dev(inp.rain_records), dev(inp.pos_evento), dev(inp.evp),
+                            dev(calib[None].astype(np.float32)), dev(sto[None].astype(np.float32)), None, dt=inp.dt,
+                            speed_type=inp.speed_type, retorno_gr=inp.retorno_gr, retorno_aq=inp.retorno_aq,
+                            calc_niter=inp.calc_niter, strict=strict, show_mean_retorno=True, save_vfluxes=True, save_rc=True)
+        np.testing.assert_allclose(out["StoOut"][0].cpu().numpy(), FG[q + "StoOut"], rtol=1e-5, atol=atol)
+        np.testing.assert_allclose(out["mean_retorno"][0].cpu().numpy(), FG[q + "mean_retorno"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(out["mean_vfluxes"][0].cpu().numpy(), FG[q + "mean_vfluxes"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(out["vfluxes"][0].cpu().numpy(), FG[q + "vfluxes"], rtol=1e-5, atol=atol)
+        np.testing.assert_allclose(out["rc_coef"][0].cpu().numpy(), FG[q + "rc_coef"], rtol=2e-5, atol=10 * atol)
+        assert not out["retorned"].any()                     # cleared after every step when the mean is shown
+    acc = ops.shia5_run(dev(helpers.cell_static(inp)), dev(inp.rain_records), dev(inp.pos_evento), dev(inp.evp),
+                        dev(calib[None].astype(np.float32)), dev(sto[None].astype(np.float32)), None, dt=inp.dt,
+                        speed_type=inp.speed_type, retorno_gr=inp.retorno_gr, retorno_aq=inp.retorno_aq,
+                        calc_niter=inp.calc_niter, with_retorned=True)
+    T = inp.pos_evento.shape[0]
+    np.testing.assert_allclose(float(acc["retorned"].sum()) / sto.shape[1], float(FG[q + "mean_retorno"].astype(np.float64).sum()),
+                               rtol=1e-4)                    # accumulated over the run = the per-step means added up

@@ -79,11 +79,13 @@ SIGNATURES = {
     "wmf_time_to_out": (_int, [_vp, _vp, _vp, _i64, _i64, _int, C.c_double, C.c_double, _vp, _vp, _sz, _vp]),
     "wmf_stream_nodes_workspace": (_sz, [_i64, _i64]),
     "wmf_stream_nodes": (_int, [_vp, _vp, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "wmf_shia5_workspace": (_sz, [_i64, _i64, _i32]),
+    "wmf_shia5_workspace": (_sz, [_i64, _i64, _i32, _i32]),
     "wmf_shia5_run": (_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp, _sz, _vp]),
     "wmf_shia5_run_snap": (_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "wmf_shia5_run_ext": (_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "wmf_basin_depth_host": (_i32, [_vp, _i64, _vp]),
     "wmf_shia5_route_workspace": (_sz, [_i64]),
     "wmf_shia5_route_run": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp,

@@ -153,6 +153,10 @@ struct Shia5Args {
     float *acum_rain;           // [N]
     double *part;               // [P][nblk][N_reg+1][K]
     int nblk;
+    float *vfluxes;             // [P][4][N] or null: the vertical fluxes of the last step (Modelos:429-433)
+    float *rc_coef;             // [P][2][N] or null: runoff-coefficient accumulators (Modelos:435-438, 543-544)
+    float *retorned;            // [P][N] or null: return flow accumulated per cell (Modelos:424)
+    int retorned_per_step;      // Retorned is cleared after every step (show_mean_retorno / save_retorno, Modelos:525-531)
     const int32_t *snap_slot;   // [N_reg] or null: slot (>= 0) that receives the storages after that step
     float *snap_out;            // [P][n_snap][5][N]
     int n_snap;
@@ -174,12 +178,13 @@ __device__ __forceinline__ float pow06(float x)
 // Per-step sums.  K = 2: {R, q} with q = (storage now - storage before) + (v4 + Evp_loss) per cell, so that
 // balance(t) = sum(q) - sum(R) (Modelos:533) needs ONE reduced quantity beside the rain; forming the
 // difference per cell in fp32 also avoids the catastrophic cancellation of the Fortran's two ~5N-term sums.
-// DIAG adds {S1,S2,S3,S4,h1,h2,h3} -> K = 9 (slot 0 of the series carries the constant sums of S5 and h4).
+// DIAG adds {S1,S2,S3,S4,h1,h2,h3} and {Ret, vflux1..4} -> K = 14 (slot 0 of the series carries the constant sums of S5
+// and h4); it also keeps the per-cell accumulators of the optional outputs (rc_coef, Retorned, the last step's vfluxes).
 // T2: some tank uses the kinematic-wave speed (speed_type 2); the all-type-1 kernel carries none of that code.
 template <bool DIAG, bool T2, bool SNAP, bool STRICT>
 __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
 {
-    constexpr int K = DIAG ? 9 : 2;
+    constexpr int K = DIAG ? 14 : 2;
     __shared__ double stage[WARPS][TB][K];
     const int64_t N = a.N, T = a.N_reg;
     const int pset = blockIdx.y;
@@ -228,12 +233,15 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
         if (DIAG) {
             v[2] = live ? S1 : 0.0f; v[3] = live ? S2 : 0.0f; v[4] = live ? S3 : 0.0f; v[5] = live ? S4 : 0.0f;
             v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
+            v[9] = v[10] = v[11] = v[12] = v[13] = 0.0f;
         }
         red.add(v);
     }
     float sto_prev = (S1 + S2) + (S3 + S4);
 
     const int32_t *rain_cc = a.rain + cc;                // this cell's column of the rain records
+    float ex_ret = 0.0f, ex_v1 = 0.0f, ex_v2 = 0.0f, ex_v3 = 0.0f, ex_v4 = 0.0f;   // (DIAG) this step's return flow and vfluxes
+    float rc1 = 0.0f, rc2 = 0.0f, ret_acc = 0.0f;
     auto one_step = [&](int64_t t, float &vR, float &vq) {
         const int pos = a.pos[t];
         float R = 0.0f;
@@ -252,7 +260,14 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
         float v3 = fminf(v2, vs[2]); S3 = (S3 + v2) - v3;
         float v4 = fminf(v3, vs[3]); S4 = (S4 + v3) - v4;
         if (raq) { float ra = fmaxf(0.0f, S4 - H3); S3 = S3 + ra; S4 = S4 - ra; }          // :414-418
-        if (rgr) { float rg = fmaxf(0.0f, S3 - H2); S2 = S2 + rg; S3 = S3 - rg; }          // :420-427
+        float rg = 0.0f;
+        if (rgr) { rg = fmaxf(0.0f, S3 - H2); S2 = S2 + rg; S3 = S3 - rg; }                // :420-427
+        if (DIAG) {                                                                        // :424-438 (optional outputs)
+            ex_ret = rg; ex_v1 = v1; ex_v2 = v2 + rg; ex_v3 = v3 - rg; ex_v4 = v4;
+            if (a.retorned_per_step) ret_acc = rg; else ret_acc = ret_acc + rg;
+            rc1 = (rc1 + ex_v2) - ex_v3;
+            rc2 = rc2 + R;
+        }
         float hf, ar;
         if (!t2_0) hf = fl[0] * S2;                                                        // :461-491
         else { ar = 0.0f; calc_speed<!STRICT>(S2 * m3mm, coef[0], expo[0], L, dt, niter, hs[0], ar); hf = fminf(((ar * hs[0]) * dt) / m3mm, S2); }
@@ -283,6 +298,8 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
             if (DIAG) {
                 v[2] = live ? S1 : 0.0f; v[3] = live ? S2 : 0.0f; v[4] = live ? S3 : 0.0f; v[5] = live ? S4 : 0.0f;
                 v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
+                v[9] = live ? ex_ret : 0.0f;
+                v[10] = live ? ex_v1 : 0.0f; v[11] = live ? ex_v2 : 0.0f; v[12] = live ? ex_v3 : 0.0f; v[13] = live ? ex_v4 : 0.0f;
             }
             red.add(v);
         }
@@ -306,6 +323,17 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
 #pragma unroll
         for (int i = 0; i < 4; i++) hso[i * N + c] = hs[i];
         if (pset == 0 && a.acum_rain) a.acum_rain[c] = acum;
+        if (DIAG) {
+            if (a.vfluxes) {
+                float *o = a.vfluxes + (int64_t)pset * 4 * N + c;
+                o[0] = ex_v1; o[N] = ex_v2; o[2 * N] = ex_v3; o[3 * N] = ex_v4;
+            }
+            if (a.rc_coef) {                                                               // :543-544
+                float *o = a.rc_coef + (int64_t)pset * 2 * N + c;
+                o[0] = rc1 > rc2 ? rc2 : rc1; o[N] = rc2;
+            }
+            if (a.retorned) a.retorned[(int64_t)pset * N + c] = a.retorned_per_step ? 0.0f : ret_acc;
+        }
     }
 }
 
@@ -313,7 +341,8 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
 // (Modelos:533); Mean_Rain(t) = rain_sum / N (:494); mean_storage (:518); mean_speed (:522).
 __global__ void k_shia5_outputs(const double *__restrict__ totals, int K, int64_t T, int64_t N, int P,
                                 float *__restrict__ balance, float *__restrict__ mean_rain,
-                                float *__restrict__ mean_storage, float *__restrict__ mean_speed)
+                                float *__restrict__ mean_storage, float *__restrict__ mean_speed,
+                                float *__restrict__ mean_retorno, float *__restrict__ mean_vfluxes)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)P * T) return;
@@ -323,7 +352,12 @@ __global__ void k_shia5_outputs(const double *__restrict__ totals, int K, int64_
     const double *now = tot + (t + 1) * K, *prev = tot + t * K;
     balance[i] = (float)(now[1] - now[0]);
     if (p == 0 && mean_rain) mean_rain[t] = (float)(now[0] / (double)N);
-    if (K == 9) {
+    if (K == 14) {
+        if (mean_retorno) mean_retorno[i] = (float)(now[9] / (double)N);                    // Modelos:525-527
+        if (mean_vfluxes) {                                                                  // Modelos:502-507
+            float *mf = mean_vfluxes + (int64_t)p * 4 * T;
+            for (int k = 0; k < 4; k++) mf[k * T + t] = (float)(now[10 + k] / (double)N);
+        }
         if (mean_storage) {
             float *ms = mean_storage + (int64_t)p * 5 * T;
             for (int k = 0; k < 4; k++) ms[k * T + t] = (float)(now[2 + k] / (double)N);
@@ -553,11 +587,12 @@ __global__ void __launch_bounds__(256) k_route_persistent(const RouteArgs a, con
 
 extern "C" {
 
-size_t wmf_shia5_workspace(int64_t N, int64_t N_reg, int32_t P)
+size_t wmf_shia5_workspace(int64_t N, int64_t N_reg, int32_t P, int32_t diagnostics)
 {
     int64_t nblk = (N + TH - 1) / TH;
-    size_t part = (size_t)P * nblk * (N_reg + 1) * 10 * sizeof(double);
-    size_t tot = (size_t)P * (N_reg + 1) * 10 * sizeof(double);
+    const size_t K = diagnostics ? 14 : 2;                   // per-step sums the run reduces (see k_shia5)
+    size_t part = (size_t)P * nblk * (N_reg + 1) * K * sizeof(double);
+    size_t tot = (size_t)P * (N_reg + 1) * K * sizeof(double);
     return wmf_align(part) + wmf_align(tot) + 1024;
 }
 
@@ -577,14 +612,26 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
                        float *mean_storage, float *mean_speed, const int32_t *snap_slot, int32_t n_snap, float *snap_out,
                        void *workspace, size_t ws_bytes, void *stream)
 {
+    return wmf_shia5_run_ext(params_host, N, N_reg, n_rec, P, cell_static, rain_records, pos_evento, evp, calib, sto, hspeed, balance,
+                             mean_rain, acum_rain, mean_storage, mean_speed, snap_slot, n_snap, snap_out, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, 0, workspace, ws_bytes, stream);
+}
+
+int wmf_shia5_run_ext(const wmf_shia5_params *params_host, int64_t N, int64_t N_reg, int64_t n_rec, int32_t P,
+                      const float *cell_static, const int32_t *rain_records, const int32_t *pos_evento, const float *evp,
+                      const float *calib, float *sto, float *hspeed, float *balance, float *mean_rain, float *acum_rain,
+                      float *mean_storage, float *mean_speed, const int32_t *snap_slot, int32_t n_snap, float *snap_out,
+                      float *mean_retorno, float *mean_vfluxes, float *vfluxes, float *rc_coef, float *retorned,
+                      int32_t retorned_per_step, void *workspace, size_t ws_bytes, void *stream)
+{
     cudaStream_t st = as_stream(stream);
     WMF_REQUIRE((snap_slot == nullptr) == (snap_out == nullptr) && n_snap >= 0 && (snap_slot == nullptr || n_snap > 0), WMF_E_ARG,
                 "snap_slot, snap_out and n_snap go together");
     WMF_REQUIRE(params_host && cell_static && rain_records && pos_evento && evp && calib && sto && hspeed && balance,
                 WMF_E_ARG, "null pointer");
     WMF_REQUIRE(N > 0 && N_reg > 0 && n_rec > 0 && P > 0 && P <= 65535, WMF_E_ARG, "bad size");
-    const bool diag = mean_storage || mean_speed;
-    const int K = diag ? 9 : 2;
+    const bool diag = mean_storage || mean_speed || mean_retorno || mean_vfluxes || vfluxes || rc_coef || retorned;
+    const int K = diag ? 14 : 2;
     const int nblk = (int)((N + TH - 1) / TH);
     WsCursor cur(workspace, ws_bytes);
     double *part = cur.take<double>((size_t)P * nblk * (N_reg + 1) * K);
@@ -595,6 +642,7 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
     a.p = *params_host; a.N = N; a.N_reg = N_reg; a.n_rec = (int32_t)n_rec; a.cs = cell_static; a.rain = rain_records; a.pos = pos_evento;
     a.evp = evp; a.calib = calib; a.sto = sto; a.hspeed = hspeed; a.acum_rain = acum_rain; a.part = part; a.nblk = nblk;
     a.snap_slot = snap_slot; a.snap_out = snap_out; a.n_snap = n_snap;
+    a.vfluxes = vfluxes; a.rc_coef = rc_coef; a.retorned = retorned; a.retorned_per_step = retorned_per_step;
     dim3 grid(nblk, P);
     const bool t2 = a.p.speed_type[0] != 1 || a.p.speed_type[1] != 1 || a.p.speed_type[2] != 1;
     const int variant = (diag ? 4 : 0) | (t2 ? 2 : 0) | (snap_slot ? 1 : 0);
@@ -614,7 +662,7 @@ int wmf_shia5_run_snap(const wmf_shia5_params *params_host, int64_t N, int64_t N
     const int64_t TK = (N_reg + 1) * K;
     fold_blocks(part, nblk, TK, P, totals, st);
     k_shia5_outputs<<<blocks_for((int64_t)P * N_reg, 256), 256, 0, st>>>(totals, K, N_reg, N, P, balance, mean_rain,
-                                                                         mean_storage, mean_speed);
+                                                                         mean_storage, mean_speed, mean_retorno, mean_vfluxes);
     WMF_LAUNCH_CHECK();
     return 0;
 }

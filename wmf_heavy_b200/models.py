@@ -42,13 +42,20 @@ sim_sediments = sim_slides = sim_floods = 0
 save_storage = save_speed = save_retorno = save_vfluxes = save_rc = 0
 show_storage = show_speed = show_mean_speed = show_mean_retorno = show_area = 0
 separate_fluxes = separate_rain = 0
-route_channels = 0        # EXTENSION (not in the reference, whose Q is 0 as shipped): 1 routes tank 5 along `drena`
+route_channels = 0       # EXTENSION (not in the reference, whose Q is 0 as shipped): 1 routes tank 5 along `drena`
+strict_arithmetic = 0    # 1: the Fortran's own operation forms in the kernel (true division, powf): ~2x slower, bit-level parity
 guarda_cond = None
 # outputs
 mean_rain = None
 acum_rain = None
 mean_storage = None
 mean_speed = None
+mean_retorno = None      # (N_reg,)   show_mean_retorno (Modelos_heavy.f90:525-527)
+mean_vfluxes = None      # (4, N_reg) save_vfluxes (:502-507)
+vfluxes = None           # (4, N) of the last step (:429-433)
+rc_coef = None           # (2, N) save_rc (:435-438, 543-544)
+retorned = None          # (1, N) return flow accumulated per cell (:424)
+guarda_vfluxes = None
 idevento = None
 posevento = None
 
@@ -196,10 +203,12 @@ def cell_static_table(n: int) -> np.ndarray:
 
 
 def _reject_out_of_scope():
-    for nm in ("sim_sediments", "sim_slides", "sim_floods", "separate_rain", "save_speed",
-               "save_retorno", "save_vfluxes", "save_rc"):
+    for nm in ("sim_sediments", "sim_slides", "sim_floods", "separate_rain", "save_speed", "save_retorno"):
         if int(globals()[nm]) == 1:
             raise NotImplementedError(f"models.{nm} = 1 is outside the B200 hot path (see DESIGN.md, out of scope)")
+    if int(save_vfluxes) == 1 and guarda_vfluxes is not None and np.any(np.asarray(guarda_vfluxes) > 0):
+        raise NotImplementedError("per-step vertical-flux records (guarda_vfluxes) are outside the hot path; "
+                                  "mean_vfluxes and the last step's vfluxes are returned")
 
 
 def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int, sto_in=None, hspeed_in=None,
@@ -207,7 +216,7 @@ def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int,
     """P parameter sets x one basin in one launch.  ``calibs`` (P, 11); ``sto_in`` (5, N) or (P, 5, N).
     ``save_records`` int [N_reg] (guarda_cond): steps with a record number > 0 return their storages in
     ``out["snapshots"]`` [P, n_snap, 5, N] together with ``out["snapshot_records"]`` (record number per slot)."""
-    global mean_rain, acum_rain, mean_storage, mean_speed
+    global mean_rain, acum_rain, mean_storage, mean_speed, mean_retorno, mean_vfluxes, vfluxes, rc_coef, retorned
     _reject_out_of_scope()
     dev = require_cuda()
     cal = np.atleast_2d(np.asarray(calibs, dtype=np.float32))
@@ -260,7 +269,9 @@ def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int,
     out = ops.shia5_run(cs[1], rr, pe, ev, to_dev(cal), sto, hs, dt=float(dt), retorno_gr=float(retorno_gr),
                         retorno_aq=float(retorno_aq), calc_niter=int(calc_niter), speed_type=tuple(st),
                         show_storage=bool(show_storage), show_mean_speed=bool(show_mean_speed), snap_slot=snap_slot,
-                        n_snap=0 if snap_recs is None else int(snap_recs.size))
+                        n_snap=0 if snap_recs is None else int(snap_recs.size), strict=bool(int(strict_arithmetic)),
+                        show_mean_retorno=bool(int(show_mean_retorno)), save_vfluxes=bool(int(save_vfluxes)),
+                        save_rc=bool(int(save_rc)), with_retorned=float(retorno_gr) > 0)
     out["snapshot_records"] = snap_recs
     mean_rain = out["mean_rain"].cpu().numpy().reshape(1, n_reg)
     acum_rain = out["acum_rain"].cpu().numpy().reshape(1, n_cel)
@@ -268,6 +279,14 @@ def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int,
         mean_storage = out["mean_storage"][0].cpu().numpy()
     if out["mean_speed"] is not None:
         mean_speed = out["mean_speed"][0].cpu().numpy()
+    if out["mean_retorno"] is not None:
+        mean_retorno = out["mean_retorno"][0].cpu().numpy()
+    if out["mean_vfluxes"] is not None:
+        mean_vfluxes, vfluxes = out["mean_vfluxes"][0].cpu().numpy(), out["vfluxes"][0].cpu().numpy()
+    if out["rc_coef"] is not None:
+        rc_coef = out["rc_coef"][0].cpu().numpy()
+    if out["retorned"] is not None:
+        retorned = out["retorned"][0].cpu().numpy().reshape(1, n_cel)
     if device_out:
         return out
     return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
@@ -291,6 +310,8 @@ def shia_v1(ruta_bin, ruta_hdr, calib, n_cel, n_cont, n_conth, n_reg, stoin=None
     if int(route_channels) == 1:
         return _shia_v1_routed(cal, records, pos, n_cel, n_cont, n_conth, n_reg, stoin)
     out = shia_v1_population(cal[None, :], records, pos, n_cel, n_reg, stoin, hspeedin, save_records=save)
+    if int(save_rc) == 1 and ruta_rc:                # Modelos_heavy.f90:543-544: one record of two columns
+        write_float_basin(ruta_rc, out["rc_coef"][0], 1, n_cel, 2)
     if out.get("snapshot_records") is not None:      # in time order, like the Fortran loop writes them
         for k, rec in enumerate(out["snapshot_records"]):
             write_float_basin(ruta_storage, out["snapshots"][0, k], int(rec), n_cel, 5)

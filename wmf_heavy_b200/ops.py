@@ -191,12 +191,16 @@ def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento:
               calib: torch.Tensor, sto: torch.Tensor, hspeed: Optional[torch.Tensor] = None, *, dt: float,
               retorno_gr: float = 0.0, retorno_aq: float = 0.0, calc_niter: int = 5, speed_type=(1, 1, 1),
               show_storage: bool = False, show_mean_speed: bool = False, snap_slot: Optional[torch.Tensor] = None,
-              n_snap: int = 0, validate: bool = True, strict: bool = False):
+              n_snap: int = 0, validate: bool = True, strict: bool = False, show_mean_retorno: bool = False,
+              save_vfluxes: bool = False, save_rc: bool = False, with_retorned: bool = False):
     """SHIA 5-tank update as shipped (Modelos_heavy.f90:169-548) for P parameter sets at once.
     ``sto`` [P,5,N] and ``hspeed`` [P,4,N] are advanced IN PLACE.  Returns a dict of device tensors.
     ``snap_slot`` int32 [N_reg] (-1 or a slot in [0, n_snap)): the storages after those steps are returned as
     ``snapshots`` [P, n_snap, 5, N] (save_storage / guarda_cond, Modelos_heavy.f90:496-500).
-    ``strict``: the Fortran's own operation forms (true division, powf) instead of the fast ones; see the header."""
+    ``strict``: the Fortran's own operation forms (true division, powf) instead of the fast ones; see the header.
+    Optional outputs of the shipped routine: ``show_mean_retorno`` -> ``mean_retorno`` [P, N_reg]; ``save_vfluxes`` ->
+    ``mean_vfluxes`` [P, 4, N_reg] and ``vfluxes`` [P, 4, N] (last step); ``save_rc`` -> ``rc_coef`` [P, 2, N];
+    ``with_retorned`` -> ``retorned`` [P, N] (zeros when the mean is shown: the Fortran clears it every step then)."""
     require_cuda()
     _chk_dev(cell_static, torch.float32, "cell_static")
     _chk_dev(rain_records, torch.int32, "rain_records")
@@ -229,20 +233,28 @@ def shia5_run(cell_static: torch.Tensor, rain_records: torch.Tensor, pos_evento:
     mv = torch.empty((P, 4, n_reg), dtype=torch.float32, device=dev) if show_mean_speed else None
     prm = _lib.Shia5Params(dt, retorno_gr, retorno_aq, int(calc_niter), (C.c_int32 * 3)(*[int(s) for s in speed_type]),
                            int(given), int(bool(strict)))
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    mret = f32(P, n_reg) if show_mean_retorno else None
+    mvf, vfl = (f32(P, 4, n_reg), f32(P, 4, N)) if save_vfluxes else (None, None)
+    rcc = f32(P, 2, N) if save_rc else None
+    rtd = f32(P, N) if (with_retorned or show_mean_retorno) else None
+    diag = any(t is not None for t in (ms, mv, mret, mvf, rcc, rtd))
     lib = _lib.load()
-    ws = workspace(lib.wmf_shia5_workspace(N, n_reg, P))
+    ws = workspace(lib.wmf_shia5_workspace(N, n_reg, P, int(diag)))
     snaps = None
     if snap_slot is not None:
         _chk_dev(snap_slot, torch.int32, "snap_slot")
         if snap_slot.shape != (n_reg,) or int(n_snap) <= 0:
             raise ValueError("snap_slot must be int32 [N_reg] and n_snap > 0")
         snaps = torch.zeros((P, int(n_snap), 5, N), dtype=torch.float32, device=dev)
-    check(lib.wmf_shia5_run_snap(C.addressof(prm), N, n_reg, n_rec, P, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
-                                 ptr(evp), ptr(calib), ptr(sto), ptr(hspeed), ptr(balance), ptr(mean_rain), ptr(acum_rain),
-                                 ptr(ms), ptr(mv), ptr(snap_slot), int(n_snap) if snaps is not None else 0, ptr(snaps),
-                                 ptr(ws), ws.numel(), stream_ptr()))
+    check(lib.wmf_shia5_run_ext(C.addressof(prm), N, n_reg, n_rec, P, ptr(cell_static), ptr(rain_records), ptr(pos_evento),
+                                ptr(evp), ptr(calib), ptr(sto), ptr(hspeed), ptr(balance), ptr(mean_rain), ptr(acum_rain),
+                                ptr(ms), ptr(mv), ptr(snap_slot), int(n_snap) if snaps is not None else 0, ptr(snaps),
+                                ptr(mret), ptr(mvf), ptr(vfl), ptr(rcc), ptr(rtd), int(bool(show_mean_retorno)),
+                                ptr(ws), ws.numel(), stream_ptr()))
     return {"StoOut": sto, "hspeed": hspeed, "balance": balance, "mean_rain": mean_rain, "acum_rain": acum_rain,
-            "mean_storage": ms, "mean_speed": mv, "snapshots": snaps}
+            "mean_storage": ms, "mean_speed": mv, "snapshots": snaps, "mean_retorno": mret, "mean_vfluxes": mvf,
+            "vfluxes": vfl, "rc_coef": rcc, "retorned": rtd}
 
 
 def path_sum(dir_t: torch.Tensor, active_t: Optional[torch.Tensor], w_t: Optional[torch.Tensor], dx: float, dy: float,
