@@ -492,7 +492,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             secondary[name] = {"input": desc, "value": n * n / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms,
                                "vs_primary": (n * n / (ms * 1e-3) / 1e6) / value,
                                "roofline_frac": gbs / peak, "algorithmic_bytes_per_cell": bpc,
-                               "tiles": st.get("tile_classes"), "sweeps": st.get("multi_sweeps")}
+                               "tiles": st.get("tile_classes"), "rounds": st.get("jump_rounds")}
         del ter, m1, m95
         ops.d8_accum(d, None, algo=algo, out=acc)           # (the parity check below looks at the benchmark raster)
 

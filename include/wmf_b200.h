@@ -68,7 +68,7 @@ int wmf_d8_accum(const int8_t *dir, const uint8_t *mask, void *acc, int acc_dtyp
                  int encoding, int algo, void *workspace, size_t ws_bytes, void *stream);
 
 /* Diagnostic: how the tiles of the last WMF_ALGO_SWEEP accumulation (32-bit arithmetic: fewer than 2^32 cells) that used
- * `workspace` were solved.  counts8_host[c] (HOST pointer, 8 entries) = tiles of class c: 0 one-pass row sweeps, 4 multi-sweep
+ * `workspace` were solved.  counts8_host[c] (HOST pointer, 8 entries) = tiles of class c: 0 one-pass row sweeps, 4 jump solver
  * (tiles with upward flow), 1 / 3 chain walk (cycles), 2 chain walk because an upstream never resolves.  Syncs the stream. */
 int wmf_d8_accum_tile_classes(const void *workspace, size_t ws_bytes, int64_t ny, int64_t nx, int64_t *counts8_host, void *stream);
 

@@ -34,4 +34,4 @@ for name, d, m in (("scheidegger", sch, None), ("scheidegger+all-true mask", sch
     ms, acc = timed(d, m)
     st = {}
     ops.d8_accum(d, m, out=acc, stats=st)
-    print(json.dumps({"input": name, "tiles": st.get("tile_classes"), "sweeps": st.get("multi_sweeps"), "ms": ms, "mcells_s": n * n / ms / 1e3, "acc_sum": int(acc.sum(dtype=torch.int64))}), flush=True)
+    print(json.dumps({"input": name, "tiles": st.get("tile_classes"), "rounds": st.get("jump_rounds"), "ms": ms, "mcells_s": n * n / ms / 1e3, "acc_sum": int(acc.sum(dtype=torch.int64))}), flush=True)

@@ -37,12 +37,13 @@ constexpr int NWD = NC / 4;             // 32-bit DIR words per lane per row
 constexpr int TW = 32 * NC;             // tile width  (one warp)
 constexpr int TH = 64;                  // tile height
 constexpr int NSLOT = 2 * TW + 2 * TH;  // boundary slots: top row, bottom row, left col, right col
+constexpr int TCELLS = TW * TH;
 constexpr int WPB = 4;                  // warps (= tiles) per block in the fast kernels
 constexpr uint32_t LNONE = 1023u;       // "no exit": above every slot, and the last bin of phase A's label histogram
 constexpr uint32_t FULL = 0xffffffffu;
 // work flags (one 32-bit word each, cleared before every accumulation): do the rarely needed tile solvers have anything to do?
-constexpr int F_COMPLEX = 0, F_CHAIN = 1, F_UNRES = 2;   // tiles for the multi-sweep solver / for the chain walk / fed by an unresolved upstream
-constexpr int F_NEXT_A = 4, F_NEXT_C = 5;                // work counters of the multi-sweep kernels
+constexpr int F_COMPLEX = 0, F_CHAIN = 1, F_UNRES = 2;   // tiles for the jump solver / for the chain walk / fed by an unresolved upstream
+constexpr int F_NEXT_A = 4, F_NEXT_C = 5;                // work counters of the jump kernels
 constexpr int NFLAGS = 8;
 
 // meta word of a boundary slot: [15:0] link, [19:16] k, [20] locally unresolved, [21] active
@@ -1093,420 +1094,9 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
 }
 
 // ---------------------------------------------------------------------------------------------
-// multi-sweep solver: tiles with in-tile upward flow (every tile of a real DEM)
-// ---------------------------------------------------------------------------------------------
-// A row sweep follows a path as long as it moves with the sweep (or sideways); flow against the sweep waits for the
-// next sweep in the opposite direction.  A path with r vertical runs is settled after r (+1) sweeps -- typically 3-5 on
-// terrain at this tile height -- and a tile whose sweeps stop making progress holds a cycle and goes to the chain-walk
-// solver.  One warp per tile as in the one-pass solver; the tile's decoded codes (a nibble per cell: 0..7, 8 none,
-// 9 inactive) stay in shared memory for all sweeps and are handed to phase C; the state that crosses sweeps lives in a
-// scratch raster (labels in phase A, waiting flow in phase C).
-//   phase A  label[c] = label[receiver(c)]: a sweep takes the labels of the row it has just left from registers and
-//            those of the row it has not reached yet from the previous sweep (LUNK until known).  The histogram of the
-//            last sweep is exit_acc.
-//   phase C  flow in transit: acc[c] counts what has arrived at c so far, wait[c] what has arrived but could not
-//            move on because c drains against the sweep.  A sweep moves everything it meets as far as it can; integer
-//            adds, so the order in which the flow arrives does not matter.  Done when nothing waits.
-// Up-sweeps run the down-sweep's row arithmetic on mirrored codes (NE<->SE, N<->S, NW<->SW).
-constexpr uint32_t LUNK = 1022u;            // label not known yet (a histogram bin no slot uses)
-constexpr int MAX_SWEEPS = 24;
-static_assert(NSLOT <= (int)LUNK, "LUNK is not a slot");
-constexpr int MWPB = 4;                     // warps (tiles) per block of the multi-sweep kernels
-
-__device__ __forceinline__ int mirror_k(int k) { return k < 8 ? ((8 - k) & 7) : k; }
-
-// decode the whole tile into nibbles: codes[lr * 32 + lane] holds the lane's NC cells of row lr.  Returns false when the
-// tile has an adjacent E -> W pair (a two-cycle: not for the sweeps); top_up: upward flow in the first row.
-template <int ENC>
-__device__ __forceinline__ bool multi_decode(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, const Geo &g, int ty, int tx,
-                                             int th, int tw, int lane, uint32_t *codes, bool &top_up)
-{
-    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
-    const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
-    bool two = false, up0 = false;
-    for (int lr = 0; lr < TH; lr++) {
-        uint32_t cw = 0x99999999u;
-        if (lr < th) {
-            cw = 0;
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                int kk = 9;
-                if (gc0 + j < g.nx) {
-                    const int64_t gi = (gr0 + lr) * g.nx + gc0 + j;
-                    if (mask == nullptr || mask[gi] != 0) {
-                        kk = d8_norm<ENC>((int)dir[gi]);
-                        if (border && kk != 8) {
-                            const int64_t rr = g.gy0 + gr0 + lr + d8_dr(kk), cc = gc0 + j + d8_dc(kk);
-                            if (rr < 0 || rr >= g.gny || cc < 0 || cc >= g.nx) kk = 8;
-                        }
-                    }
-                }
-                cw |= (uint32_t)kk << (4 * j);
-            }
-            // E -> W adjacent pairs, inside the lane and across lanes
-            const uint32_t first_right = __shfl_down_sync(FULL, cw & 15u, 1);
-            bool tc = lane < 31 && (cw >> 28) == 0u && first_right == 4u;
-#pragma unroll
-            for (int j = 0; j + 1 < NC; j++) tc = tc || (((cw >> (4 * j)) & 15u) == 0u && ((cw >> (4 * j + 4)) & 15u) == 4u);
-            two = two || tc;
-            if (lr == 0) {
-#pragma unroll
-                for (int j = 0; j < NC; j++) { const uint32_t kk = (cw >> (4 * j)) & 15u; up0 = up0 || (kk >= 5u && kk <= 7u); }
-            }
-        }
-        codes[lr * 32 + lane] = cw;
-    }
-    top_up = __any_sync(FULL, up0);
-    return !__any_sync(FULL, two);
-}
-
-// Label row, branch-free.  The candidate labels of a row are staged in a small per-lane table in shared memory --
-// [0..9] the row behind with one cell of halo on either side, [10..19] the row ahead likewise, then eight copies each of
-// "no exit", the East marker and the West marker -- and a cell fetches entry j + OFF[code]: OFF is a 6-bit-per-code
-// lookup word, mirrored for the sweeps that run top -> bottom.
-constexpr int LTAB = 45;                    // words per lane (44 used; odd stride: no bank conflicts)
-constexpr uint32_t MARK_E = 0x10000u, MARK_W = 0x20000u;
-__host__ __device__ constexpr unsigned long long off_lut(bool mirrored)
-{
-    // code (real orientation) -> table offset; behind = the row below for a bottom -> top sweep
-    //   bottom -> top: SE 1 -> 2, S 2 -> 1, SW 3 -> 0 (behind); NW 5 -> 10, N 6 -> 11, NE 7 -> 12 (ahead)
-    //   top -> bottom: the roles of the two rows swap: NE 7 -> 2, N 6 -> 1, NW 5 -> 0; SW 3 -> 10, S 2 -> 11, SE 1 -> 12
-    const int nat[10] = {28, 2, 1, 0, 36, 10, 11, 12, 20, 20}, mir[10] = {28, 12, 11, 10, 36, 0, 1, 2, 20, 20};
-    unsigned long long v = 0;
-    for (int k = 0; k < 10; k++) v |= (unsigned long long)(mirrored ? mir[k] : nat[k]) << (6 * k);
-    return v;
-}
-
-template <int ENC>
-__global__ void __launch_bounds__(MWPB * 32) k_multiA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
-                                                      uint32_t *__restrict__ meta, int32_t *__restrict__ exit_acc,
-                                                      uint8_t *__restrict__ tile_class, unsigned long long *__restrict__ wq,
-                                                      uint8_t *__restrict__ tile_top, uint32_t *__restrict__ codes4,
-                                                      uint16_t *__restrict__ labels, unsigned long long *__restrict__ sweeps_of,
-                                                      uint32_t *__restrict__ flags)
-{
-    extern __shared__ __align__(16) uint32_t s_dyn[];   // [MWPB][TH * 32] codes + [MWPB][HBINS] histogram + [MWPB][32 * LTAB] tables
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (flags[F_COMPLEX] == 0u) return;               // (nearly always: no tile has upward flow, e.g. a Scheidegger network)
-  // the warps take tiles from a counter: tiles differ in the number of sweeps they need
-  for (;;) {
-    int tile = 0;
-    if (lane == 0) tile = (int)atomicAdd(&flags[F_NEXT_A], 1u);
-    tile = __shfl_sync(FULL, tile, 0);
-    if (tile >= ntiles) return;
-    if (tile_class[tile] != 1) continue;
-    int ty, tx, th, tw;
-    tile_dims(g, tile, ty, tx, th, tw);
-    uint32_t *codes = s_dyn + (size_t)warp * TH * 32;
-    int *hist = reinterpret_cast<int *>(s_dyn + (size_t)MWPB * TH * 32) + HBINS * warp;
-    uint32_t *tab = s_dyn + (size_t)MWPB * (TH * 32 + HBINS) + (size_t)warp * 32 * LTAB + lane * LTAB;
-    const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
-    uint32_t *m_t = meta + (int64_t)tile * NSLOT;
-    uint16_t *lab_t = labels + (int64_t)tile * TH * TW + NC * lane;
-    const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;
-    bool top_up = false;
-    bool ok = multi_decode<ENC>(dir, mask, g, ty, tx, th, tw, lane, codes, top_up);
-#pragma unroll
-    for (int j = 0; j < 8; j++) { tab[20 + j] = LNONE; tab[28 + j] = MARK_E; tab[36 + j] = MARK_W; }
-    __syncwarp();
-    {   // phase C of this tile starts from the decoded codes
-        uint32_t *c4 = codes4 + (int64_t)tile * TH * 32;
-        for (int lr = 0; lr < TH; lr++) c4[lr * 32 + lane] = codes[lr * 32 + lane];
-    }
-    int prev_unknown = TH * TW + 1, nsweeps = 0;
-    for (int sweep = 0; ok; sweep++) {
-        nsweeps = sweep + 1;
-        const bool up = (sweep & 1) == 0;           // sweep 0 runs bottom -> top: it settles every path that only descends
-        const unsigned long long lut = up ? off_lut(false) : off_lut(true);
-#pragma unroll
-        for (int q = 0; q < HBINS / 128; q++) *reinterpret_cast<int4 *>(hist + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
-        __syncwarp();
-        uint32_t lbB[NC];                            // labels of the row the sweep has just left ("behind")
-#pragma unroll
-        for (int j = 0; j < NC; j++) lbB[j] = LNONE;
-        int unknown;
-        for (int step = 0; step < th; step++) {
-            const int lr = up ? th - 1 - step : step;
-            const uint32_t cw = codes[lr * 32 + lane];
-            uint32_t lbA[NC];                        // labels of the row ahead, as the previous sweep left them
-            if (sweep > 0 && step + 1 < th) {
-                const uint4 q = __ldcg(reinterpret_cast<const uint4 *>(lab_t + (int64_t)(up ? lr - 1 : lr + 1) * TW));
-                lbA[0] = q.x & 0xFFFFu; lbA[1] = q.x >> 16; lbA[2] = q.y & 0xFFFFu; lbA[3] = q.y >> 16;
-                lbA[4] = q.z & 0xFFFFu; lbA[5] = q.z >> 16; lbA[6] = q.w & 0xFFFFu; lbA[7] = q.w >> 16;
-            } else {
-#pragma unroll
-                for (int j = 0; j < NC; j++) lbA[j] = LUNK;
-            }
-            // candidate table of this lane
-            tab[0] = __shfl_up_sync(FULL, lbB[NC - 1], 1);
-            tab[9] = __shfl_down_sync(FULL, lbB[0], 1);
-            tab[10] = __shfl_up_sync(FULL, lbA[NC - 1], 1);
-            tab[19] = __shfl_down_sync(FULL, lbA[0], 1);
-#pragma unroll
-            for (int j = 0; j < NC; j++) { tab[1 + j] = lbB[j]; tab[11 + j] = lbA[j]; }
-            __syncwarp();
-            uint32_t own[NC];
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const uint32_t kr = (cw >> (4 * j)) & 15u;
-                own[j] = tab[j + ((uint32_t)(lut >> (6u * kr)) & 63u)];
-            }
-            __syncwarp();
-            // cells whose receiver lies outside the tile carry their own slot: the first / last row of the sweep entirely,
-            // otherwise only the two side columns (codes SW / W / NW on the left, NE / E / SE on the right: the same sets
-            // in either sweep direction)
-            if (step == 0 || step == th - 1 || tw != TW) {
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const int lc = NC * lane + j, kr = (int)((cw >> (4 * j)) & 15u);
-                    const int kk = up ? kr : mirror_k(kr);       // sweep coordinates: 1..3 drain behind, 5..7 ahead
-                    const bool exits = (step == 0 && kk >= 1 && kk <= 3) || (step == th - 1 && kk >= 5 && kk <= 7) ||
-                                       (lc == tw - 1 && (kk == 0 || kk == 1 || kk == 7)) || (lc == 0 && kk >= 3 && kk <= 5);
-                    if (exits) own[j] = (uint32_t)slot_of(lr, lc, th, tw);
-                }
-            } else {
-                const uint32_t k0 = cw & 15u, k7 = cw >> 28;
-                if (lane == 0 && k0 >= 3u && k0 <= 5u) own[0] = (uint32_t)(2 * TW + lr);
-                if (lane == 31 && (k7 <= 1u || k7 == 7u)) own[NC - 1] = (uint32_t)(2 * TW + TH + lr);
-            }
-            uint32_t lab[NC];
-            {   // East cells copy the label of the chain end on their right
-                uint32_t V = LNONE;
-                bool P = true;
-#pragma unroll
-                for (int j = NC - 1; j >= 0; j--) { const bool e = own[j] == MARK_E; V = e ? V : own[j]; P = P && e; }
-                uint32_t cur = label_carry_from_right(V, P, lane);
-#pragma unroll
-                for (int j = NC - 1; j >= 0; j--) { cur = own[j] == MARK_E ? cur : own[j]; lab[j] = cur; }
-            }
-            bool anyw = false;
-#pragma unroll
-            for (int j = 0; j < NC; j++) anyw = anyw || own[j] == MARK_W;
-            if (__any_sync(FULL, anyw)) {
-                uint32_t V = LNONE;
-                bool P = true;
-#pragma unroll
-                for (int j = 0; j < NC; j++) { const bool ww = own[j] == MARK_W; V = ww ? V : lab[j]; P = P && ww; }
-                uint32_t cur = label_carry_from_left(V, P, lane);
-#pragma unroll
-                for (int j = 0; j < NC; j++) { cur = own[j] == MARK_W ? cur : lab[j]; lab[j] = cur; }
-            }
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                lbB[j] = lab[j];
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_sa + 4u * lab[j]) : "memory");
-            }
-            *reinterpret_cast<uint4 *>(lab_t + (int64_t)lr * TW) =
-                make_uint4(lab[0] | (lab[1] << 16), lab[2] | (lab[3] << 16), lab[4] | (lab[5] << 16), lab[6] | (lab[7] << 16));
-            // boundary slots (the last sweep's values stand)
-            if (lr == 0 || lr == th - 1) {
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const int kr = (int)((cw >> (4 * j)) & 15u);
-                    if (NC * lane + j < tw) m_t[(lr == 0 ? 0 : TW) + NC * lane + j] = meta_pack(lab[j], kr < 8 ? kr : 8, false, kr != 9);
-                }
-            } else {
-                if (lane == 0) { const int kr = (int)(cw & 15u); m_t[2 * TW + lr] = meta_pack(lab[0], kr < 8 ? kr : 8, false, kr != 9); }
-                if (lane == rlane && tw > 1) {
-#pragma unroll
-                    for (int j = 0; j < NC; j++) {
-                        const int kr = (int)((cw >> (4 * j)) & 15u);
-                        if (j == rj) m_t[2 * TW + TH + lr] = meta_pack(lab[j], kr < 8 ? kr : 8, false, kr != 9);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        unknown = hist[LUNK];                        // the labels still unknown are one of the bins
-        if (unknown == 0) break;
-        if (unknown >= prev_unknown || sweep + 1 >= MAX_SWEEPS) { ok = false; break; }   // no progress: a cycle
-        prev_unknown = unknown;
-    }
-    if (!ok) {                                       // the chain-walk solver redoes this tile
-        if (lane == 0) { tile_class[tile] = 3; tile_top[tile] = 1; flags[F_CHAIN] = 1u; }
-        __syncwarp();
-        continue;
-    }
-    if (lane == 0) { tile_class[tile] = 4; tile_top[tile] = (top_up || th != TH || tw != TW) ? 1 : 0; sweeps_of[tile] = (unsigned long long)nsweeps; }
-    // unused slots of a ragged tile: inactive
-    if (th != TH || tw != TW) {
-        for (int s = lane; s < NSLOT; s += 32) { int lr, lc; if (!cell_of(s, th, tw, lr, lc)) m_t[s] = 0u; }
-    }
-    __syncwarp();
-    // exit_acc of every slot = its bin; the forest word = one pending arrival | code | weight
-    int32_t *x_t = exit_acc ? exit_acc + (int64_t)tile * NSLOT : nullptr;
-    unsigned long long *w_t = wq + (int64_t)tile * NSLOT;
-    for (int s = lane; s < NSLOT; s += 32) {
-        const uint32_t m = __ldcg(m_t + s);
-        const int h = hist[s];
-        if (x_t) x_t[s] = h;
-        w_t[s] = PEND1 | ((unsigned long long)((m >> 16) & 0xFu) << W_K) | (uint32_t)h;
-    }
-    __syncwarp();
-  }
-}
-
-template <typename TO, typename T>
-__device__ __forceinline__ T acc_in(TO v)
-{
-    if (sizeof(T) == 4 && sizeof(TO) == 8) return (T)(uint32_t)v;          // (see acc_out)
-    return (T)v;
-}
-
-// NC consecutive values of the scratch raster (16-byte pieces; the tile rows are 16-byte aligned)
-template <typename T>
-__device__ __forceinline__ void load8(const T *p, T (&v)[NC])
-{
-    constexpr int PER = 16 / sizeof(T);
-#pragma unroll
-    for (int q = 0; q < NC / PER; q++) {
-        const uint4 x = __ldcg(reinterpret_cast<const uint4 *>(p) + q);
-        memcpy(&v[PER * q], &x, 16);
-    }
-}
-template <typename T>
-__device__ __forceinline__ void store8(T *p, const T (&v)[NC])
-{
-    constexpr int PER = 16 / sizeof(T);
-#pragma unroll
-    for (int q = 0; q < NC / PER; q++) {
-        uint4 x;
-        memcpy(&x, &v[PER * q], 16);
-        reinterpret_cast<uint4 *>(p)[q] = x;
-    }
-}
-
-template <typename T, typename TO>
-__global__ void __launch_bounds__(MWPB * 32) k_multiC(Geo g, int ntiles, const uint32_t *__restrict__ codes4,
-                                                      const unsigned long long *__restrict__ wq, const uint8_t *__restrict__ tile_top,
-                                                      const T *__restrict__ extra, const uint8_t *__restrict__ tile_class,
-                                                      T *__restrict__ wait, TO *__restrict__ acc, unsigned long long *__restrict__ sweeps_of,
-                                                      uint32_t *__restrict__ flags)
-{
-    extern __shared__ __align__(16) uint32_t s_dyn[];   // [MWPB][TH * 32] codes + [MWPB][NSLOT] boundary inflows (T)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (flags[F_COMPLEX] == 0u) return;
-  for (;;) {
-    int tile = 0;
-    if (lane == 0) tile = (int)atomicAdd(&flags[F_NEXT_C], 1u);
-    tile = __shfl_sync(FULL, tile, 0);
-    if (tile >= ntiles) return;
-    if (tile_class[tile] != 4) continue;
-    int ty, tx, th, tw;
-    tile_dims(g, tile, ty, tx, th, tw);
-    uint32_t *codes = s_dyn + (size_t)warp * TH * 32;
-    T *ext = reinterpret_cast<T *>(s_dyn + (size_t)MWPB * TH * 32) + NSLOT * warp;
-    {
-        const uint32_t *c4 = codes4 + (int64_t)tile * TH * 32;
-        for (int lr = 0; lr < TH; lr++) codes[lr * 32 + lane] = __ldcg(c4 + lr * 32 + lane);
-    }
-    tile_inflow<T>(g, wq, tile_top, extra, tile, ty, tx, th, tw, lane, ext);
-    const T *extL = ext + 2 * TW, *extR = ext + 2 * TW + TH;
-    const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;
-    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
-    const bool al = (g.nx % NC == 0) && ((reinterpret_cast<uintptr_t>(acc) & 31) == 0);
-    TO *acc_t = acc + gr0 * g.nx + gc0;
-    T *wait_t = wait + (int64_t)tile * TH * TW + NC * lane;
-    bool dummy = false;
-    unsigned long long rows_waiting = 0;             // rows that hold waiting flow (warp-uniform)
-    for (int sweep = 0; sweep < MAX_SWEEPS + 2; sweep++) {
-        const bool down = (sweep & 1) == 0;
-        unsigned long long next_waiting = 0;
-        T d[NC];
-#pragma unroll
-        for (int j = 0; j < NC; j++) d[j] = 0;
-        bool d_any = false;
-        for (int step = 0; step < th; step++) {
-            const int lr = down ? step : th - 1 - step;
-            // later sweeps touch a row only when something waits in it or arrives from the row behind
-            if (sweep > 0 && !d_any && !((rows_waiting >> lr) & 1ull)) continue;
-            const uint32_t cw = codes[lr * 32 + lane];
-            int k[NC], am = 0;
-            bool holds[NC];
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const int kr = (int)((cw >> (4 * j)) & 15u);
-                am |= (kr != 9) << j;
-                k[j] = kr >= 8 ? 8 : (down ? kr : mirror_k(kr));  // sweep coordinates: 1..3 drain ahead, 5..7 behind
-                holds[j] = k[j] >= 5 && k[j] <= 7;
-            }
-            T a[NC], w[NC], b[NC];
-            if (sweep == 0) {                        // everything starts as "arrived, not moved on": 1 + the external inflow
-                T ex[NC];
-#pragma unroll
-                for (int j = 0; j < NC; j++) ex[j] = 0;
-                if (lr == 0 || lr == th - 1) {
-                    const T *e4 = ext + (lr == 0 ? 0 : TW) + NC * lane;
-#pragma unroll
-                    for (int j = 0; j < NC; j++) ex[j] = e4[j];
-                } else {
-                    if (lane == 0) ex[0] = extL[lr];
-                    if (lane == rlane && tw > 1) {
-#pragma unroll
-                        for (int j = 0; j < NC; j++) if (j == rj) ex[j] += extR[lr];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < NC; j++) { w[j] = ((am >> j) & 1) ? (T)1 + ex[j] : (T)0; a[j] = w[j]; }
-            } else {
-                if (al && gc0 < g.nx) {
-                    TO av[NC];
-                    if (sizeof(TO) == 4) {
-                        const uint4 *p = reinterpret_cast<const uint4 *>(acc_t + (int64_t)lr * g.nx);
-                        const uint4 x = __ldcg(p), y = __ldcg(p + 1);
-                        uint32_t u[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-#pragma unroll
-                        for (int j = 0; j < NC; j++) memcpy(&av[j], &u[j], 4);
-                    } else {
-                        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(acc_t + (int64_t)lr * g.nx);
-#pragma unroll
-                        for (int q = 0; q < NC / 2; q++) { const ulonglong2 x = __ldcg(p + q); memcpy(&av[2 * q], &x.x, 8); memcpy(&av[2 * q + 1], &x.y, 8); }
-                    }
-#pragma unroll
-                    for (int j = 0; j < NC; j++) a[j] = acc_in<TO, T>(av[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NC; j++) a[j] = gc0 + j < g.nx ? acc_in<TO, T>(__ldcg(acc_t + (int64_t)lr * g.nx + j)) : (T)0;
-                }
-                load8<T>(wait_t + (int64_t)lr * TW, w);
-            }
-            // cells that do not drain against the sweep release what waits in them
-            T rel[NC];
-#pragma unroll
-            for (int j = 0; j < NC; j++) { rel[j] = holds[j] ? (T)0 : w[j]; b[j] = ((am >> j) & 1) ? d[j] + rel[j] : (T)0; }
-            T tot[NC];
-            sweep_row_down<T>(k, am, b, tot, d, lane, dummy);      // d: what moves on into the row ahead
-            bool wany = false, dn = false;
-            T tt[NC];
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const T arrived = tot[j] - rel[j];                 // new at this cell in this sweep
-                tt[j] = a[j] + arrived;
-                w[j] = holds[j] ? w[j] + arrived : (T)0;
-                wany = wany || w[j] != 0;
-                dn = dn || d[j] != 0;
-            }
-            store_row<true, T, TO>(acc_t + (int64_t)lr * g.nx, tt, al ? gc0 : g.nx, g.nx);
-            if (!al) {
-#pragma unroll
-                for (int j = 0; j < NC; j++) if (gc0 + j < g.nx) acc_t[(int64_t)lr * g.nx + j] = acc_out<TO, T>(tt[j]);
-            }
-            store8<T>(wait_t + (int64_t)lr * TW, w);
-            if (__any_sync(FULL, wany)) next_waiting |= 1ull << lr;
-            d_any = __any_sync(FULL, dn);
-        }
-        rows_waiting = next_waiting;
-        if (rows_waiting == 0) { if (lane == 0) sweeps_of[tile] |= (unsigned long long)(sweep + 1) << 32; break; }
-    }
-    __syncwarp();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // general tile solver (one block per tile, chain walk in shared memory), phases A and C
 // ---------------------------------------------------------------------------------------------
 constexpr int GTH = 256;   // threads per block
-constexpr int TCELLS = TW * TH;
 
 template <int ENC>
 __device__ __forceinline__ void general_load(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, const Geo &g,
@@ -1664,7 +1254,7 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
   if (flags[F_CHAIN] == 0u && flags[F_UNRES] == 0u) return;
   const int per = (ntiles + gridDim.x - 1) / gridDim.x, t_lo = blockIdx.x * per, t_hi = ntiles < t_lo + per ? ntiles : t_lo + per;
   bool any_mine = false;
-  // classes: 0 one-pass sweeps, 4 multi-sweep; everything else (1 / 3: the sweeps cannot solve it, 2: fed by an unresolved
+  // classes: 0 one-pass sweeps, 4 jump solver; everything else (1 / 3: the sweeps cannot solve it, 2: fed by an unresolved
   // upstream) is solved here
   for (int t = t_lo + threadIdx.x; t < t_hi; t += GTH) any_mine = any_mine || (tile_class[t] != 0 && tile_class[t] != 4);
   if (!__syncthreads_or(any_mine)) return;
@@ -1702,6 +1292,423 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
         if (lr < th && lc < tw) out[((int64_t)ty * TH + lr) * g.nx + (int64_t)tx * TW + lc] = acc_out<TO, T>(acc[idx]);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// jump solver: tiles with in-tile upward flow (every tile of a real DEM)
+// ---------------------------------------------------------------------------------------------
+// A row sweep settles a path only as long as it runs with the sweep, so terrain needs a sweep per vertical run of its
+// paths (4-5 on average at this tile height, each as dear as the whole one-pass solve).  These tiles are solved by
+// pointer jumping over the tile's 16384 cells in shared memory instead, one thread block per tile:
+//   phase A  ptr[c] = the receiver of c, or -- resolved -- the exit label of c (an exit cell labels itself, a cell
+//            without receiver carries "no exit").  ptr[c] = ptr[ptr[c]] until every pointer is a label; done in place
+//            and asynchronously, which only makes the pointers run ahead.  log2(longest path) rounds; exit_acc is the
+//            histogram of the labels.  Pointers that are still unresolved after 2^JROUNDS >= 16384 steps sit on a
+//            cycle: the tile goes to the chain-walk solver.
+//   phase C  subtree sums by doubling: with A_k[c] = what lies upstream of c at a distance below 2^k (A_0 = the cell's
+//            own 1 + its external inflow) and ptr_k = the 2^k-th receiver, A_{k+1}[c] = A_k[c] + the sum of A_k[u] over
+//            the cells u with ptr_k[u] = c -- a scatter-add of every cell that still has a pointer, then ptr_{k+1} =
+//            ptr_k[ptr_k].  Rounds are synchronous here (pointers are double buffered); a cell drops out once its
+//            pointer runs off its path.
+// The tile's decoded codes (a nibble per cell: 0..7, 8 none, 9 inactive) are handed from phase A to phase C.
+constexpr int JTA = 512, JTC = 1024;        // threads per block, phases A / C
+constexpr int JROUNDS = 15;
+constexpr uint32_t JRES = 0x8000u;          // phase A: the pointer is resolved, the low bits are the label
+constexpr uint32_t JNONE = 0xFFFFu;         // phase C: no (further) receiver inside the tile
+static_assert(TCELLS <= 0x4000, "a cell index fits below the flag bits of a 16-bit pointer");
+
+// four internal-coded cells (one byte each) and their mask bytes -> four nibbles: the code, 8 for anything that is not
+// a direction, 9 for an inactive cell
+__device__ __forceinline__ uint32_t jump_nibbles_internal(uint32_t w, uint32_t m)
+{
+    const uint32_t bad = byte_nonzero(w & 0xF8F8F8F8u), off = byte_zero(m);       // 0x01 per byte
+    uint32_t x = (w & 0x07070707u & ~(bad * 0xFFu)) | (bad << 3);                 // code, or 8
+    x = (x & ~(off * 0xFFu)) | (off * 9u);                                        // ... or 9
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    return (x | (x >> 8)) & 0xFFFFu;
+}
+
+// decode the whole tile into nibbles: codes[lr * 32 + l] holds the cells 8 l .. 8 l + 7 of row lr (cells beyond a ragged
+// tile's extent are inactive).  vec: rows can be fetched eight bytes at a time.
+template <int ENC>
+__device__ __forceinline__ void jump_decode(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, const Geo &g, int ty, int tx,
+                                            int th, bool vec, uint32_t *codes, uint32_t *codes_out)
+{
+    const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW;
+    const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
+    for (int q = threadIdx.x; q < TH * 32; q += blockDim.x) {
+        const int lr = q >> 5, l = q & 31;
+        const int64_t gr = gr0 + lr, gc = gc0 + NC * l;
+        uint32_t cw = 0x99999999u;
+        if (lr < th && gc < g.nx) {
+            uint32_t dw[2] = {0u, 0u}, mw[2] = {0x01010101u, 0x01010101u};
+            const int64_t gi = gr * g.nx + gc;
+            if (vec) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(dir + gi));
+                dw[0] = v.x; dw[1] = v.y;
+                if (mask) { const uint2 m = __ldg(reinterpret_cast<const uint2 *>(mask + gi)); mw[0] = m.x; mw[1] = m.y; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const bool in = gc + j < g.nx;
+                    const uint32_t d = in ? (uint32_t)(uint8_t)dir[gi + j] : 0u, m = in ? (mask ? (uint32_t)(mask[gi + j] != 0) : 1u) : 0u;
+                    dw[j / 4] |= d << (8 * (j % 4));
+                    mw[j / 4] = (mw[j / 4] & ~(0xFFu << (8 * (j % 4)))) | (m << (8 * (j % 4)));
+                }
+            }
+            if (ENC == WMF_ENC_INTERNAL && !border) {
+                cw = jump_nibbles_internal(dw[0], mw[0]) | (jump_nibbles_internal(dw[1], mw[1]) << 16);
+            } else {
+                cw = 0;
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    int kk = d8_norm<ENC>((int)(int8_t)(dw[j / 4] >> (8 * (j % 4))));
+                    if (border && kk != 8) {
+                        const int64_t rr = g.gy0 + gr + d8_dr(kk), cc = gc + j + d8_dc(kk);
+                        if (rr < 0 || rr >= g.gny || cc < 0 || cc >= g.nx) kk = 8;
+                    }
+                    if (((mw[j / 4] >> (8 * (j % 4))) & 0xFFu) == 0u) kk = 9;
+                    cw |= (uint32_t)kk << (4 * j);
+                }
+            }
+        }
+        codes[q] = cw;
+        if (codes_out) codes_out[q] = cw;
+    }
+}
+
+// in-tile receiver of cell c with code kr (0..7), for a cell that is not on the tile's boundary: c + dr * TW + dc
+__device__ __forceinline__ uint32_t jump_recv(uint32_t c, uint32_t kr)
+{
+    const uint32_t dr1 = (0x01A9u >> (2u * kr)) & 3u, dc1 = (0x901Au >> (2u * kr)) & 3u;      // dr + 1, dc + 1 (d8_dr / d8_dc)
+    return c - (uint32_t)(TW + 1) + dr1 * (uint32_t)TW + dc1;
+}
+__device__ __forceinline__ uint32_t jump_code(const uint32_t *codes, int lr, int lc) { return (codes[lr * 32 + lc / NC] >> (4 * (lc % NC))) & 15u; }
+
+// The pointers of a whole tile, eight cells per step.  Cells without a direction get `none`.  On a full tile every chunk
+// takes the interior formula, which is wrong for the boundary cells only: the caller puts those right (one thread per
+// boundary slot) -- a per-chunk test would split every warp, lanes 0 and 31 hold the side columns.  out_of_tile(lr, lc)
+// gives the pointer of a cell whose receiver lies outside the tile.
+template <typename OutFn>
+__device__ __forceinline__ void jump_pointers(const uint32_t *codes, int th, int tw, uint32_t none, uint32_t *ptr32, OutFn out_of_tile)
+{
+    const bool full = th == TH && tw == TW;
+    for (int q = threadIdx.x; q < TH * 32; q += blockDim.x) {
+        const uint32_t cw = codes[q];
+        uint32_t pv[NC];
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const uint32_t kr = (cw >> (4 * j)) & 15u;
+                pv[j] = (kr < 8u ? jump_recv((uint32_t)(NC * q + j), kr) : none) & 0xFFFFu;
+            }
+        } else {
+            const int lr = q >> 5, l = q & 31;
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const int kr = (int)((cw >> (4 * j)) & 15u), lc = NC * l + j;
+                uint32_t v = none;
+                if (kr < 8) {
+                    const int rr = lr + d8_dr(kr), cc = lc + d8_dc(kr);
+                    v = (rr < 0 || rr >= th || cc < 0 || cc >= tw) ? out_of_tile(lr, lc) : (uint32_t)(rr * TW + cc);
+                }
+                pv[j] = v;
+            }
+        }
+        *reinterpret_cast<uint4 *>(ptr32 + 4 * q) = make_uint4(pv[0] | (pv[1] << 16), pv[2] | (pv[3] << 16), pv[4] | (pv[5] << 16), pv[6] | (pv[7] << 16));
+    }
+}
+// ... of one boundary cell of a full tile
+template <typename OutFn>
+__device__ __forceinline__ uint32_t jump_pointer_boundary(uint32_t kr, int lr, int lc, uint32_t none, OutFn out_of_tile)
+{
+    if (kr >= 8u) return none;
+    const int rr = lr + d8_dr((int)kr), cc = lc + d8_dc((int)kr);
+    return (rr < 0 || rr >= TH || cc < 0 || cc >= TW) ? out_of_tile(lr, lc) : (uint32_t)(rr * TW + cc);
+}
+
+// next tile of a persistent block (thread 0 draws, everybody learns through shared memory)
+__device__ __forceinline__ int jump_next_tile(uint32_t *counter, int *slot)
+{
+    __syncthreads();                                   // (the previous tile is done with shared memory, *slot included)
+    if (threadIdx.x == 0) *slot = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    return *slot;
+}
+
+template <int ENC>
+__global__ void __launch_bounds__(JTA, 4) k_jumpA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
+                                               uint32_t *__restrict__ meta, int32_t *__restrict__ exit_acc,
+                                               uint8_t *__restrict__ tile_class, unsigned long long *__restrict__ wq,
+                                               uint8_t *__restrict__ tile_top, uint32_t *__restrict__ codes4,
+                                               unsigned long long *__restrict__ rounds_of, uint32_t *__restrict__ flags, bool vec)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [TCELLS / 2] pointers (16 bit) + [TH * 32] codes + [HBINS] histogram + 1
+    if (flags[F_COMPLEX] == 0u) return;               // (nearly always: no tile has upward flow, e.g. a Scheidegger network)
+    uint32_t *ptr32 = s_dyn;
+    uint16_t *ptr16 = reinterpret_cast<uint16_t *>(s_dyn);
+    uint32_t *codes = s_dyn + TCELLS / 2;
+    int *hist = reinterpret_cast<int *>(codes + TH * 32);
+    int *slot = hist + HBINS;
+    for (;;) {
+        const int tile = jump_next_tile(&flags[F_NEXT_A], slot);
+        if (tile >= ntiles) return;
+        if (tile_class[tile] != 1) continue;
+        int ty, tx, th, tw;
+        tile_dims(g, tile, ty, tx, th, tw);
+        jump_decode<ENC>(dir, mask, g, ty, tx, th, vec, codes, codes4 + (int64_t)tile * TH * 32);   // (phase C starts from the codes)
+        for (int b = threadIdx.x; b < HBINS; b += JTA) hist[b] = 0;
+        __syncthreads();
+        auto exit_label = [&](int lr, int lc) { return JRES | (uint32_t)slot_of(lr, lc, th, tw); };
+        jump_pointers(codes, th, tw, JRES | LNONE, ptr32, exit_label);
+        const bool full = th == TH && tw == TW;
+        if (full) {
+            __syncthreads();
+            for (int s = threadIdx.x; s < NSLOT; s += JTA) {
+                int lr, lc;
+                cell_of(s, TH, TW, lr, lc);
+                ptr16[lr * TW + lc] = (uint16_t)jump_pointer_boundary(jump_code(codes, lr, lc), lr, lc, JRES | LNONE, exit_label);
+            }
+        }
+        bool up0 = false;                                // upward flow in the first row?
+        for (int l = threadIdx.x; l < 32; l += JTA) {
+            const uint32_t cw = codes[l];
+#pragma unroll
+            for (int j = 0; j < NC; j++) { const uint32_t kr = (cw >> (4 * j)) & 15u; up0 = up0 || (kr >= 5u && kr <= 7u); }
+        }
+        const bool top_up = __syncthreads_or(up0) != 0;
+        int rounds = 0;
+        bool open = true;
+        for (; open && rounds < JROUNDS; rounds++) {
+            // four cells per step, no branches: a resolved cell reads the pointer of cell `label` (< 1024: harmless) and keeps its own
+            uint32_t all = 0x80008000u;
+            uint2 *ptr64 = reinterpret_cast<uint2 *>(ptr32);
+            for (int i = threadIdx.x; i < TCELLS / 4; i += JTA) {
+                uint2 w = ptr64[i];
+                if ((w.x & w.y & 0x80008000u) == 0x80008000u) continue;
+                const uint32_t a0 = w.x & 0xFFFFu, a1 = w.x >> 16, a2 = w.y & 0xFFFFu, a3 = w.y >> 16;
+                const uint32_t b0 = ptr16[a0 & 0x3FFFu], b1 = ptr16[a1 & 0x3FFFu], b2 = ptr16[a2 & 0x3FFFu], b3 = ptr16[a3 & 0x3FFFu];
+                w.x = ((a0 & JRES) ? a0 : b0) | (((a1 & JRES) ? a1 : b1) << 16);
+                w.y = ((a2 & JRES) ? a2 : b2) | (((a3 & JRES) ? a3 : b3) << 16);
+                ptr64[i] = w;
+                all &= w.x & w.y;
+            }
+            open = __syncthreads_or(all != 0x80008000u) != 0;
+        }
+        if (open) {                                      // a cycle: the chain-walk solver redoes this tile
+            if (threadIdx.x == 0) { tile_class[tile] = 3; tile_top[tile] = 1; flags[F_CHAIN] = 1u; }
+            continue;
+        }
+        // exit_acc: the histogram of the labels (runs of equal labels along a row are counted at once)
+        for (int q = threadIdx.x; q < TH * 32; q += JTA) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(ptr32 + 4 * q);
+            const uint32_t lab[NC] = {x.x & 0x3FFu, (x.x >> 16) & 0x3FFu, x.y & 0x3FFu, (x.y >> 16) & 0x3FFu,
+                                      x.z & 0x3FFu, (x.z >> 16) & 0x3FFu, x.w & 0x3FFu, (x.w >> 16) & 0x3FFu};
+            uint32_t cur = lab[0];
+            int n = 1;
+#pragma unroll
+            for (int j = 1; j < NC; j++) {
+                if (lab[j] == cur) n++;
+                else { atomicAdd(&hist[cur], n); cur = lab[j]; n = 1; }
+            }
+            atomicAdd(&hist[cur], n);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tile_class[tile] = 4;
+            tile_top[tile] = (top_up || !full) ? 1 : 0;
+            rounds_of[tile] = (unsigned long long)rounds;
+        }
+        // the boundary slots: link = the cell's label, the forest word = one pending arrival | code | weight
+        uint32_t *m_t = meta + (int64_t)tile * NSLOT;
+        int32_t *x_t = exit_acc ? exit_acc + (int64_t)tile * NSLOT : nullptr;
+        unsigned long long *w_t = wq + (int64_t)tile * NSLOT;
+        for (int s = threadIdx.x; s < NSLOT; s += JTA) {
+            int lr, lc;
+            uint32_t m = 0u;
+            if (cell_of(s, th, tw, lr, lc)) {
+                const int kr = (int)jump_code(codes, lr, lc);
+                m = meta_pack((uint32_t)ptr16[lr * TW + lc] & 0x3FFu, kr < 8 ? kr : 8, false, kr != 9);
+            }
+            const int h = hist[s];
+            m_t[s] = m;
+            if (x_t) x_t[s] = h;
+            w_t[s] = PEND1 | ((unsigned long long)((m >> 16) & 0xFu) << W_K) | (uint32_t)h;
+        }
+    }
+}
+
+// Phase C.  32-bit sums (ONE = true): every thread keeps the running totals of its 16 cells in registers and the adds of
+// round k go into buffer k & 1, which the owners of still-live cells fold into their totals (and clear) behind the round's
+// only barrier, while round k + 1 already adds into the other buffer; a cell whose pointer has run out folds nothing any
+// more, what still arrives for it stays in the two buffers and is added at the end.  64-bit sums (two such buffers do not
+// fit): one array, every value read before the barrier and the adds behind it, a second barrier after the adds.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(JTC, 1) k_jumpC(Geo g, int ntiles, const uint32_t *__restrict__ codes4,
+                                                  const unsigned long long *__restrict__ wq, const uint8_t *__restrict__ tile_top,
+                                                  const T *__restrict__ extra, const uint8_t *__restrict__ tile_class,
+                                                  TO *__restrict__ acc, unsigned long long *__restrict__ rounds_of,
+                                                  uint32_t *__restrict__ flags, bool al)
+{
+    // [TCELLS] sums (T; twice for 32-bit sums) + 2 x [TCELLS / 2] pointers (16 bit) + [TH * 32] codes + [NSLOT] boundary inflows (T) + 1
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    constexpr bool ONE = sizeof(T) == 4;
+    if (flags[F_COMPLEX] == 0u) return;
+    T *A = reinterpret_cast<T *>(s_dyn);
+    T *B = A + TCELLS;                                  // (ONE only)
+    uint32_t *pbuf = reinterpret_cast<uint32_t *>(A + (ONE ? 2 : 1) * TCELLS);
+    uint32_t *codes = pbuf + TCELLS;
+    T *ext = reinterpret_cast<T *>(codes + TH * 32);
+    int *slot = reinterpret_cast<int *>(ext + NSLOT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int QPT = TCELLS / 4 / JTC;               // pointer quads (four cells each) per thread
+    for (;;) {
+        const int tile = jump_next_tile(&flags[F_NEXT_C], slot);
+        if (tile >= ntiles) return;
+        if (tile_class[tile] != 4) continue;
+        int ty, tx, th, tw;
+        tile_dims(g, tile, ty, tx, th, tw);
+        const bool full = th == TH && tw == TW;
+        const uint32_t *c4 = codes4 + (int64_t)tile * TH * 32;
+        for (int q = threadIdx.x; q < TH * 32; q += JTC) codes[q] = __ldcg(c4 + q);
+        if (warp == 0) tile_inflow<T>(g, wq, tile_top, extra, tile, ty, tx, th, tw, lane, ext);
+        __syncthreads();
+        // pointers and the cells' own weight.  A cell draining into an inactive cell simply adds to it: an inactive cell has
+        // no pointer, passes nothing on, and the store at the end writes zero for it.
+        uint32_t *cur32 = pbuf, *nxt32 = pbuf + TCELLS / 2;
+        auto no_receiver = [](int, int) { return JNONE; };
+        jump_pointers(codes, th, tw, JNONE, cur32, no_receiver);
+        for (int q = threadIdx.x; q < TH * 32; q += JTC) {
+            const uint32_t cw = codes[q];
+            T av[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) av[j] = ((cw >> (4 * j)) & 15u) != 9u ? (T)1 : (T)0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) A[NC * q + j] = av[j];
+            if (ONE) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) B[NC * q + j] = 0;
+            }
+        }
+        __syncthreads();
+        for (int s = threadIdx.x; s < NSLOT; s += JTC) {   // the boundary cells: pointers of a full tile, external inflow
+            int lr, lc;
+            if (!cell_of(s, th, tw, lr, lc)) continue;
+            const uint32_t kr = jump_code(codes, lr, lc);
+            if (full) reinterpret_cast<uint16_t *>(cur32)[lr * TW + lc] = (uint16_t)jump_pointer_boundary(kr, lr, lc, JNONE, no_receiver);
+            if (kr != 9u) A[lr * TW + lc] += ext[s];
+        }
+        __syncthreads();
+        int rounds = 0;
+        if constexpr (ONE) {
+            uint2 pw[QPT];
+            T tot[4 * QPT];
+#pragma unroll
+            for (int k = 0; k < QPT; k++) {
+                const int i = threadIdx.x + JTC * k;
+                pw[k] = reinterpret_cast<const uint2 *>(cur32)[i];
+                const uint4 v = *reinterpret_cast<const uint4 *>(A + 4 * i);
+                tot[4 * k] = (T)v.x; tot[4 * k + 1] = (T)v.y; tot[4 * k + 2] = (T)v.z; tot[4 * k + 3] = (T)v.w;
+                *reinterpret_cast<uint4 *>(A + 4 * i) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncthreads();                             // (buffer 0 is clear before anybody adds to it)
+            for (; rounds < JROUNDS; rounds++) {
+                T *buf = (rounds & 1) ? B : A;
+                const uint16_t *cur16 = reinterpret_cast<const uint16_t *>(cur32);
+                uint2 *nxt64 = reinterpret_cast<uint2 *>(nxt32);
+                bool mine = false;
+#pragma unroll
+                for (int k = 0; k < QPT; k++) {
+                    const int i = threadIdx.x + JTC * k;
+                    const uint2 w = pw[k];
+                    if ((w.x & w.y) == 0xFFFFFFFFu) { nxt64[i] = w; continue; }   // (others read "none" from either buffer)
+                    const uint32_t p0 = w.x & 0xFFFFu, p1 = w.x >> 16, p2 = w.y & 0xFFFFu, p3 = w.y >> 16;
+                    if (p0 != JNONE) smem_add<T>(&buf[p0], tot[4 * k]);
+                    if (p1 != JNONE) smem_add<T>(&buf[p1], tot[4 * k + 1]);
+                    if (p2 != JNONE) smem_add<T>(&buf[p2], tot[4 * k + 2]);
+                    if (p3 != JNONE) smem_add<T>(&buf[p3], tot[4 * k + 3]);
+                    // (no branches: a cell without pointer reads some cell's pointer and keeps "none")
+                    const uint32_t n0 = cur16[p0 & 0x3FFFu], n1 = cur16[p1 & 0x3FFFu], n2 = cur16[p2 & 0x3FFFu], n3 = cur16[p3 & 0x3FFFu];
+                    pw[k] = make_uint2((p0 == JNONE ? JNONE : n0) | ((p1 == JNONE ? JNONE : n1) << 16),
+                                       (p2 == JNONE ? JNONE : n2) | ((p3 == JNONE ? JNONE : n3) << 16));
+                    nxt64[i] = pw[k];
+                    mine = true;
+                }
+                if (!__syncthreads_or(mine)) break;
+#pragma unroll
+                for (int k = 0; k < QPT; k++) {         // still-live cells fold what has just arrived for them
+                    const uint2 w = pw[k];
+                    if ((w.x & w.y) == 0xFFFFFFFFu) continue;
+                    const int i = threadIdx.x + JTC * k;
+                    uint4 v = *reinterpret_cast<const uint4 *>(buf + 4 * i);
+                    if ((w.x & 0xFFFFu) != JNONE) { tot[4 * k] += (T)v.x; v.x = 0u; }
+                    if ((w.x >> 16) != JNONE) { tot[4 * k + 1] += (T)v.y; v.y = 0u; }
+                    if ((w.y & 0xFFFFu) != JNONE) { tot[4 * k + 2] += (T)v.z; v.z = 0u; }
+                    if ((w.y >> 16) != JNONE) { tot[4 * k + 3] += (T)v.w; v.w = 0u; }
+                    *reinterpret_cast<uint4 *>(buf + 4 * i) = v;
+                }
+                uint32_t *t = cur32; cur32 = nxt32; nxt32 = t;
+            }
+            // the sums: own total + what is left in the two buffers.  (Behind the last barrier nobody adds any more; the
+            // folds above touch own cells only.)
+#pragma unroll
+            for (int k = 0; k < QPT; k++) {
+                const int i = threadIdx.x + JTC * k;
+                const uint4 va = *reinterpret_cast<const uint4 *>(A + 4 * i), vb = *reinterpret_cast<const uint4 *>(B + 4 * i);
+                *reinterpret_cast<uint4 *>(A + 4 * i) = make_uint4((uint32_t)tot[4 * k] + va.x + vb.x, (uint32_t)tot[4 * k + 1] + va.y + vb.y,
+                                                                  (uint32_t)tot[4 * k + 2] + va.z + vb.z, (uint32_t)tot[4 * k + 3] + va.w + vb.w);
+            }
+            __syncthreads();
+        } else {
+            for (; rounds < JROUNDS; rounds++) {
+                const uint16_t *cur16 = reinterpret_cast<const uint16_t *>(cur32);
+                const uint2 *cur64 = reinterpret_cast<const uint2 *>(cur32);
+                uint2 *nxt64 = reinterpret_cast<uint2 *>(nxt32);
+                uint2 pw[QPT];
+                T a[4 * QPT];
+                bool mine = false;
+#pragma unroll
+                for (int k = 0; k < QPT; k++) {
+                    const int i = threadIdx.x + JTC * k;
+                    const uint2 w = cur64[i];
+                    pw[k] = w;
+                    if ((w.x & w.y) == 0xFFFFFFFFu) { nxt64[i] = w; continue; }
+                    const uint32_t p0 = w.x & 0xFFFFu, p1 = w.x >> 16, p2 = w.y & 0xFFFFu, p3 = w.y >> 16;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) a[4 * k + j] = A[4 * i + j];
+                    const uint32_t n0 = cur16[p0 & 0x3FFFu], n1 = cur16[p1 & 0x3FFFu], n2 = cur16[p2 & 0x3FFFu], n3 = cur16[p3 & 0x3FFFu];
+                    nxt64[i] = make_uint2((p0 == JNONE ? JNONE : n0) | ((p1 == JNONE ? JNONE : n1) << 16),
+                                          (p2 == JNONE ? JNONE : n2) | ((p3 == JNONE ? JNONE : n3) << 16));
+                    mine = true;
+                }
+                if (!__syncthreads_or(mine)) break;     // (the barrier also puts every read of A before the adds)
+#pragma unroll
+                for (int k = 0; k < QPT; k++) {
+                    if ((pw[k].x & pw[k].y) == 0xFFFFFFFFu) continue;
+                    const uint32_t p0 = pw[k].x & 0xFFFFu, p1 = pw[k].x >> 16, p2 = pw[k].y & 0xFFFFu, p3 = pw[k].y >> 16;
+                    if (p0 != JNONE) smem_add<T>(&A[p0], a[4 * k]);
+                    if (p1 != JNONE) smem_add<T>(&A[p1], a[4 * k + 1]);
+                    if (p2 != JNONE) smem_add<T>(&A[p2], a[4 * k + 2]);
+                    if (p3 != JNONE) smem_add<T>(&A[p3], a[4 * k + 3]);
+                }
+                __syncthreads();
+                uint32_t *t = cur32; cur32 = nxt32; nxt32 = t;
+            }
+        }
+        if (threadIdx.x == 0) rounds_of[tile] |= (unsigned long long)rounds << 32;
+        const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW;
+        for (int q = threadIdx.x; q < TH * 32; q += JTC) {
+            const int lr = q >> 5, l = q & 31;
+            if (lr >= th || gc0 + NC * l >= g.nx) continue;
+            const uint32_t cw = codes[q];
+            T tot[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) tot[j] = ((cw >> (4 * j)) & 15u) != 9u ? A[NC * q + j] : (T)0;
+            TO *out = acc + (gr0 + lr) * g.nx + gc0 + NC * l;
+            if (al) store_row<true, T, TO>(out, tot, gc0 + NC * l, g.nx);
+            else store_row<false, T, TO>(out, tot, gc0 + NC * l, g.nx);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2104,7 +2111,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
 // arrives from the other stripes.
 struct SweepWs {
     uint32_t *meta; unsigned long long *wq; int32_t *par; uint8_t *tile_class, *tile_top; unsigned long long *row_plain, *gcnt;
-    uint32_t *flags; uint32_t *codes4; void *scratch;                                          // multi-sweep solver: decoded tiles, state across sweeps
+    uint32_t *flags; uint32_t *codes4;                                                         // jump solver: the tiles' decoded codes, phase A -> phase C
     int32_t *exit_acc, *parent, *cnt; int64_t *A, *inflow; uint8_t *blocked, *ext_unres;   // wide
     int2 *pe; void *extra; uint8_t *extra_unres;                              // stripe
     StripePaths sp;
@@ -2128,7 +2135,6 @@ static SweepWs carve_ws(void *ws, size_t ws_bytes, const Geo &g, bool wide, bool
     w.flags = cur.take<uint32_t>(NFLAGS);                     // (right behind the counters: one memset clears both)
     if (!wide) {                                              // (the 64-bit forest engine keeps the chain-walk solver for such tiles)
         w.codes4 = cur.take<uint32_t>(nt * TH * 32);
-        w.scratch = stripe ? (void *)cur.take<int64_t>(nt * TH * TW) : (void *)cur.take<int32_t>(nt * TH * TW);
     }
     if (wide) {
         w.exit_acc = cur.take<int32_t>(nn);
@@ -2203,20 +2209,12 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     if (mask) { if (al) WMF_LAUNCH_A(true, true); else WMF_LAUNCH_A(false, true); }
     else { if (al) WMF_LAUNCH_A(true, false); else WMF_LAUNCH_A(false, false); }
 #undef WMF_LAUNCH_A
-    if (w.codes4) {                                          // tiles with upward flow: alternating sweeps
-        const size_t smemM = (size_t)MWPB * (TH * 32 * sizeof(uint32_t) + HBINS * sizeof(int) + 32 * LTAB * sizeof(uint32_t));
-        {
-            static bool done[64];
-            int dev = 0;
-            WMF_CUDA_CHECK(cudaGetDevice(&dev));
-            if (dev < 0 || dev >= 64 || !done[dev]) {
-                WMF_CUDA_CHECK(cudaFuncSetAttribute(k_multiA<ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemM));
-                if (dev >= 0 && dev < 64) done[dev] = true;
-            }
-        }
-        const int want = (ntiles + MWPB - 1) / MWPB, cap = sm_count() * 3;      // three blocks per SM fit (shared memory)
-        k_multiA<ENC><<<want < cap ? want : cap, MWPB * 32, smemM, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.wq,
-                                                                         w.tile_top, w.codes4, (uint16_t *)w.scratch, w.row_plain, w.flags);
+    if (w.codes4) {                                          // tiles with upward flow: pointer jumping, one block per tile
+        const size_t smemJ = sizeof(uint32_t) * (TCELLS / 2 + TH * 32 + HBINS + 4);
+        static_assert(sizeof(uint32_t) * (TCELLS / 2 + TH * 32 + HBINS + 4) <= 48 * 1024, "k_jumpA fits the default dynamic shared memory");
+        const int cap = sm_count() * 4;
+        k_jumpA<ENC><<<ntiles < cap ? ntiles : cap, JTA, smemJ, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.wq,
+                                                                       w.tile_top, w.codes4, w.row_plain, w.flags, al);
     }
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq, w.flags);
     WMF_LAUNCH_CHECK();
@@ -2232,13 +2230,14 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     const unsigned gen_blocks = (unsigned)(ntiles < sm_count() * 4 ? ntiles : sm_count() * 4);
     const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * NSLOT * sizeof(T) + WPB * 8;
+    const size_t smemJ = sizeof(T) * TCELLS * (sizeof(T) == 4 ? 2 : 1) + sizeof(uint32_t) * (TCELLS + TH * 32) + sizeof(T) * NSLOT + 16;   // k_jumpC
     {   // once per device and instantiation
         static bool done[64];
         int dev = 0;
         WMF_CUDA_CHECK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !done[dev]) {
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_multiC<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_jumpC<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemJ));
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -2252,10 +2251,9 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     else { if (al) WMF_LAUNCH_C(true, false); else WMF_LAUNCH_C(false, false); }
 #undef WMF_LAUNCH_C
     if (w.codes4 && wq) {
-        const size_t smemM = (size_t)MWPB * (TH * 32 * sizeof(uint32_t) + NSLOT * sizeof(T));
-        const int want = (ntiles + MWPB - 1) / MWPB, cap = sm_count() * 4;
-        k_multiC<T, TO><<<want < cap ? want : cap, MWPB * 32, smemM, st>>>(g, ntiles, w.codes4, wq, w.tile_top, extra, w.tile_class,
-                                                                           (T *)w.scratch, acc, w.row_plain, w.flags);
+        const int cap = sm_count();                          // one block per SM fits (shared memory)
+        k_jumpC<T, TO><<<ntiles < cap ? ntiles : cap, JTC, smemJ, st>>>(g, ntiles, w.codes4, wq, w.tile_top, extra, w.tile_class, acc,
+                                                                         w.row_plain, w.flags, al);
     }
     k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, wq, w.par, extra, extra_unres, acc, w.flags);
     WMF_LAUNCH_CHECK();
@@ -2411,7 +2409,7 @@ size_t d8_sweep_workspace(int64_t ny, int64_t nx, int acc_dtype)
 }
 
 // How the tiles of the last accumulation that used this workspace were solved: counts[c] = tiles of class c
-// (0 one-pass sweeps, 4 multi-sweep, 1 / 3 chain walk, 2 chain walk because of an unresolved upstream).  Syncs.
+// (0 one-pass sweeps, 4 jump solver, 1 / 3 chain walk, 2 chain walk because of an unresolved upstream).  Syncs.
 int d8_sweep_tile_classes(const void *ws, size_t ws_bytes, int64_t ny, int64_t nx, int64_t *counts8, cudaStream_t st)
 {
     const Geo g = make_geo(ny, nx, 0, ny);
@@ -2425,7 +2423,7 @@ int d8_sweep_tile_classes(const void *ws, size_t ws_bytes, int64_t ny, int64_t n
     if (e != cudaSuccess) { free(h); wmf_set_error("d8_sweep_tile_classes: %s", cudaGetErrorString(e)); return (int)e; }
     for (int c = 0; c < 8; c++) counts8[c] = 0;
     for (size_t t = 0; t < nt; t++) counts8[h[t] & 7]++;
-    // sweeps the multi-sweep tiles took: [5] phase A total, [6] phase C total, [7] the largest of either
+    // jump rounds of the class-4 tiles: [5] phase A total, [6] phase C total, [7] the largest of either
     unsigned long long *sw = (unsigned long long *)malloc(nt * 8);
     if (sw && cudaMemcpy(sw, w.row_plain, nt * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
         for (size_t t = 0; t < nt; t++)

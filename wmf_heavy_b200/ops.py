@@ -46,9 +46,9 @@ def d8_accum(dir_t: torch.Tensor, mask_t: Optional[torch.Tensor] = None, acc_dty
         cnt = (C.c_int64 * 8)()
         check(lib.wmf_d8_accum_tile_classes(ptr(ws), ws.numel(), ny, nx, C.addressof(cnt), stream_ptr()))
         c = list(cnt)
-        stats["tile_classes"] = {"one_pass": c[0], "multi_sweep": c[4], "chain_walk": c[1] + c[3], "chain_walk_unresolved_upstream": c[2]}
+        stats["tile_classes"] = {"one_pass": c[0], "jump": c[4], "chain_walk": c[1] + c[3], "chain_walk_unresolved_upstream": c[2]}
         if c[4]:
-            stats["multi_sweeps"] = {"phase_a_mean": c[5] / c[4], "phase_c_mean": c[6] / c[4], "max": c[7]}
+            stats["jump_rounds"] = {"phase_a_mean": c[5] / c[4], "phase_c_mean": c[6] / c[4], "max": c[7]}
     return out
 
 
