@@ -482,7 +482,10 @@ int wmf_basin_structure(const int8_t *dir, int64_t nrows, int64_t ncols, int32_t
 
     k_scatter_cells<<<blocks_for(n, th), th, 0, st>>>(flag32, cidx, n, cell);
     k_parent_compact<<<blocks_for(nb, th), th, 0, st>>>(dir, cell, cidx, nb, ny, nx, (int32_t)outlet, parentC);
-    rc = forest_accum_i32(parentC, nullptr, size, cnt, nb, st);
+    // subtree sizes (the basin is a tree rooted at the outlet: doubling, not the chain walk whose run time is the main stem).
+    // Scratch: pA, qA, dA and pB follow each other in the workspace and are not in use yet.
+    (void)cnt;
+    rc = forest_subtree_sums_i32(parentC, nullptr, size, pA, nb, st);
     if (rc) return rc;
     k_sibling_offset<<<blocks_for(nb, th), th, 0, st>>>(dir, cell, cidx, parentC, size, nb, ny, nx, off);
     k_jump_init<<<blocks_for(nb, th), th, 0, st>>>(parentC, off, nb, pA, qA, dA);
@@ -521,11 +524,14 @@ int wmf_basin_acum_vec(const int32_t *structure, int64_t stride, int64_t n, int3
     WMF_REQUIRE(n < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "n must be < 2^31");
     if (n == 0) return 0;
     WsCursor cur(workspace, ws_bytes);
-    int32_t *parent = cur.take<int32_t>((size_t)n), *cnt = cur.take<int32_t>((size_t)n);
+    int32_t *parent = cur.take<int32_t>((size_t)n), *scratch = cur.take<int32_t>((size_t)n);
+    cur.take<int32_t>((size_t)n);
+    cur.take<int32_t>((size_t)n);
+    cur.take<int32_t>((size_t)n);                       // (scratch: 3 n + 64, contiguous)
     WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
     k_vec_parent<<<blocks_for(n, 256), 256, 0, st>>>(structure, n, parent);
     WMF_LAUNCH_CHECK();
-    return forest_accum_i32(parent, nullptr, acum, cnt, n, st);
+    return forest_subtree_sums_i32(parent, nullptr, acum, scratch, n, st);
 }
 
 int wmf_basin_coordxy(const int32_t *structure, int64_t stride, int64_t n, float xll, float yll, float dx,

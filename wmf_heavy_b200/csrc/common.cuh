@@ -113,5 +113,7 @@ int forest_accum_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int3
                      const uint8_t *blocked = nullptr);
 int forest_accum_i64(const int32_t *parent, const int32_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st,
                      const uint8_t *blocked = nullptr);
+// acyclic forests only: the same sums in log2(depth) rounds of scatter-adds (scratch: 3 n int32 + 64)
+int forest_subtree_sums_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int32_t *scratch, int64_t n, cudaStream_t st);
 int forest_accum_i64w(const int32_t *parent, const int64_t *w, int64_t *acc, int32_t *cnt, int64_t n, cudaStream_t st,
                       const uint8_t *blocked = nullptr);

@@ -101,6 +101,70 @@ int forest_accum_i64w(const int32_t *parent, const int64_t *w, int64_t *acc, int
     return forest_accum_t<int64_t, int64_t>(parent, w, acc, cnt, blocked, n, st);
 }
 
+// ---- acyclic forests: subtree sums by doubling ---------------------------------------------------
+// The chain walk above is O(n) work but its run time is the longest path (the main stem of a basin: thousands of
+// dependent L2 round trips).  For a forest that is known to be acyclic -- the BFS structure of a basin -- the sums are
+// formed in log2(depth) rounds instead: with ptr_k = the 2^k-th ancestor and V_k[u] = the weight within distance < 2^k
+// upstream of u, every node that still has a pointer adds V_k[u] into V_{k+1}[ptr_k[u]] and into its own V_{k+1}.
+// The two value buffers swap roles every round; a node whose pointer has run out stops moving its value, so what it
+// holds and what still arrives for it end up spread over both buffers and the result is their sum.  One kernel per
+// round, no host round trip: a round that finds every pointer exhausted leaves its flag down and the rounds behind it
+// return at once.
+namespace {
+__global__ void k_dbl_init(const int32_t *__restrict__ parent, const int32_t *__restrict__ w, int32_t *__restrict__ a0,
+                           int32_t *__restrict__ a1, int32_t *__restrict__ p0, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a0[i] = w ? w[i] : 1;
+    a1[i] = 0;
+    p0[i] = parent[i];
+}
+__global__ void k_dbl_round(const int32_t *__restrict__ pc, int32_t *__restrict__ pn, int32_t *aold, int32_t *anew, int64_t n,
+                            int32_t *flags, int r)
+{
+    if (r > 0 && flags[r - 1] == 0) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t p = pc[i];
+    if (p < 0) { pn[i] = -1; return; }
+    const int32_t a = aold[i];
+    aold[i] = 0;                                         // (only this thread reads it; nothing is added to `aold` in this round)
+    atomicAdd(&anew[i], a);
+    atomicAdd(&anew[p], a);
+    pn[i] = pc[p];
+    flags[r] = 1;
+}
+__global__ void k_dbl_final(int32_t *__restrict__ acc, const int32_t *__restrict__ a1, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += a1[i];
+}
+}  // namespace
+
+// scratch: 3 n int32 + 64.  parent must describe an acyclic forest (-1 = root).
+int forest_subtree_sums_i32(const int32_t *parent, const int32_t *w, int32_t *acc, int32_t *scratch, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    int32_t *a1 = scratch, *p0 = scratch + n, *p1 = scratch + 2 * n, *flags = scratch + 3 * n;
+    int rounds = 1;
+    while (((int64_t)1 << rounds) < n + 1) rounds++;
+    rounds += 1;
+    if (rounds > 32) rounds = 32;
+    WMF_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int32_t) * 64, st));
+    const int th = 256;
+    k_dbl_init<<<blocks_for(n, th), th, 0, st>>>(parent, w, acc, a1, p0, n);
+    int32_t *aold = acc, *anew = a1;
+    for (int r = 0; r < rounds; r++) {
+        k_dbl_round<<<blocks_for(n, th), th, 0, st>>>(p0, p1, aold, anew, n, flags, r);
+        int32_t *t = p0; p0 = p1; p1 = t;
+        t = aold; aold = anew; anew = t;
+    }
+    k_dbl_final<<<blocks_for(n, th), th, 0, st>>>(acc, a1, n);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
 namespace {
 __global__ void k_resolved(const int32_t *__restrict__ cnt, uint8_t *__restrict__ resolved, int64_t n)
 {
