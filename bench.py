@@ -42,12 +42,22 @@ METRIC = "D8 flow-accum Mcells/s (16k² raster); SHIA cell-timesteps/s at 1/2/4/
 SEED = 20260101
 
 
+def stripe_rows_per_rank(n: int, world: int) -> int:
+    """Rows of one rank's stripe.  N = 1: the n x n raster of BASELINE config 2.  N > 1: n - 64 rows (one tile row less)
+    on EVERY rank count, so that the whole raster stays below 2^31 cells up to N = 8 and the accumulation type (int32)
+    -- hence the bytes written per cell -- is the same at every N: the weak-scaling curve compares like with like.
+    (The N = 8 raster of 8 x n x n cells is exactly 2^31, one more than int32 counts; it is timed beside it as
+    `int64_variant`.)"""
+    return n if world == 1 else n - 64
+
+
 def workload_config(n: int, world: int, acc_name: str, algo: str = "auto") -> dict:
     """`config` of the JSON line: the same for both arms (the reference arm names its bounded sample in cpu_baseline)."""
-    return {"workload": f"D8 flow accumulation, synthetic Scheidegger DIR {n}x{n} per GPU (seed {SEED}), "
+    rows = stripe_rows_per_rank(n, world)
+    return {"workload": f"D8 flow accumulation, synthetic Scheidegger DIR {rows}x{n} per GPU (seed {SEED}), "
                         f"int8 DIR -> {acc_name} ACC, mask = all valid", "algo": algo,
             "parallelism": "1 GPU" if world == 1 else
-            f"{world} row stripes of {n} rows of one {world * n}x{n} raster, one NCCL all-gather of the "
+            f"{world} row stripes of {rows} rows of one {world * rows}x{n} raster, one NCCL all-gather of the "
             "boundary records per accumulation",
             "l2": "inputs (DIR 0.27 GB + ACC 1.07 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -165,7 +175,7 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": mcells, "unit": "Mcells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(n, max(args.gpus, 1), "int32" if max(args.gpus, 1) * n * n <= 2**31 - 1 else "int64"),
+        "config": workload_config(n, max(args.gpus, 1), "int32"),
         "cpu_baseline": {"value": mcells, "unit": "Mcells/s", "cores": 1, "kind": "port",
                          "sample": f"per step: the first {rows} rows x {n} columns of the benchmark raster ({rows * n} cells); "
                                    "C restatement of wmf_py basin_acum (oracle/wmf_oracle.c, gcc -O2, 1 thread; the algorithm is "
@@ -368,8 +378,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     peak, peak_src = measured_peaks()
     algo = {"auto": _lib.ALGO_AUTO, "walk": _lib.ALGO_WALK, "sweep": _lib.ALGO_SWEEP}[args.algo]
 
-    # ---- workload: this rank's stripe of the (world*n) x n Scheidegger raster, generated on the device
-    d = ops.synth_scheidegger(n, n, seed=SEED, row0=rank * n, nx_total=n)
+    # ---- workload: this rank's stripe of the (world*rows) x n Scheidegger raster, generated on the device
+    rows = stripe_rows_per_rank(n, world)
+    d = ops.synth_scheidegger(rows, n, seed=SEED, row0=rank * rows, nx_total=n)
     if world == 1:
         acc = torch.empty((n, n), dtype=torch.int32, device=dev)
 
@@ -379,12 +390,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # row stripes with one boundary exchange (all-gather over NCCL); int64 ACC when the whole raster can
         # exceed 2^31 - 1 cells
         from wmf_heavy_b200 import stripes
-        wide = world * n * n > 2**31 - 1
-        acc = torch.empty((n, n), dtype=torch.int64 if wide else torch.int32, device=dev)
+        wide = world * rows * n > 2**31 - 1
+        acc = torch.empty((rows, n), dtype=torch.int64 if wide else torch.int32, device=dev)
         stripe_dtype = _lib.ACC_I64 if wide else _lib.ACC_I32
 
         def step():
-            stripes.accumulate_striped(d, rank * n, world * n, acc_dtype=stripe_dtype, out=acc)
+            stripes.accumulate_striped(d, rank * rows, world * rows, acc_dtype=stripe_dtype, out=acc)
 
     def barrier():
         if world > 1:
@@ -408,12 +419,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    cells_total = float(n) * n * world
+    cells_total = float(rows) * n * world
     value = cells_total / (ms_per_step * 1e-3) / 1e6
     op_ms = statistics.mean(per)
     acc_name = str(acc.dtype).replace("torch.", "")
     bytes_per_cell = 1.0 + acc.element_size()                       # int8 DIR read + ACC write
-    achieved = bytes_per_cell * n * n / (op_ms * 1e-3) / 1e9
+    achieved = bytes_per_cell * rows * n / (op_ms * 1e-3) / 1e9
 
     # ---- e2e through the reference-facing API: host flowdir + mask in (pinned), float64 raster out
     e2e = None
@@ -439,13 +450,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     if args.e2e_steps > 0 and world > 1:
         from wmf_heavy_b200 import stripes
-        h_dir = torch.empty((n, n), dtype=torch.int8).pin_memory()
+        h_dir = torch.empty((rows, n), dtype=torch.int8).pin_memory()
         h_dir.copy_(d)
-        h_out = torch.empty((n, n), dtype=acc.dtype).pin_memory()
+        h_out = torch.empty((rows, n), dtype=acc.dtype).pin_memory()
 
         def e2e_step():
             dd = h_dir.to(dev, non_blocking=True)
-            a = stripes.accumulate_striped(dd, rank * n, world * n, acc_dtype=stripe_dtype)
+            a = stripes.accumulate_striped(dd, rank * rows, world * rows, acc_dtype=stripe_dtype)
             h_out.copy_(a)
 
         e2e_step()
@@ -458,10 +469,55 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-        e2e = {"value": cells_total / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": n * n,
-               "d2h_bytes_per_step": acc.element_size() * n * n, "ms_per_step": 1e3 * e2e_s,
+        e2e = {"value": cells_total / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": rows * n,
+               "d2h_bytes_per_step": acc.element_size() * rows * n, "ms_per_step": 1e3 * e2e_s,
                "api": "wmf_heavy_b200.stripes.accumulate_striped(host int8 stripe) -> host stripe, per rank"}
         del h_dir, h_out
+
+    # ---- N > 1: the same stripes accumulated into int64 at the size where int32 no longer counts the raster (N * n * n
+    # cells: 2^31 at N = 8), and BASELINE config 4 itself -- ONE 65536^2 raster over the N ranks (strong scaling)
+    striped_extra = None
+    if world > 1 and not args.no_secondary:
+        from wmf_heavy_b200 import stripes
+        striped_extra = {}
+
+        def timed_stripes(fn, steps_):
+            for _ in range(2):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps_):
+                fn()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / steps_], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        d64 = ops.synth_scheidegger(n, n, seed=SEED, row0=rank * n, nx_total=n)
+        a64 = torch.empty((n, n), dtype=torch.int64, device=dev)
+        ms64 = timed_stripes(lambda: stripes.accumulate_striped(d64, rank * n, world * n, acc_dtype=_lib.ACC_I64, out=a64), 10)
+        striped_extra["int64_variant"] = {"raster": f"{world * n}x{n}, {n} rows per rank", "dtype": "int64", "ms_per_step": ms64,
+                                          "value": float(n) * n * world / (ms64 * 1e-3) / 1e6, "unit": "Mcells/s",
+                                          "algorithmic_bytes_per_cell": 9.0}
+        del d64, a64
+        big = args.c4_size
+        if big % world == 0 and (big // world) * big <= 2**33:
+            rows_r = big // world
+            n_local = max(1, -(-rows_r * big // (2**30)))          # stripes of at most 2^30 cells (< 2^31 each)
+            while rows_r % n_local:
+                n_local += 1
+            dbig = ops.synth_scheidegger(rows_r, big, seed=SEED + 4, row0=rank * rows_r, nx_total=big)
+            abig = torch.empty((rows_r, big), dtype=torch.int64, device=dev)
+            msb = timed_stripes(lambda: stripes.accumulate_striped_multi(dbig, rank * rows_r, big, n_local, acc_dtype=_lib.ACC_I64,
+                                                                         out=abig), 3)
+            striped_extra["c4_strong"] = {"raster": f"{big}x{big} (BASELINE config 4), {rows_r} rows per rank in {n_local} stripe(s)",
+                                          "dtype": "int64", "scaling": "strong", "ms_per_step": msb,
+                                          "value": float(big) * big / (msb * 1e-3) / 1e6, "unit": "Mcells/s",
+                                          "roofline_frac_per_gpu": 9.0 * rows_r * big / (msb * 1e-3) / 1e9 / peak}
+            del dbig, abig
+        torch.cuda.empty_cache()
 
     # ---- the other input classes, same size (N = 1)
     secondary = None
@@ -545,7 +601,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "kernel": "wmf_d8_accum, all passes of one accumulation "
                                    f"({bytes_per_cell:.0f} B/cell algorithmic)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "clocks": clk.summary(), "secondary": secondary, "basin": basin, "shia": shia,
+            "clocks": clk.summary(), "secondary": secondary, "striped": striped_extra, "basin": basin, "shia": shia,
         }
         if saved_stdout is not None:
             sys.stdout.flush()
@@ -570,6 +626,7 @@ def main():
     ap.add_argument("--shia-steps", type=int, default=1000)
     ap.add_argument("--pop-sets", type=int, default=512)
     ap.add_argument("--pop-cells", type=int, default=250000)
+    ap.add_argument("--c4-size", type=int, default=65536, help="side of the strong-scaling raster of BASELINE config 4 (N > 1)")
     ap.add_argument("--no-shia", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
