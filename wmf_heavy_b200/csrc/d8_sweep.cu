@@ -56,6 +56,7 @@ struct Geo {
     int64_t ny, nx;          // this raster (or row stripe)
     int tiles_x, tiles_y;
     int64_t gy0, gny;        // the stripe holds rows [gy0, gy0 + ny) of a raster of gny rows (gy0 = 0, gny = ny when whole)
+    int extra_edge;          // stripes, 32-bit sums: `extra` holds inflow only for the stripe's first / last tile row
 };
 
 // canonical boundary slot of local cell (lr, lc) in a tile of th x tw cells, or -1
@@ -989,7 +990,8 @@ __device__ __forceinline__ void tile_inflow(const Geo &g, const unsigned long lo
     } else {
         for (int s = lane; s < NSLOT; s += 32) ext[s] = 0;
     }
-    if (extra) {
+    // (extra_edge: only the stripe's own first / last tile row holds anything -- the rest went into the forest words)
+    if (extra && (!g.extra_edge || ty == 0 || ty == g.tiles_y - 1)) {
         const T *x = extra + (int64_t)tile * NSLOT;
         for (int s = lane; s < NSLOT; s += 32) ext[s] += x[s];
     }
@@ -1279,7 +1281,7 @@ __global__ void __launch_bounds__(GTH) k_generalC(const int8_t *__restrict__ dir
         if (!(kk[idx] & 16)) continue;
         bool un = false;
         T v = wq ? (T)pull_slot(g, tg, wq, ty, tx, th, tw, s, un, [&](int64_t node) { return par[node] != PAR_NONE; }) : (T)0;
-        if (extra) v += extra[(int64_t)tile * NSLOT + s];
+        if (extra && (!g.extra_edge || ty == 0 || ty == g.tiles_y - 1)) v += extra[(int64_t)tile * NSLOT + s];
         if (extra_unres && extra_unres[(int64_t)tile * NSLOT + s]) un = true;
         acc[idx] = v;
         if (un) cnt[idx] = cnt[idx] == 0xFF ? 1 : cnt[idx] + 1;   // phantom donor: an unresolved upstream never arrives
@@ -2065,8 +2067,13 @@ template <typename T>
 __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
                                StripePaths sp, const int64_t *__restrict__ ext_inflow, const uint8_t *__restrict__ ext_un,
                                T *__restrict__ extra, uint8_t *__restrict__ extra_unres, uint8_t *__restrict__ tile_class,
-                               uint32_t *__restrict__ flags)
+                               uint32_t *__restrict__ flags, unsigned long long *wq)
 {
+    // 32-bit sums (VIA_WQ): the inflow goes into the forest word of every EXIT on the path -- phase C pulls it from there
+    // like everything else, and only the boundary cell itself (the path's first entry) gets it through `extra`.  64-bit
+    // sums (the whole raster holds 2^32 cells or more: the 32-bit sum field cannot take it): into `extra` of every entry.
+    constexpr bool VIA_WQ = sizeof(T) == 4;
+    auto to_exit = [&](int64_t x, int64_t v) { if (VIA_WQ && x >= 0) atomicAdd(&wq[x], (unsigned long long)(uint32_t)v); };
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n2 = 2 * g.nx;
     if (i >= n2) return;
     const int plen = sp.plen[i];
@@ -2077,25 +2084,28 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
     for (int h = blockIdx.y; h < plen; h += gridDim.y) {
         const int32_t item = sp.path[(int64_t)h * n2 + i];
         int64_t e = item & ~JUMP;
-        inflow_add<T>(&extra[e], (T)v);
+        if (!VIA_WQ || h == 0) inflow_add<T>(&extra[e], (T)v);
         if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
+        int64_t x = (VIA_WQ || (item & JUMP)) ? first_exit(meta, e) : -1;
+        to_exit(x, v);
         if (item & JUMP) {                                   // the entries the jump skipped inside its group of tile rows
             const int mr = macro_of(g, e);
-            int64_t x = first_exit(meta, e);
             for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
                 const int2 r = pe[x];
                 const int32_t en = r.y;
                 if (en < 0 || macro_of(g, en) != mr) break;
-                inflow_add<T>(&extra[en], (T)v);
+                if (!VIA_WQ) inflow_add<T>(&extra[en], (T)v);
                 if (u) { extra_unres[en] = 1; tile_class[en / NSLOT] = 2; flags[F_UNRES] = 1u; }
                 x = r.x;
+                to_exit(x, v);
             }
         }
     }
     if (blockIdx.y == 0 && sp.pce[i] >= 0) {
         int64_t e = sp.pce[i], x = sp.pcx[i];
         for (int64_t hops = 0; hops <= nnodes; hops++) {
-            inflow_add<T>(&extra[e], (T)v);
+            if (!VIA_WQ) inflow_add<T>(&extra[e], (T)v);
+            to_exit(x, v);
             if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
             if (x < 0) break;
             const int2 r = pe[x];
@@ -2167,7 +2177,7 @@ static SweepWs carve_ws(void *ws, size_t ws_bytes, const Geo &g, bool wide, bool
 static Geo make_geo(int64_t ny, int64_t nx, int64_t gy0, int64_t gny)
 {
     Geo g;
-    g.ny = ny; g.nx = nx; g.gy0 = gy0; g.gny = gny;
+    g.ny = ny; g.nx = nx; g.gy0 = gy0; g.gny = gny; g.extra_edge = 0;
     g.tiles_x = (int)((nx + TW - 1) / TW);
     g.tiles_y = (int)((ny + TH - 1) / TH);
     return g;
@@ -2379,7 +2389,8 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny,
                     int64_t ny_total, const int64_t *ext_inflow, const uint8_t *ext_un, void *ws, size_t ws_bytes,
                     cudaStream_t st)
 {
-    const Geo g = make_geo(ny, nx, row0, ny_total);
+    Geo g = make_geo(ny, nx, row0, ny_total);
+    g.extra_edge = sizeof(T) == 4;                            // (see k_stripe_route)
     const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
     const int ntiles = (int)ntiles64;
     const int64_t nnodes = ntiles64 * NSLOT;
@@ -2390,7 +2401,7 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny,
     // stripes send is routed along the contracted paths into `extra`, and phase C adds it to what it pulls.
     T *extra = (T *)w.extra;                                 // (cleared by the local pass)
     k_stripe_route<T><<<dim3(blocks_for(2 * nx, 128), (unsigned)(w.sp.pcap < 32 ? w.sp.pcap : 32)), 128, 0, st>>>(g, nnodes, w.meta, w.pe, w.sp, ext_inflow, ext_un,
-                                                                                          extra, w.extra_unres, w.tile_class, w.flags);
+                                                                                          extra, w.extra_unres, w.tile_class, w.flags, w.wq);
     WMF_LAUNCH_CHECK();
     return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, w.wq, (const T *)extra, w.extra_unres, al, acc, st);
 }
