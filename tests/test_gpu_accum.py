@@ -105,6 +105,24 @@ def test_wide_arithmetic_path(monkeypatch):
         assert np.array_equal(run(sch, None, _lib.ALGO_SWEEP, _lib.ACC_F64), exp2)
 
 
+def test_tma_bulk_staging(monkeypatch):
+    """WMF_D8_BULK=1 stages the tile rows with TMA bulk copies (cp.async.bulk + mbarrier) instead of cp.async: rasters
+    whose width is a multiple of the tile width, with and without a mask, ragged in height, plus a width that falls back."""
+    rng = np.random.default_rng(5)
+    for ny, nx in ((300, 512), (64, 256), (131, 1024), (200, 520)):
+        sch = ops.synth_scheidegger_host(ny, nx, seed=11)
+        mask = rng.random((ny, nx)) > 0.05
+        exp = oracle.basin_acum(sch, np.ones(sch.shape, bool))
+        expm = oracle.basin_acum(sch, mask)
+        for bulk in ("1", "0"):
+            monkeypatch.setenv("WMF_D8_BULK", bulk)
+            assert np.array_equal(run(sch, None, _lib.ALGO_SWEEP, _lib.ACC_I32), exp.astype(np.int32)), (ny, nx, bulk)
+            assert np.array_equal(run(sch, mask, _lib.ALGO_SWEEP, _lib.ACC_I64), expm.astype(np.int64)), (ny, nx, bulk)
+    fd, m = CASES["random_cycles"]()
+    monkeypatch.setenv("WMF_D8_BULK", "1")
+    assert np.array_equal(run(fd, m, _lib.ALGO_SWEEP, _lib.ACC_I64), oracle.basin_acum(fd, m).astype(np.int64))
+
+
 def test_accumulations_beyond_int32_in_32_bit_arithmetic():
     """A raster of 2^31 + 65536 cells that drains through ONE cell: every row runs east, the last column south.  Its
     64-bit output is computed in 32-bit (unsigned) arithmetic because the raster has fewer than 2^32 cells; the last

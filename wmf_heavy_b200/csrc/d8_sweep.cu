@@ -386,7 +386,30 @@ __device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <bool AL>
+// TM variant (rasters whose width is a multiple of the tile width, 16-byte aligned): the chunk is fetched by the TMA
+// unit instead -- one bulk copy (cp.async.bulk, SASS UBLKCP) of a whole 256-byte tile row per lane 0..CH-1, completion
+// counted in bytes on an mbarrier the warp waits on.  No per-lane address arithmetic, nothing in the L1TEX queue.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWMF_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra WMF_DONE;\n\tbra WMF_WAIT;\n\tWMF_DONE:\n\t}"
+                 ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");      // (the hint lets the warp sleep instead of spinning)
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool AL, bool TM = false>
 struct TileRows {
     uint32_t *wbase, *mbase;    // this lane's NWD words in the two DIR / mask chunk buffers (ROWW per row, CH*ROWW per buffer)
     const int8_t *dir0;         // &dir[gr0][gc0]
@@ -394,19 +417,40 @@ struct TileRows {
     int64_t nx, gc0;
     int th;
 
+    // TM: `bar` = shared address of the warp's two mbarriers (8 bytes each), handed in by the kernel at every call so
+    // that it does not occupy a register of its own; the parity a wait expects follows from the chunk's place `seq` in
+    // the order the chunks are fetched (the buffers alternate, so a buffer's n-th use is chunk 2n or 2n + 1 of that order).
     __device__ __forceinline__ void init(uint32_t *smem_words, int warp, int lane, const int8_t *dir, const uint8_t *mask,
-                                         int64_t nx_, int64_t gr0, int64_t gc0_, int th_)
+                                         int64_t nx_, int64_t gr0, int64_t gc0_, int th_, uint32_t bar = 0u)
     {
         wbase = smem_words + (size_t)warp * 2 * CH * ROWW + lane * NWD;
         mbase = smem_words + (size_t)(WPB + warp) * 2 * CH * ROWW + lane * NWD;
         dir0 = dir + gr0 * nx_ + gc0_;
         mask0 = mask ? mask + gr0 * nx_ + gc0_ : nullptr;
         nx = nx_; gc0 = gc0_; th = th_;
+        if (TM) {
+            if (lane == 0) { mbar_init(bar, 1u); mbar_init(bar + 8u, 1u); mbar_init_fence(); }
+            __syncwarp();
+        }
     }
-    __device__ __forceinline__ void prefetch(int c) const      // chunk c -> buffer c & 1
+    __device__ __forceinline__ void prefetch(int c, uint32_t bar = 0u) const      // chunk c -> buffer c & 1
     {
+        const int lane_ = threadIdx.x & 31;
         uint32_t *dw = wbase + (c & 1) * CH * ROWW, *dm = mbase + (c & 1) * CH * ROWW;
         const int r0 = c * CH;
+        if (TM) {
+            // (the warp has finished reading this buffer: the __syncwarp of arrive(), or nothing has used it yet)
+            const int nrows = th - r0 < CH ? th - r0 : CH;
+            const uint32_t b = bar + 8u * (uint32_t)(c & 1);
+            if (lane_ == 0) mbar_expect_tx(b, (uint32_t)nrows * (uint32_t)TW * (mask0 ? 2u : 1u));
+            __syncwarp();
+            if (lane_ < nrows) {
+                const int64_t off = (int64_t)(r0 + lane_) * nx - NC * lane_;             // row r0 + lane, the tile's first column
+                bulk_g2s((uint32_t)__cvta_generic_to_shared(dw - lane_ * NWD + lane_ * ROWW), dir0 + off, (uint32_t)TW, b);
+                if (mask0) bulk_g2s((uint32_t)__cvta_generic_to_shared(dm - lane_ * NWD + lane_ * ROWW), mask0 + off, (uint32_t)TW, b);
+            }
+            return;
+        }
         if (AL) {
             if (gc0 < nx) {
                 const int8_t *sd = dir0 + (int64_t)r0 * nx;
@@ -449,12 +493,20 @@ struct TileRows {
         }
         cp_async_commit();
     }
-    // chunk c has arrived; start fetching chunk `next` (or nothing when out of range) into the other buffer
-    __device__ __forceinline__ void arrive(int next, int nchunks) const
+    // wait for chunk c; start fetching chunk `next` (or nothing when out of range) into the other buffer
+    __device__ __forceinline__ void arrive(int c, int seq, int next, int nchunks, uint32_t bar = 0u) const
     {
-        cp_async_wait_all();
+        if (TM) mbar_wait(bar + 8u * (uint32_t)(c & 1), (uint32_t)(seq >> 1) & 1u);
+        else cp_async_wait_all();
         __syncwarp();
-        if (next >= 0 && next < nchunks) prefetch(next);
+        if (next >= 0 && next < nchunks) prefetch(next, bar);
+    }
+    // nothing may be in flight into the warp's buffers when it leaves (`pending`: a chunk was prefetched and not waited for)
+    __device__ __forceinline__ void drain(int pending, int seq, uint32_t bar = 0u) const
+    {
+        if (TM) { if (pending >= 0) mbar_wait(bar + 8u * (uint32_t)(pending & 1), (uint32_t)(seq >> 1) & 1u); }
+        else cp_async_wait_all();
+        __syncwarp();
     }
     // this lane's words of chunk c: word q of row r of the chunk at [r * ROWW + q]
     __device__ __forceinline__ const uint32_t *chunk(int c) const { return wbase + (c & 1) * CH * ROWW; }
@@ -721,7 +773,7 @@ __device__ __forceinline__ bool flag_of(const uint32_t (&f)[NWD], int j) { retur
 // ---------------------------------------------------------------------------------------------
 // phase A, fast solver
 // ---------------------------------------------------------------------------------------------
-template <int ENC, bool AL, bool MK>
+template <int ENC, bool AL, bool MK, bool TM>
 __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
                                                      Geo g, int ntiles, uint32_t *__restrict__ meta,
                                                      int32_t *__restrict__ exit_acc, uint8_t *__restrict__ tile_class,
@@ -748,8 +800,6 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     // such an exit no entry.  Only the raster's last row (S / SE / SW leave the raster) stays generic.
     const bool plain_tile = full;                            // (MK: the raster has a mask)
     const int last_generic = (g.gy0 + gr0 + th == g.gny) ? th - 1 : -1;
-    TileRows<AL> rows;
-    rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
     const int nch = (th + CH - 1) / CH;
 
     // boundary-row stores: NC consecutive slots per lane
@@ -766,7 +816,13 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
     for (int q = 0; q < HBINS / 128; q++) *reinterpret_cast<int4 *>(hist + 128 * q + 4 * lane) = make_int4(0, 0, 0, 0);
     __syncwarp();
+    // (TM: the warp's two mbarriers live in bins no label uses -- labels are slots < NSLOT, or LNONE)
+    constexpr int BAR_BIN = 1000;
+    static_assert(BAR_BIN >= NSLOT && BAR_BIN + 4 <= (int)LNONE && (BAR_BIN * 4) % 8 == 0, "the mbarriers sit in unused histogram bins");
     const uint32_t hist_sa = (uint32_t)__cvta_generic_to_shared(hist);
+#define WMF_BAR_A (hist_sa + 4u * BAR_BIN)
+    TileRows<AL, TM> rows;
+    rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th, WMF_BAR_A);
     auto count_labels = [&](const uint32_t (&lab)[NC]) {      // (a label is a bin index as it is: slot or LNONE)
 #pragma unroll
         for (int j = 0; j < NC; j++) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_sa + 4u * lab[j]) : "memory");
@@ -780,9 +836,11 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     uint32_t lb[NC];
 #pragma unroll
     for (int j = 0; j < NC; j++) lb[j] = LNONE;      // labels of the row below
-    rows.prefetch(nch - 1);
+    rows.prefetch(nch - 1, WMF_BAR_A);
+    int c_left = nch - 1;                            // the chunk that is in flight when the loop ends early (-1: none)
     for (int c = nch - 1; c >= 0 && !complex_tile; c--) {
-        rows.arrive(c - 1, nch);
+        rows.arrive(c, nch - 1 - c, c - 1, nch, WMF_BAR_A);
+        c_left = c - 1;
         const int cbeg = c * CH;
         const uint32_t *wc = rows.chunk(c);
         for (int lr = (th < (c + 1) * CH ? th : (c + 1) * CH) - 1; lr >= cbeg; lr--) {
@@ -894,8 +952,8 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             count_labels(lab);
         }
     }
-    cp_async_wait_all();
-    __syncwarp();
+    rows.drain(c_left, nch - 1 - c_left, WMF_BAR_A);
+#undef WMF_BAR_A
     if (complex_tile) {                              // the general solver redoes this tile
         if (lane == 0) { tile_class[tile] = 1; tile_top[tile] = 1; flags[has_multi ? F_COMPLEX : F_CHAIN] = 1u; }
         return;
@@ -998,7 +1056,7 @@ __device__ __forceinline__ void tile_inflow(const Geo &g, const unsigned long lo
     __syncwarp();
 }
 
-template <int ENC, bool AL, bool MK, typename T, typename TO>
+template <int ENC, bool AL, bool MK, bool TM, typename T, typename TO>
 __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask,
                                                      Geo g, int ntiles, const unsigned long long *__restrict__ wq,
                                                      const uint8_t *__restrict__ tile_top, const T *__restrict__ extra,
@@ -1015,10 +1073,12 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
     const int64_t gr0 = (int64_t)ty * TH, gc0 = (int64_t)tx * TW + NC * lane;
     const int rlane = (tw - 1) / NC, rj = (tw - 1) % NC;
     const bool border = ty == 0 || tx == 0 || ty == g.tiles_y - 1 || tx == g.tiles_x - 1;
-    TileRows<AL> rows;
-    rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th);
+    // (TM: the warp's two mbarriers sit behind the per-chunk lean-row masks, at the end of the block's shared memory)
+#define WMF_BAR_C ((uint32_t)__cvta_generic_to_shared(s_dyn + (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW) + (uint32_t)(WPB * NSLOT * sizeof(T) + WPB * 8) + 16u * (threadIdx.x >> 5))
+    TileRows<AL, TM> rows;
+    rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th, WMF_BAR_C);
     const int nch = (th + CH - 1) / CH;
-    rows.prefetch(0);
+    rows.prefetch(0, WMF_BAR_C);
     // external inflow of the boundary cells: first row, last row, first column, last column
     T *ext = reinterpret_cast<T *>(s_dyn + (mask ? 2 : 1) * WPB * 2 * CH * ROWW) + NSLOT * warp;
     const T *extL = ext + 2 * TW, *extR = ext + 2 * TW + TH;
@@ -1034,7 +1094,7 @@ __global__ void __launch_bounds__(WPB * 32, sizeof(T) == 8 ? 4 : 6) k_sweepC(con
     if (lane == 0) *reinterpret_cast<unsigned long long *>(pchunk) = row_plain[tile];
     const bool is_l = lane == 0, is_r = lane == 31;
     for (int c = 0; c < nch; c++) {
-        rows.arrive(c + 1, nch);
+        rows.arrive(c, c, c + 1, nch, WMF_BAR_C);
         const int cend = th < (c + 1) * CH ? th : (c + 1) * CH;
         int lr = c * CH;
         const uint32_t *wp = rows.chunk(c);              // row lr of this chunk at wp
@@ -2197,8 +2257,8 @@ static int sm_count()
 }
 
 template <int ENC>
-int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs &w, bool al, cudaStream_t st)
-{
+int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs &w, int al, cudaStream_t st)
+{   // al: 0 byte-wise staging (any width / alignment), 1 cp.async staging, 2 TMA bulk copies (see stage_mode)
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
     const unsigned gen_blocks = (unsigned)(ntiles < sm_count() * 4 ? ntiles : sm_count() * 4);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
@@ -2213,18 +2273,18 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
     }
     const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * HBINS * sizeof(int);
     static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
-#define WMF_LAUNCH_A(AL_, MK_)                                                                                                   \
-    k_sweepA<ENC, AL_, MK_><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, \
-                                                                  w.wq, w.tile_top, w.flags, w.codes4 != nullptr)
-    if (mask) { if (al) WMF_LAUNCH_A(true, true); else WMF_LAUNCH_A(false, true); }
-    else { if (al) WMF_LAUNCH_A(true, false); else WMF_LAUNCH_A(false, false); }
+#define WMF_LAUNCH_A(AL_, MK_, TM_)                                                                                              \
+    k_sweepA<ENC, AL_, MK_, TM_><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, \
+                                                                       w.wq, w.tile_top, w.flags, w.codes4 != nullptr)
+    if (mask) { if (al == 2) WMF_LAUNCH_A(true, true, true); else if (al) WMF_LAUNCH_A(true, true, false); else WMF_LAUNCH_A(false, true, false); }
+    else { if (al == 2) WMF_LAUNCH_A(true, false, true); else if (al) WMF_LAUNCH_A(true, false, false); else WMF_LAUNCH_A(false, false, false); }
 #undef WMF_LAUNCH_A
     if (w.codes4) {                                          // tiles with upward flow: pointer jumping, one block per tile
         const size_t smemJ = sizeof(uint32_t) * (TCELLS / 2 + TH * 32 + HBINS + 4);
         static_assert(sizeof(uint32_t) * (TCELLS / 2 + TH * 32 + HBINS + 4) <= 48 * 1024, "k_jumpA fits the default dynamic shared memory");
         const int cap = sm_count() * 4;
         k_jumpA<ENC><<<ntiles < cap ? ntiles : cap, JTA, smemJ, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.wq,
-                                                                       w.tile_top, w.codes4, w.row_plain, w.flags, al);
+                                                                       w.tile_top, w.codes4, w.row_plain, w.flags, al != 0);
     }
     k_generalA<ENC><<<gen_blocks, GTH, smemA, st>>>(dir, mask, g, ntiles, w.tile_class, w.meta, w.exit_acc, w.wq, w.flags);
     WMF_LAUNCH_CHECK();
@@ -2234,12 +2294,12 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
 // wq: the packed forest words phase C pulls from (nullptr: everything comes from `extra`)
 template <int ENC, typename T, typename TO>
 int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs &w, const unsigned long long *wq,
-                 const T *extra, const uint8_t *extra_unres, bool al, TO *acc, cudaStream_t st)
+                 const T *extra, const uint8_t *extra_unres, int al, TO *acc, cudaStream_t st)
 {
     const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
     const unsigned gen_blocks = (unsigned)(ntiles < sm_count() * 4 ? ntiles : sm_count() * 4);
     const size_t smemC = sizeof(T) * TCELLS + 2 * TCELLS;
-    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * NSLOT * sizeof(T) + WPB * 8;
+    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * NSLOT * sizeof(T) + WPB * 8 + 16 * WPB;
     const size_t smemJ = sizeof(T) * TCELLS * (sizeof(T) == 4 ? 2 : 1) + sizeof(uint32_t) * (TCELLS + TH * 32) + sizeof(T) * NSLOT + 16;   // k_jumpC
     {   // once per device and instantiation
         static bool done[64];
@@ -2248,22 +2308,24 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
         if (dev < 0 || dev >= 64 || !done[dev]) {
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_generalC<ENC, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
             WMF_CUDA_CHECK(cudaFuncSetAttribute(k_jumpC<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemJ));
-            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, true, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, true, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, false, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, false, false, false, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, true, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            WMF_CUDA_CHECK(cudaFuncSetAttribute(k_sweepC<ENC, true, false, true, T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
-#define WMF_LAUNCH_C(AL_, MK_) \
-    k_sweepC<ENC, AL_, MK_, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, wq, w.tile_top, extra, w.tile_class, w.row_plain, acc)
-    if (mask) { if (al) WMF_LAUNCH_C(true, true); else WMF_LAUNCH_C(false, true); }
-    else { if (al) WMF_LAUNCH_C(true, false); else WMF_LAUNCH_C(false, false); }
+#define WMF_LAUNCH_C(AL_, MK_, TM_) \
+    k_sweepC<ENC, AL_, MK_, TM_, T, TO><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, wq, w.tile_top, extra, w.tile_class, w.row_plain, acc)
+    if (mask) { if (al == 2) WMF_LAUNCH_C(true, true, true); else if (al) WMF_LAUNCH_C(true, true, false); else WMF_LAUNCH_C(false, true, false); }
+    else { if (al == 2) WMF_LAUNCH_C(true, false, true); else if (al) WMF_LAUNCH_C(true, false, false); else WMF_LAUNCH_C(false, false, false); }
 #undef WMF_LAUNCH_C
     if (w.codes4 && wq) {
         const int cap = sm_count();                          // one block per SM fits (shared memory)
         k_jumpC<T, TO><<<ntiles < cap ? ntiles : cap, JTC, smemJ, st>>>(g, ntiles, w.codes4, wq, w.tile_top, extra, w.tile_class, acc,
-                                                                         w.row_plain, w.flags, al);
+                                                                         w.row_plain, w.flags, al != 0);
     }
     k_generalC<ENC, T, TO><<<gen_blocks, GTH, smemC, st>>>(dir, mask, g, ntiles, w.tile_class, wq, w.par, extra, extra_unres, acc, w.flags);
     WMF_LAUNCH_CHECK();
@@ -2284,6 +2346,18 @@ static bool aligned4(const void *dir, const void *mask, const void *acc, int64_t
 {
     return (nx % NC == 0) && (((uintptr_t)dir & (NC - 1)) == 0) && (mask == nullptr || ((uintptr_t)mask & (NC - 1)) == 0) &&
            (((uintptr_t)acc & 31) == 0);
+}
+// How the fast kernels stage the DIR (and mask) rows of a tile: 0 byte by byte (any width, any alignment), 1 cp.async
+// (rows of whole 8-byte pieces), 2 TMA bulk copies of whole 256-byte tile rows -- every tile is full width and every row
+// piece 16-byte aligned.  Mode 2 is opt-in (WMF_D8_BULK=1 in the environment): measured on the 16384^2 raster it is 1 %
+// SLOWER than cp.async (0.706 vs 0.698 ms; phase A 266 vs 257 us, 214 M vs 204 M warp instructions) -- these kernels are
+// bound by instruction issue, and polling an mbarrier costs issue slots where cp.async.wait_group stalls for free.
+static int stage_mode(const void *dir, const void *mask, const void *acc, int64_t nx)
+{
+    if (!aligned4(dir, mask, acc, nx)) return 0;
+    const char *e = getenv("WMF_D8_BULK");
+    if (!(e && e[0] == '1')) return 1;
+    return (nx % TW == 0 && ((uintptr_t)dir & 15) == 0 && (mask == nullptr || ((uintptr_t)mask & 15) == 0)) ? 2 : 1;
 }
 
 // The only state the library keeps between calls: one helper stream and two events per device, created on first use;
@@ -2321,7 +2395,7 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int
     const bool wide = sizeof(T) == 8;
     const SweepWs w = carve_ws(ws, ws_bytes, g, wide, false);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
-    const bool al = aligned4(dir, mask, acc, nx);
+    const int al = stage_mode(dir, mask, acc, nx);
     if (!wide) {
         WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, (size_t)((char *)(w.flags + NFLAGS) - (char *)w.gcnt), st));
         int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
@@ -2357,7 +2431,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     const int64_t nnodes = ntiles64 * NSLOT;
     const SweepWs w = carve_ws(ws, ws_bytes, g, false, true);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
-    const bool al = aligned4(dir, mask, nullptr, nx);
+    const int al = stage_mode(dir, mask, nullptr, nx);
     WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, (size_t)((char *)(w.flags + NFLAGS) - (char *)w.gcnt), st));
     int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
     if (rc) return rc;
@@ -2396,7 +2470,7 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny,
     const int64_t nnodes = ntiles64 * NSLOT;
     const SweepWs w = carve_ws(ws, ws_bytes, g, false, true);
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
-    const bool al = aligned4(dir, mask, acc, nx);
+    const int al = stage_mode(dir, mask, acc, nx);
     // phase-A state and the finalised forest words of the stripe-local pass are still in the workspace: what the other
     // stripes send is routed along the contracted paths into `extra`, and phase C adds it to what it pulls.
     T *extra = (T *)w.extra;                                 // (cleared by the local pass)
