@@ -354,8 +354,9 @@ def bench_basin(torch, ops, dev, peak: float, n: int = 2048):
             "structure_basin_cells_per_s": nb / (t_st * 1e-3),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic_bytes": by,
-                         "note": "basin_find + basin_cut (BFS-ordered structure): membership by pointer jumping, order by one "
-                                 "radix sort; includes the host round trips of the call (cell count, convergence tests)"}}
+                         "note": "basin_find + basin_cut (BFS-ordered structure): membership by the tile contraction (labels per tile "
+                                 "in shared memory, pointer jumping over the tiles' exit cells), order by one radix sort; "
+                                 "includes the host round trips of the call (outlet code, cell count)"}}
 
 
 # ------------------------------------------------------------------------------------------ the GPU arm

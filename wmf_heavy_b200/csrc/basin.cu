@@ -18,71 +18,15 @@
 
 #include "common.cuh"
 
+size_t d8_basin_membership_workspace(int64_t ny, int64_t nx);
+int d8_basin_membership(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int encoding, int64_t outlet, uint8_t *bm,
+                        int32_t *flag32, unsigned long long *count, void *ws, size_t ws_bytes, cudaStream_t st);
+
 namespace {
 
-// ------------------------------------------------------------------ pointer jumping on the raster
-template <int ENC>
-__global__ void k_ptr_init(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, int32_t *__restrict__ ptr,
-                           int64_t ny, int64_t nx, int64_t outlet)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ny * nx) return;
-    int64_t p = i;
-    if (i != outlet && cell_active(mask, i)) {
-        int64_t r = i / nx, c = i - r * nx;
-        int64_t j = raster_recv<ENC>(dir, mask, ny, nx, r, c);
-        if (j >= 0) p = j;
-    }
-    ptr[i] = (int32_t)p;
-}
-
-__global__ void k_ptr_jump(int32_t *ptr, int64_t n, int *changed)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int32_t p = ptr[i];
-    int32_t pp = ptr[p];
-    if (pp != p) {
-        ptr[i] = pp;
-        *changed = 1;
-    }
-}
-
-// flags (int32) + count
-__global__ void k_mask_from_ptr(const int32_t *__restrict__ ptr, int64_t n, int32_t outlet, uint8_t *__restrict__ bm,
-                                int32_t *__restrict__ flag32, unsigned long long *count)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool in = i < n && ptr[i] == outlet;
-    if (i < n) {
-        if (bm) bm[i] = in ? 1 : 0;
-        if (flag32) flag32[i] = in ? 1 : 0;
-    }
-    unsigned b = __ballot_sync(0xffffffffu, in);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
-}
-
-template <int ENC>
-int resolve_membership(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int64_t outlet, int32_t *ptr,
-                       int *d_changed, cudaStream_t st)
-{
-    int64_t n = ny * nx;
-    const int th = 256;
-    k_ptr_init<ENC><<<blocks_for(n, th), th, 0, st>>>(dir, mask, ptr, ny, nx, outlet);
-    int max_rounds = 2;
-    while (((int64_t)1 << max_rounds) < n) max_rounds++;
-    max_rounds += 2;                      // cycles never converge: cap at ~log2(n) rounds
-    for (int r = 0; r < max_rounds;) {
-        WMF_CUDA_CHECK(cudaMemsetAsync(d_changed, 0, sizeof(int), st));
-        for (int k = 0; k < 4 && r < max_rounds; k++, r++) k_ptr_jump<<<blocks_for(n, th), th, 0, st>>>(ptr, n, d_changed);
-        int h = 0;
-        WMF_CUDA_CHECK(cudaMemcpyAsync(&h, d_changed, sizeof(int), cudaMemcpyDeviceToHost, st));
-        WMF_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (!h) break;
-    }
-    WMF_LAUNCH_CHECK();
-    return 0;
-}
+// ------------------------------------------------------------------ membership
+// "My D8 path reaches the outlet": the tile contraction of d8_sweep.cu (labels per tile in shared memory, pointer
+// jumping over the tiles' exit cells only) -- see d8_basin_membership there.
 
 // ------------------------------------------------------------------ structure building (keypad)
 __global__ void k_scatter_cells(const int32_t *__restrict__ flag32, const int32_t *__restrict__ cidx, int64_t n,
@@ -341,7 +285,7 @@ __global__ void k_nod_trazado(const int32_t *__restrict__ st, const int32_t *__r
 // =================================================================== C ABI
 extern "C" {
 
-size_t wmf_basin_mask_workspace(int64_t ny, int64_t nx) { return wmf_align((size_t)(ny * nx) * 4) + 1024; }
+size_t wmf_basin_mask_workspace(int64_t ny, int64_t nx) { return d8_basin_membership_workspace(ny, nx) + 1024; }
 
 int wmf_basin_mask(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int encoding, int64_t outlet_r,
                    int64_t outlet_c, uint8_t *basin_mask, int64_t *ncells_host, void *workspace, size_t ws_bytes,
@@ -360,17 +304,14 @@ int wmf_basin_mask(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
         WMF_REQUIRE(m != 0, WMF_E_OUTLET_MASK, "outlet not in mask");
     }
     WsCursor cur(workspace, ws_bytes);
-    int32_t *ptr = cur.take<int32_t>((size_t)n);
     unsigned long long *d_count = cur.take<unsigned long long>(1);
-    int *d_changed = cur.take<int>(1);
+    const size_t mws = d8_basin_membership_workspace(ny, nx);
+    void *mw = cur.take<char>(mws);
     WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
-    int rc = encoding == WMF_ENC_INTERNAL
-                 ? resolve_membership<WMF_ENC_INTERNAL>(dir, mask, ny, nx, outlet, ptr, d_changed, st)
-                 : resolve_membership<WMF_ENC_KEYPAD>(dir, mask, ny, nx, outlet, ptr, d_changed, st);
-    if (rc) return rc;
+    (void)n;
     WMF_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
-    k_mask_from_ptr<<<blocks_for(n, 256), 256, 0, st>>>(ptr, n, (int32_t)outlet, basin_mask, nullptr, d_count);
-    WMF_LAUNCH_CHECK();
+    int rc = d8_basin_membership(dir, mask, ny, nx, encoding, outlet, basin_mask, nullptr, d_count, mw, mws, st);
+    if (rc) return rc;
     unsigned long long h = 0;
     WMF_CUDA_CHECK(cudaMemcpyAsync(&h, d_count, sizeof(h), cudaMemcpyDeviceToHost, st));
     WMF_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -392,14 +333,15 @@ void wmf_coord2fil_col_host(float x, float y, float xll, float yll, float dx, in
     *fil = f;
 }
 
-static size_t structure_ws(int64_t n, int64_t nb)
+static size_t structure_ws(int64_t n, int64_t nb, int64_t nrows, int64_t ncols)
 {
     size_t scan_tmp = 0, sort_tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (int32_t *)nullptr, (int32_t *)nullptr, (int)n);
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (int32_t *)nullptr, (int32_t *)nullptr, (int)nb);
     size_t s = 0;
-    s += 3 * wmf_align((size_t)n * 4);                   // ptr, flag32, cidx
+    s += 2 * wmf_align((size_t)n * 4);                   // flag32, cidx
+    s += wmf_align(d8_basin_membership_workspace(nrows, ncols));
     s += wmf_align(scan_tmp) + wmf_align(sort_tmp);
     s += 13 * wmf_align((size_t)nb * 4);                 // cell,parentC,size,cnt,off, 2x(ptr,pre,dep), vals x2
     s += 2 * wmf_align((size_t)nb * 8);                  // keys x2
@@ -408,7 +350,7 @@ static size_t structure_ws(int64_t n, int64_t nb)
 
 size_t wmf_basin_structure_workspace(int64_t nrows, int64_t ncols)
 {
-    return structure_ws(nrows * ncols, nrows * ncols);
+    return structure_ws(nrows * ncols, nrows * ncols, nrows, ncols);
 }
 
 int wmf_basin_structure(const int8_t *dir, int64_t nrows, int64_t ncols, int32_t col, int32_t fil, int32_t *structure,
@@ -428,21 +370,19 @@ int wmf_basin_structure(const int8_t *dir, int64_t nrows, int64_t ncols, int32_t
         WMF_REQUIRE(code != 5, WMF_E_CODE5, "outlet cell has keypad code 5 (drains to itself)");
     }
     WsCursor cur(workspace, ws_bytes);
-    int32_t *ptr = cur.take<int32_t>((size_t)n);
+    const size_t mws = d8_basin_membership_workspace(ny, nx);
+    void *mw = cur.take<char>(mws);
     int32_t *flag32 = cur.take<int32_t>((size_t)n);
     int32_t *cidx = cur.take<int32_t>((size_t)n);
     unsigned long long *d_count = cur.take<unsigned long long>(1);
-    int *d_changed = cur.take<int>(1);
     size_t scan_tmp_b = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_b, flag32, cidx, (int)n);
     void *scan_tmp = cur.take<char>(scan_tmp_b);
     WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
 
-    int rc = resolve_membership<WMF_ENC_KEYPAD>(dir, nullptr, ny, nx, outlet, ptr, d_changed, st);
-    if (rc) return rc;
     WMF_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
-    k_mask_from_ptr<<<blocks_for(n, th), th, 0, st>>>(ptr, n, (int32_t)outlet, nullptr, flag32, d_count);
-    WMF_LAUNCH_CHECK();
+    int rc = d8_basin_membership(dir, nullptr, ny, nx, WMF_ENC_KEYPAD, outlet, nullptr, flag32, d_count, mw, mws, st);
+    if (rc) return rc;
     unsigned long long h_count = 0;
     WMF_CUDA_CHECK(cudaMemcpyAsync(&h_count, d_count, sizeof(h_count), cudaMemcpyDeviceToHost, st));
     // cycle through the outlet: the outlet's own downstream path comes back to it
@@ -459,10 +399,10 @@ int wmf_basin_structure(const int8_t *dir, int64_t nrows, int64_t ncols, int32_t
         }
     }
     if (recv_outlet >= 0) {
-        WMF_CUDA_CHECK(cudaMemcpyAsync(&h_ptr_recv, ptr + recv_outlet, 4, cudaMemcpyDeviceToHost, st));
+        WMF_CUDA_CHECK(cudaMemcpyAsync(&h_ptr_recv, flag32 + recv_outlet, 4, cudaMemcpyDeviceToHost, st));   // is the receiver in the basin?
     }
     WMF_CUDA_CHECK(cudaStreamSynchronize(st));
-    WMF_REQUIRE(!(recv_outlet >= 0 && h_ptr_recv == (int32_t)outlet), WMF_E_CYCLE, "drainage cycle through the outlet");
+    WMF_REQUIRE(!(recv_outlet >= 0 && h_ptr_recv == 1), WMF_E_CYCLE, "drainage cycle through the outlet");
     const int64_t nb = (int64_t)h_count;
     *ncells_host = nb;
     WMF_REQUIRE(nb <= capacity, WMF_E_CAPACITY, "structure capacity too small");

@@ -1774,6 +1774,160 @@ __global__ void __launch_bounds__(JTC, 1) k_jumpC(Geo g, int ntiles, const uint3
 }
 
 // ---------------------------------------------------------------------------------------------
+// basin membership (wmf_py/cu_py/basics.py:206-248, cuencas_heavy.f90:507-576): which cells drain to the outlet?
+// ---------------------------------------------------------------------------------------------
+// The same contraction as the accumulation, with a boolean instead of a sum.  (Pointer jumping over the WHOLE raster,
+// which this replaces, costs log2(cells) rounds of random 4-byte gathers over every cell: 16.8 ms for a 8192^2 raster.)
+//   k_membA   per tile, pointer jumping in shared memory exactly like k_jumpA: every cell gets the label of the exit its
+//             path leaves the tile through -- or LOUT when the path reaches the outlet inside the tile (the outlet is a
+//             sink: it keeps no receiver), or LNONE.  Labels go to global memory (2 bytes per cell), the boundary cells'
+//             labels and codes into the meta words.  Cycles never resolve and end as LNONE: not in the basin.
+//   k_memb_build  per boundary slot: the exit the flow leaving here leaves the NEXT tile through (state >= 0), or the
+//             verdict when the path ends in that tile: MEMB_YES at the outlet, MEMB_NO anywhere else.
+//   k_memb_jump   state[x] = state[state[x]] over the exits (3.9 % of the cells) until every state is a verdict;
+//             a round that changes nothing switches the remaining launches off (no host round trip).
+//   k_membC   per cell: label -> LOUT, or the verdict of that exit.  Writes the mask, counts the cells.
+constexpr uint32_t LOUT = 1022u;
+constexpr int32_t MEMB_NO = -1, MEMB_YES = -2;
+constexpr int MEMB_ROUNDS = 26;
+static_assert(LOUT >= (uint32_t)NSLOT && LOUT != LNONE, "the outlet label is no slot");
+
+template <int ENC>
+__global__ void __launch_bounds__(JTA, 4) k_membA(const int8_t *__restrict__ dir, const uint8_t *__restrict__ mask, Geo g, int ntiles,
+                                               int64_t outlet, uint32_t *__restrict__ meta, uint16_t *__restrict__ labels, bool vec)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];   // [TCELLS / 2] pointers (16 bit) + [TH * 32] codes
+    uint32_t *ptr32 = s_dyn;
+    uint16_t *ptr16 = reinterpret_cast<uint16_t *>(s_dyn);
+    uint32_t *codes = s_dyn + TCELLS / 2;
+    const int64_t orow = outlet / g.nx, ocol = outlet - orow * g.nx;
+    const int otile = (int)(orow / TH) * g.tiles_x + (int)(ocol / TW);
+    const int ol = (int)(orow % TH) * TW + (int)(ocol % TW);             // the outlet's cell index inside its tile
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();                               // (the previous tile is done with shared memory)
+        int ty, tx, th, tw;
+        tile_dims(g, tile, ty, tx, th, tw);
+        jump_decode<ENC>(dir, mask, g, ty, tx, th, vec, codes, nullptr);
+        __syncthreads();
+        if (tile == otile && threadIdx.x == 0) {       // the outlet keeps no receiver
+            const int q = (ol / TW) * 32 + (ol % TW) / NC, sh = 4 * ((ol % TW) % NC);
+            if (((codes[q] >> sh) & 15u) != 9u) codes[q] = (codes[q] & ~(15u << sh)) | (8u << sh);
+        }
+        __syncthreads();
+        auto exit_label = [&](int lr, int lc) { return JRES | (uint32_t)slot_of(lr, lc, th, tw); };
+        jump_pointers(codes, th, tw, JRES | LNONE, ptr32, exit_label);
+        const bool full = th == TH && tw == TW;
+        if (full) {
+            __syncthreads();
+            for (int s = threadIdx.x; s < NSLOT; s += JTA) {
+                int lr, lc;
+                cell_of(s, TH, TW, lr, lc);
+                ptr16[lr * TW + lc] = (uint16_t)jump_pointer_boundary(jump_code(codes, lr, lc), lr, lc, JRES | LNONE, exit_label);
+            }
+        }
+        __syncthreads();
+        if (tile == otile && threadIdx.x == 0 && jump_code(codes, ol / TW, ol % TW) != 9u) ptr16[ol] = (uint16_t)(JRES | LOUT);
+        __syncthreads();
+        bool open = true;
+        for (int rounds = 0; open && rounds < JROUNDS; rounds++) {
+            uint32_t all = 0x80008000u;
+            uint2 *ptr64 = reinterpret_cast<uint2 *>(ptr32);
+            for (int i = threadIdx.x; i < TCELLS / 4; i += JTA) {
+                uint2 w = ptr64[i];
+                if ((w.x & w.y & 0x80008000u) == 0x80008000u) continue;
+                const uint32_t a0 = w.x & 0xFFFFu, a1 = w.x >> 16, a2 = w.y & 0xFFFFu, a3 = w.y >> 16;
+                const uint32_t b0 = ptr16[a0 & 0x3FFFu], b1 = ptr16[a1 & 0x3FFFu], b2 = ptr16[a2 & 0x3FFFu], b3 = ptr16[a3 & 0x3FFFu];
+                w.x = ((a0 & JRES) ? a0 : b0) | (((a1 & JRES) ? a1 : b1) << 16);
+                w.y = ((a2 & JRES) ? a2 : b2) | (((a3 & JRES) ? a3 : b3) << 16);
+                ptr64[i] = w;
+                all &= w.x & w.y;
+            }
+            open = __syncthreads_or(all != 0x80008000u) != 0;
+        }
+        // labels of all cells (an unresolved pointer sits on a cycle: no exit), eight cells per store
+        uint16_t *l_t = labels + (int64_t)tile * TCELLS;
+        for (int q = threadIdx.x; q < TCELLS / 8; q += JTA) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(ptr32 + 4 * q);
+            auto fix = [](uint32_t w) {
+                const uint32_t lo = (w & JRES) ? (w & 0x3FFu) : LNONE, hi = (w & (JRES << 16)) ? ((w >> 16) & 0x3FFu) : LNONE;
+                return lo | (hi << 16);
+            };
+            *reinterpret_cast<uint4 *>(l_t + 8 * q) = make_uint4(fix(x.x), fix(x.y), fix(x.z), fix(x.w));
+        }
+        uint32_t *m_t = meta + (int64_t)tile * NSLOT;
+        for (int s = threadIdx.x; s < NSLOT; s += JTA) {
+            int lr, lc;
+            uint32_t m = 0u;
+            if (cell_of(s, th, tw, lr, lc)) {
+                const int kr = (int)jump_code(codes, lr, lc);
+                const uint32_t pw = ptr16[lr * TW + lc];
+                m = meta_pack((pw & JRES) ? (pw & 0x3FFu) : LNONE, kr < 8 ? kr : 8, false, kr != 9);
+            }
+            m_t[s] = m;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_memb_build(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, int32_t *__restrict__ state)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    const int tile = (int)(i / NSLOT), s = (int)(i - (int64_t)tile * NSLOT);
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
+    int s2 = 0;
+    const int t2 = build_target(g, ty, tx, last_th, last_tw, s, meta[i], s2);
+    int32_t st = MEMB_NO;
+    if (t2 >= 0) {
+        const uint32_t me = meta[(int64_t)t2 * NSLOT + s2];
+        const uint32_t link = me & 0xFFFFu;
+        if ((me >> 21) & 1) st = link == LOUT ? MEMB_YES : (link == LNONE ? MEMB_NO : t2 * NSLOT + (int32_t)link);
+    }
+    state[i] = st;
+}
+
+// flags[r] != 0: round r moved something (round 0 always runs)
+__global__ void __launch_bounds__(256) k_memb_jump(int64_t nnodes, int32_t *state, int *flags, int round)
+{
+    if (round > 0 && flags[round - 1] == 0) return;                      // (persistent grid: a switched-off round costs a launch)
+    bool moved = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnodes; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t p = state[i];
+        if (p < 0) continue;
+        state[i] = __ldcg(&state[p]);                                    // a farther exit, or its verdict
+        moved = true;
+    }
+    if (moved) flags[round] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_membC(Geo g, int ntiles, const uint16_t *__restrict__ labels, const int32_t *__restrict__ state,
+                                               uint8_t *__restrict__ bm, int32_t *__restrict__ flag32, unsigned long long *count)
+{
+    __shared__ uint8_t yes[NSLOT];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        for (int s = threadIdx.x; s < NSLOT; s += blockDim.x) yes[s] = state[(int64_t)tile * NSLOT + s] == MEMB_YES;
+        __syncthreads();
+        int ty, tx, th, tw;
+        tile_dims(g, tile, ty, tx, th, tw);
+        const uint16_t *l_t = labels + (int64_t)tile * TCELLS;
+        unsigned int n = 0;
+        for (int idx = threadIdx.x; idx < TCELLS; idx += blockDim.x) {
+            const int lr = idx / TW, lc = idx - lr * TW;
+            if (lr >= th || lc >= tw) continue;
+            const uint32_t lab = l_t[idx];
+            const bool in = lab == LOUT || (lab < (uint32_t)NSLOT && yes[lab]);
+            const int64_t gi = ((int64_t)ty * TH + lr) * g.nx + (int64_t)tx * TW + lc;
+            if (bm) bm[gi] = in ? 1 : 0;
+            if (flag32) flag32[gi] = in ? 1 : 0;
+            n += in;
+        }
+        n = __reduce_add_sync(FULL, n);
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, (unsigned long long)n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // phase G: contracted forest over boundary slots
 // ---------------------------------------------------------------------------------------------
 // entry slot (node id) that exit slot (tile, s) drains to; -1 when s is not an exit; -2 when the
@@ -2481,6 +2635,44 @@ int stripe_finish_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny,
 }
 
 }  // namespace
+
+// ---- basin membership: entry points for basin.cu ------------------------------------------------------
+size_t d8_basin_membership_workspace(int64_t ny, int64_t nx)
+{
+    const Geo g = make_geo(ny, nx, 0, ny);
+    const size_t nt = (size_t)g.tiles_x * (size_t)g.tiles_y, nn = nt * NSLOT;
+    return 2 * wmf_align(nn * 4) + wmf_align(nt * TCELLS * 2) + wmf_align(MEMB_ROUNDS * sizeof(int)) + 1024;
+}
+
+// bm (nullable): 1 byte per cell; flag32 (nullable): the same as int32 (for a prefix sum); *count (device) += basin cells
+int d8_basin_membership(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t nx, int encoding, int64_t outlet, uint8_t *bm,
+                        int32_t *flag32, unsigned long long *count, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const Geo g = make_geo(ny, nx, 0, ny);
+    const int64_t ntiles64 = (int64_t)g.tiles_x * g.tiles_y;
+    WMF_REQUIRE(ntiles64 * NSLOT < ((int64_t)1 << 31), WMF_E_TOO_LARGE, "raster too large for the tiled basin delineation");
+    const int ntiles = (int)ntiles64;
+    const int64_t nnodes = ntiles64 * NSLOT;
+    WsCursor cur(ws, ws_bytes);
+    uint32_t *meta = cur.take<uint32_t>((size_t)nnodes);
+    int32_t *state = cur.take<int32_t>((size_t)nnodes);
+    uint16_t *labels = cur.take<uint16_t>((size_t)ntiles * TCELLS);
+    int *flags = cur.take<int>(MEMB_ROUNDS);
+    WMF_REQUIRE(cur.ok, WMF_E_WORKSPACE, "workspace too small");
+    const bool vec = aligned4(dir, mask, nullptr, nx);
+    const size_t smemA = sizeof(uint32_t) * (TCELLS / 2 + TH * 32);
+    const int cap = sm_count() * 4, blocksA = ntiles < cap ? ntiles : cap;
+    WMF_CUDA_CHECK(cudaMemsetAsync(flags, 0, MEMB_ROUNDS * sizeof(int), st));
+    if (encoding == WMF_ENC_INTERNAL) k_membA<WMF_ENC_INTERNAL><<<blocksA, JTA, smemA, st>>>(dir, mask, g, ntiles, outlet, meta, labels, vec);
+    else k_membA<WMF_ENC_KEYPAD><<<blocksA, JTA, smemA, st>>>(dir, mask, g, ntiles, outlet, meta, labels, vec);
+    k_memb_build<<<blocks_for(nnodes, 256), 256, 0, st>>>(g, nnodes, meta, state);
+    const int64_t jb = blocks_for(nnodes, 256), jcap = (int64_t)sm_count() * 8;
+    for (int r = 0; r < MEMB_ROUNDS; r++) k_memb_jump<<<(unsigned)(jb < jcap ? jb : jcap), 256, 0, st>>>(nnodes, state, flags, r);
+    const int capC = sm_count() * 8;
+    k_membC<<<ntiles < capC ? ntiles : capC, 256, 0, st>>>(g, ntiles, labels, state, bm, flag32, count);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
 
 int d8_convert_i64_to_f64(void *buf, int64_t n, cudaStream_t st);
 
