@@ -300,7 +300,8 @@ def bench_shia(torch, ops, dev, args, rank: int, world: int, peak: float):
         out["s4_fp64"] = {"value": n_cells * nt3 / (ms * 1e-3), "unit": "cell-timesteps/s", "ms_per_run": ms, "cells": n_cells,
                           "intervals": nt3, "mode": "wmf_py 3-tank balance, fp64, time-fused",
                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                                       "algorithmic_bytes_per_cell_step": 8.0}}
+                                       "algorithmic_bytes_per_cell_step": 8.0,
+                                       "issue_slot_utilisation": profiled("shia_s4_issue_util")}}
         del rain
     # ---- config 5: NSGA-II population, 512 parameter sets x 250 k cells (sets sharded across the ranks)
     P, n5 = args.pop_sets, args.pop_cells
