@@ -242,19 +242,23 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
     const int32_t *rain_cc = a.rain + cc;                // this cell's column of the rain records
     float ex_ret = 0.0f, ex_v1 = 0.0f, ex_v2 = 0.0f, ex_v3 = 0.0f, ex_v4 = 0.0f;   // (DIAG) this step's return flow and vfluxes
     float rc1 = 0.0f, rc2 = 0.0f, ret_acc = 0.0f;
-    auto one_step = [&](int64_t t, float &vR, float &vq) {
+    // record 1 = no rain (:366-367); a record beyond the file is the Fortran's 'fuera del rango' read error, whose
+    // RainInt is undefined: defined here as no rain (the host layer rejects such headers before the launch).
+    // Row offset of step t's record in the rain array, -1 = no rain:
+    auto rain_row = [&](int64_t t) -> int64_t {
         const int pos = a.pos[t];
+        return (unsigned)(pos - 2) < (unsigned)(a.n_rec - 1) ? (int64_t)(pos - 1) * N : (int64_t)-1;
+    };
+    auto one_step = [&](int64_t t, int64_t row, float evp_t, float &vR, float &vq) {
         float R = 0.0f;
-        // record 1 = no rain (:366-367); a record beyond the file is the Fortran's 'fuera del rango' read error, whose
-        // RainInt is undefined: defined here as no rain (the host layer rejects such headers before the launch)
-        if ((unsigned)(pos - 2) < (unsigned)(a.n_rec - 1)) {                                // :370 (RainInt/1000.)
-            const float ri = (float)rain_cc[(int64_t)(pos - 1) * N];
+        if (row >= 0) {                                                                     // :370 (RainInt/1000.)
+            const float ri = (float)rain_cc[row];
             R = STRICT ? ri / 1000.0f : ri * 0.001f;
         }
         acum = acum + R;                                                                   // :380
         float v1 = fmaxf(0.0f, (R - H1) + S1);                                             // :393
         S1 = (S1 + R) - v1;                                                                // :394
-        float evl = fminf((a.evp[t] * vs[0]) * (STRICT ? powf(S1 / H1, 0.6f) : pow06(S1 * invH1)), S1);   // :396-398
+        float evl = fminf((evp_t * vs[0]) * (STRICT ? powf(S1 / H1, 0.6f) : pow06(S1 * invH1)), S1);   // :396-398
         S1 = S1 - evl;                                                                     // :407
         float v2 = fminf(v1, vs[1]); S2 = (S2 + v1) - v2;                                  // :409-412
         float v3 = fminf(v2, vs[2]); S3 = (S3 + v2) - v3;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
     if (DIAG) {
         for (int64_t t = 0; t < T; t++) {
             float v[K];
-            one_step(t, v[0], v[1]);
+            one_step(t, rain_row(t), a.evp[t], v[0], v[1]);
             if (DIAG) {
                 v[2] = live ? S1 : 0.0f; v[3] = live ? S2 : 0.0f; v[4] = live ? S3 : 0.0f; v[5] = live ? S4 : 0.0f;
                 v[6] = live ? hs[0] : 0.0f; v[7] = live ? hs[1] : 0.0f; v[8] = live ? hs[2] : 0.0f;
@@ -305,12 +309,22 @@ __global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
         }
     } else {
         red.flush();                                      // slot 0 is out; batches of TB steps follow
+        // The batch's record rows and evaporation rates are the same for every cell: one thread per step looks them up
+        // (and checks the record index) once per block and batch, the step itself reads them from shared memory.
+        __shared__ long long s_row[TB];
+        __shared__ float s_evp[TB];
         for (int64_t tb = 0; tb < T; tb += TB) {
+            if (threadIdx.x < TB) {
+                const int64_t t = tb + threadIdx.x;
+                s_row[threadIdx.x] = t < T ? rain_row(t) : -1;
+                s_evp[threadIdx.x] = t < T ? a.evp[t] : 0.0f;
+            }
+            __syncthreads();                              // (the flush at the end of the batch keeps the next batch's writes behind these reads)
             float q[2][TB];
 #pragma unroll
             for (int u = 0; u < TB; u++) {
                 q[0][u] = 0.0f; q[1][u] = 0.0f;
-                if (tb + u < T) one_step(tb + u, q[0][u], q[1][u]);
+                if (tb + u < T) one_step(tb + u, (int64_t)s_row[u], s_evp[u], q[0][u], q[1][u]);
             }
             red.add_batch(q, (int)(T - tb < TB ? T - tb : TB));
             red.flush();
