@@ -39,22 +39,43 @@ def combine_cell_shards(parts: List[Dict[str, torch.Tensor]], counts: List[int])
     return out
 
 
+_DIAG_KEYS = ("balance", "mean_rain", "mean_storage", "mean_speed")
+
+
 def shia5_run_cell_sharded(cell_static, rain_records, pos_evento, evp, calib, sto, hspeed=None, group=None, **kw):
     """Each rank holds a contiguous range of the basin's cells (its columns of cell_static / rain_records /
-    sto): run the local shard, then gather the diagnostics.  Returns (local outputs, whole-basin diagnostics)."""
+    sto): run the local shard, then gather the diagnostics.  Returns (local outputs, whole-basin diagnostics).
+    ONE collective and no host round trip: the shard's cell count and every per-step series travel in one packed fp64
+    buffer, and the ranks' rows are combined on the device in rank order (`combine_cell_shards`' arithmetic)."""
     import torch.distributed as dist
     local = ops.shia5_run(cell_static, rain_records, pos_evento, evp, calib, sto, hspeed, **kw)
-    n_local = cell_static.shape[1]
-    counts = [int(c.item()) for c in _all_gather(torch.tensor([n_local], device=sto.device), group)]
-    parts: List[Dict[str, torch.Tensor]] = [dict() for _ in counts]
-    for key in ("balance", "mean_rain", "mean_storage", "mean_speed"):
-        if local.get(key) is None:
-            for p in parts:
-                p[key] = None
-            continue
-        for g, t in enumerate(_all_gather(local[key], group)):
-            parts[g][key] = t
-    return local, combine_cell_shards(parts, counts)
+    dev = sto.device
+    keys = [k for k in _DIAG_KEYS if local.get(k) is not None]
+    shapes = [tuple(local[k].shape) for k in keys]
+    sizes = [int(local[k].numel()) for k in keys]
+    pack = torch.cat([torch.full((1,), float(cell_static.shape[1]), dtype=torch.float64, device=dev)] +
+                     [local[k].reshape(-1).double() for k in keys])
+    world = dist.get_world_size(group)
+    if pack.is_cuda:
+        rows = torch.empty((world, pack.numel()), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(rows, pack, group=group)
+    else:                                                 # gloo (the CPU tests)
+        rows = torch.stack(_all_gather(pack, group))
+    share = rows[:, 0] / rows[:, 0].sum()                 # cell-count weights of the means (fp64, like the Fortran's N_cel)
+    acc = torch.zeros(pack.numel() - 1, dtype=torch.float64, device=dev)
+    weight_one = torch.ones((), dtype=torch.float64, device=dev)
+    off_bal = sizes[0] if keys and keys[0] == "balance" else 0
+    for r in range(world):                                # rank order: the result does not depend on a reduction schedule
+        row = rows[r, 1:]
+        if off_bal:
+            acc[:off_bal] += row[:off_bal] * weight_one
+        acc[off_bal:] += row[off_bal:] * share[r]
+    out: Dict[str, torch.Tensor] = {}
+    o = 0
+    for k, shp, n in zip(keys, shapes, sizes):
+        out[k] = acc[o:o + n].reshape(shp).float()
+        o += n
+    return local, out
 
 
 def shia5_run_population_sharded(cell_static, rain_records, pos_evento, evp, calibs, sto0, group=None, **kw):
