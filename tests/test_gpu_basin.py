@@ -58,6 +58,55 @@ def test_cut_vs_oracle(case):
         assert np.array_equal(got[k], exp[k]), k
 
 
+@pytest.mark.parametrize("shape,kind,seed", [((64, 256), "steep", 41), ((65, 257), "random", 42), ((300, 517), "steep", 43),
+                                             ((129, 1000), "random", 44), ((700, 300), "sch", 45), ((1, 700), "random", 46),
+                                             ((513, 1), "random", 47)])
+def test_cut_many_outlets(shape, kind, seed):
+    """The tile contraction behind basin_cut on ragged rasters: outlets on tile edges and corners, on the raster's rim,
+    inside cycles (random codes), at the largest accumulation and at random active cells -- mask identical to the oracle."""
+    ny, nx = shape
+    rng = np.random.default_rng(seed)
+    if kind == "steep":
+        fd = helpers.steepest(ny, nx, seed)
+    elif kind == "random":
+        fd = helpers.random_codes(ny, nx, seed)
+    else:
+        fd = ops.synth_scheidegger_host(ny, nx, seed=seed)
+    mask = rng.random((ny, nx)) > 0.05
+    acc = oracle.basin_acum(fd, mask)
+    cand = [np.unravel_index(np.argmax(acc), acc.shape)]
+    for r in (0, 63, 64, ny - 1):
+        for c in (0, 255, 256, nx - 1):
+            if 0 <= r < ny and 0 <= c < nx:
+                cand.append((r, c))
+    cand += [(int(rng.integers(ny)), int(rng.integers(nx))) for _ in range(6)]
+    dem = rng.random(fd.shape)
+    done = 0
+    for r0, c0 in cand:
+        if not mask[r0, c0]:
+            continue
+        exp = oracle.basin_cut(dem, (int(r0), int(c0)), fd.astype(np.int64), mask)
+        got = basics.basin_cut(dem, (int(r0), int(c0)), fd, mask)
+        assert np.array_equal(got["mask"], exp["mask"]), (shape, kind, r0, c0, int(exp["mask"].sum()), int(got["mask"].sum()))
+        done += 1
+    assert done >= 3
+
+
+def test_cut_serpentine():
+    """One path through every cell of a 1000 x 1030 raster (rows alternate east / west): the chain of tile exits is
+    ~5000 long, the outlet is its last cell and the basin is the whole raster; from a cell half way, half of it."""
+    ny, nx = 1000, 1030
+    fd = helpers.serpentine(ny, nx)
+    mask = np.ones((ny, nx), bool)
+    dem = np.zeros((ny, nx))
+    last = ny - 1
+    out_rc = (last, nx - 1 if last % 2 == 0 else 0)
+    got = basics.basin_cut(dem, out_rc, fd, mask)
+    assert got["mask"].all()
+    got = basics.basin_cut(dem, (500, 0), fd, mask)       # row 500 runs east: (500, 0) is its first cell
+    assert int(got["mask"].sum()) == 500 * nx + 1 and got["mask"][:500].all() and not got["mask"][501:].any()
+
+
 def _basin_case(ny, nx, seed, kind="steep"):
     fd = helpers.steepest(ny, nx, seed) if kind == "steep" else ops.synth_scheidegger_host(ny, nx, seed=seed)
     acc = oracle.basin_acum(fd, np.ones(fd.shape, bool))
