@@ -124,18 +124,21 @@ __device__ __forceinline__ void calc_speed(float sm, float coef, float expo, flo
                                            float &area)
 {
     for (int i = 0; i < niter; i++) {
-        area = sm / (L + sp * dt);
-        float pw;
         if (FAST) {
-            float l;
+            // the two divisions of the iteration as an SFU reciprocal (1 ulp) and a multiply by 1/3: an IEEE division is
+            // ~9 instructions, and the iteration -- a weighted average with the previous speed -- damps a rounding error
+            float l, pw, r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(L + sp * dt));
+            area = sm * r;
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(area));
             l = l * expo;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(l));
+            sp = (2.0f * (coef * pw) + sp) * 0.33333334f;
         } else {
-            pw = powf(area, expo);
+            area = sm / (L + sp * dt);
+            const float nw = coef * powf(area, expo);
+            sp = (2.0f * nw + sp) / 3.0f;
         }
-        float nw = coef * pw;
-        sp = (2.0f * nw + sp) / 3.0f;
     }
 }
 
