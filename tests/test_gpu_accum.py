@@ -123,6 +123,31 @@ def test_tma_bulk_staging(monkeypatch):
     assert np.array_equal(run(fd, m, _lib.ALGO_SWEEP, _lib.ACC_I64), oracle.basin_acum(fd, m).astype(np.int64))
 
 
+@pytest.mark.parametrize("bands", ["2", "3", "16"])
+def test_band_schedule(monkeypatch, bands):
+    """WMF_D8_BANDS switches the band schedule on (phase G of a band of tile rows beside phase A of the next): bands of a few -- or single --
+    tile rows, every tile solver present (cycles, upward flow, masks), ragged sizes.  Bit-identical to the oracle and to
+    the unbanded schedule."""
+    rng = np.random.default_rng(7)
+    cases = [(name, *CASES[name]()) for name in ("random_cycles", "steep_700x513", "steep_mask", "all_north", "serpentine", "sch_ragged")]
+    sch = ops.synth_scheidegger_host(900, 700, seed=5)
+    cases.append(("sch", sch, None))
+    cases.append(("sch_mask", sch, rng.random(sch.shape) > 0.04))
+    mix = ops.synth_scheidegger_host(1100, 600, seed=6).copy()
+    mix[300:420, 100:500] = helpers.random_codes(120, 400, 9)            # a block of random codes (cycles) inside a river network
+    mix[700:760, :] = helpers.steepest(60, 600, 10)
+    cases.append(("mix", mix, None))
+    for name, fd, mask in cases:
+        m = np.ones(fd.shape, bool) if mask is None else mask
+        exp = oracle.basin_acum(fd, m)
+        monkeypatch.setenv("WMF_D8_BANDS", bands)
+        got = run(fd, mask, _lib.ALGO_SWEEP, _lib.ACC_I64)
+        monkeypatch.setenv("WMF_D8_BANDS", "0")
+        ref = run(fd, mask, _lib.ALGO_SWEEP, _lib.ACC_I64)
+        assert np.array_equal(got, exp.astype(np.int64)), (name, bands)
+        assert np.array_equal(ref, got), (name, bands)
+
+
 def test_accumulations_beyond_int32_in_32_bit_arithmetic():
     """A raster of 2^31 + 65536 cells that drains through ONE cell: every row runs east, the last column south.  Its
     64-bit output is computed in 32-bit (unsigned) arithmetic because the raster has fewer than 2^32 cells; the last

@@ -57,6 +57,7 @@ struct Geo {
     int tiles_x, tiles_y;
     int64_t gy0, gny;        // the stripe holds rows [gy0, gy0 + ny) of a raster of gny rows (gy0 = 0, gny = ny when whole)
     int extra_edge;          // stripes, 32-bit sums: `extra` holds inflow only for the stripe's first / last tile row
+    int tile0;               // band launches: the first tile this launch handles (the `ntiles` argument is the end)
 };
 
 // canonical boundary slot of local cell (lr, lc) in a tile of th x tw cells, or -1
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 {
     extern __shared__ __align__(16) uint32_t s_dyn[];   // [WPB][2][CH][ROWW] DIR words (+ the same again for mask words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * WPB + warp;
+    const int tile = g.tile0 + blockIdx.x * WPB + warp;
     if (tile >= ntiles) return;
     int ty, tx, th, tw;
     tile_dims(g, tile, ty, tx, th, tw);
@@ -1979,21 +1980,65 @@ __global__ void k_build_forest(Geo g, int64_t nnodes, const uint32_t *__restrict
 // into a neighbouring row stripe), PAR_NONE (not an exit, or its receiver is inactive: never walked).
 // pe (nullable; the stripe kernels chase it): one 8-byte record {parent exit, entry cell} per node.
 constexpr int BU = 4;
+// Band schedule (whole rasters, 32-bit sums; see sweep_phaseAG_bands): the forest is built and walked band by band of
+// tile rows, behind phase A.  gstate[tile]: 0 nothing yet, 1 built, 2 walk started.
+//   mode 0  every tile of the launch (stripes, small rasters)
+//   mode 1  band: a tile is BUILT when the fast solver has finished its whole 3 x 3 neighbourhood (tile_class 0 -- tiles
+//           of the jump / chain-walk solvers get their meta words only after all bands) and STARTED when its whole
+//           neighbourhood is built; as long as no tile anywhere went to those solvers (flags) that is every tile
+//   mode 2  rest, after the jump / chain-walk solvers: whatever mode 1 left out; nothing when no tile went there
+struct BandCtl { const uint8_t *tile_class; uint8_t *gstate; const uint32_t *flags; int mode; };
+__device__ __forceinline__ bool band_clean(const BandCtl &bc) { return bc.flags[F_COMPLEX] == 0u && bc.flags[F_CHAIN] == 0u; }
+// does every tile around `tile` (itself included) satisfy v[t] <relation>?  built: v = gstate >= 1; done: v = tile_class == 0
+__device__ __forceinline__ bool band_around(const Geo &g, int tile, const uint8_t *v, bool want_zero)
+{
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    bool ok = true;
+    for (int y = ty - 1; y <= ty + 1; y++)
+        for (int x = tx - 1; x <= tx + 1; x++)
+            if (y >= 0 && y < g.tiles_y && x >= 0 && x < g.tiles_x) {
+                const uint8_t b = v[y * g.tiles_x + x];
+                ok = ok && (want_zero ? b == 0 : b != 0);
+            }
+    return ok;
+}
+
 __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta,
                                                    const uint8_t *__restrict__ tile_top, int32_t *__restrict__ par,
-                                                   int2 *__restrict__ pe, unsigned long long *wq)
+                                                   int2 *__restrict__ pe, unsigned long long *wq,
+                                                   BandCtl bc = BandCtl{nullptr, nullptr, nullptr, 0})
 {
+  if (bc.mode == 2 && band_clean(bc)) return;
+  const int nblk = (ntiles - g.tile0 + BU - 1) / BU;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {          // (mode 2 runs a persistent grid)
     // last tiles first: what this kernel leaves in L2 is then weighted towards the FIRST tile rows, where the walk
     // that follows starts its chains
-    const int tile0 = (int)(gridDim.x - 1 - blockIdx.x) * BU, s = threadIdx.x;
+    const int tile0 = g.tile0 + (nblk - 1 - blk) * BU, s = threadIdx.x;
     const int last_th = (int)(g.ny - (int64_t)(g.tiles_y - 1) * TH), last_tw = (int)(g.nx - (int64_t)(g.tiles_x - 1) * TW);
     uint32_t m[BU], me[BU];
     int t2[BU], s2[BU];
     bool skip[BU];                                           // an inner first-row slot of a tile that has no exit there (tile_top)
+    bool mine[BU];                                           // band schedule: this launch builds the tile
 #pragma unroll
-    for (int u = 0; u < BU; u++) skip[u] = tile0 + u >= ntiles || (s > 0 && s < TW - 1 && !tile_top[tile0 + u]);
+    for (int u = 0; u < BU; u++)                             // (in flight before the band tests below)
+        m[u] = (tile0 + u < ntiles && !(s > 0 && s < TW - 1 && !tile_top[tile0 + u])) ? meta[(int64_t)(tile0 + u) * NSLOT + s] : 0u;
 #pragma unroll
-    for (int u = 0; u < BU; u++) m[u] = !skip[u] ? meta[(int64_t)(tile0 + u) * NSLOT + s] : 0u;
+    for (int u = 0; u < BU; u++) {
+        mine[u] = tile0 + u < ntiles;
+        if (mine[u] && bc.mode == 1) mine[u] = band_clean(bc) || band_around(g, tile0 + u, bc.tile_class, true);
+        if (mine[u] && bc.mode == 2) mine[u] = bc.gstate[tile0 + u] == 0;
+    }
+    if (bc.mode != 0) {
+        __syncthreads();                                     // (mode 2: everybody has read gstate before it changes)
+        if (s == 0) {
+#pragma unroll
+            for (int u = 0; u < BU; u++) if (mine[u]) bc.gstate[tile0 + u] = 1;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < BU; u++) skip[u] = !mine[u] || (s > 0 && s < TW - 1 && !tile_top[tile0 + u]);
+#pragma unroll
+    for (int u = 0; u < BU; u++) if (skip[u]) m[u] = 0u;
     int ty = tile0 / g.tiles_x, tx = tile0 - ty * g.tiles_x;            // block-uniform; the next tiles follow in row-major order
 #pragma unroll
     for (int u = 0; u < BU; u++) {
@@ -2021,6 +2066,7 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
         par[(int64_t)(tile0 + u) * NSLOT + s] = p >= 0 ? p : (en >= 0 ? PAR_ROOT : (en == -2 ? PAR_STRIPE : PAR_NONE));
         if (pe) pe[(int64_t)(tile0 + u) * NSLOT + s] = make_int2(p, en);
     }
+  }
 }
 
 // "Did every exit finalise?" without a host round trip: GCNT words (one 32-byte sector each, so the
@@ -2036,13 +2082,28 @@ __device__ __forceinline__ bool node_is_skipped(const uint8_t *__restrict__ tile
 
 
 __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *__restrict__ tile_top, const int32_t *__restrict__ par,
-                                                unsigned long long *wq, unsigned long long *__restrict__ gcnt)
+                                                unsigned long long *wq, unsigned long long *__restrict__ gcnt, int64_t node0 = 0,
+                                                Geo g = Geo{}, BandCtl bc = BandCtl{nullptr, nullptr, nullptr, 0})
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int32_t p = (i < nnodes && !node_is_skipped(tile_top, i)) ? par[i] : PAR_NONE;
+  if (bc.mode == 2 && band_clean(bc)) return;
+  unsigned int nexit_all = 0, nfin = 0;
+  // one node per thread; mode 2 runs a persistent grid over all nodes (whole warps stay together for the ballot)
+  const int64_t stride = bc.mode == 2 ? (int64_t)gridDim.x * blockDim.x : ((int64_t)1 << 62);
+  for (int64_t i = node0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i - (threadIdx.x & 31) < nnodes; i += stride) {
+    bool mine = i < nnodes;
+    int32_t p = (mine && !node_is_skipped(tile_top, i)) ? par[i] : PAR_NONE;     // (in flight before the band tests below)
+    if (mine && bc.mode != 0) {
+        const int tile = (int)(i / NSLOT);
+        if (bc.mode == 1) mine = band_clean(bc) || band_around(g, tile, bc.gstate, false);
+        else mine = bc.gstate[tile] != 2;
+        // The tile's mark is set by the thread of its slot 0: 2 in a band launch -- others in the same launch only ask
+        // "built?", and 1 and 2 both say yes -- and 3 in the rest launch, whose test "!= 2" it does not change.
+        if (mine && i - (int64_t)tile * NSLOT == 0) bc.gstate[tile] = bc.mode == 1 ? 2 : 3;
+    }
+    if (!mine) p = PAR_NONE;
     const bool walk = p != PAR_NONE;
     const unsigned int nexit = __popc(__ballot_sync(FULL, walk));
-    unsigned int nfin = 0;
+    nexit_all += nexit;
     if (walk) {                                             // an exit: carry its total downstream
         unsigned long long old = atomicAdd(&wq[i], (unsigned long long)(-(long long)PEND1));   // own arrival
         uint32_t add = 0;
@@ -2058,9 +2119,10 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *_
         }
     }
     __syncwarp();
+  }
     nfin = __reduce_add_sync(FULL, nfin);
-    if ((threadIdx.x & 31) == 0 && nexit)
-        atomicAdd(&gcnt[4 * (blockIdx.x & (GCNT - 1))], ((unsigned long long)nexit << 32) | nfin);
+    if ((threadIdx.x & 31) == 0 && nexit_all)
+        atomicAdd(&gcnt[4 * (blockIdx.x & (GCNT - 1))], ((unsigned long long)nexit_all << 32) | nfin);
 }
 
 // Exits that never finalised (cycles, or fed by one) poison the tile they drain into: it goes to the general solver,
@@ -2335,7 +2397,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
 // arrives from the other stripes.
 struct SweepWs {
     uint32_t *meta; unsigned long long *wq; int32_t *par; uint8_t *tile_class, *tile_top; unsigned long long *row_plain, *gcnt;
-    uint32_t *flags; uint32_t *codes4;                                                         // jump solver: the tiles' decoded codes, phase A -> phase C
+    uint32_t *flags; uint8_t *gstate; uint32_t *codes4;                                                         // jump solver: the tiles' decoded codes, phase A -> phase C
     int32_t *exit_acc, *parent, *cnt; int64_t *A, *inflow; uint8_t *blocked, *ext_unres;   // wide
     int2 *pe; void *extra; uint8_t *extra_unres;                              // stripe
     StripePaths sp;
@@ -2357,6 +2419,7 @@ static SweepWs carve_ws(void *ws, size_t ws_bytes, const Geo &g, bool wide, bool
     w.row_plain = cur.take<unsigned long long>(nt);
     w.gcnt = cur.take<unsigned long long>(GCNT_BYTES / sizeof(unsigned long long));
     w.flags = cur.take<uint32_t>(NFLAGS);                     // (right behind the counters: one memset clears both)
+    w.gstate = cur.take<uint8_t>(nt);                         // band schedule: built / started marks (cleared by the same memset)
     if (!wide) {                                              // (the 64-bit forest engine keeps the chain-walk solver for such tiles)
         w.codes4 = cur.take<uint32_t>(nt * TH * 32);
     }
@@ -2391,7 +2454,7 @@ static SweepWs carve_ws(void *ws, size_t ws_bytes, const Geo &g, bool wide, bool
 static Geo make_geo(int64_t ny, int64_t nx, int64_t gy0, int64_t gny)
 {
     Geo g;
-    g.ny = ny; g.nx = nx; g.gy0 = gy0; g.gny = gny; g.extra_edge = 0;
+    g.ny = ny; g.nx = nx; g.gy0 = gy0; g.gny = gny; g.extra_edge = 0; g.tile0 = 0;
     g.tiles_x = (int)((nx + TW - 1) / TW);
     g.tiles_y = (int)((ny + TH - 1) / TH);
     return g;
@@ -2411,9 +2474,11 @@ static int sm_count()
 }
 
 template <int ENC>
-int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs &w, int al, cudaStream_t st)
+int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, const SweepWs &w, int al, cudaStream_t st,
+                 bool fast = true, bool rare = true, size_t smem_pad = 0)
 {   // al: 0 byte-wise staging (any width / alignment), 1 cp.async staging, 2 TMA bulk copies (see stage_mode)
-    const unsigned fast_blocks = (unsigned)((ntiles + WPB - 1) / WPB);
+    // fast: the one-pass kernel over the tiles [g.tile0, ntiles); rare: the jump / chain-walk solvers (all tiles)
+    const unsigned fast_blocks = (unsigned)((ntiles - g.tile0 + WPB - 1) / WPB);
     const unsigned gen_blocks = (unsigned)(ntiles < sm_count() * 4 ? ntiles : sm_count() * 4);   // persistent: most tiles are skipped
     const size_t smemA = sizeof(int32_t) * TCELLS + 2 * TCELLS;
     {   // once per device and instantiation
@@ -2425,14 +2490,18 @@ int sweep_phaseA(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
             if (dev >= 0 && dev < 64) done[dev] = true;
         }
     }
-    const size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * HBINS * sizeof(int);
+    size_t smemF = (size_t)(mask ? 2 : 1) * WPB * 2 * CH * ROWW * sizeof(uint32_t) + (size_t)WPB * HBINS * sizeof(int);
     static_assert(2 * WPB * 2 * CH * ROWW * sizeof(uint32_t) + WPB * HBINS * sizeof(int) <= 48 * 1024, "phase A fits the default dynamic shared memory");
+    if (smemF + smem_pad <= 48 * 1024) smemF += smem_pad;    // (unused shared memory: fewer resident blocks, see the band schedule)
+  if (fast) {
 #define WMF_LAUNCH_A(AL_, MK_, TM_)                                                                                              \
     k_sweepA<ENC, AL_, MK_, TM_><<<fast_blocks, WPB * 32, smemF, st>>>(dir, mask, g, ntiles, w.meta, w.exit_acc, w.tile_class, w.row_plain, \
                                                                        w.wq, w.tile_top, w.flags, w.codes4 != nullptr)
     if (mask) { if (al == 2) WMF_LAUNCH_A(true, true, true); else if (al) WMF_LAUNCH_A(true, true, false); else WMF_LAUNCH_A(false, true, false); }
     else { if (al == 2) WMF_LAUNCH_A(true, false, true); else if (al) WMF_LAUNCH_A(true, false, false); else WMF_LAUNCH_A(false, false, false); }
 #undef WMF_LAUNCH_A
+  }
+  if (!rare) { WMF_LAUNCH_CHECK(); return 0; }
     if (w.codes4) {                                          // tiles with upward flow: pointer jumping, one block per tile
         const size_t smemJ = sizeof(uint32_t) * (TCELLS / 2 + TH * 32 + HBINS + 4);
         static_assert(sizeof(uint32_t) * (TCELLS / 2 + TH * 32 + HBINS + 4) <= 48 * 1024, "k_jumpA fits the default dynamic shared memory");
@@ -2536,6 +2605,110 @@ static SideStream *side_stream()
     return &tab[dev];
 }
 
+// ---- band schedule: phase G of one band of tile rows beside phase A of the next -------------------------------------
+// Whole rasters, 32-bit sums.  Phases A and G used to be three kernels with the whole raster between them, and the walk
+// is a latency chain (the longest river, ~0.5 us per tile crossed) during which the machine idles.  Here the raster is
+// cut into B bands of tile rows: phase A of the bands runs on two alternating streams (so that a band fills the SMs the
+// previous one's last blocks leave), and behind every band a high-priority stream builds the tiles whose 3 x 3
+// neighbourhood is done and starts the walk of the tiles whose neighbourhood is built (k_g_build / k_g_walk, mode 1) --
+// walkers stop at nodes of tiles that have not started, and whoever starts those carries on.  Only the last band's
+// build and walk remain behind phase A.  Phase A is held to four blocks per SM (padding of unused shared memory) so
+// that the small blocks of the forest kernels find registers beside it.  Tiles of the jump / chain-walk solvers get their
+// meta words after all bands: they and their neighbours are built and started by the mode-2 launches that follow.
+// OPT-IN (WMF_D8_BANDS=B in the environment), because the gain does not survive: a first version for rasters of
+// one-pass tiles only measured 0.700 -> 0.634 ms at 16384^2 with 8 bands (5 blocks per SM 0.662, 6 blocks 0.674; 4 / 12 /
+// 16 bands 0.637 / 0.670 / 0.702), but with the marks and the trailing launches that mixed rasters need it is 0.66 to
+// 0.71 ms depending on nothing but the order and size of the small launches around it -- how the block scheduler
+// interleaves three streams is not something this code controls.  Bit-identical either way (test_band_schedule).
+constexpr int MAXB = 16;
+struct BandRes { cudaStream_t sA, sG; cudaEvent_t fork, evA[MAXB], evG; std::mutex busy; };
+static BandRes *band_res()
+{
+    static BandRes tab[64];
+    static bool made[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!made[dev]) {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&tab[dev].sA, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&tab[dev].sG, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&tab[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&tab[dev].evG, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int b = 0; b < MAXB; b++)
+            if (cudaEventCreateWithFlags(&tab[dev].evA[b], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        made[dev] = true;
+    }
+    return &tab[dev];
+}
+// bands for a raster of tiles_y tile rows: WMF_D8_BANDS in the environment (absent / 0 / 1 = off)
+static int band_count(const Geo &g)
+{
+    const char *e = getenv("WMF_D8_BANDS");
+    int b = e ? atoi(e) : 0;
+    if (b > MAXB) b = MAXB;
+    if (b > g.tiles_y) b = g.tiles_y;                        // (the tests force bands of a single tile row)
+    return b < 2 ? 0 : b;
+}
+static size_t band_smem_pad()
+{
+    const char *e = getenv("WMF_D8_BAND_SMEM");
+    return e ? (size_t)atoi(e) : 14000;
+}
+
+template <int ENC>
+int sweep_phaseAG_bands(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntiles, int64_t nnodes, const SweepWs &w, int al, int B,
+                        cudaStream_t st)
+{
+    BandRes *br = band_res();
+    WMF_REQUIRE(br != nullptr, (int)cudaErrorUnknown, "cannot create the band streams");
+    std::lock_guard<std::mutex> lock(br->busy);              // (the streams and events are shared by the device's callers)
+    const BandCtl band{w.tile_class, w.gstate, w.flags, 1}, rest{w.tile_class, w.gstate, w.flags, 2};
+    WMF_CUDA_CHECK(cudaEventRecord(br->fork, st));
+    WMF_CUDA_CHECK(cudaStreamWaitEvent(br->sA, br->fork, 0));
+    WMF_CUDA_CHECK(cudaStreamWaitEvent(br->sG, br->fork, 0));
+    const int ty_n = g.tiles_y;
+    auto row_of = [&](int b) { return (int)((int64_t)ty_n * b / B); };
+    for (int b = 0; b < B; b++) {
+        const int r0 = row_of(b), r1 = row_of(b + 1);
+        cudaStream_t sa = (b & 1) ? br->sA : st;
+        Geo gb = g;
+        gb.tile0 = r0 * g.tiles_x;
+        int rc = sweep_phaseA<ENC>(dir, mask, gb, r1 * g.tiles_x, w, al, sa, true, false, band_smem_pad());
+        if (rc) return rc;
+        WMF_CUDA_CHECK(cudaEventRecord(br->evA[b], sa));
+        WMF_CUDA_CHECK(cudaStreamWaitEvent(br->sG, br->evA[b], 0));
+        const bool last = b == B - 1;
+        const int b0 = r0 > 0 ? r0 - 1 : 0, b1 = last ? ty_n : r1 - 1;                  // rows to build: their neighbourhoods are done
+        const int w0 = r0 > 1 ? r0 - 2 : 0, w1 = last ? ty_n : (r1 > 1 ? r1 - 2 : 0);   // rows to start: their neighbourhoods are built
+        if (b1 > b0) {
+            Geo gg = g;
+            gg.tile0 = b0 * g.tiles_x;
+            const int te = b1 * g.tiles_x;
+            k_g_build<<<(te - gg.tile0 + BU - 1) / BU, NSLOT, 0, br->sG>>>(gg, te, w.meta, w.tile_top, w.par, nullptr, w.wq, band);
+        }
+        if (w1 > w0) {
+            const int64_t n0 = (int64_t)w0 * g.tiles_x * NSLOT, n1 = (int64_t)w1 * g.tiles_x * NSLOT;
+            k_g_walk<<<blocks_for(n1 - n0, 128), 128, 0, br->sG>>>(n1, w.tile_top, w.par, w.wq, w.gcnt, n0, g, band);
+        }
+    }
+    WMF_CUDA_CHECK(cudaEventRecord(br->evG, br->sG));
+    WMF_CUDA_CHECK(cudaStreamWaitEvent(st, br->evG, 0));     // (sG has waited for every band of both phase-A streams)
+    // The jump / chain-walk solvers.  (Launched beside the last band's phase G -- they touch their own tiles only -- they
+    // cost 10 us instead of saving some: even empty, their large blocks take the SM slots the walk is waiting for.)
+    int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st, false, true);
+    if (rc) return rc;
+    // whatever the bands had to leave out because of those solvers (nothing: the launches return at once)
+    const int nblk = (ntiles + BU - 1) / BU, cap = sm_count() * 3;
+    k_g_build<<<nblk < cap ? nblk : cap, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, nullptr, w.wq, rest);
+    k_g_walk<<<sm_count() * 8, 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt, 0, g, rest);
+    k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt, w.flags);
+    WMF_LAUNCH_CHECK();
+    return 0;
+}
+
 // T: the type the accumulation is computed in; TO: the type it is stored as (acc_out)
 template <int ENC, typename T, typename TO>
 int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int64_t nx, void *ws, size_t ws_bytes,
@@ -2551,8 +2724,14 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int
     WMF_REQUIRE(w.ok, WMF_E_WORKSPACE, "workspace too small");
     const int al = stage_mode(dir, mask, acc, nx);
     if (!wide) {
-        WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, (size_t)((char *)(w.flags + NFLAGS) - (char *)w.gcnt), st));
-        int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
+        WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, (size_t)((char *)(w.gstate + ntiles) - (char *)w.gcnt), st));   // counters, flags, band marks
+        int rc;
+        if (const int B = band_count(g)) {                   // large rasters: the forest grows band by band behind phase A
+            rc = sweep_phaseAG_bands<ENC>(dir, mask, g, ntiles, nnodes, w, al, B, st);
+            if (rc) return rc;
+            return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, w.wq, (const T *)nullptr, nullptr, al, acc, st);
+        }
+        rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
         if (rc) return rc;
         rc = sweep_phaseG_packed(g, ntiles, nnodes, w, nullptr, st);
         if (rc) return rc;
