@@ -2003,14 +2003,15 @@ __device__ __forceinline__ bool band_around(const Geo &g, int tile, const uint8_
     return ok;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint32_t *__restrict__ meta,
                                                    const uint8_t *__restrict__ tile_top, int32_t *__restrict__ par,
                                                    int2 *__restrict__ pe, unsigned long long *wq,
                                                    BandCtl bc = BandCtl{nullptr, nullptr, nullptr, 0})
 {
-  if (bc.mode == 2 && band_clean(bc)) return;
+  if (MODE == 2 && band_clean(bc)) return;
   const int nblk = (ntiles - g.tile0 + BU - 1) / BU;
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {          // (mode 2 runs a persistent grid)
+  for (int blk = blockIdx.x; MODE != 2 || blk < nblk; blk += gridDim.x) {   // (mode 2 runs a persistent grid; the others one block per BU tiles)
     // last tiles first: what this kernel leaves in L2 is then weighted towards the FIRST tile rows, where the walk
     // that follows starts its chains
     const int tile0 = g.tile0 + (nblk - 1 - blk) * BU, s = threadIdx.x;
@@ -2025,10 +2026,10 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
 #pragma unroll
     for (int u = 0; u < BU; u++) {
         mine[u] = tile0 + u < ntiles;
-        if (mine[u] && bc.mode == 1) mine[u] = band_clean(bc) || band_around(g, tile0 + u, bc.tile_class, true);
-        if (mine[u] && bc.mode == 2) mine[u] = bc.gstate[tile0 + u] == 0;
+        if (MODE == 1 && mine[u]) mine[u] = band_clean(bc) || band_around(g, tile0 + u, bc.tile_class, true);
+        if (MODE == 2 && mine[u]) mine[u] = bc.gstate[tile0 + u] == 0;
     }
-    if (bc.mode != 0) {
+    if (MODE != 0) {
         __syncthreads();                                     // (mode 2: everybody has read gstate before it changes)
         if (s == 0) {
 #pragma unroll
@@ -2066,6 +2067,7 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
         par[(int64_t)(tile0 + u) * NSLOT + s] = p >= 0 ? p : (en >= 0 ? PAR_ROOT : (en == -2 ? PAR_STRIPE : PAR_NONE));
         if (pe) pe[(int64_t)(tile0 + u) * NSLOT + s] = make_int2(p, en);
     }
+    if (MODE != 2) break;
   }
 }
 
@@ -2081,24 +2083,25 @@ __device__ __forceinline__ bool node_is_skipped(const uint8_t *__restrict__ tile
 }
 
 
+template <int MODE>
 __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *__restrict__ tile_top, const int32_t *__restrict__ par,
                                                 unsigned long long *wq, unsigned long long *__restrict__ gcnt, int64_t node0 = 0,
                                                 Geo g = Geo{}, BandCtl bc = BandCtl{nullptr, nullptr, nullptr, 0})
 {
-  if (bc.mode == 2 && band_clean(bc)) return;
+  if (MODE == 2 && band_clean(bc)) return;
   unsigned int nexit_all = 0, nfin = 0;
   // one node per thread; mode 2 runs a persistent grid over all nodes (whole warps stay together for the ballot)
-  const int64_t stride = bc.mode == 2 ? (int64_t)gridDim.x * blockDim.x : ((int64_t)1 << 62);
-  for (int64_t i = node0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i - (threadIdx.x & 31) < nnodes; i += stride) {
+  for (int64_t i = node0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; MODE != 2 || i - (threadIdx.x & 31) < nnodes;
+       i += (int64_t)gridDim.x * blockDim.x) {
     bool mine = i < nnodes;
     int32_t p = (mine && !node_is_skipped(tile_top, i)) ? par[i] : PAR_NONE;     // (in flight before the band tests below)
-    if (mine && bc.mode != 0) {
+    if (MODE != 0 && mine) {
         const int tile = (int)(i / NSLOT);
-        if (bc.mode == 1) mine = band_clean(bc) || band_around(g, tile, bc.gstate, false);
+        if (MODE == 1) mine = band_clean(bc) || band_around(g, tile, bc.gstate, false);
         else mine = bc.gstate[tile] != 2;
         // The tile's mark is set by the thread of its slot 0: 2 in a band launch -- others in the same launch only ask
         // "built?", and 1 and 2 both say yes -- and 3 in the rest launch, whose test "!= 2" it does not change.
-        if (mine && i - (int64_t)tile * NSLOT == 0) bc.gstate[tile] = bc.mode == 1 ? 2 : 3;
+        if (mine && i - (int64_t)tile * NSLOT == 0) bc.gstate[tile] = MODE == 1 ? 2 : 3;
     }
     if (!mine) p = PAR_NONE;
     const bool walk = p != PAR_NONE;
@@ -2119,6 +2122,7 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *_
         }
     }
     __syncwarp();
+    if (MODE != 2) break;
   }
     nfin = __reduce_add_sync(FULL, nfin);
     if ((threadIdx.x & 31) == 0 && nexit_all)
@@ -2227,6 +2231,20 @@ __device__ __forceinline__ int macro_top(const Geo &g, int64_t e)
 }
 __device__ __forceinline__ int macro_of(const Geo &g, int64_t e) { return (int)(e / NSLOT) / g.tiles_x / MR; }
 
+// A chase along parent exits must not spin on a drainage cycle of the contracted forest (cycles are legal input): Brent's
+// cycle detection, one comparison per hop -- the chase stops at the first exit it meets again.
+struct ChaseGuard {
+    int64_t mark;
+    uint32_t steps, limit;
+    __device__ ChaseGuard() : mark(-1), steps(0), limit(2) {}
+    __device__ __forceinline__ bool seen(int64_t x)
+    {
+        if (x == mark) return true;
+        if (++steps == limit) { mark = x; limit *= 2; steps = 0; }
+        return false;
+    }
+};
+
 // mlink[macro row][col]: the exit (node id) through which flow entering at that top-row cell leaves the
 // group of tile rows (its entry lies in another group, in another stripe, or nowhere); -1: ends inside.
 __global__ void k_macro_links(Geo g, int64_t nnodes, const uint32_t *__restrict__ meta, const int2 *__restrict__ pe,
@@ -2242,7 +2260,9 @@ __global__ void k_macro_links(Geo g, int64_t nnodes, const uint32_t *__restrict_
     int32_t out = -1;
     if ((meta[e0] >> 21) & 1) {
         int64_t x = first_exit(meta, e0);
+        ChaseGuard cg;
         for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
+            if (cg.seen(x)) break;                           // a cycle inside the group: the path never leaves it
             const int2 r = pe[x];
             if (r.y < 0 || macro_of(g, r.y) != mr) { out = (int32_t)x; break; }
             x = r.x;
@@ -2263,7 +2283,9 @@ __global__ void k_stripe_paths(Geo g, int64_t nnodes, const uint32_t *__restrict
     int32_t len = 0, link = -1, ce = -1, cx = -1;
     if ((meta[node] >> 21) & 1) {
         int64_t e = node, x = -2, last = -1;                 // x == -2: not looked up yet
+        ChaseGuard cg;
         for (int64_t hops = 0; hops <= nnodes; hops++) {
+            if (cg.seen(e)) break;                           // a cycle: the path ends inside the stripe
             const int mr = macro_top(g, e);
             if (len >= sp.pcap) {                            // out of room: the serial tail takes over at e (no jumps there)
                 if (ce < 0) { ce = (int32_t)e; cx = (int32_t)(x == -2 ? first_exit(meta, e) : x); }
@@ -2366,7 +2388,9 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
         to_exit(x, v);
         if (item & JUMP) {                                   // the entries the jump skipped inside its group of tile rows
             const int mr = macro_of(g, e);
+            ChaseGuard cg;
             for (int64_t hops = 0; x >= 0 && hops <= nnodes; hops++) {
+                if (cg.seen(x)) break;
                 const int2 r = pe[x];
                 const int32_t en = r.y;
                 if (en < 0 || macro_of(g, en) != mr) break;
@@ -2379,7 +2403,9 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
     }
     if (blockIdx.y == 0 && sp.pce[i] >= 0) {
         int64_t e = sp.pce[i], x = sp.pcx[i];
+        ChaseGuard cg;
         for (int64_t hops = 0; hops <= nnodes; hops++) {
+            if (cg.seen(e)) break;
             if (!VIA_WQ) inflow_add<T>(&extra[e], (T)v);
             to_exit(x, v);
             if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
@@ -2558,8 +2584,8 @@ int sweep_phaseC(const int8_t *dir, const uint8_t *mask, const Geo &g, int ntile
 // the packed forest (int32 sums): build, walk, flag what never finalised
 static int sweep_phaseG_packed(const Geo &g, int ntiles, int64_t nnodes, const SweepWs &w, int2 *pe, cudaStream_t st)
 {
-    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, pe, w.wq);
-    k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
+    k_g_build<0><<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, pe, w.wq);
+    k_g_walk<0><<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
     k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt, w.flags);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -2687,11 +2713,11 @@ int sweep_phaseAG_bands(const int8_t *dir, const uint8_t *mask, const Geo &g, in
             Geo gg = g;
             gg.tile0 = b0 * g.tiles_x;
             const int te = b1 * g.tiles_x;
-            k_g_build<<<(te - gg.tile0 + BU - 1) / BU, NSLOT, 0, br->sG>>>(gg, te, w.meta, w.tile_top, w.par, nullptr, w.wq, band);
+            k_g_build<1><<<(te - gg.tile0 + BU - 1) / BU, NSLOT, 0, br->sG>>>(gg, te, w.meta, w.tile_top, w.par, nullptr, w.wq, band);
         }
         if (w1 > w0) {
             const int64_t n0 = (int64_t)w0 * g.tiles_x * NSLOT, n1 = (int64_t)w1 * g.tiles_x * NSLOT;
-            k_g_walk<<<blocks_for(n1 - n0, 128), 128, 0, br->sG>>>(n1, w.tile_top, w.par, w.wq, w.gcnt, n0, g, band);
+            k_g_walk<1><<<blocks_for(n1 - n0, 128), 128, 0, br->sG>>>(n1, w.tile_top, w.par, w.wq, w.gcnt, n0, g, band);
         }
     }
     WMF_CUDA_CHECK(cudaEventRecord(br->evG, br->sG));
@@ -2702,8 +2728,8 @@ int sweep_phaseAG_bands(const int8_t *dir, const uint8_t *mask, const Geo &g, in
     if (rc) return rc;
     // whatever the bands had to leave out because of those solvers (nothing: the launches return at once)
     const int nblk = (ntiles + BU - 1) / BU, cap = sm_count() * 3;
-    k_g_build<<<nblk < cap ? nblk : cap, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, nullptr, w.wq, rest);
-    k_g_walk<<<sm_count() * 8, 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt, 0, g, rest);
+    k_g_build<2><<<nblk < cap ? nblk : cap, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, nullptr, w.wq, rest);
+    k_g_walk<2><<<sm_count() * 8, 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt, 0, g, rest);
     k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt, w.flags);
     WMF_LAUNCH_CHECK();
     return 0;
@@ -2768,7 +2794,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
     WMF_CUDA_CHECK(cudaMemsetAsync(w.gcnt, 0, (size_t)((char *)(w.flags + NFLAGS) - (char *)w.gcnt), st));
     int rc = sweep_phaseA<ENC>(dir, mask, g, ntiles, w, al, st);
     if (rc) return rc;
-    k_g_build<<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, w.pe, w.wq);
+    k_g_build<0><<<(ntiles + BU - 1) / BU, NSLOT, 0, st>>>(g, ntiles, w.meta, w.tile_top, w.par, w.pe, w.wq);
     // the path chase needs the forest only: it runs beside the walk (both are latency-bound chains)
     SideStream *ss = side_stream();
     WMF_REQUIRE(ss != nullptr, (int)cudaErrorUnknown, "cannot create the side stream");
@@ -2782,7 +2808,7 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
         k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp.mlink);
         k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp);
         WMF_CUDA_CHECK(cudaEventRecord(ss->join, ss->stream));
-        k_g_walk<<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
+        k_g_walk<0><<<blocks_for(nnodes, 256), 256, 0, st>>>(nnodes, w.tile_top, w.par, w.wq, w.gcnt);
         k_g_unres<<<sm_count() * 8, 256, 0, st>>>(g, nnodes, w.tile_top, w.par, w.wq, w.tile_class, w.gcnt, w.flags);
         WMF_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
     }
