@@ -2022,7 +2022,7 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
     bool mine[BU];                                           // band schedule: this launch builds the tile
 #pragma unroll
     for (int u = 0; u < BU; u++)                             // (in flight before the band tests below)
-        m[u] = (tile0 + u < ntiles && !(s > 0 && s < TW - 1 && !tile_top[tile0 + u])) ? meta[(int64_t)(tile0 + u) * NSLOT + s] : 0u;
+        m[u] = (tile0 + u < ntiles && !(s > 0 && s < TW - 1 && !tile_top[tile0 + u])) ? __ldcs(&meta[(int64_t)(tile0 + u) * NSLOT + s]) : 0u;
 #pragma unroll
     for (int u = 0; u < BU; u++) {
         mine[u] = tile0 + u < ntiles;
@@ -2048,7 +2048,7 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
         if (++tx == g.tiles_x) { tx = 0; ty++; }
     }
 #pragma unroll
-    for (int u = 0; u < BU; u++) me[u] = t2[u] >= 0 ? meta[t2[u] * NSLOT + s2[u]] : 0u;
+    for (int u = 0; u < BU; u++) me[u] = t2[u] >= 0 ? __ldcs(&meta[t2[u] * NSLOT + s2[u]]) : 0u;
 #pragma unroll
     for (int u = 0; u < BU; u++) {
         if (skip[u]) continue;                               // (its slot is never walked: see node_is_skipped)
@@ -2094,7 +2094,7 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *_
   for (int64_t i = node0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; MODE != 2 || i - (threadIdx.x & 31) < nnodes;
        i += (int64_t)gridDim.x * blockDim.x) {
     bool mine = i < nnodes;
-    int32_t p = (mine && !node_is_skipped(tile_top, i)) ? par[i] : PAR_NONE;     // (in flight before the band tests below)
+    int32_t p = (mine && !node_is_skipped(tile_top, i)) ? __ldcs(&par[i]) : PAR_NONE;     // (in flight before the band tests below)
     if (MODE != 0 && mine) {
         const int tile = (int)(i / NSLOT);
         if (MODE == 1) mine = band_clean(bc) || band_around(g, tile, bc.gstate, false);
