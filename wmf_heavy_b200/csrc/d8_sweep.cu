@@ -2776,6 +2776,9 @@ int run_sweep_t(const int8_t *dir, const uint8_t *mask, TO *acc, int64_t ny, int
     return sweep_phaseC<ENC, T, TO>(dir, mask, g, ntiles, w, nullptr, (const T *)w.inflow, w.ext_unres, al, acc, st);
 }
 
+// (WMF_ACC_WIDE=1 in the environment keeps 64-bit arithmetic for 64-bit outputs: the tests use it to cover that path)
+static bool force_wide() { const char *e = getenv("WMF_ACC_WIDE"); return e && e[0] == '1'; }
+
 // ---- stripe entry points --------------------------------------------------------------------------
 // The stripe-local pass always runs the packed int32 forest walk (a stripe holds < 2^31 cells); only
 // the finish pass is typed by the output accumulation.
@@ -2803,7 +2806,14 @@ int stripe_local_t(const int8_t *dir, const uint8_t *mask, int64_t ny, int64_t n
         WMF_CUDA_CHECK(cudaEventRecord(ss->fork, st));
         WMF_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
         // (the finish pass adds what the other stripes send into `extra`: cleared here, beside the walk, where DRAM idles)
-        WMF_CUDA_CHECK(cudaMemsetAsync(w.extra, 0, sizeof(int64_t) * (size_t)nnodes, ss->stream));
+        if (ny_total * nx <= 0xFFFFFFFFLL && !force_wide()) {
+            // 32-bit sums (see wmf_d8_stripe_finish): the routed inflow goes into the forest words, `extra` (int32 there)
+            // holds something only for the boundary cells themselves, in the stripe's first and last tile row
+            const size_t rown = (size_t)g.tiles_x * NSLOT;
+            WMF_CUDA_CHECK(cudaMemsetAsync(w.extra, 0, sizeof(int32_t) * rown, ss->stream));
+            WMF_CUDA_CHECK(cudaMemsetAsync((int32_t *)w.extra + ((size_t)nnodes - rown), 0, sizeof(int32_t) * rown, ss->stream));
+        } else
+            WMF_CUDA_CHECK(cudaMemsetAsync(w.extra, 0, sizeof(int64_t) * (size_t)nnodes, ss->stream));
         WMF_CUDA_CHECK(cudaMemsetAsync(w.extra_unres, 0, (size_t)nnodes, ss->stream));
         k_macro_links<<<blocks_for((int64_t)((g.tiles_y + MR - 1) / MR) * nx, 128), 128, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp.mlink);
         k_stripe_paths<<<blocks_for(2 * nx, 64), 64, 0, ss->stream>>>(g, nnodes, w.meta, w.pe, w.sp);
@@ -2925,7 +2935,7 @@ int d8_sweep_tile_classes(const void *ws, size_t ws_bytes, int64_t ny, int64_t n
 // whatever the output type: no accumulation can reach 2^32, so the unsigned value is exact and is widened (or turned
 // into a double) only when it is stored.
 // (WMF_ACC_WIDE=1 in the environment keeps 64-bit arithmetic for 64-bit outputs: the tests use it to cover that path)
-static bool force_wide() { const char *e = getenv("WMF_ACC_WIDE"); return e && e[0] == '1'; }
+
 #define WMF_ENC_DISPATCH(FN, T, TO, ...)                                                                     \
     (encoding == WMF_ENC_INTERNAL ? FN<WMF_ENC_INTERNAL, T, TO>(__VA_ARGS__) : FN<WMF_ENC_KEYPAD, T, TO>(__VA_ARGS__))
 
