@@ -14,9 +14,18 @@
  *   - return value: 0 ok, <0 argument/semantic error (WMF_E_*), >0 a cudaError_t;
  *     wmf_last_error() returns a thread-local message for the last failure;
  *   - the library keeps no data between calls (the f2py-style module state of the reference lives in the
- *     Python shim, not here); the only lasting objects are one helper stream and two events per device that
- *     wmf_d8_stripe_local creates on first use -- do not overlap calls of it on one device across host threads;
- *   - workspaces are caller-owned: query the size, allocate, pass in.
+ *     Python shim, not here); the only lasting objects are helper streams and events per device, created on
+ *     first use (wmf_d8_stripe_local: one stream, two events; the optional band schedule of wmf_d8_accum: two
+ *     streams and their events).  Enqueueing through them is serialised by a per-device mutex inside the call;
+ *   - threading: a call only touches the buffers it is given, so calls from several host threads are
+ *     safe as long as they do not share a workspace or an output (give every thread its own workspace; two
+ *     calls that share one must be ordered on one stream).  wmf_last_error() is per thread;
+ *   - workspaces are caller-owned: query the size, allocate, pass in;
+ *   - environment switches, read at every call (all off by default; every setting gives bit-identical
+ *     results and is covered by the GPU tests):  WMF_ACC_WIDE=1 keeps 64-bit arithmetic for 64-bit outputs of
+ *     rasters below 2^32 cells;  WMF_D8_BULK=1 stages tile rows with TMA bulk copies (cp.async.bulk) instead
+ *     of cp.async;  WMF_D8_BANDS=B runs the forest phase of wmf_d8_accum band by band beside phase A
+ *     (WMF_D8_BAND_SMEM: bytes of shared-memory padding that hold phase A to fewer blocks per SM there).
  */
 #ifndef WMF_B200_H
 #define WMF_B200_H
