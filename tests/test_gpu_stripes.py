@@ -39,6 +39,32 @@ def test_striped_equals_oracle(case, G):
     assert np.array_equal(got.cpu().numpy(), exp), f"{(got.cpu().numpy() != exp).sum()} cells differ"
 
 
+def test_cycle_through_two_stripes_and_two_tile_columns():
+    """A drainage cycle that crosses a stripe boundary twice, through different tile columns: its cells never finalise
+    (they keep what their finalised donors bring, without their own +1, and pass nothing on -- basics.py:166-175).  Each
+    stripe alone sees an open chain and finalises it; the finish pass has to take that back along the whole path, also
+    across tile edges.  (Found by tools/soak.py: random codes 1216 x 1320 in three stripes.)"""
+    ny, nx = 12, 520
+    fd = np.full((ny, nx), 2, np.int8)                 # everything runs south ...
+    fd[-1, :] = -1                                     # ... into pits in the last row
+    # the cycle: (5,256) -SW-> (6,255) -E-> (6,256) -N-> (5,256); rows 5 | 6 is the stripe boundary, columns 255 | 256 a tile edge
+    fd[5, 256], fd[6, 255], fd[6, 256] = 3, 0, 6
+    fd[5, 257] = 4                                     # a finalised donor of (5,256) from the east (column 257 above it runs south into it)
+    fd[7, 255] = 2
+    mask = np.ones((ny, nx), bool)
+    exp = oracle.basin_acum(fd, mask).astype(np.int64)
+    assert exp[5, 256] == exp[:5, 256].size + 6 and exp[6, 256] == 0     # (5 cells above + 6 through (5,257); no own +1)
+    d = torch.from_numpy(fd).cuda()
+    for G in (2, 3, 4):
+        got = stripes.accumulate_striped_single_device(d, G).cpu().numpy()
+        assert np.array_equal(got, exp), (G, np.argwhere(got != exp)[:5].tolist())
+    # the case the soak found
+    fd = helpers.random_codes(1216, 1320, 566697308)
+    exp = oracle.basin_acum(fd, np.ones(fd.shape, bool)).astype(np.int64)
+    got = stripes.accumulate_striped_single_device(torch.from_numpy(fd).cuda(), 3).cpu().numpy()
+    assert np.array_equal(got, exp), np.argwhere(got != exp)[:5].tolist()
+
+
 def test_striped_records_match_numpy_restatement():
     fd = ops.synth_scheidegger_host(130, 200, seed=11)
     rows = stripes.stripe_rows(130, 2)

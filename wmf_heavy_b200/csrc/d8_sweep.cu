@@ -2371,21 +2371,34 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
     // like everything else, and only the boundary cell itself (the path's first entry) gets it through `extra`.  64-bit
     // sums (the whole raster holds 2^32 cells or more: the 32-bit sum field cannot take it): into `extra` of every entry.
     constexpr bool VIA_WQ = sizeof(T) == 4;
-    auto to_exit = [&](int64_t x, int64_t v) { if (VIA_WQ && x >= 0) atomicAdd(&wq[x], (unsigned long long)(uint32_t)v); };
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, n2 = 2 * g.nx;
     if (i >= n2) return;
     const int plen = sp.plen[i];
     if ((int)blockIdx.y >= plen) return;
-    const int64_t v = ext_inflow[i];
+    const int64_t v0 = ext_inflow[i];
     const bool u = ext_un && ext_un[i];
-    if (v == 0 && !u) return;
+    if (v0 == 0 && !u) return;
+    // A boundary cell fed by an exit that never finalises (a drainage cycle through several stripes) never finalises
+    // either: it keeps what its finalised donors bring (v0, in `extra`), passes NOTHING on, and neither does any cell
+    // further down its path.  The stripe-local pass could not know and finalised those exits: they are marked pending
+    // again here, so that phase C's pull sees an unresolved donor instead of their (local) totals.
+    const int64_t v = u ? 0 : v0;
+    auto at_entry = [&](int64_t e, bool first) {
+        if (first) inflow_add<T>(&extra[e], (T)v0);
+        else if (!VIA_WQ && v) inflow_add<T>(&extra[e], (T)v);
+        if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
+    };
+    auto at_exit = [&](int64_t x) {
+        if (x < 0) return;
+        if (VIA_WQ && v) atomicAdd(&wq[x], (unsigned long long)(uint32_t)v);
+        if (u) atomicOr(&wq[x], PEND1);
+    };
     for (int h = blockIdx.y; h < plen; h += gridDim.y) {
         const int32_t item = sp.path[(int64_t)h * n2 + i];
         int64_t e = item & ~JUMP;
-        if (!VIA_WQ || h == 0) inflow_add<T>(&extra[e], (T)v);
-        if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
-        int64_t x = (VIA_WQ || (item & JUMP)) ? first_exit(meta, e) : -1;
-        to_exit(x, v);
+        at_entry(e, h == 0);
+        int64_t x = (VIA_WQ || u || (item & JUMP)) ? first_exit(meta, e) : -1;
+        at_exit(x);
         if (item & JUMP) {                                   // the entries the jump skipped inside its group of tile rows
             const int mr = macro_of(g, e);
             ChaseGuard cg;
@@ -2394,10 +2407,9 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
                 const int2 r = pe[x];
                 const int32_t en = r.y;
                 if (en < 0 || macro_of(g, en) != mr) break;
-                if (!VIA_WQ) inflow_add<T>(&extra[en], (T)v);
-                if (u) { extra_unres[en] = 1; tile_class[en / NSLOT] = 2; flags[F_UNRES] = 1u; }
+                at_entry(en, false);
                 x = r.x;
-                to_exit(x, v);
+                at_exit(x);
             }
         }
     }
@@ -2406,9 +2418,8 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
         ChaseGuard cg;
         for (int64_t hops = 0; hops <= nnodes; hops++) {
             if (cg.seen(e)) break;
-            if (!VIA_WQ) inflow_add<T>(&extra[e], (T)v);
-            to_exit(x, v);
-            if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
+            at_entry(e, false);
+            at_exit(x);
             if (x < 0) break;
             const int2 r = pe[x];
             if (r.y < 0) break;
