@@ -1,6 +1,7 @@
 """Randomised soak of the D8 paths against the CPU oracle (more seeds / shapes than the test suite):
     python tools/soak.py [rounds]
-accumulation (both algorithms, masks, cycles), the same in row stripes on one device, basin_cut at random outlets."""
+accumulation (both algorithms, masks, cycles, keypad codes, the optional schedules), the same in row stripes on one device,
+basin_cut at random outlets, the BFS-ordered structure."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -40,6 +41,31 @@ for it in range(rounds):
         if not np.array_equal(got, exp.astype(np.int64)):
             bad += 1
             print("MISMATCH accum", it, kind, ny, nx, algo)
+    for bands in ("2", "5"):                                  # the optional band schedule
+        os.environ["WMF_D8_BANDS"] = bands
+        got = ops.d8_accum(d, mt, acc_dtype=_lib.ACC_I64, algo=_lib.ALGO_SWEEP).cpu().numpy()
+        os.environ["WMF_D8_BANDS"] = "0"
+        if not np.array_equal(got, exp.astype(np.int64)):
+            bad += 1
+            print("MISMATCH bands", it, kind, ny, nx, bands)
+    os.environ["WMF_D8_BULK"] = "1"                           # TMA bulk-copy staging
+    got = ops.d8_accum(d, mt, acc_dtype=_lib.ACC_I32, algo=_lib.ALGO_SWEEP).cpu().numpy()
+    os.environ["WMF_D8_BULK"] = "0"
+    if not np.array_equal(got, exp.astype(np.int32)):
+        bad += 1
+        print("MISMATCH bulk", it, kind, ny, nx)
+    key = torch.from_numpy(helpers.to_keypad(fd)).cuda()
+    got = ops.d8_accum(key, mt, acc_dtype=_lib.ACC_F64, encoding=_lib.ENC_KEYPAD).cpu().numpy()
+    if not np.array_equal(got, exp.astype(np.float64)):
+        bad += 1
+        print("MISMATCH keypad/f64", it, kind, ny, nx)
+    if kind in ("steep", "sch") and mask is None:            # BFS-ordered structure (the Fortran flavour has no mask)
+        r0, c0 = np.unravel_index(np.argmax(exp), exp.shape)
+        est = oracle.f_basin_find(helpers.to_keypad(fd), int(c0) + 1, int(r0) + 1)
+        st = ops.basin_structure(key, int(c0) + 1, int(r0) + 1).cpu().numpy()
+        if not np.array_equal(st, est):
+            bad += 1
+            print("MISMATCH structure", it, kind, ny, nx)
     for G in (2, 3, 5):
         if ny >= 2 * G:
             got = stripes.accumulate_striped_single_device(d, G, mask_t=mt, acc_dtype=_lib.ACC_I64).cpu().numpy()
