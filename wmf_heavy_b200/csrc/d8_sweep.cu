@@ -126,7 +126,8 @@ __device__ __forceinline__ T chain_carry_from_right(T A, bool P, int lane)
     return lane == 31 ? (T)0 : c;
 }
 // copy-scans for labels: value of the chain end is copied back along the chain
-__device__ __forceinline__ uint32_t label_carry_from_right(uint32_t V, bool P, int lane)
+// (phase A keeps a label as the shared-memory ADDRESS of its histogram bin -- see k_sweepA --, so "no exit" is a parameter)
+__device__ __forceinline__ uint32_t label_carry_from_right(uint32_t V, bool P, int lane, uint32_t none = LNONE)
 {
     if (__ballot_sync(FULL, P) != 0) {
         int p = P;
@@ -135,13 +136,13 @@ __device__ __forceinline__ uint32_t label_carry_from_right(uint32_t V, bool P, i
             uint32_t v2 = __shfl_down_sync(FULL, V, off);
             int p2 = __shfl_down_sync(FULL, p, off);
             if (lane + off < 32) { if (p) V = v2; p &= p2; }
-            else if (p) { V = LNONE; }
+            else if (p) { V = none; }
         }
     }
     uint32_t c = __shfl_down_sync(FULL, V, 1);
-    return lane == 31 ? LNONE : c;
+    return lane == 31 ? none : c;
 }
-__device__ __forceinline__ uint32_t label_carry_from_left(uint32_t V, bool P, int lane)
+__device__ __forceinline__ uint32_t label_carry_from_left(uint32_t V, bool P, int lane, uint32_t none = LNONE)
 {
     if (__ballot_sync(FULL, P) != 0) {
         int p = P;
@@ -150,11 +151,11 @@ __device__ __forceinline__ uint32_t label_carry_from_left(uint32_t V, bool P, in
             uint32_t v2 = __shfl_up_sync(FULL, V, off);
             int p2 = __shfl_up_sync(FULL, p, off);
             if (lane >= off) { if (p) V = v2; p &= p2; }
-            else if (p) { V = LNONE; }
+            else if (p) { V = none; }
         }
     }
     uint32_t c = __shfl_up_sync(FULL, V, 1);
-    return lane == 0 ? LNONE : c;
+    return lane == 0 ? none : c;
 }
 
 // ---- packed variant for int32 accumulations -----------------------------------------------------
@@ -725,16 +726,21 @@ __device__ __forceinline__ void plain_row_down_mk(const uint32_t (&kw)[NWD], con
 // Upward (label) step of a plain row of a full interior tile.  A plain row has no pits, so an East
 // cell's own term is 0 and "copy the chain end" is own + next * E.  slotL / slotR: boundary slots of
 // the left- / right-column cell of this row.  BOTTOM: the tile's last row, where S / SE / SW leave the tile.
+// Labels are kept as base + 4 * slot -- the shared-memory address of the label's histogram bin, so that counting a label
+// is one `red.shared` with no address arithmetic; every step below only ever selects ONE label, so the form survives.
 template <bool BOTTOM, bool MK>
 __device__ __forceinline__ void plain_row_up(const uint32_t (&kw)[NWD], const uint32_t (&dv)[NWD], uint32_t (&lb)[NC], int lane,
-                                             uint32_t slotL, uint32_t slotR)
+                                             uint32_t slotL, uint32_t slotR, uint32_t base)
 {
+    const uint32_t none = base + 4u * LNONE;
+    slotL = base + 4u * slotL; slotR = base + 4u * slotR;
     RowBits m = MK ? row_bits_mk(kw, dv, nullptr) : row_bits(kw);
     uint32_t own[NC];
     if (BOTTOM) {
+        const uint32_t first = base + 4u * (uint32_t)(TW + NC * lane);
 #pragma unroll
         for (int j = 0; j < NC; j++)
-            own[j] = MK ? (uint32_t)(TW + NC * lane + j) * (m.se[j] + m.s[j] + m.sw[j]) : (uint32_t)(TW + NC * lane + j) * (1u - m.e[j]);
+            own[j] = MK ? (first + 4u * j) * (m.se[j] + m.s[j] + m.sw[j]) : (first + 4u * j) * (1u - m.e[j]);
     } else {
         const uint32_t lbR0 = __shfl_down_sync(FULL, lb[0], 1), lbL = __shfl_up_sync(FULL, lb[NC - 1], 1);
 #pragma unroll
@@ -747,17 +753,17 @@ __device__ __forceinline__ void plain_row_up(const uint32_t (&kw)[NWD], const ui
         uint32_t has[NC];
         byte_flags(dv, has);
 #pragma unroll
-        for (int j = 0; j < NC; j++) own[j] += LNONE * (1u - has[j]);
+        for (int j = 0; j < NC; j++) own[j] += none * (1u - has[j]);
     }
     const uint32_t kR = (kw[NWD - 1] >> 24) & 0xFFu, kL = kw[0] & 0xFFu;
     const bool dR = !MK || (dv[NWD - 1] >> 24) != 0, dL = !MK || (dv[0] & 0xFFu) != 0;
     if (lane == 31 && dR && kR <= 1u) { own[NC - 1] = slotR; m.e[NC - 1] = 0; }   // E / SE leave through the right column
     if (lane == 0 && dL && kL == 3u) own[0] = slotL;                              // SW leaves through the left column
-    uint32_t V = own[NC - 1] + LNONE * m.e[NC - 1];          // label at cell 0 if nothing comes from the right
+    uint32_t V = own[NC - 1] + none * m.e[NC - 1];           // label at cell 0 if nothing comes from the right
     uint32_t allE = m.e[NC - 1];
 #pragma unroll
     for (int j = NC - 2; j >= 0; j--) { V = V * m.e[j] + own[j]; allE &= m.e[j]; }
-    uint32_t cur = label_carry_from_right(V, allE != 0, lane);
+    uint32_t cur = label_carry_from_right(V, allE != 0, lane, none);
 #pragma unroll
     for (int j = NC - 1; j >= 0; j--) { cur = cur * m.e[j] + own[j]; lb[j] = cur; }
 }
@@ -824,9 +830,13 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #define WMF_BAR_A (hist_sa + 4u * BAR_BIN)
     TileRows<AL, TM> rows;
     rows.init(s_dyn, warp, lane, dir, mask, g.nx, gr0, gc0, th, WMF_BAR_A);
-    auto count_labels = [&](const uint32_t (&lab)[NC]) {      // (a label is a bin index as it is: slot or LNONE)
+    // A label is kept as the shared-memory address of its bin, hist_sa + 4 * (slot or LNONE): counting it needs no
+    // address arithmetic (8 instructions per row of ~195); slot_label() gives the slot back where a meta word is packed.
+    const uint32_t lnone = hist_sa + 4u * LNONE;
+    auto slot_label = [&](uint32_t lab) { return (lab - hist_sa) >> 2; };
+    auto count_labels = [&](const uint32_t (&lab)[NC]) {
 #pragma unroll
-        for (int j = 0; j < NC; j++) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_sa + 4u * lab[j]) : "memory");
+        for (int j = 0; j < NC; j++) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(lab[j]) : "memory");
     };
     // side-column slots of a full tile sit in lanes 0 / 31; their forest words are set in one go at the end
     uint32_t *m_side = m_t + 2 * TW + (lane == 31 ? TH : 0);
@@ -836,7 +846,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     unsigned long long plain_rows = 0;               // bit lr set: row lr takes the lean path (here and in phase C)
     uint32_t lb[NC];
 #pragma unroll
-    for (int j = 0; j < NC; j++) lb[j] = LNONE;      // labels of the row below
+    for (int j = 0; j < NC; j++) lb[j] = lnone;      // labels of the row below
     rows.prefetch(nch - 1, WMF_BAR_A);
     int c_left = nch - 1;                            // the chunk that is in flight when the loop ends early (-1: none)
     for (int c = nch - 1; c >= 0 && !complex_tile; c--) {
@@ -855,19 +865,20 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             if (!gen) {
                 plain_rows |= 1ull << lr;
                 if (lr == 0 || lr == TH - 1) {        // first / last row of the tile: every cell is a boundary slot
-                    if (lr == 0) plain_row_up<false, MK>(kw, dv, lb, lane, 0u, (uint32_t)(TW - 1));
-                    else plain_row_up<true, MK>(kw, dv, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1));
+                    if (lr == 0) plain_row_up<false, MK>(kw, dv, lb, lane, 0u, (uint32_t)(TW - 1), hist_sa);
+                    else plain_row_up<true, MK>(kw, dv, lb, lane, (uint32_t)TW, (uint32_t)(2 * TW - 1), hist_sa);
                     uint32_t mw[NC];
 #pragma unroll
                     for (int j = 0; j < NC; j++)
-                        mw[j] = MK ? meta_pack(lb[j], plain_k_mk(kw, dv, j), false, flag_of(av, j)) : meta_pack(lb[j], plain_k(kw, j), false, true);
+                        mw[j] = MK ? meta_pack(slot_label(lb[j]), plain_k_mk(kw, dv, j), false, flag_of(av, j))
+                                   : meta_pack(slot_label(lb[j]), plain_k(kw, j), false, true);
                     store_meta_row(lr == 0 ? 0 : TW, mw);
                 } else {
-                    plain_row_up<false, MK>(kw, dv, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr));
+                    plain_row_up<false, MK>(kw, dv, lb, lane, (uint32_t)(2 * TW + lr), (uint32_t)(2 * TW + TH + lr), hist_sa);
                     if (lane == 0 || lane == 31) {
                         const int js = lane ? NC - 1 : 0;
-                        m_side[lr] = MK ? meta_pack(lane ? lb[NC - 1] : lb[0], plain_k_mk(kw, dv, js), false, flag_of(av, js))
-                                        : meta_pack(lane ? lb[NC - 1] : lb[0], plain_k(kw, js), false, true);
+                        const uint32_t ls = slot_label(lane ? lb[NC - 1] : lb[0]);
+                        m_side[lr] = MK ? meta_pack(ls, plain_k_mk(kw, dv, js), false, flag_of(av, js)) : meta_pack(ls, plain_k(kw, js), false, true);
                     }
                 }
                 count_labels(lb);
@@ -902,10 +913,10 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
                 const bool top = lr == 0, bot = lr == th - 1, lft = lc == 0, rgt = lc == tw - 1;
                 bool exits = (bot && kk >= 1 && kk <= 3) || (top && kk >= 5 && kk <= 7) ||
                              (rgt && (kk == 0 || kk == 1 || kk == 7)) || (lft && kk >= 3 && kk <= 5);
-                uint32_t v = LNONE;
+                uint32_t v = lnone;
                 pe[j] = pw[j] = false;
                 if (kk != 8) {
-                    if (exits) v = (uint32_t)slot_of(lr, lc, th, tw);
+                    if (exits) v = hist_sa + 4u * (uint32_t)slot_of(lr, lc, th, tw);
                     else if (kk == 2) v = lb[j];
                     else if (kk == 1) v = (j < NC - 1) ? lb[j < NC - 1 ? j + 1 : 0] : lb_right0;
                     else if (kk == 3) v = (j > 0) ? lb[j > 0 ? j - 1 : 0] : lb_left;
@@ -916,11 +927,11 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
             }
             uint32_t lab[NC];
             {   // East cells copy the label of the chain end on their right
-                uint32_t V = LNONE;
+                uint32_t V = lnone;
                 bool P = true;
 #pragma unroll
                 for (int j = NC - 1; j >= 0; j--) { V = pe[j] ? V : own[j]; P = P && pe[j]; }
-                uint32_t cur = label_carry_from_right(V, P, lane);
+                uint32_t cur = label_carry_from_right(V, P, lane, lnone);
 #pragma unroll
                 for (int j = NC - 1; j >= 0; j--) { cur = pe[j] ? cur : own[j]; lab[j] = cur; }
             }
@@ -928,11 +939,11 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
             for (int j = 0; j < NC; j++) anyw = anyw || pw[j];
             if (__any_sync(FULL, anyw)) {
-                uint32_t V = LNONE;
+                uint32_t V = lnone;
                 bool P = true;
 #pragma unroll
                 for (int j = 0; j < NC; j++) { V = pw[j] ? V : lab[j]; P = P && pw[j]; }
-                uint32_t cur = label_carry_from_left(V, P, lane);
+                uint32_t cur = label_carry_from_left(V, P, lane, lnone);
 #pragma unroll
                 for (int j = 0; j < NC; j++) { cur = pw[j] ? cur : lab[j]; lab[j] = cur; }
             }
@@ -940,7 +951,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
 #pragma unroll
             for (int j = 0; j < NC; j++) {
                 lb[j] = lab[j];
-                mw[j] = meta_pack(lab[j], k[j], false, (am >> j) & 1);
+                mw[j] = meta_pack(slot_label(lab[j]), k[j], false, (am >> j) & 1);
             }
             if (lr == 0 || lr == th - 1) store_meta_row(lr == 0 ? 0 : TW, mw);
             else {
