@@ -45,6 +45,12 @@ constexpr uint32_t FULL = 0xffffffffu;
 constexpr int F_COMPLEX = 0, F_CHAIN = 1, F_UNRES = 2;   // tiles for the jump solver / for the chain walk / fed by an unresolved upstream
 constexpr int F_NEXT_A = 4, F_NEXT_C = 5;                // work counters of the jump kernels
 constexpr int NFLAGS = 8;
+// raise a work flag: on a terrain raster EVERY tile raises the same one, so only those who still read 0 store (measured:
+// no difference -- the 190 us k_sweepA spends on a 16384^2 terrain raster before its tiles give up are not these stores)
+__device__ __forceinline__ void raise_flag(uint32_t *flags, int which)
+{
+    if (__ldcg(&flags[which]) == 0u) flags[which] = 1u;
+}
 
 // meta word of a boundary slot: [15:0] link, [19:16] k, [20] locally unresolved, [21] active
 __host__ __device__ __forceinline__ uint32_t meta_pack(uint32_t link, int k, bool unres, bool active)
@@ -967,7 +973,7 @@ __global__ void __launch_bounds__(WPB * 32, 6) k_sweepA(const int8_t *__restrict
     rows.drain(c_left, nch - 1 - c_left, WMF_BAR_A);
 #undef WMF_BAR_A
     if (complex_tile) {                              // the general solver redoes this tile
-        if (lane == 0) { tile_class[tile] = 1; tile_top[tile] = 1; flags[has_multi ? F_COMPLEX : F_CHAIN] = 1u; }
+        if (lane == 0) { tile_class[tile] = 1; tile_top[tile] = 1; raise_flag(flags, has_multi ? F_COMPLEX : F_CHAIN); }
         return;
     }
     // tile_top: can an inner first-row slot of this tile be an exit?  Only through upward flow in row 0 (never in a
@@ -1570,7 +1576,7 @@ __global__ void __launch_bounds__(JTA, 4) k_jumpA(const int8_t *__restrict__ dir
             open = __syncthreads_or(all != 0x80008000u) != 0;
         }
         if (open) {                                      // a cycle: the chain-walk solver redoes this tile
-            if (threadIdx.x == 0) { tile_class[tile] = 3; tile_top[tile] = 1; flags[F_CHAIN] = 1u; }
+            if (threadIdx.x == 0) { tile_class[tile] = 3; tile_top[tile] = 1; raise_flag(flags, F_CHAIN); }
             continue;
         }
         // exit_acc: the histogram of the labels (runs of equal labels along a row are counted at once)
@@ -2164,7 +2170,7 @@ __global__ void k_g_unres(Geo g, int64_t nnodes, const uint8_t *__restrict__ til
         const int tile = (int)(i / NSLOT), ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
         int s2;
         const int te = exit_target(g, tg, ty, tx, (int)(i - (int64_t)tile * NSLOT), w_k(w), true, s2);
-        if (te >= 0) { tile_class[te] = 2; flags[F_UNRES] = 1u; }   // (racing writers all store the same values)
+        if (te >= 0) { tile_class[te] = 2; raise_flag(flags, F_UNRES); }   // (racing writers all store the same values)
     }
 }
 
@@ -2397,7 +2403,7 @@ __global__ void k_stripe_route(Geo g, int64_t nnodes, const uint32_t *__restrict
     auto at_entry = [&](int64_t e, bool first) {
         if (first) inflow_add<T>(&extra[e], (T)v0);
         else if (!VIA_WQ && v) inflow_add<T>(&extra[e], (T)v);
-        if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; flags[F_UNRES] = 1u; }
+        if (u) { extra_unres[e] = 1; tile_class[e / NSLOT] = 2; raise_flag(flags, F_UNRES); }
     };
     auto at_exit = [&](int64_t x) {
         if (x < 0) return;
