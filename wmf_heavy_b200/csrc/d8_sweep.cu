@@ -2047,7 +2047,7 @@ __global__ void __launch_bounds__(NSLOT) k_g_build(Geo g, int ntiles, const uint
         if (MODE == 2 && mine[u]) mine[u] = bc.gstate[tile0 + u] == 0;
     }
     if (MODE != 0) {
-        __syncthreads();                                     // (mode 2: everybody has read gstate before it changes)
+        if (MODE == 2) __syncthreads();                      // (mode 2: everybody has read gstate before it changes)
         if (s == 0) {
 #pragma unroll
             for (int u = 0; u < BU; u++) if (mine[u]) bc.gstate[tile0 + u] = 1;
@@ -2095,8 +2095,8 @@ constexpr size_t GCNT_BYTES = sizeof(unsigned long long) * 4 * GCNT;
 // inner first-row slots of a full tile whose row 0 has no upward flow are never exits: k_g_build left their words alone
 __device__ __forceinline__ bool node_is_skipped(const uint8_t *__restrict__ tile_top, int64_t i)
 {
-    const int tile = (int)(i / NSLOT), s = (int)(i - (int64_t)tile * NSLOT);
-    return s > 0 && s < TW - 1 && !tile_top[tile];
+    const uint32_t iu = (uint32_t)i, tile = iu / (uint32_t)NSLOT, s = iu - tile * (uint32_t)NSLOT;   // (node ids are below 2^31)
+    return s > 0u && s < (uint32_t)(TW - 1) && !tile_top[tile];
 }
 
 
@@ -2113,12 +2113,12 @@ __global__ void __launch_bounds__(256) k_g_walk(int64_t nnodes, const uint8_t *_
     bool mine = i < nnodes;
     int32_t p = (mine && !node_is_skipped(tile_top, i)) ? __ldcs(&par[i]) : PAR_NONE;     // (in flight before the band tests below)
     if (MODE != 0 && mine) {
-        const int tile = (int)(i / NSLOT);
+        const int tile = (int)((uint32_t)i / (uint32_t)NSLOT);
         if (MODE == 1) mine = band_clean(bc) || band_around(g, tile, bc.gstate, false);
         else mine = bc.gstate[tile] != 2;
         // The tile's mark is set by the thread of its slot 0: 2 in a band launch -- others in the same launch only ask
         // "built?", and 1 and 2 both say yes -- and 3 in the rest launch, whose test "!= 2" it does not change.
-        if (mine && i - (int64_t)tile * NSLOT == 0) bc.gstate[tile] = MODE == 1 ? 2 : 3;
+        if (mine && (uint32_t)i == (uint32_t)tile * (uint32_t)NSLOT) bc.gstate[tile] = MODE == 1 ? 2 : 3;
     }
     if (!mine) p = PAR_NONE;
     const bool walk = p != PAR_NONE;
@@ -2669,11 +2669,11 @@ static SideStream *side_stream()
 // build and walk remain behind phase A.  Phase A is held to four blocks per SM (padding of unused shared memory) so
 // that the small blocks of the forest kernels find registers beside it.  Tiles of the jump / chain-walk solvers get their
 // meta words after all bands: they and their neighbours are built and started by the mode-2 launches that follow.
-// OPT-IN (WMF_D8_BANDS=B in the environment), because the gain does not survive: a first version for rasters of
-// one-pass tiles only measured 0.700 -> 0.634 ms at 16384^2 with 8 bands (5 blocks per SM 0.662, 6 blocks 0.674; 4 / 12 /
-// 16 bands 0.637 / 0.670 / 0.702), but with the marks and the trailing launches that mixed rasters need it is 0.66 to
-// 0.71 ms depending on nothing but the order and size of the small launches around it -- how the block scheduler
-// interleaves three streams is not something this code controls.  Bit-identical either way (test_band_schedule).
+// OPT-IN (WMF_D8_BANDS=B in the environment), because the gain is small and has a narrow sweet spot: a first version for
+// rasters of one-pass tiles only measured 0.700 -> 0.634 ms at 16384^2 with 8 bands (5 blocks per SM 0.662, 6 blocks
+// 0.674; 4 / 12 / 16 bands 0.637 / 0.670 / 0.702); with the marks (+8 us) and the trailing launches (+16 us) that mixed
+// rasters need, 8 bands take 0.678 ms against 0.695 unbanded, and 4 / 6 / 10 bands 0.695 / 0.687 / 0.704 -- how the block
+// scheduler interleaves three streams is not something this code controls.  Bit-identical either way (test_band_schedule).
 constexpr int MAXB = 16;
 struct BandRes { cudaStream_t sA, sG; cudaEvent_t fork, evA[MAXB], evG; std::mutex busy; };
 static BandRes *band_res()
