@@ -180,7 +180,7 @@ def calc_speed(sm, coef, expo, elem_long, speed, dt, calc_niter):
 def shia_v1(N_cel, N_reg, calib, v_coef, h_coef, h_exp, Max_capilar, Max_gravita, Max_aquifer, hill_long, elem_area,
             rain_records, posEvento, EvpSerie, dt, speed_type, retorno_gr, retorno_aq, calc_niter, StoIn=None, HspeedIn=None,
             Storage=None, storage_constant=0.001, show_storage=0, show_mean_speed=0, show_mean_retorno=0, save_vfluxes=0,
-            save_rc=0):
+            save_rc=0, save_speed=0, save_retorno=0, step_records=None):
     """The time and cell loops as shipped (no routing: tank 5, drena and Q are never touched).
 
     Per-cell tables are (k, N_cel) arrays indexed [i - 1, celda - 1] where the Fortran says (i, celda); rain record r is
@@ -278,6 +278,12 @@ def shia_v1(N_cel, N_reg, calib, v_coef, h_coef, h_exp, Max_capilar, Max_gravita
         if save_vfluxes == 1:
             for i in range(4):
                 mean_vfluxes[i, tiempo - 1] = _sum_seq(vfluxes[i]) / f32(N_cel)
+            if step_records is not None:                 # :504-506 (the caller picks the steps guarda_vfluxes marks)
+                step_records.setdefault("vfluxes", []).append(vfluxes.copy())
+        if save_speed == 1 and step_records is not None:         # :509-511 write_float_basin(ruta_speed, hspeed, tiempo, ...)
+            step_records.setdefault("speed", []).append(hspeed.copy())
+        if save_retorno == 1 and step_records is not None:       # :513-515 write_float_basin(ruta_retorno, Retorned, tiempo, ...)
+            step_records.setdefault("retorno", []).append(Retorned.copy())
         if show_storage == 1:
             for i in range(5):
                 mean_storage[i, tiempo - 1] = _sum_seq(StoOut[i]) / f32(N_cel)
@@ -286,6 +292,7 @@ def shia_v1(N_cel, N_reg, calib, v_coef, h_coef, h_exp, Max_capilar, Max_gravita
                 mean_speed[i, tiempo - 1] = _sum_seq(hspeed[i]) / f32(N_cel)
         if show_mean_retorno == 1:
             mean_retorno[tiempo - 1] = _sum_seq(Retorned) / f32(N_cel)
+        if show_mean_retorno == 1 or save_retorno == 1:          # :529-531
             Retorned[:] = f32(0.0)
         balance[tiempo - 1] = _sum_seq(StoOut) - StoAtras - entradas + salidas
         entradas = f32(0.0)

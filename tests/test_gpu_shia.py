@@ -280,6 +280,67 @@ def test_shia_v1_writes_storage_records(tmp_path):
         np.testing.assert_allclose(res2[9], res[9], rtol=1e-6, atol=1e-6)  # (speed_type 1: hspeed carries no state)
 
 
+def test_shia_v1_writes_step_records(tmp_path):
+    """models.shia_v1 with save_speed / save_retorno / save_vfluxes + guarda_vfluxes (Modelos_heavy.f90:502-515): record t
+    of ruta_speed = hspeed after step t, record t of ruta_retorno = the return flow of step t, record guarda_vfluxes(t)
+    of ruta_vfluxes = the vertical fluxes of step t -- against the literal transliteration run with the same flags
+    (kinematic speeds in two tanks so that hspeed changes from step to step, returns on)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fortran_transliteration",
+                                                  os.path.join(os.path.dirname(__file__), "golden", "fortran_transliteration.py"))
+    ft = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ft)
+    N, T = 60, 14
+    inp = helpers.shia5_inputs(oracle, N, T, 191, speed_type=(2, 1, 2))
+    models.v_coef, models.h_coef, models.h_exp = inp.v_coef, inp.h_coef, inp.h_exp
+    models.max_capilar, models.max_gravita, models.max_aquifer = (a[None] for a in (inp.max_capilar, inp.max_gravita, inp.max_aquifer))
+    models.hill_long, models.elem_area = inp.hill_long[None], inp.elem_area[None]
+    models.speed_type, models.evpserie, models.dt = np.array([2, 1, 2]), inp.evp, inp.dt
+    models.storage, models.storage_constant, models.rain_first_point = None, 0.001, 1
+    models.retorno_gr, models.retorno_aq, models.calc_niter = 1, 1, 5
+    models.control, models.control_h = np.zeros((1, N), np.int32), np.zeros((1, N), np.int32)
+    path = str(tmp_path / "rain")
+    models.write_rain(path + ".bin", path + ".hdr", inp.rain_records, inp.pos_evento)
+    sp_path, re_path, vf_path = (str(tmp_path / nm) for nm in ("speed.bin", "retorno.bin", "vfluxes.bin"))
+    gv = np.zeros(T, np.int32)
+    gv[[2, 7, 13]] = [1, 2, 3]
+    models.save_speed = models.save_retorno = models.save_vfluxes = 1
+    models.guarda_vfluxes = gv
+    models.strict_arithmetic = 1
+    cal = np.linspace(0.8, 1.3, 11).astype(np.float32)
+    try:
+        res = models.shia_v1(path + ".bin", path + ".hdr", cal, N, 1, 0, T, None, None, None, sp_path, vf_path,
+                             None, None, None, None, re_path, None)
+    finally:
+        models.save_speed = models.save_retorno = models.save_vfluxes = 0
+        models.guarda_vfluxes = None
+        models.strict_arithmetic = 0
+        models.retorno_gr = models.retorno_aq = 0
+    recs = {}
+    exp = ft.shia_v1(N, T, cal, inp.v_coef, inp.h_coef, inp.h_exp, inp.max_capilar, inp.max_gravita, inp.max_aquifer,
+                     inp.hill_long, inp.elem_area, inp.rain_records, inp.pos_evento, inp.evp, inp.dt, (2, 1, 2, 1), 1, 1, 5,
+                     save_vfluxes=1, save_speed=1, save_retorno=1, step_records=recs)
+    assert os.path.getsize(sp_path) == T * 4 * N * 4 and os.path.getsize(re_path) == T * N * 4
+    assert os.path.getsize(vf_path) == 3 * 4 * N * 4
+    changed = 0
+    for t in range(T):
+        v, rc = models.read_float_basin_ncol(sp_path, t + 1, N, 4)
+        assert rc == 0
+        np.testing.assert_allclose(v, recs["speed"][t], rtol=3e-4, atol=1e-9)
+        changed += t > 0 and not np.array_equal(recs["speed"][t], recs["speed"][t - 1])
+        r, rc = models.read_float_basin(re_path, t + 1, N)
+        assert rc == 0
+        np.testing.assert_allclose(r, recs["retorno"][t], rtol=1e-5, atol=ATOL_STRICT)
+    assert changed > T // 2                                   # (the kinematic speeds do move)
+    assert any(r.any() for r in recs["retorno"])              # (and there is return flow to record)
+    for rec, t in ((1, 2), (2, 7), (3, 13)):
+        v, rc = models.read_float_basin_ncol(vf_path, rec, N, 4)
+        assert rc == 0
+        np.testing.assert_allclose(v, recs["vfluxes"][t], rtol=1e-5, atol=ATOL_STRICT)
+    np.testing.assert_allclose(res[9], exp["StoOut"], rtol=1e-5, atol=ATOL_STRICT)           # the run's ordinary outputs
+
+
 def test_shia5_population_many_sets():
     """BASELINE config 5 in small: many parameter sets in one launch (grid.y), each equal to its own oracle run."""
     N, T, P = 3000, 37, 96

@@ -203,29 +203,20 @@ def cell_static_table(n: int) -> np.ndarray:
 
 
 def _reject_out_of_scope():
-    for nm in ("sim_sediments", "sim_slides", "sim_floods", "separate_rain", "save_speed", "save_retorno"):
+    for nm in ("sim_sediments", "sim_slides", "sim_floods", "separate_rain"):
         if int(globals()[nm]) == 1:
             raise NotImplementedError(f"models.{nm} = 1 is outside the B200 hot path (see DESIGN.md, out of scope)")
-    if int(save_vfluxes) == 1 and guarda_vfluxes is not None and np.any(np.asarray(guarda_vfluxes) > 0):
-        raise NotImplementedError("per-step vertical-flux records (guarda_vfluxes) are outside the hot path; "
-                                  "mean_vfluxes and the last step's vfluxes are returned")
 
 
-def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int, sto_in=None, hspeed_in=None,
-                       device_out: bool = False, save_records=None):
-    """P parameter sets x one basin in one launch.  ``calibs`` (P, 11); ``sto_in`` (5, N) or (P, 5, N).
-    ``save_records`` int [N_reg] (guarda_cond): steps with a record number > 0 return their storages in
-    ``out["snapshots"]`` [P, n_snap, 5, N] together with ``out["snapshot_records"]`` (record number per slot)."""
-    global mean_rain, acum_rain, mean_storage, mean_speed, mean_retorno, mean_vfluxes, vfluxes, rc_coef, retorned
-    _reject_out_of_scope()
-    dev = require_cuda()
+def _prepare_inputs(calibs, rain_records, pos_evento, n_cel: int, n_reg: int, sto_in, hspeed_in):
+    """Device copies of everything one shia_v1 run reads: (cell_static, rain records, posEvento, evp, calib, sto, hspeed
+    or None, speed_type).  Packed and uploaded on every call: the tables are module state the caller edits in place between
+    runs (a calibration loop scales h_coef / max_capilar ...), and 68 B/cell is small next to the run itself."""
     cal = np.atleast_2d(np.asarray(calibs, dtype=np.float32))
     if cal.shape[1] != 11:
         raise ValueError("calib must have 11 entries (Modelos_heavy.f90:177)")
     P = cal.shape[0]
-    # packed and uploaded on every call: the tables are module state the caller edits in place between runs (a
-    # calibration loop scales h_coef / max_capilar ...), and 68 B/cell is small next to the run itself
-    cs = (None, to_dev(cell_static_table(n_cel)))
+    cs = to_dev(cell_static_table(n_cel))
     rr = rain_records if isinstance(rain_records, torch.Tensor) else to_dev(np.ascontiguousarray(rain_records, dtype=np.int32))
     pe = pos_evento if isinstance(pos_evento, torch.Tensor) else to_dev(np.asarray(pos_evento, dtype=np.int32)[:n_reg])
     if evpserie is None:
@@ -250,7 +241,56 @@ def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int,
         h0 = np.asarray(hspeed_in, dtype=np.float32)
         h0 = np.broadcast_to(h0.reshape((-1, 4, n_cel)), (P, 4, n_cel))
         hs = to_dev(np.ascontiguousarray(h0))
-    st = np.asarray(speed_type).astype(int).reshape(-1)[:3]
+    st = tuple(np.asarray(speed_type).astype(int).reshape(-1)[:3])
+    return cs, rr, pe, ev, to_dev(cal), sto, hs, st
+
+
+def write_step_records(calib, rain_records, pos_evento, n_cel: int, n_reg: int, sto_in=None, hspeed_in=None,
+                       ruta_speed=None, ruta_retorno=None, ruta_vfluxes=None) -> None:
+    """The per-step record files of the shipped routine (Modelos_heavy.f90:502-515): with ``save_speed`` record t of
+    ``ruta_speed`` holds hspeed (4 columns) after step t, with ``save_retorno`` record t of ``ruta_retorno`` the return
+    flow of step t (Retorned is cleared after every step then, :529-531), and with ``save_vfluxes`` record
+    ``guarda_vfluxes(t)`` (> 0) of ``ruta_vfluxes`` the vertical fluxes of step t.  The time-fused kernel keeps none of this
+    per step, so the records come from a SECOND pass that advances the same kernel one step at a time (state and speeds
+    carried on the device); the run's ordinary outputs are those of the single fused run and do not depend on it."""
+    want_speed = int(save_speed) == 1 and bool(ruta_speed)
+    want_ret = int(save_retorno) == 1 and bool(ruta_retorno)
+    gv = None
+    if int(save_vfluxes) == 1 and ruta_vfluxes and guarda_vfluxes is not None:
+        gv = np.asarray(guarda_vfluxes).astype(np.int64).reshape(-1)
+        if gv.size < n_reg:
+            raise ValueError("guarda_vfluxes is shorter than N_reg")
+        if not np.any(gv[:n_reg] > 0):
+            gv = None
+    if not (want_speed or want_ret or gv is not None):
+        return
+    cs, rr, pe, ev, cal, sto, hs, st = _prepare_inputs(np.asarray(calib, dtype=np.float32).reshape(1, -1), rain_records,
+                                                        pos_evento, n_cel, n_reg, sto_in, hspeed_in)
+    ops._check_pos_evento(pe, rr.shape[0])
+    for t in range(n_reg):
+        want_vf = gv is not None and gv[t] > 0
+        out = ops.shia5_run(cs, rr, pe[t:t + 1], ev[t:t + 1], cal, sto, hs, dt=float(dt), retorno_gr=float(retorno_gr),
+                            retorno_aq=float(retorno_aq), calc_niter=int(calc_niter), speed_type=st, validate=False,
+                            strict=bool(int(strict_arithmetic)), save_vfluxes=bool(want_vf), with_retorned=want_ret)
+        sto, hs = out["StoOut"], out["hspeed"]
+        if want_speed:
+            write_float_basin(ruta_speed, hs[0].cpu().numpy(), t + 1, n_cel, 4)
+        if want_ret:
+            write_float_basin(ruta_retorno, out["retorned"][0].cpu().numpy().reshape(1, n_cel), t + 1, n_cel, 1)
+        if want_vf:
+            write_float_basin(ruta_vfluxes, out["vfluxes"][0].cpu().numpy(), int(gv[t]), n_cel, 4)
+
+
+def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int, sto_in=None, hspeed_in=None,
+                       device_out: bool = False, save_records=None):
+    """P parameter sets x one basin in one launch.  ``calibs`` (P, 11); ``sto_in`` (5, N) or (P, 5, N).
+    ``save_records`` int [N_reg] (guarda_cond): steps with a record number > 0 return their storages in
+    ``out["snapshots"]`` [P, n_snap, 5, N] together with ``out["snapshot_records"]`` (record number per slot)."""
+    global mean_rain, acum_rain, mean_storage, mean_speed, mean_retorno, mean_vfluxes, vfluxes, rc_coef, retorned
+    _reject_out_of_scope()
+    dev = require_cuda()
+    cs_dev, rr, pe, ev, cal_dev, sto, hs, st = _prepare_inputs(calibs, rain_records, pos_evento, n_cel, n_reg, sto_in, hspeed_in)
+    P = cal_dev.shape[0]
     snap_slot, snap_recs = None, None
     if save_records is not None:
         g = np.asarray(save_records).astype(np.int64).reshape(-1)
@@ -266,7 +306,7 @@ def shia_v1_population(calibs, rain_records, pos_evento, n_cel: int, n_reg: int,
             slot = np.full(n_reg, -1, dtype=np.int32)
             slot[steps] = np.arange(steps.size, dtype=np.int32)
             snap_slot, snap_recs = to_dev(slot), g[steps].copy()
-    out = ops.shia5_run(cs[1], rr, pe, ev, to_dev(cal), sto, hs, dt=float(dt), retorno_gr=float(retorno_gr),
+    out = ops.shia5_run(cs_dev, rr, pe, ev, cal_dev, sto, hs, dt=float(dt), retorno_gr=float(retorno_gr),
                         retorno_aq=float(retorno_aq), calc_niter=int(calc_niter), speed_type=tuple(st),
                         show_storage=bool(show_storage), show_mean_speed=bool(show_mean_speed), snap_slot=snap_slot,
                         n_snap=0 if snap_recs is None else int(snap_recs.size), strict=bool(int(strict_arithmetic)),
@@ -310,6 +350,7 @@ def shia_v1(ruta_bin, ruta_hdr, calib, n_cel, n_cont, n_conth, n_reg, stoin=None
     if int(route_channels) == 1:
         return _shia_v1_routed(cal, records, pos, n_cel, n_cont, n_conth, n_reg, stoin)
     out = shia_v1_population(cal[None, :], records, pos, n_cel, n_reg, stoin, hspeedin, save_records=save)
+    write_step_records(cal, records, pos, n_cel, n_reg, stoin, hspeedin, ruta_speed, ruta_retorno, ruta_vfluxes)
     if int(save_rc) == 1 and ruta_rc:                # Modelos_heavy.f90:543-544: one record of two columns
         write_float_basin(ruta_rc, out["rc_coef"][0], 1, n_cel, 2)
     if out.get("snapshot_records") is not None:      # in time order, like the Fortran loop writes them
