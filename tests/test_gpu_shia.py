@@ -309,8 +309,11 @@ def test_shia_v1_writes_step_records(tmp_path):
     models.guarda_vfluxes = gv
     models.strict_arithmetic = 1
     cal = np.linspace(0.8, 1.3, 11).astype(np.float32)
+    rng = np.random.default_rng(192)                          # tanks 3 / 4 above capacity in many cells: return flow from step 1 on
+    sto0 = np.stack([0.5 * inp.max_capilar, np.full(N, 5.0, np.float32), inp.max_gravita * rng.uniform(0.6, 1.6, N),
+                     inp.max_aquifer * rng.uniform(0.8, 1.2, N), np.full(N, 0.001, np.float32)]).astype(np.float32)
     try:
-        res = models.shia_v1(path + ".bin", path + ".hdr", cal, N, 1, 0, T, None, None, None, sp_path, vf_path,
+        res = models.shia_v1(path + ".bin", path + ".hdr", cal, N, 1, 0, T, sto0, None, None, sp_path, vf_path,
                              None, None, None, None, re_path, None)
     finally:
         models.save_speed = models.save_retorno = models.save_vfluxes = 0
@@ -320,7 +323,7 @@ def test_shia_v1_writes_step_records(tmp_path):
     recs = {}
     exp = ft.shia_v1(N, T, cal, inp.v_coef, inp.h_coef, inp.h_exp, inp.max_capilar, inp.max_gravita, inp.max_aquifer,
                      inp.hill_long, inp.elem_area, inp.rain_records, inp.pos_evento, inp.evp, inp.dt, (2, 1, 2, 1), 1, 1, 5,
-                     save_vfluxes=1, save_speed=1, save_retorno=1, step_records=recs)
+                     StoIn=sto0, save_vfluxes=1, save_speed=1, save_retorno=1, step_records=recs)
     assert os.path.getsize(sp_path) == T * 4 * N * 4 and os.path.getsize(re_path) == T * N * 4
     assert os.path.getsize(vf_path) == 3 * 4 * N * 4
     changed = 0
