@@ -185,7 +185,7 @@ __device__ __forceinline__ float pow06(float x)
 // and h4); it also keeps the per-cell accumulators of the optional outputs (rc_coef, Retorned, the last step's vfluxes).
 // T2: some tank uses the kinematic-wave speed (speed_type 2); the all-type-1 kernel carries none of that code.
 template <bool DIAG, bool T2, bool SNAP, bool STRICT>
-__global__ void __launch_bounds__(TH) k_shia5(const Shia5Args a)
+__global__ void __launch_bounds__(TH, DIAG ? 2 : (T2 ? 3 : 4)) k_shia5(const Shia5Args a)
 {
     constexpr int K = DIAG ? 14 : 2;
     __shared__ double stage[WARPS][TB][K];
