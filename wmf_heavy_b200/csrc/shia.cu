@@ -398,7 +398,7 @@ struct Shia3Args {
     double *part;               // [nblk][nsteps+1][6]
 };
 
-__global__ void __launch_bounds__(TH) k_shia3(const Shia3Args a)
+__global__ void __launch_bounds__(TH, 4) k_shia3(const Shia3Args a)
 {
     constexpr int K = 6;        // {q_total, storage, P, ET, q_super, q_base}
     __shared__ double stage[WARPS][TB][K];
