@@ -589,10 +589,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 shia["cpu_baseline"] = {"value": v, "unit": "cell-timesteps/s", "cores": 1, "kind": "port",
                                         "sample": f"1 Mi cells x 50 intervals, C restatement of Modelos_heavy.f90 shia_v1 "
                                                   f"(oracle/wmf_oracle.c, 1 thread); {dt_s:.2f} s"}
-        # kernels of libwmfb200.so per accumulation: sweepA, multiA, generalA, g_build, g_walk, g_unres, sweepC, multiC,
+        # kernels of libwmfb200.so per accumulation: sweepA, jumpA, generalA, g_build, g_walk, g_unres, sweepC, jumpC,
         # generalC; stripes = local (those six of phases A + G, macro_links, stripe_paths, stripe_summary) + boundary forest
-        # (6) + finish (route, sweepC, multiC, generalC)
-        launches_per_step = ({"walk": 2, "sweep": 9, "auto": 9}[args.algo] if world == 1 else 19)
+        # (3) + finish (route, sweepC, jumpC, generalC)
+        launches_per_step = ({"walk": 2, "sweep": 9, "auto": 9}[args.algo] if world == 1 else 16)
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
