@@ -448,10 +448,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.e2e_steps
         assert float(out_np[-1, -1]) == float(acc[-1, -1].item())
-        e2e = {"value": cells_total / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 2 * n * n,
-               "d2h_bytes_per_step": 8 * n * n, "ms_per_step": 1e3 * e2e_s,
-               "api": "wmf_heavy_b200.cu_py.basics.basin_acum(flowdir int8, mask bool, out=pinned float64 buffer) -> float64; "
-                      "`out=` is an extension of the reference signature (without it the result lands in pageable memory)"}
+        # the reference's own signature, no `out=`: the result arrives in a page-locked block of torch's host allocator
+        r = basics.basin_acum(fd_np, mk_np)
+        assert r.dtype == np.float64 and float(r[-1, -1]) == float(acc[-1, -1].item()) and float(r[n // 2, n // 3]) == float(acc[n // 2, n // 3].item())
+        del r
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r = basics.basin_acum(fd_np, mk_np)
+            del r
+        torch.cuda.synchronize()
+        e2e_plain_s = (time.perf_counter() - t0) / args.e2e_steps
+        e2e = {"value": cells_total / e2e_plain_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 2 * n * n,
+               "d2h_bytes_per_step": 8 * n * n, "ms_per_step": 1e3 * e2e_plain_s,
+               "api": "wmf_heavy_b200.cu_py.basics.basin_acum(flowdir int8, mask bool) -> float64: exactly the reference's "
+                      "signature (wmf_py/cu_py/basics.py:124); inputs in pinned host arrays, the result comes back in a "
+                      "page-locked block of torch's caching host allocator",
+               "with_out_buffer": {"value": cells_total / e2e_s / 1e6, "ms_per_step": 1e3 * e2e_s,
+                                   "api": "the same with out=<pinned float64 buffer of the caller> (an extension of the signature)"}}
         del h_dir, h_mask, h_out
 
     if args.e2e_steps > 0 and world > 1:
